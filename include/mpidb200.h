@@ -1,0 +1,144 @@
+/* MPIDB200 -- C ABI of the B200-native MPIDForce engine.
+ *
+ * This is the drop-in boundary below the OpenMM plugin's kernel contract
+ *   class CalcMPIDForceKernel  (reference: openmmapi/include/openmm/mpidKernels.h:50-104)
+ * Every entry point takes plain pointers and sizes; nothing here knows about OpenMM, torch or
+ * Python.  The C++ platform kernel (mpidopenmmplugin_b200/plugin/, B200CalcMPIDForceKernel) and the
+ * Python host (mpidopenmmplugin_b200/api.py) both sit on top of exactly these calls.
+ *
+ * Array orderings are those of MPIDForce::getMultipoleParameters
+ *   (reference: openmmapi/include/openmm/MPIDForce.h:262-290, platforms/reference/src/
+ *    MPIDReferenceKernels.cpp:84-177):
+ *   dipoles[3N]      x y z
+ *   quadrupoles[6N]  XX XY YY XZ YZ ZZ
+ *   octopoles[10N]   XXX XXY XYY YYY XXZ XYZ YYZ XZZ YZZ ZZZ
+ *   alphas[3N]       molecular-frame polarizability diagonal
+ * Units: nm, kJ/mol, elementary charges.
+ *
+ * All functions return 0 on success; on failure they return non-zero and mpidb200_last_error()
+ * describes the problem (the C++ plugin layer turns that into an OpenMMException).  There is no CPU
+ * fallback: creating a handle without a usable CUDA device fails.
+ */
+#ifndef MPIDB200_H_
+#define MPIDB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpidb200_engine* mpidb200_handle;
+
+/* MPIDForce::NonbondedMethod / PolarizationType / precision (MPIDForce.h:58-95) */
+enum { MPIDB200_NOCUTOFF = 0, MPIDB200_PME = 1 };
+enum { MPIDB200_MUTUAL = 0, MPIDB200_DIRECT = 1, MPIDB200_EXTRAPOLATED = 2 };
+enum { MPIDB200_MIXED = 0, MPIDB200_DOUBLE = 1 };
+/* induced-dipole solver for MPIDB200_MUTUAL: DIIS reproduces the reference's iteration
+ * (MPIDReferenceForce.cpp:1182-1252); CG is the preconditioned conjugate-gradient alternative. */
+enum { MPIDB200_SOLVER_DIIS = 0, MPIDB200_SOLVER_CG = 1 };
+
+typedef struct {
+    int    num_particles;
+    int    nonbonded_method;          /* MPIDForce::getNonbondedMethod            */
+    int    polarization_type;         /* MPIDForce::getPolarizationType           */
+    double cutoff;                    /* MPIDForce::getCutoffDistance   (PME only) */
+    double ewald_alpha;               /* MPIDForce::getPMEParameters; 0 = derive from ewald_tolerance */
+    int    grid[3];                   /*   "            "            ; 0 = derive  */
+    double ewald_tolerance;           /* MPIDForce::getEwaldErrorTolerance        */
+    double default_thole_width;       /* MPIDForce::getDefaultTholeWidth          */
+    double scale14;                   /* MPIDForce::get14ScaleFactor              */
+    int    max_iterations;            /* MPIDForce::getMutualInducedMaxIterations */
+    double target_epsilon;            /* MPIDForce::getMutualInducedTargetEpsilon */
+    int    num_extrapolation_coefficients;
+    double extrapolation_coefficients[8];  /* MPIDForce::getExtrapolationCoefficients */
+    int    precision;                 /* MPIDB200_MIXED | MPIDB200_DOUBLE (platform property "Precision") */
+    int    solver;                    /* MPIDB200_SOLVER_*                         */
+    int    device;                    /* CUDA device ordinal                       */
+    int    frameless_alpha_fix;       /* 0: reference behaviour (atoms without a z anchor have zero
+                                         lab-frame polarizability, MPIDReferenceForce.cpp:795-800) */
+} mpidb200_config;
+
+const char* mpidb200_last_error(void);
+
+/* Fill a config with MPIDForce's defaults (openmmapi/src/MPIDForce.cpp:43-50). */
+void mpidb200_default_config(mpidb200_config* cfg);
+
+/* replaces CalcMPIDForceKernel::initialize (mpidKernels.h:68) -- part 1: allocate the engine */
+int mpidb200_create(const mpidb200_config* cfg, mpidb200_handle* out);
+void mpidb200_destroy(mpidb200_handle h);
+
+/* replaces CalcMPIDForceKernel::initialize / copyParametersToContext (mpidKernels.h:68,96):
+ * per-particle parameters, MPIDReferenceKernels.cpp:84-141 */
+int mpidb200_set_particles(mpidb200_handle h, const double* charges, const double* dipoles,
+                           const double* quadrupoles, const double* octopoles,
+                           const int* axis_types, const int* atom_z, const int* atom_x, const int* atom_y,
+                           const double* tholes, const double* alphas);
+
+/* covalent maps as CSR: for MPIDForce::CovalentType t (0..7) atom i owns
+ * indices[offsets[t*(N+1)+i] .. offsets[t*(N+1)+i+1])   (MPIDForce::getCovalentMaps, MPIDForce.h:322-339) */
+int mpidb200_set_covalent_maps(mpidb200_handle h, const int* offsets, const int* indices);
+
+/* periodic box vectors (ContextImpl::getPeriodicBoxVectors; MPIDReferenceKernels.cpp:188-198) */
+int mpidb200_set_box(mpidb200_handle h, const double* a, const double* b, const double* c);
+
+/* replaces CalcMPIDForceKernel::execute (mpidKernels.h:77): positions[3N] in, energy out, forces
+ * ACCUMULATED into forces[3N] (MPIDReferenceKernels.cpp:225-239).  Host pointers; the copies are part
+ * of the call.  forces may be NULL when include_forces is 0. */
+int mpidb200_execute(mpidb200_handle h, const double* positions, int include_forces, int include_energy,
+                     double* energy, double* forces);
+
+/* Same evaluation with positions / forces already resident on the engine's device (double[3N]);
+ * forces are accumulated.  Asynchronous on the engine's stream except for the solver's convergence
+ * read-back; *energy is valid on return. */
+int mpidb200_execute_device(mpidb200_handle h, const double* d_positions, int include_forces, int include_energy,
+                            double* energy, double* d_forces);
+
+/* replaces getInducedDipoles / getLabFramePermanentDipoles / getTotalDipoles (mpidKernels.h:79-84):
+ * evaluate at `positions` and return double[3N].  which: 0 induced, 1 lab-frame permanent, 2 total */
+int mpidb200_get_dipoles(mpidb200_handle h, const double* positions, int which, double* out);
+
+/* replaces getSystemMultipoleMoments (mpidKernels.h:94): 13 values, Debye-based units
+ * (MPIDReferenceForce.cpp:2349-2462).  masses[N] give the centre used as origin. */
+int mpidb200_get_system_multipole_moments(mpidb200_handle h, const double* positions, const double* masses, double* out13);
+
+/* replaces getElectrostaticPotential (mpidKernels.h:86): potential at num_points points
+ * (MPIDReferenceForce.cpp:2464-2537; no octopole term, as in the reference). */
+int mpidb200_get_electrostatic_potential(mpidb200_handle h, const double* positions, int num_points,
+                                         const double* points, double* out);
+
+/* replaces getPMEParameters (mpidKernels.h:103) */
+int mpidb200_get_pme_parameters(mpidb200_handle h, double* alpha, int* nx, int* ny, int* nz);
+
+/* Solver and timing statistics of the last execute: iterations, final epsilon, and CUDA-event
+ * milliseconds per stage (see MPIDB200_STAGE_*). */
+enum {
+    MPIDB200_STAGE_NEIGHBOR = 0,   /* sort + lab frames + neighbour list       */
+    MPIDB200_STAGE_FIXED_PME,      /* spread/FFT/convolution/gather, permanent */
+    MPIDB200_STAGE_FIXED_REAL,     /* real-space permanent field               */
+    MPIDB200_STAGE_INDUCED_PME,    /* all induced reciprocal passes            */
+    MPIDB200_STAGE_INDUCED_REAL,   /* all induced real-space passes            */
+    MPIDB200_STAGE_SOLVER,         /* DIIS/CG/OPT vector work + collectives    */
+    MPIDB200_STAGE_ELECTROSTATICS, /* pair energy/force/torque                 */
+    MPIDB200_STAGE_FINISH,         /* reciprocal terms, torque mapping, output */
+    MPIDB200_NUM_STAGES
+};
+int mpidb200_get_stats(mpidb200_handle h, int* iterations, double* epsilon, double* stage_ms, long long* num_pairs);
+/* enable per-stage CUDA-event timing (adds synchronisations; off by default) */
+int mpidb200_set_profiling(mpidb200_handle h, int enabled);
+/* number of kernel launches issued by the last execute */
+long long mpidb200_last_launch_count(mpidb200_handle h);
+
+/* Neighbour list of the last execute, for the bit-exactness tests: pairs (i<j, original indices) with
+ * class 0 = ordinary, 1 = excluded (1-2, 1-3), 2 = 1-4.  Call with pairs == NULL to get the count. */
+int mpidb200_get_pair_list(mpidb200_handle h, long long capacity, int* pairs_i, int* pairs_j, int* pair_class, long long* count);
+
+/* ---- multi-GPU (one engine per rank / GPU) -------------------------------------------------------
+ * Real-space rows and PME atoms are partitioned by atom block; partial fields and the charge grid are
+ * summed across ranks with NCCL on the engine's stream.  unique_id is the 128-byte ncclUniqueId made by
+ * mpidb200_nccl_unique_id on rank 0 and distributed by the host (e.g. torch.distributed broadcast). */
+int mpidb200_nccl_unique_id(unsigned char* out128);
+int mpidb200_comm_init(mpidb200_handle h, int rank, int num_ranks, const unsigned char* unique_id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1000 @@
+// MPIDB200 -- engine: owns the device buffers, drives the stage kernels of mpid_kernels.cuh on one
+// CUDA stream, runs the induced-dipole solvers, and exports the C ABI of include/mpidb200.h.
+//
+// Host-side control flow restates ReferenceCalcMPIDForceKernel::execute and
+// MPIDReferenceForce::calculateForceAndEnergy (reference: platforms/reference/src/MPIDReferenceKernels.cpp:
+// 179-239, SimTKReference/MPIDReferenceForce.cpp:2193-2269); the stage order is our own.
+#include "../../include/mpidb200.h"
+#include "mpid_kernels.cuh"
+
+#include <cub/cub.cuh>
+#include <cufft.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace mpid;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+struct CudaError : public std::runtime_error {
+    explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+#define CUDA_CHECK(expr) do { cudaError_t err__ = (expr); if (err__ != cudaSuccess) { \
+    throw CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(err__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); } } while (0)
+#define CUFFT_CHECK(expr) do { cufftResult r__ = (expr); if (r__ != CUFFT_SUCCESS) { \
+    throw CudaError(std::string(#expr) + " failed with cufftResult " + std::to_string((int) r__)); } } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void ensure(size_t count) {
+        if (count <= cap) return;
+        if (p) { cudaFree(p); p = nullptr; }
+        size_t want = count + count/8 + 64;
+        CUDA_CHECK(cudaMalloc((void**) &p, want*sizeof(T)));
+        cap = want;
+    }
+    void upload(const std::vector<T>& v, cudaStream_t st) {
+        ensure(std::max<size_t>(v.size(), 1));
+        if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+};
+
+// ---- NCCL through dlopen: no link-time dependency, and the process-wide libnccl (e.g. torch's) is reused
+struct Id128 { char bytes[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool loadNccl() {
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return false;
+    g_nccl.GetUniqueId = (int (*)(void*)) dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int)) dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*)) dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int)) dlsym(g_nccl.lib, "ncclGetErrorString");
+    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+// ncclDataType_t / ncclRedOp_t values (nccl.h): ncclInt64 = 4, ncclUint64 = 5, ncclFloat32 = 7, ncclFloat64 = 8; ncclSum = 0
+enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct EngineBase {
+    virtual ~EngineBase() {}
+    virtual void setParticles(const double*, const double*, const double*, const double*, const int*, const int*, const int*, const int*,
+                              const double*, const double*) = 0;
+    virtual void setCovalent(const int* offsets, const int* indices) = 0;
+    virtual void setBox(const double* a, const double* b, const double* c) = 0;
+    virtual void execute(const double* pos, bool onDevice, bool includeForces, bool includeEnergy, double* energy, double* forces) = 0;
+    virtual void getDipoles(const double* pos, int which, double* out) = 0;
+    virtual void getPme(double& alpha, int& nx, int& ny, int& nz) = 0;
+    virtual void getStats(int* it, double* eps, double* ms, long long* pairs) = 0;
+    virtual long long getPairList(long long cap, int* pi, int* pj, int* pc) = 0;
+    virtual void commInit(int rank, int nranks, const unsigned char* id) = 0;
+    virtual void systemMoments(const double* pos, const double* masses, double* out13) = 0;
+    virtual void potential(const double* pos, int npts, const double* pts, double* out) = 0;
+    bool profiling = false;
+    long long launches = 0;
+};
+
+template <typename real> struct FftTraits;
+template <> struct FftTraits<float> {
+    typedef cufftComplex cplx;
+    static const cufftType fwdType = CUFFT_R2C, bwdType = CUFFT_C2R;
+    static cufftResult fwd(cufftHandle p, float* in, cplx* out) { return cufftExecR2C(p, in, out); }
+    static cufftResult bwd(cufftHandle p, cplx* in, float* out) { return cufftExecC2R(p, in, out); }
+};
+template <> struct FftTraits<double> {
+    typedef cufftDoubleComplex cplx;
+    static const cufftType fwdType = CUFFT_D2Z, bwdType = CUFFT_Z2D;
+    static cufftResult fwd(cufftHandle p, double* in, cplx* out) { return cufftExecD2Z(p, in, out); }
+    static cufftResult bwd(cufftHandle p, cplx* in, double* out) { return cufftExecZ2D(p, in, out); }
+};
+
+inline int blocksFor(long long count, int block) { return (int) std::max<long long>(1, (count + block - 1)/block); }
+
+template <typename real>
+struct Engine : public EngineBase {
+    typedef typename Real4<real>::type real4;
+    typedef typename FftTraits<real>::cplx cplx;
+    mpidb200_config cfg;
+    int n;
+    cudaStream_t stream = nullptr;
+    bool haveParticles = false, haveBox = false, pmeReady = false;
+    // host copies
+    std::vector<double> hCharge, hDipole, hQuad, hOct, hThole, hAlpha, hDamp;
+    std::vector<int> hAxis, hZ, hX, hY;
+    std::vector<int> hSpStart, hSpPartner, hSpClass, hSpLo, hSpHi, hSpPairClass;
+    double boxA[3], boxB[3], boxC[3];
+    DevParams P;
+    double alphaEwald = 0; int grid[3] = {0, 0, 0};
+    // static device data
+    DevBuf<double> dCharge, dDipole, dQuad, dOct, dThole, dAlpha, dDamp;
+    DevBuf<int> dAxis, dZ, dX, dY;
+    DevBuf<int> dSpStart, dSpPartner, dSpClass, dSpLo, dSpHi, dSpPairClass;
+    // per-evaluation device data
+    DevBuf<double> dPos, dPosW, dForcesOut;
+    DevBuf<int> dCellKey, dAtomIdx, dSortedKey, dOrder, dInv, dCellStart;
+    DevBuf<unsigned char> dSortTemp, dScanTemp;
+    DevBuf<double4> dPosS; DevBuf<float4> dPosF;
+    DevBuf<double> dCartD, dPkD, dSphD, dAlphaLab;
+    DevBuf<real> dCartR, dPkR;
+    DevBuf<int> dAniso;
+    DevBuf<double2> dDampThole;
+    DevBuf<real4> dMud;
+    DevBuf<unsigned> dFullCount, dHalfCount, dFullStart, dHalfStart, dNbr, dPairI, dPairJ;
+    DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
+    DevBuf<unsigned long long> dForce, dTorque, dEnergy;
+    DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp;
+    DevBuf<cplx> dGridC;
+    DevBuf<double> dModX, dModY, dModZ;
+    DevBuf<double> dHistDip, dHistErr, dDotPartial, dDots;
+    DevBuf<double> dPtDip, dPtField, dPtGrad;
+    cufftHandle planF = 0, planB = 0;
+    bool plansMade = false;
+    double* hPinned = nullptr;      // small pinned scratch (dot products, energy, totals)
+    double* hPinnedPos = nullptr; size_t hPinnedPosCap = 0;
+    // statistics
+    int lastIterations = 0; double lastEps = 0; double stageMs[MPIDB200_NUM_STAGES]; long long lastPairs = 0, lastFull = 0;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    // multi-GPU
+    void* comm = nullptr; int rank = 0, numRanks = 1;
+    std::vector<double> hLastMu;
+
+    explicit Engine(const mpidb200_config& c) : cfg(c), n(c.num_particles) {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaMallocHost((void**) &hPinned, 256*sizeof(double)));
+        CUDA_CHECK(cudaEventCreate(&evA));
+        CUDA_CHECK(cudaEventCreate(&evB));
+        memset(&P, 0, sizeof(P));
+        memset(stageMs, 0, sizeof(stageMs));
+        if (cfg.nonbonded_method == MPIDB200_NOCUTOFF) {
+            double a[3] = {1, 0, 0}, b[3] = {0, 1, 0}, cc[3] = {0, 0, 1};
+            setBox(a, b, cc);
+        }
+    }
+    ~Engine() {
+        cudaSetDevice(cfg.device);
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); }
+        if (hPinned) cudaFreeHost(hPinned);
+        if (hPinnedPos) cudaFreeHost(hPinnedPos);
+        if (evA) cudaEventDestroy(evA);
+        if (evB) cudaEventDestroy(evB);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+#define LAUNCH(kernel, gridDim, blockDim, ...) do { kernel<<<(gridDim), (blockDim), 0, stream>>>(__VA_ARGS__); launches++; \
+        cudaError_t le__ = cudaGetLastError(); if (le__ != cudaSuccess) throw CudaError(std::string("launch of " #kernel " failed: ") + cudaGetErrorString(le__)); } while (0)
+
+    // ---- parameters --------------------------------------------------------------------------------
+    void setParticles(const double* charges, const double* dipoles, const double* quadrupoles, const double* octopoles,
+                      const int* axis, const int* az, const int* ax, const int* ay, const double* tholes, const double* alphas) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        hCharge.assign(charges, charges + n); hDipole.assign(dipoles, dipoles + 3*(size_t) n);
+        hQuad.assign(quadrupoles, quadrupoles + 6*(size_t) n); hOct.assign(octopoles, octopoles + 10*(size_t) n);
+        hAxis.assign(axis, axis + n); hZ.assign(az, az + n); hX.assign(ax, ax + n); hY.assign(ay, ay + n);
+        hThole.assign(tholes, tholes + n); hAlpha.assign(alphas, alphas + 3*(size_t) n);
+        hDamp.resize(n);
+        for (int i = 0; i < n; i++) {
+            // validation mirrors MPIDForceImpl::initialize (openmmapi/src/MPIDForceImpl.cpp:121-149)
+            if (hAxis[i] < 0 || hAxis[i] > 5) throw std::runtime_error("MPIDForce: axis type not recognized for particle " + std::to_string(i));
+            int idx[3] = {hZ[i], hX[i], hY[i]};
+            for (int k = 0; k < 3; k++)
+                if (idx[k] >= n) throw std::runtime_error("MPIDForce: invalid axis particle index for particle " + std::to_string(i));
+            if (hAxis[i] != NoAxisType && hZ[i] < 0) throw std::runtime_error("MPIDForce: particle " + std::to_string(i) + " has an axis type but no z-axis particle");
+            if (hAxis[i] != NoAxisType && hAxis[i] != ZOnly && hZ[i] >= 0 && hX[i] < 0)
+                throw std::runtime_error("MPIDForce: particle " + std::to_string(i) + " needs an x-axis particle for its axis type");
+            if ((hAxis[i] == ZBisect || hAxis[i] == ThreeFold) && hY[i] < 0)
+                throw std::runtime_error("MPIDForce: particle " + std::to_string(i) + " needs a y-axis particle for its axis type");
+            // dampingFactor (MPIDReferenceKernels.cpp:123)
+            hDamp[i] = pow((hAlpha[3*i] + hAlpha[3*i+1] + hAlpha[3*i+2])/3.0, 1.0/6.0);
+        }
+        dCharge.upload(hCharge, stream); dDipole.upload(hDipole, stream); dQuad.upload(hQuad, stream); dOct.upload(hOct, stream);
+        dAxis.upload(hAxis, stream); dZ.upload(hZ, stream); dX.upload(hX, stream); dY.upload(hY, stream);
+        dThole.upload(hThole, stream); dAlpha.upload(hAlpha, stream); dDamp.upload(hDamp, stream);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        haveParticles = true;
+        if (hSpStart.empty()) {   // no covalent maps yet: empty special lists
+            std::vector<int> off(8*(size_t) (n+1), 0), idx(1, 0);
+            setCovalent(off.data(), idx.data());
+        }
+    }
+
+    // Pair classes exactly as setupScaleMaps (MPIDReferenceForce.cpp:190-225): lists 0..3 (1-2, 1-3, 1-4, 1-5)
+    // give scale 0, 0, scale14, 1; only partners with a higher index than the owner count; a later list wins.
+    void setCovalent(const int* offsets, const int* indices) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        std::vector<std::map<int, int> > cls(n);
+        for (int i = 0; i < n; i++)
+            for (int t = 0; t < 4; t++) {
+                int b = offsets[(size_t) t*(n+1) + i], e = offsets[(size_t) t*(n+1) + i + 1];
+                for (int k = b; k < e; k++) {
+                    int j = indices[k];
+                    if (j < 0 || j >= n) throw std::runtime_error("MPIDForce: covalent map of particle " + std::to_string(i) + " holds an invalid index");
+                    if (j <= i) continue;
+                    cls[i][j] = t < 2 ? 1 : (t == 2 ? 2 : 0);
+                }
+            }
+        std::vector<std::vector<std::pair<int, int> > > directed(n);
+        hSpLo.clear(); hSpHi.clear(); hSpPairClass.clear();
+        for (int i = 0; i < n; i++)
+            for (auto& kv : cls[i]) {
+                if (kv.second == 0) continue;
+                hSpLo.push_back(i); hSpHi.push_back(kv.first); hSpPairClass.push_back(kv.second);
+                directed[i].push_back(std::make_pair(kv.first, kv.second));
+                directed[kv.first].push_back(std::make_pair(i, kv.second));
+            }
+        hSpStart.assign(n+1, 0); hSpPartner.clear(); hSpClass.clear();
+        for (int i = 0; i < n; i++) {
+            std::sort(directed[i].begin(), directed[i].end());
+            hSpStart[i] = (int) hSpPartner.size();
+            for (auto& pr : directed[i]) { hSpPartner.push_back(pr.first); hSpClass.push_back(pr.second); }
+        }
+        hSpStart[n] = (int) hSpPartner.size();
+        dSpStart.upload(hSpStart, stream); dSpPartner.upload(hSpPartner, stream); dSpClass.upload(hSpClass, stream);
+        dSpLo.upload(hSpLo, stream); dSpHi.upload(hSpHi, stream); dSpPairClass.upload(hSpPairClass, stream);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    // B-spline moduli, identical construction to initializeBSplineModuli (MPIDReferenceForce.cpp:2720-2810)
+    static void bsplineModuli(int size, std::vector<double>& mod) {
+        double th[6][5];
+        bsplineWeights<double>(0.0, th);
+        mod.assign(size, 0.0);
+        for (int i = 0; i < size; i++) {
+            double s1 = 0, s2 = 0;
+            for (int j = 1; j <= 6 && j < size; j++) {
+                double arg = 2.0*MPID_PI*i*j/size;
+                s1 += th[j-1][0]*cos(arg); s2 += th[j-1][0]*sin(arg);
+            }
+            mod[i] = s1*s1 + s2*s2;
+        }
+        const double eps = 1.0e-7;
+        if (mod[0] < eps) mod[0] = 0.5*mod[1];
+        for (int i = 1; i < size-1; i++) if (mod[i] < eps) mod[i] = 0.5*(mod[i-1] + mod[i+1]);
+        if (mod[size-1] < eps) mod[size-1] = 0.5*mod[size-2];
+        for (int i = 1; i <= size; i++) {
+            int k = i - 1;
+            if (i > size/2) k -= size;
+            double zeta = 1.0;
+            if (k != 0) {
+                double s1 = 1, s2 = 1, f = MPID_PI*k/size;
+                for (int j = 1; j <= 50; j++) { double a = f/(f + MPID_PI*j); s1 += pow(a, 6); s2 += pow(a, 12); }
+                for (int j = 1; j <= 50; j++) { double a = f/(f - MPID_PI*j); s1 += pow(a, 6); s2 += pow(a, 12); }
+                zeta = s2/s1;
+            }
+            mod[i-1] *= zeta*zeta;
+        }
+    }
+
+    static int legalFftSize(int m) {   // smallest 2,3,5,7-smooth size >= m (what CudaFFT3D::findLegalDimension does)
+        if (m < 1) m = 1;
+        for (;; m++) {
+            int u = m;
+            for (int f : {2, 3, 5, 7}) while (u % f == 0) u /= f;
+            if (u == 1) return m;
+        }
+    }
+
+    void setBox(const double* a, const double* b, const double* c) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        for (int i = 0; i < 3; i++) { boxA[i] = a[i]; boxB[i] = b[i]; boxC[i] = c[i]; }
+        const bool pme = cfg.nonbonded_method == MPIDB200_PME;
+        if (pme) {
+            if (a[0] == 0.0 || b[1] == 0.0 || c[2] == 0.0) throw std::runtime_error("Box size of zero is invalid.");
+            // MPIDReferenceKernels.cpp:193-197
+            double minAllowed = 1.999999*cfg.cutoff;
+            if (a[0] < minAllowed || b[1] < minAllowed || c[2] < minAllowed)
+                throw std::runtime_error("The periodic box size has decreased to less than twice the nonbonded cutoff.");
+        }
+        P.n = n; P.method = cfg.nonbonded_method; P.polarization = cfg.polarization_type;
+        P.numRanks = numRanks; P.rank = rank;
+        P.cutoff = cfg.cutoff; P.cutoff2 = cfg.cutoff*cfg.cutoff;
+        P.defaultThole = cfg.default_thole_width; P.scale14 = cfg.scale14;
+        makeBox(P.box, a, b, c);
+        for (int sx = -1; sx <= 1; sx++) for (int sy = -1; sy <= 1; sy++) for (int sz = -1; sz <= 1; sz++) {
+            int code = (sx+1)*9 + (sy+1)*3 + (sz+1);
+            for (int k = 0; k < 3; k++) P.shift[code][k] = pme ? sx*a[k] + sy*b[k] + sz*c[k] : 0.0;
+        }
+        if (!pme) {
+            P.ncell[0] = P.ncell[1] = P.ncell[2] = 1;
+            P.alpha = 0; P.selfFieldTerm = 0;
+            P.grid[0] = P.grid[1] = P.grid[2] = 0;
+            haveBox = true;
+            return;
+        }
+        // PME parameters: explicit, or the OpenMM rule the reference delegates to
+        // (NonbondedForceImpl::calcPMEParameters; call site MPIDReferenceKernels.cpp:161-170)
+        double al = cfg.ewald_alpha; int g[3] = {cfg.grid[0], cfg.grid[1], cfg.grid[2]};
+        if (al == 0.0 || g[0] == 0) {
+            double tol = cfg.ewald_tolerance;
+            al = sqrt(-log(2.0*tol))/cfg.cutoff;
+            double len[3] = {a[0], b[1], c[2]};
+            for (int d = 0; d < 3; d++) g[d] = legalFftSize(std::max((int) ceil(2.0*al*len[d]/(3.0*pow(tol, 0.2))), 6));
+        }
+        bool gridChanged = !(g[0] == grid[0] && g[1] == grid[1] && g[2] == grid[2]);
+        alphaEwald = al; grid[0] = g[0]; grid[1] = g[1]; grid[2] = g[2];
+        if (g[0] < 6 || g[1] < 6 || g[2] < 6) throw std::runtime_error("MPIDForce: PME grid dimensions must be at least 6");
+        P.alpha = al; P.grid[0] = g[0]; P.grid[1] = g[1]; P.grid[2] = g[2];
+        P.selfFieldTerm = (4.0/3.0)*al*al*al/MPID_SQRT_PI;
+        makePmeGeom(P.geom, P.box, g[0], g[1], g[2]);
+        // cell grid: perpendicular widths of the (reduced) triclinic cell
+        double vol = a[0]*b[1]*c[2];
+        double bxc[3] = {b[1]*c[2] - b[2]*c[1], b[2]*c[0] - b[0]*c[2], b[0]*c[1] - b[1]*c[0]};
+        double cxa[3] = {c[1]*a[2] - c[2]*a[1], c[2]*a[0] - c[0]*a[2], c[0]*a[1] - c[1]*a[0]};
+        double axb[3] = {a[1]*b[2] - a[2]*b[1], a[2]*b[0] - a[0]*b[2], a[0]*b[1] - a[1]*b[0]};
+        double w[3] = {vol/sqrt(bxc[0]*bxc[0] + bxc[1]*bxc[1] + bxc[2]*bxc[2]), vol/sqrt(cxa[0]*cxa[0] + cxa[1]*cxa[1] + cxa[2]*cxa[2]),
+                       vol/sqrt(axb[0]*axb[0] + axb[1]*axb[1] + axb[2]*axb[2])};
+        for (int d = 0; d < 3; d++) {
+            int nc = (int) floor(w[d]/(cfg.cutoff*1.0001));
+            if (nc < 3) nc = 1;
+            nc = std::min(nc, 1024);
+            P.ncell[d] = nc;
+        }
+        // FFT plans + convolution table
+        size_t G = (size_t) g[0]*g[1]*g[2], GC = (size_t) g[0]*g[1]*(g[2]/2 + 1);
+        if (gridChanged || !plansMade) {
+            if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); plansMade = false; }
+            CUFFT_CHECK(cufftPlan3d(&planF, g[0], g[1], g[2], FftTraits<real>::fwdType));
+            CUFFT_CHECK(cufftPlan3d(&planB, g[0], g[1], g[2], FftTraits<real>::bwdType));
+            CUFFT_CHECK(cufftSetStream(planF, stream));
+            CUFFT_CHECK(cufftSetStream(planB, stream));
+            plansMade = true;
+            std::vector<double> mx, my, mz;
+            bsplineModuli(g[0], mx); bsplineModuli(g[1], my); bsplineModuli(g[2], mz);
+            dModX.upload(mx, stream); dModY.upload(my, stream); dModZ.upload(mz, stream);
+        }
+        dGrid.ensure(G); dGridC.ensure(GC); dEterm.ensure(GC);
+        LAUNCH((k_eterm_table<real>), blocksFor((long long) GC, 256), 256, P, dModX.p, dModY.p, dModZ.p, dEterm.p);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        haveBox = true;
+    }
+
+    // ---- timing helpers ------------------------------------------------------------------------------
+    int curStage = -1;
+    void stageBegin(int st) {
+        if (!profiling) return;
+        curStage = st;
+        CUDA_CHECK(cudaEventRecord(evA, stream));
+    }
+    void stageEnd() {
+        if (!profiling || curStage < 0) return;
+        CUDA_CHECK(cudaEventRecord(evB, stream));
+        CUDA_CHECK(cudaEventSynchronize(evB));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, evA, evB));
+        stageMs[curStage] += ms;
+        curStage = -1;
+    }
+
+    void allReduce(void* buf, size_t count, int dtype) {
+        if (numRanks <= 1) return;
+        int rc = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, comm, stream);
+        if (rc != 0) throw CudaError(std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    }
+
+    // ---- stages --------------------------------------------------------------------------------------
+    ParticleParams particleParams() {
+        ParticleParams pp;
+        pp.charge = dCharge.p; pp.dipole = dDipole.p; pp.quadrupole = dQuad.p; pp.octopole = dOct.p;
+        pp.axis = dAxis.p; pp.atomZ = dZ.p; pp.atomX = dX.p; pp.atomY = dY.p;
+        pp.thole = dThole.p; pp.alpha = dAlpha.p; pp.damp = dDamp.p;
+        return pp;
+    }
+
+    void buildNeighbors(const double* dPosIn) {
+        const int B = 256;
+        int numCells = P.ncell[0]*P.ncell[1]*P.ncell[2];
+        dPosW.ensure(3*(size_t) n); dCellKey.ensure(n); dAtomIdx.ensure(n); dSortedKey.ensure(n); dOrder.ensure(n); dInv.ensure(n);
+        dCellStart.ensure((size_t) numCells + 2);
+        LAUNCH(k_wrap_cells, blocksFor(n, B), B, P, dPosIn, dPosW.p, dCellKey.p, dAtomIdx.p);
+        if (numCells > 1) {
+            int bits = 1;
+            while ((1 << bits) < numCells) bits++;
+            size_t tempBytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, dCellKey.p, dSortedKey.p, dAtomIdx.p, dOrder.p, n, 0, bits, stream);
+            dSortTemp.ensure(tempBytes + 16);
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(dSortTemp.p, tempBytes, dCellKey.p, dSortedKey.p, dAtomIdx.p, dOrder.p, n, 0, bits, stream));
+            launches += 4;
+        } else {
+            CUDA_CHECK(cudaMemcpyAsync(dSortedKey.p, dCellKey.p, n*sizeof(int), cudaMemcpyDeviceToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(dOrder.p, dAtomIdx.p, n*sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        }
+        LAUNCH(k_cell_starts, blocksFor(numCells + 1, B), B, n, numCells, dSortedKey.p, dCellStart.p);
+        LAUNCH(k_inverse_order, blocksFor(n, B), B, n, dOrder.p, dInv.p);
+        // row partition of the sorted atoms across ranks
+        P.rowBegin = (int) ((long long) n*rank/numRanks);
+        P.rowEnd = (int) ((long long) n*(rank+1)/numRanks);
+        // lab frames
+        dPosS.ensure(n); dPosF.ensure(n); dCartD.ensure(20*(size_t) n); dPkD.ensure(16*(size_t) n); dSphD.ensure(16*(size_t) n);
+        dAlphaLab.ensure(6*(size_t) n); dAniso.ensure(n); dDampThole.ensure(n); dMud.ensure(n);
+        real* cartR; real* pkR;
+        if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
+        else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
+        LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
+               dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p);
+        // neighbour list: count, scan, fill
+        int rows = P.rowEnd - P.rowBegin;
+        dFullCount.ensure((size_t) rows + 1); dHalfCount.ensure((size_t) rows + 1); dFullStart.ensure((size_t) rows + 1); dHalfStart.ensure((size_t) rows + 1);
+        CUDA_CHECK(cudaMemsetAsync(dFullCount.p, 0, ((size_t) rows + 1)*sizeof(unsigned), stream));
+        CUDA_CHECK(cudaMemsetAsync(dHalfCount.p, 0, ((size_t) rows + 1)*sizeof(unsigned), stream));
+        if (rows > 0)
+            LAUNCH((k_neighbor_list<false>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
+                   dSpStart.p, dSpPartner.p, dFullCount.p, dHalfCount.p, (const unsigned*) nullptr, (const unsigned*) nullptr,
+                   (unsigned*) nullptr, (unsigned*) nullptr, (unsigned*) nullptr);
+        size_t tempBytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dFullCount.p, dFullStart.p, rows + 1, stream);
+        dScanTemp.ensure(tempBytes + 16);
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dFullCount.p, dFullStart.p, rows + 1, stream));
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dHalfCount.p, dHalfStart.p, rows + 1, stream));
+        launches += 2;
+        unsigned* totals = (unsigned*) hPinned;
+        CUDA_CHECK(cudaMemcpyAsync(&totals[0], dFullStart.p + rows, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaMemcpyAsync(&totals[1], dHalfStart.p + rows, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        lastFull = totals[0]; lastPairs = totals[1];
+        dNbr.ensure((size_t) lastFull + 1); dPairI.ensure((size_t) lastPairs + 1); dPairJ.ensure((size_t) lastPairs + 1);
+        if (rows > 0)
+            LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
+                   dSpStart.p, dSpPartner.p, (unsigned*) nullptr, (unsigned*) nullptr, dFullStart.p, dHalfStart.p, dNbr.p, dPairI.p, dPairJ.p);
+    }
+
+    void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
+        size_t GC = (size_t) grid[0]*grid[1]*(grid[2]/2 + 1);
+        if (numRanks > 1) allReduce(dGrid.p, (size_t) grid[0]*grid[1]*grid[2], sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64);
+        CUFFT_CHECK(FftTraits<real>::fwd(planF, dGrid.p, dGridC.p));
+        LAUNCH((k_convolution<cplx, real>), blocksFor((long long) GC, 256), 256, GC, dEterm.p, dGridC.p);
+        CUFFT_CHECK(FftTraits<real>::bwd(planB, dGridC.p, dGrid.p));
+        launches += 2;
+    }
+
+    real* cartR() { return sizeof(real) == sizeof(double) ? (real*) dCartD.p : dCartR.p; }
+    real* pkR() { return sizeof(real) == sizeof(double) ? (real*) dPkD.p : dPkR.p; }
+
+    void fixedFieldStage(const double* dPosIn) {
+        const bool pme = P.method == PME;
+        const int rows = P.rowEnd - P.rowBegin;
+        size_t G = (size_t) grid[0]*grid[1]*grid[2];
+        dField.ensure(3*(size_t) n); dEfix.ensure(3*(size_t) n); dMu.ensure(3*(size_t) n);
+        dPhi.ensure(35*(size_t) n); dPhidp.ensure(35*(size_t) n);
+        if (pme) {
+            stageBegin(MPIDB200_STAGE_FIXED_PME);
+            dFrac.ensure(20*(size_t) n);
+            LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
+            CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), stream));
+            if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
+            reciprocalPass();
+            if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhi.p);
+            stageEnd();
+        }
+        stageBegin(MPIDB200_STAGE_FIXED_REAL);
+        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), stream));
+        if (rows > 0) {
+            if (pme) LAUNCH((k_fixed_field<real, true>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dFullStart.p, dNbr.p, dField.p);
+            else LAUNCH((k_fixed_field<real, false>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dFullStart.p, dNbr.p, dField.p);
+            if (!hSpPartner.empty())
+                LAUNCH((k_special_field<0>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
+                       dCartD.p, dDampThole.p, (const double*) nullptr, dField.p, (double*) nullptr);
+            if (pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
+        }
+        allReduce(dField.p, 3*(size_t) n, NCCL_FLOAT64);
+        LAUNCH((k_fixed_mu<real>), blocksFor(n, 256), 256, P, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
+        stageEnd();
+    }
+
+    // Field of the current induced dipoles into dIfield (and gradient into `grad`, which the caller zeroed).
+    // level: highest derivative order gathered from the reciprocal grid (1 field, 2 +gradient, 4 everything)
+    void inducedFieldPass(const double* dPosIn, int level, double* grad, bool realSpace) {
+        const bool pme = P.method == PME;
+        const int rows = P.rowEnd - P.rowBegin;
+        size_t G = (size_t) grid[0]*grid[1]*grid[2];
+        dIfield.ensure(3*(size_t) n);
+        if (pme) {
+            stageBegin(MPIDB200_STAGE_INDUCED_PME);
+            CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), stream));
+            if (rows > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, (const real*) nullptr, dMu.p, dGrid.p);
+            reciprocalPass();
+            if (rows > 0) {
+                if (level == 1) LAUNCH((k_gather<real, 1>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
+                else if (level == 2) LAUNCH((k_gather<real, 2>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
+                else LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
+            }
+            stageEnd();
+        }
+        if (!realSpace) return;
+        stageBegin(MPIDB200_STAGE_INDUCED_REAL);
+        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dIfield.p, 0, 3*(size_t) n*sizeof(double), stream));
+        if (rows > 0) {
+            const int nb = blocksFor((long long) rows*MPID_LANES, 256);
+            if (grad) {
+                if (pme) LAUNCH((k_induced_field<real, true, true>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, grad);
+                else LAUNCH((k_induced_field<real, false, true>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, grad);
+            } else {
+                if (pme) LAUNCH((k_induced_field<real, true, false>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, (double*) nullptr);
+                else LAUNCH((k_induced_field<real, false, false>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, (double*) nullptr);
+            }
+            if (!hSpPartner.empty()) {
+                if (grad) LAUNCH((k_special_field<2>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
+                                 dCartD.p, dDampThole.p, dMu.p, dIfield.p, grad);
+                else LAUNCH((k_special_field<1>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
+                            dCartD.p, dDampThole.p, dMu.p, dIfield.p, (double*) nullptr);
+            }
+            if (pme) {
+                if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, grad);
+                else LAUNCH((k_induced_finish<real, false>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
+            }
+        }
+        // the per-iteration collective of the partitioned solver: partial induced fields -> full field
+        allReduce(dIfield.p, 3*(size_t) n, NCCL_FLOAT64);
+        if (grad) allReduce(grad, 6*(size_t) n, NCCL_FLOAT64);
+        stageEnd();
+    }
+
+    // Gauss-Jordan with partial pivoting for the (m+1)x(m+1) DIIS system (:1254-1291 solves the same
+    // system through an SVD)
+    static void solveDiis(int m, const std::vector<double>& Bm, int ld, std::vector<double>& coef) {
+        int rank = m + 1, w = rank + 1;
+        std::vector<double> a((size_t) rank*w, 0.0);
+        for (int i = 0; i < rank; i++)
+            for (int j = 0; j < rank; j++)
+                a[(size_t) i*w + j] = (i == 0 && j == 0) ? 0.0 : ((i == 0 || j == 0) ? -1.0 : Bm[(size_t) (i-1)*ld + (j-1)]);
+        a[rank] = -1.0;
+        for (int c = 0; c < rank; c++) {
+            int piv = c;
+            for (int r = c+1; r < rank; r++) if (fabs(a[(size_t) r*w + c]) > fabs(a[(size_t) piv*w + c])) piv = r;
+            if (piv != c) for (int k = 0; k < w; k++) std::swap(a[(size_t) c*w + k], a[(size_t) piv*w + k]);
+            double d = a[(size_t) c*w + c];
+            if (d == 0.0) continue;
+            for (int r = 0; r < rank; r++) {
+                if (r == c) continue;
+                double f = a[(size_t) r*w + c]/d;
+                if (f == 0.0) continue;
+                for (int k = c; k < w; k++) a[(size_t) r*w + k] -= f*a[(size_t) c*w + k];
+            }
+        }
+        coef.assign(m, 0.0);
+        for (int i = 0; i < m; i++) {
+            double d = a[(size_t) (i+1)*w + (i+1)];
+            coef[i] = d != 0.0 ? a[(size_t) (i+1)*w + rank]/d : 0.0;
+        }
+    }
+
+    void dots(const double* vec, const VecList& list, int m, double* hostOut) {
+        const int nb = 296;   // 2 x 148 SMs
+        dDotPartial.ensure((size_t) nb*(MPID_MAX_HISTORY + 1)); dDots.ensure(MPID_MAX_HISTORY + 1);
+        LAUNCH(k_dots_partial, nb, 256, 3*(size_t) n, m, vec, list, dDotPartial.p);
+        LAUNCH(k_dots_final, 1, 32, nb, m, dDotPartial.p, dDots.p);
+        CUDA_CHECK(cudaMemcpyAsync(hostOut, dDots.p, m*sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    // convergeInduceDipolesByDIIS (:1182-1252)
+    void solveMutualDiis(const double* dPosIn) {
+        const int H = MPID_MAX_HISTORY;
+        dHistDip.ensure((size_t) H*3*n); dHistErr.ensure((size_t) H*3*n);
+        std::vector<int> slots;                 // history slots in age order
+        std::vector<double> Bm((size_t) H*H, 0.0);
+        std::vector<int> freeSlots;
+        for (int k = H-1; k >= 0; k--) freeSlots.push_back(k);
+        lastIterations = 0; lastEps = 0;
+        for (int it = 0; ; it++) {
+            inducedFieldPass(dPosIn, 1, nullptr, true);
+            stageBegin(MPIDB200_STAGE_SOLVER);
+            if ((int) slots.size() == H) {     // drop the oldest (:1232-1236)
+                freeSlots.push_back(slots.front());
+                slots.erase(slots.begin());
+                for (int a = 0; a + 1 < H; a++) for (int b = 0; b + 1 < H; b++) Bm[(size_t) a*H + b] = Bm[(size_t) (a+1)*H + (b+1)];
+            }
+            int slot = freeSlots.back(); freeSlots.pop_back();
+            slots.push_back(slot);
+            int m = (int) slots.size();
+            double* hd = dHistDip.p + (size_t) slot*3*n;
+            double* he = dHistErr.p + (size_t) slot*3*n;
+            LAUNCH(k_diis_record, blocksFor(n, 256), 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he);
+            VecList list;
+            for (int k = 0; k < m; k++) list.v[k] = dHistErr.p + (size_t) slots[k]*3*n;
+            dots(he, list, m, hPinned + 8);
+            for (int k = 0; k < m; k++) Bm[(size_t) (m-1)*H + k] = Bm[(size_t) k*H + (m-1)] = hPinned[8 + k];
+            double eps = MPID_DEBYE*sqrt(hPinned[8 + m - 1]/n);
+            lastIterations = it; lastEps = eps;
+            bool done = eps < cfg.target_epsilon;
+            if (done || it == cfg.max_iterations) {
+                stageEnd();
+                if (!done) throw std::runtime_error("Induced dipoles did not converge:  iterations=" + std::to_string(it) + " eps=" + std::to_string(eps));
+                return;
+            }
+            std::vector<double> coef(m, 1.0);
+            if (m > 1) solveDiis(m, Bm, H, coef);
+            VecList dl; CoefList cl;
+            for (int k = 0; k < m; k++) { dl.v[k] = dHistDip.p + (size_t) slots[k]*3*n; cl.c[k] = coef[k]; }
+            LAUNCH((k_combine<real>), blocksFor(n, 256), 256, n, m, dl, cl, dMu.p, dMud.p);
+            stageEnd();
+        }
+    }
+
+    // convergeInduceDipolesByExtrapolation (:1125-1180)
+    std::vector<double> optPart;
+    void solveExtrapolated(const double* dPosIn) {
+        int K = cfg.num_extrapolation_coefficients;
+        if (K < 1 || K > 8) throw std::runtime_error("MPIDForce: between 1 and 8 extrapolation coefficients are supported");
+        optPart.assign(K, 0.0);
+        for (int i = 0; i < K; i++) for (int j = i; j < K; j++) optPart[i] += cfg.extrapolation_coefficients[j];
+        dPtDip.ensure((size_t) K*3*n); dPtField.ensure((size_t) K*3*n); dPtGrad.ensure((size_t) K*6*n);
+        CUDA_CHECK(cudaMemcpyAsync(dPtDip.p, dMu.p, 3*(size_t) n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        for (int order = 1; order < K; order++) {
+            double* g = dPtGrad.p + (size_t) (order-1)*6*n;
+            CUDA_CHECK(cudaMemsetAsync(g, 0, 6*(size_t) n*sizeof(double), stream));
+            inducedFieldPass(dPosIn, 2, g, true);
+            stageBegin(MPIDB200_STAGE_SOLVER);
+            LAUNCH((k_opt_step<real>), blocksFor(n, 256), 256, P, dAlphaLab.p, dIfield.p, dMu.p, dMud.p,
+                   dPtDip.p + (size_t) order*3*n, dPtField.p + (size_t) (order-1)*3*n);
+            stageEnd();
+        }
+        stageBegin(MPIDB200_STAGE_SOLVER);
+        VecList dl; CoefList cl;
+        for (int k = 0; k < K; k++) { dl.v[k] = dPtDip.p + (size_t) k*3*n; cl.c[k] = optPart[k]; }
+        LAUNCH((k_combine<real>), blocksFor(n, 256), 256, n, K, dl, cl, dMu.p, dMud.p);
+        stageEnd();
+        // the reference evaluates the field of the final dipoles once more; only its reciprocal potential
+        // (phidp) is consumed afterwards (:1178)
+        if (P.method == PME) inducedFieldPass(dPosIn, 4, nullptr, false);
+    }
+
+    void evaluate(const double* dPosIn, bool includeForces, bool includeEnergy, double* energy, double* dForcesOut, bool dipolesOnly) {
+        if (!haveParticles) throw std::runtime_error("mpidb200: particles have not been set");
+        if (!haveBox) throw std::runtime_error("mpidb200: periodic box vectors have not been set");
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        launches = 0;
+        memset(stageMs, 0, sizeof(stageMs));
+        const bool pme = P.method == PME;
+        P.numRanks = numRanks; P.rank = rank;
+        stageBegin(MPIDB200_STAGE_NEIGHBOR);
+        buildNeighbors(dPosIn);
+        dForce.ensure(3*(size_t) n); dTorque.ensure(3*(size_t) n); dEnergy.ensure(2);
+        CUDA_CHECK(cudaMemsetAsync(dForce.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
+        CUDA_CHECK(cudaMemsetAsync(dTorque.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
+        CUDA_CHECK(cudaMemsetAsync(dEnergy.p, 0, 2*sizeof(unsigned long long), stream));
+        stageEnd();
+        const int rows = P.rowEnd - P.rowBegin;
+
+        fixedFieldStage(dPosIn);
+        lastIterations = 0; lastEps = 0;
+        if (P.polarization == Direct) {
+            if (pme && !dipolesOnly) inducedFieldPass(dPosIn, 4, nullptr, false);
+        } else if (P.polarization == Mutual) {
+            if (cfg.solver != MPIDB200_SOLVER_DIIS) throw std::runtime_error("mpidb200: only the DIIS solver is available in this build");
+            solveMutualDiis(dPosIn);
+            if (pme && !dipolesOnly && rows > 0) {
+                // the converged dipoles' reciprocal potential is still on the grid: fetch all 35 derivatives
+                stageBegin(MPIDB200_STAGE_INDUCED_PME);
+                LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
+                stageEnd();
+            }
+        } else {
+            solveExtrapolated(dPosIn);
+        }
+        if (dipolesOnly) return;
+
+        stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
+        const bool mutual = P.polarization == Mutual;
+        if (lastPairs > 0) {
+            const int nb = blocksFor(lastPairs, 128);
+#define ES_LAUNCH(EW, MU) LAUNCH((k_electrostatics<real, EW, MU>), nb, 128, P, lastPairs, dPairI.p, dPairJ.p, dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p)
+            if (pme) { if (mutual) ES_LAUNCH(true, true); else ES_LAUNCH(true, false); }
+            else { if (mutual) ES_LAUNCH(false, true); else ES_LAUNCH(false, false); }
+#undef ES_LAUNCH
+        }
+        if (!hSpLo.empty()) {
+            const int ns = (int) hSpLo.size();
+            if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                               dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+            else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                        dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+        }
+        stageEnd();
+
+        stageBegin(MPIDB200_STAGE_FINISH);
+        if (pme && rows > 0)
+            LAUNCH((k_reciprocal_terms<real>), blocksFor(rows, 128), 128, P, dPhi.p, dPhidp.p, dCartD.p, dSphD.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+        if (P.polarization == Extrapolated && rows > 0) {
+            OptLists L;
+            L.K = cfg.num_extrapolation_coefficients;
+            for (int k = 0; k < 8; k++) { L.dip[k] = L.field[k] = L.grad[k] = nullptr; L.part[k] = 0; }
+            for (int k = 0; k < L.K; k++) {
+                L.dip[k] = dPtDip.p + (size_t) k*3*n; L.part[k] = optPart[k];
+                L.field[k] = dPtField.p + (size_t) k*3*n; L.grad[k] = dPtGrad.p + (size_t) k*6*n;
+            }
+            LAUNCH(k_opt_force, blocksFor(rows, 128), 128, P, L, dAniso.p, dForce.p, dTorque.p);
+        }
+        if (numRanks > 1) {
+            allReduce(dForce.p, 3*(size_t) n, NCCL_UINT64);
+            allReduce(dTorque.p, 3*(size_t) n, NCCL_UINT64);
+            allReduce(dEnergy.p, 1, NCCL_UINT64);
+        }
+        if (includeForces) {
+            LAUNCH(k_torque_to_force, blocksFor(n, 128), 128, P, particleParams(), dOrder.p, dInv.p, dPosIn, dTorque.p, dForce.p);
+            LAUNCH(k_output_forces, blocksFor(n, 256), 256, n, dOrder.p, dForce.p, dForcesOut);
+        }
+        unsigned long long* he = (unsigned long long*) hPinned;
+        CUDA_CHECK(cudaMemcpyAsync(he, dEnergy.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        stageEnd();
+        if (energy) *energy = includeEnergy ? (double) ((long long) he[0])*(1.0/MPID_FIXED_SCALE) : 0.0;
+    }
+
+    const double* stagePositions(const double* pos, bool onDevice) {
+        if (onDevice) return pos;
+        size_t bytes = 3*(size_t) n*sizeof(double);
+        if (hPinnedPosCap < bytes) {
+            if (hPinnedPos) cudaFreeHost(hPinnedPos);
+            CUDA_CHECK(cudaMallocHost((void**) &hPinnedPos, 2*bytes));
+            hPinnedPosCap = bytes;
+        }
+        memcpy(hPinnedPos, pos, bytes);
+        dPos.ensure(3*(size_t) n);
+        CUDA_CHECK(cudaMemcpyAsync(dPos.p, hPinnedPos, bytes, cudaMemcpyHostToDevice, stream));
+        return dPos.p;
+    }
+
+    void execute(const double* pos, bool onDevice, bool includeForces, bool includeEnergy, double* energy, double* forces) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        const double* dp = stagePositions(pos, onDevice);
+        size_t bytes = 3*(size_t) n*sizeof(double);
+        double* df = nullptr;
+        if (includeForces) {
+            if (onDevice) df = forces;
+            else {
+                dForcesOut.ensure(3*(size_t) n);
+                CUDA_CHECK(cudaMemsetAsync(dForcesOut.p, 0, bytes, stream));
+                df = dForcesOut.p;
+            }
+        }
+        evaluate(dp, includeForces, includeEnergy, energy, df, false);
+        if (includeForces && !onDevice) {
+            double* stage = hPinnedPos + 3*(size_t) n;
+            CUDA_CHECK(cudaMemcpyAsync(stage, dForcesOut.p, bytes, cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            for (size_t k = 0; k < 3*(size_t) n; k++) forces[k] += stage[k];   // accumulate (MPIDReferenceKernels.cpp:229-238)
+        }
+    }
+
+    void getDipoles(const double* pos, int which, double* out) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        const double* dp = stagePositions(pos, false);
+        double e;
+        evaluate(dp, false, false, &e, nullptr, true);
+        dForcesOut.ensure(3*(size_t) n);
+        LAUNCH(k_unsort_vec3, blocksFor(n, 256), 256, n, dOrder.p, dMu.p, dCartD.p, which, dForcesOut.p);
+        CUDA_CHECK(cudaMemcpyAsync(out, dForcesOut.p, 3*(size_t) n*sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    // calculateMPIDSystemMultipoleMoments (MPIDReferenceForce.cpp:2349-2462): host-side sums over the
+    // lab-frame moments and total dipoles (off the hot path).
+    void systemMoments(const double* pos, const double* masses, double* out) override {
+        std::vector<double> total(3*(size_t) n);
+        getDipoles(pos, 2, total.data());
+        std::vector<double> cart(20*(size_t) n);
+        std::vector<int> order(n);
+        CUDA_CHECK(cudaMemcpy(cart.data(), dCartD.p, cart.size()*sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(order.data(), dOrder.p, n*sizeof(int), cudaMemcpyDeviceToHost));
+        double tm = 0, cm[3] = {0, 0, 0};
+        for (int i = 0; i < n; i++) { tm += masses[i]; for (int k = 0; k < 3; k++) cm[k] += masses[i]*pos[3*i+k]; }
+        if (tm > 0) for (int k = 0; k < 3; k++) cm[k] /= tm;
+        double net = 0, dpl[3] = {0, 0, 0}, q[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, aq[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int s = 0; s < n; s++) {
+            int o = order[s];
+            double r[3] = {pos[3*o] - cm[0], pos[3*o+1] - cm[1], pos[3*o+2] - cm[2]};
+            const double* c = &cart[20*(size_t) s];
+            const double* u = &total[3*(size_t) o];      // permanent + induced dipole
+            net += c[0];
+            for (int a = 0; a < 3; a++) dpl[a] += r[a]*c[0] + u[a];
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) q[a][b] += r[a]*r[b]*c[0] + r[a]*u[b] + r[b]*u[a];
+            aq[0][0] += c[4]; aq[0][1] += c[5]; aq[0][2] += c[6]; aq[1][1] += c[7]; aq[1][2] += c[8]; aq[2][2] += c[9];
+        }
+        aq[1][0] = aq[0][1]; aq[2][0] = aq[0][2]; aq[2][1] = aq[1][2];
+        const double qave = (q[0][0] + q[1][1] + q[2][2])/3.0;
+        const double debye = 4.80321;
+        out[0] = net;
+        for (int a = 0; a < 3; a++) out[1+a] = 10.0*debye*dpl[a];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++)
+                out[4 + 3*a + b] = 100.0*3.0*debye*(0.5*(q[a][b] - (a == b ? qave : 0.0)) + aq[a][b]);
+    }
+
+    // calculateElectrostaticPotential (MPIDReferenceForce.cpp:2464-2537): charge, total dipole and
+    // quadrupole terms, no periodic images, no octopoles -- host-side, off the hot path.
+    void potential(const double* pos, int npts, const double* pts, double* out) override {
+        std::vector<double> induced(3*(size_t) n);
+        getDipoles(pos, 0, induced.data());
+        std::vector<double> cart(20*(size_t) n);
+        std::vector<int> order(n);
+        CUDA_CHECK(cudaMemcpy(cart.data(), dCartD.p, cart.size()*sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(order.data(), dOrder.p, n*sizeof(int), cudaMemcpyDeviceToHost));
+        for (int g = 0; g < npts; g++) {
+            double v = 0;
+            for (int s = 0; s < n; s++) {
+                int o = order[s];
+                const double* c = &cart[20*(size_t) s];
+                double d[3] = {pos[3*o] - pts[3*g], pos[3*o+1] - pts[3*g+1], pos[3*o+2] - pts[3*g+2]};
+                if (P.method == PME) periodicDelta(P.box, d[0], d[1], d[2]);
+                double r2 = d[0]*d[0] + d[1]*d[1] + d[2]*d[2];
+                double rr1 = 1.0/sqrt(r2), rr2 = rr1*rr1, rr3 = rr1*rr2, rr5 = 3.0*rr3*rr2;
+                double pot = c[0]*rr1;
+                double sd = (c[1] + induced[3*o])*d[0] + (c[2] + induced[3*o+1])*d[1] + (c[3] + induced[3*o+2])*d[2];
+                pot -= sd*rr3;
+                double sq = d[0]*(c[4]*d[0] + c[5]*d[1] + c[6]*d[2]) + d[1]*(c[5]*d[0] + c[7]*d[1] + c[8]*d[2]) + d[2]*(c[6]*d[0] + c[8]*d[1] + c[9]*d[2]);
+                pot += sq*rr5;
+                v += pot;
+            }
+            out[g] = v*MPID_ELECTRIC;
+        }
+    }
+
+    void getPme(double& alpha, int& nx, int& ny, int& nz) override {
+        if (cfg.nonbonded_method != MPIDB200_PME) throw std::runtime_error("getPMEParametersInContext: This Context is not using PME");
+        alpha = alphaEwald; nx = grid[0]; ny = grid[1]; nz = grid[2];
+    }
+    void getStats(int* it, double* eps, double* ms, long long* pairs) override {
+        if (it) *it = lastIterations;
+        if (eps) *eps = lastEps;
+        if (ms) for (int k = 0; k < MPIDB200_NUM_STAGES; k++) ms[k] = stageMs[k];
+        if (pairs) *pairs = lastPairs;
+    }
+
+    long long getPairList(long long cap, int* pi, int* pj, int* pc) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        long long total = lastPairs + (long long) hSpLo.size();
+        if (!pi) return total;
+        std::vector<unsigned> hi(lastPairs), hj(lastPairs);
+        std::vector<int> order(n);
+        if (lastPairs) {
+            CUDA_CHECK(cudaMemcpy(hi.data(), dPairI.p, lastPairs*sizeof(unsigned), cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(hj.data(), dPairJ.p, lastPairs*sizeof(unsigned), cudaMemcpyDeviceToHost));
+        }
+        CUDA_CHECK(cudaMemcpy(order.data(), dOrder.p, n*sizeof(int), cudaMemcpyDeviceToHost));
+        long long k = 0;
+        for (long long p = 0; p < lastPairs && k < cap; p++, k++) {
+            int a = order[hi[p]], b = order[hj[p] & MPID_JMASK];
+            pi[k] = std::min(a, b); pj[k] = std::max(a, b); pc[k] = 0;
+        }
+        // the static covalently scaled pairs (the kernels apply the cutoff test to them at run time)
+        for (size_t s = 0; s < hSpLo.size() && k < cap; s++, k++) { pi[k] = hSpLo[s]; pj[k] = hSpHi[s]; pc[k] = hSpPairClass[s]; }
+        return k;
+    }
+
+    void commInit(int rk, int nr, const unsigned char* id) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        if (!loadNccl()) throw std::runtime_error("mpidb200: libnccl.so.2 could not be loaded");
+        Id128 uid;
+        memcpy(uid.bytes, id, 128);
+        int rc = g_nccl.CommInitRank(&comm, nr, uid, rk);
+        if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        rank = rk; numRanks = nr;
+        P.rank = rk; P.numRanks = nr;
+    }
+};
+
+EngineBase* asEngine(mpidb200_handle h) { return reinterpret_cast<EngineBase*>(h); }
+
+template <typename F> int guarded(F f) {
+    try { f(); return 0; }
+    catch (const std::exception& e) { g_lastError = e.what(); return 1; }
+    catch (...) { g_lastError = "unknown error"; return 1; }
+}
+
+} // namespace
+
+extern "C" {
+
+const char* mpidb200_last_error(void) { return g_lastError.c_str(); }
+
+void mpidb200_default_config(mpidb200_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->nonbonded_method = MPIDB200_NOCUTOFF;
+    c->polarization_type = MPIDB200_EXTRAPOLATED;
+    c->cutoff = 1.0;
+    c->ewald_tolerance = 5e-4;
+    c->default_thole_width = 5.0;
+    c->scale14 = 1.0;
+    c->max_iterations = 60;
+    c->target_epsilon = 1e-5;
+    c->num_extrapolation_coefficients = 4;
+    c->extrapolation_coefficients[0] = -0.154; c->extrapolation_coefficients[1] = 0.017;
+    c->extrapolation_coefficients[2] = 0.658;  c->extrapolation_coefficients[3] = 0.474;
+    c->precision = MPIDB200_MIXED;
+    c->solver = MPIDB200_SOLVER_DIIS;
+}
+
+int mpidb200_create(const mpidb200_config* cfg, mpidb200_handle* out) {
+    return guarded([&] {
+        if (!cfg || !out) throw std::runtime_error("mpidb200_create: null argument");
+        if (cfg->num_particles <= 0) throw std::runtime_error("mpidb200_create: num_particles must be positive");
+        if (cfg->num_particles > (int) MPID_JMASK) throw std::runtime_error("mpidb200_create: too many particles for the neighbour-list encoding");
+        int count = 0;
+        cudaError_t err = cudaGetDeviceCount(&count);
+        if (err != cudaSuccess || count == 0)
+            throw std::runtime_error(std::string("mpidb200_create: no CUDA device available (") + cudaGetErrorString(err) + "); there is no CPU fallback");
+        if (cfg->device < 0 || cfg->device >= count) throw std::runtime_error("mpidb200_create: invalid device ordinal");
+        EngineBase* e;
+        if (cfg->precision == MPIDB200_DOUBLE) e = new Engine<double>(*cfg);
+        else e = new Engine<float>(*cfg);
+        *out = reinterpret_cast<mpidb200_handle>(e);
+    });
+}
+
+void mpidb200_destroy(mpidb200_handle h) { delete asEngine(h); }
+
+int mpidb200_set_particles(mpidb200_handle h, const double* charges, const double* dipoles, const double* quadrupoles,
+                           const double* octopoles, const int* axis_types, const int* atom_z, const int* atom_x, const int* atom_y,
+                           const double* tholes, const double* alphas) {
+    return guarded([&] { asEngine(h)->setParticles(charges, dipoles, quadrupoles, octopoles, axis_types, atom_z, atom_x, atom_y, tholes, alphas); });
+}
+int mpidb200_set_covalent_maps(mpidb200_handle h, const int* offsets, const int* indices) {
+    return guarded([&] { asEngine(h)->setCovalent(offsets, indices); });
+}
+int mpidb200_set_box(mpidb200_handle h, const double* a, const double* b, const double* c) {
+    return guarded([&] { asEngine(h)->setBox(a, b, c); });
+}
+int mpidb200_execute(mpidb200_handle h, const double* positions, int include_forces, int include_energy, double* energy, double* forces) {
+    return guarded([&] { asEngine(h)->execute(positions, false, include_forces != 0, include_energy != 0, energy, forces); });
+}
+int mpidb200_execute_device(mpidb200_handle h, const double* d_positions, int include_forces, int include_energy, double* energy, double* d_forces) {
+    return guarded([&] { asEngine(h)->execute(d_positions, true, include_forces != 0, include_energy != 0, energy, d_forces); });
+}
+int mpidb200_get_dipoles(mpidb200_handle h, const double* positions, int which, double* out) {
+    return guarded([&] { asEngine(h)->getDipoles(positions, which, out); });
+}
+int mpidb200_get_system_multipole_moments(mpidb200_handle h, const double* positions, const double* masses, double* out13) {
+    return guarded([&] { asEngine(h)->systemMoments(positions, masses, out13); });
+}
+int mpidb200_get_electrostatic_potential(mpidb200_handle h, const double* positions, int num_points, const double* points, double* out) {
+    return guarded([&] { asEngine(h)->potential(positions, num_points, points, out); });
+}
+int mpidb200_get_pme_parameters(mpidb200_handle h, double* alpha, int* nx, int* ny, int* nz) {
+    return guarded([&] { asEngine(h)->getPme(*alpha, *nx, *ny, *nz); });
+}
+int mpidb200_get_stats(mpidb200_handle h, int* iterations, double* epsilon, double* stage_ms, long long* num_pairs) {
+    return guarded([&] { asEngine(h)->getStats(iterations, epsilon, stage_ms, num_pairs); });
+}
+int mpidb200_set_profiling(mpidb200_handle h, int enabled) {
+    return guarded([&] { asEngine(h)->profiling = enabled != 0; });
+}
+long long mpidb200_last_launch_count(mpidb200_handle h) { return asEngine(h)->launches; }
+int mpidb200_get_pair_list(mpidb200_handle h, long long capacity, int* pairs_i, int* pairs_j, int* pair_class, long long* count) {
+    return guarded([&] { *count = asEngine(h)->getPairList(capacity, pairs_i, pairs_j, pair_class); });
+}
+int mpidb200_nccl_unique_id(unsigned char* out128) {
+    return guarded([&] {
+        if (!loadNccl()) throw std::runtime_error("mpidb200: libnccl.so.2 could not be loaded");
+        int rc = g_nccl.GetUniqueId(out128);
+        if (rc != 0) throw std::runtime_error("ncclGetUniqueId failed");
+    });
+}
+int mpidb200_comm_init(mpidb200_handle h, int rank, int num_ranks, const unsigned char* unique_id128) {
+    return guarded([&] { asEngine(h)->commInit(rank, num_ranks, unique_id128); });
+}
+
+} // extern "C"

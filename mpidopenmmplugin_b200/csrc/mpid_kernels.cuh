@@ -1,0 +1,979 @@
+// MPIDB200 -- sm_100a kernels of the MPIDForce hot path (one kernel per stage).
+//
+// Layout conventions (all per-atom arrays are in the SORTED order produced by the cell sort unless a
+// name ends in "Orig"):
+//   posS      double4  wrapped position (x,y,z,unused)           -- pair kernels, PME
+//   posF      float4   same, single precision                    -- neighbour-list pre-test only
+//   cart      real[20] lab Cartesian moments   q d(3) Q(6) O(10) -- permanent-field kernel, PME spread
+//   pk        real[16] packed traceless moments (packPairMoments) -- energy kernel
+//   mud       real4    (mu_x, mu_y, mu_z, damping factor)        -- induced-field and energy kernels
+//   field/... double   accumulators written by exactly one thread per atom (no atomics)
+//   force/torque/energy  64-bit fixed point (2^32), atomics, order independent => deterministic
+// Neighbour list: full CSR list for the gather-style field kernels, flat i-major half list for the
+// energy kernel.  Entries pack the sorted index of j (27 bits) and the periodic image code (5 bits).
+#ifndef MPIDB200_KERNELS_CUH_
+#define MPIDB200_KERNELS_CUH_
+
+#include "mpid_math.h"
+#include <cuda_runtime.h>
+
+namespace mpid {
+
+#define MPID_JMASK 0x07FFFFFFu
+#define MPID_CODE_SHIFT 27
+#define MPID_FIXED_SCALE 4294967296.0
+#define MPID_MAX_HISTORY 20
+
+struct DevParams {
+    int n;
+    int method, polarization;
+    int ncell[3];
+    int grid[3];
+    int numRanks, rank;          // multi-GPU row partition
+    int rowBegin, rowEnd;        // sorted-atom range owned by this rank
+    double cutoff, cutoff2;
+    double alpha, defaultThole, scale14;
+    double selfFieldTerm;        // (4/3) alpha^3 / sqrt(pi)
+    Box box;
+    PmeGeom geom;
+    double shift[27][3];         // lattice translation of each image code
+};
+
+template <typename real> struct Real4;
+template <> struct Real4<float>  { typedef float4 type; };
+template <> struct Real4<double> { typedef double4 type; };
+
+__device__ __forceinline__ void atomicAddFixed(unsigned long long* p, double v) {
+    atomicAdd(p, (unsigned long long) __double2ll_rn(v*MPID_FIXED_SCALE));
+}
+__device__ __forceinline__ double fixedToDouble(unsigned long long v) {
+    return (double) ((long long) v)*(1.0/MPID_FIXED_SCALE);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 0: wrap, bin, sort support
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_wrap_cells(DevParams P, const double* __restrict__ posOrig, double* __restrict__ poswOrig,
+                             int* __restrict__ cellKey, int* __restrict__ atomIdx) {
+    int o = blockIdx.x*blockDim.x + threadIdx.x;
+    if (o >= P.n) return;
+    double x = posOrig[3*o], y = posOrig[3*o+1], z = posOrig[3*o+2];
+    int key = 0;
+    if (P.method == PME) {
+        double s = floor(z*P.box.rc[2]);
+        x -= P.box.c[0]*s; y -= P.box.c[1]*s; z -= P.box.c[2]*s;
+        s = floor(y*P.box.rb[1]);
+        x -= P.box.b[0]*s; y -= P.box.b[1]*s;
+        s = floor(x*P.box.ra[0]);
+        x -= P.box.a[0]*s;
+        double f[3];
+        f[0] = x*P.box.ra[0] + y*P.box.rb[0] + z*P.box.rc[0];
+        f[1] = x*P.box.ra[1] + y*P.box.rb[1] + z*P.box.rc[1];
+        f[2] = x*P.box.ra[2] + y*P.box.rb[2] + z*P.box.rc[2];
+        int c[3];
+        for (int d = 0; d < 3; d++) {
+            int v = (int) floor(f[d]*P.ncell[d]);
+            c[d] = min(max(v, 0), P.ncell[d]-1);
+        }
+        key = (c[0]*P.ncell[1] + c[1])*P.ncell[2] + c[2];
+    }
+    poswOrig[3*o] = x; poswOrig[3*o+1] = y; poswOrig[3*o+2] = z;
+    cellKey[o] = key;
+    atomIdx[o] = o;
+}
+
+// cellStart[c] = first sorted atom whose cell key is >= c   (c = 0..numCells)
+__global__ void k_cell_starts(int n, int numCells, const int* __restrict__ sortedKey, int* __restrict__ cellStart) {
+    int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c > numCells) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (sortedKey[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    cellStart[c] = lo;
+}
+
+__global__ void k_inverse_order(int n, const int* __restrict__ order, int* __restrict__ inv) {
+    int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s < n) inv[order[s]] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 1: lab-frame moments (one thread per sorted atom)
+// ---------------------------------------------------------------------------------------------------
+struct ParticleParams {       // original order, as handed to mpidb200_set_particles
+    const double* charge; const double* dipole; const double* quadrupole; const double* octopole;
+    const int* axis; const int* atomZ; const int* atomX; const int* atomY;
+    const double* thole; const double* alpha; const double* damp;
+};
+
+template <typename real>
+__global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restrict__ order,
+                            const double* __restrict__ posOrig, const double* __restrict__ poswOrig,
+                            double4* __restrict__ posS, float4* __restrict__ posF,
+                            double* __restrict__ cartD, double* __restrict__ pkD, real* __restrict__ cartR, real* __restrict__ pkR,
+                            double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso,
+                            double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud) {
+    int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    int o = order[s];
+    int az = pp.atomZ[o], ax = pp.atomX[o], ay = pp.atomY[o];
+    const double* pi = posOrig + 3*o;
+    const double* pz = az >= 0 ? posOrig + 3*az : pi;
+    const double* px = ax >= 0 ? posOrig + 3*ax : pi;
+    const double* py = ay >= 0 ? posOrig + 3*ay : pi;
+    LabAtom a;
+    labFrameAtom(pi, pz, px, py, pp.axis[o], az, ax, ay, pp.charge[o], pp.dipole + 3*o, pp.quadrupole + 6*o,
+                 pp.octopole + 10*o, pp.alpha + 3*o, a);
+    if (framelessFix && az < 0) {
+        a.alpha[0] = pp.alpha[3*o]; a.alpha[3] = pp.alpha[3*o+1]; a.alpha[5] = pp.alpha[3*o+2];
+    }
+    double c[20], pk[16];
+    c[0] = a.charge;
+    for (int k = 0; k < 3; k++) c[1+k] = a.dip[k];
+    for (int k = 0; k < 6; k++) c[4+k] = a.quad[k];
+    for (int k = 0; k < 10; k++) c[10+k] = a.oct[k];
+    packPairMoments(a, pk);
+    for (int k = 0; k < 20; k++) cartD[20*(size_t) s + k] = c[k];
+    for (int k = 0; k < 16; k++) pkD[16*(size_t) s + k] = pk[k];
+    if ((void*) cartR != (void*) cartD) {
+        for (int k = 0; k < 20; k++) cartR[20*(size_t) s + k] = (real) c[k];
+        for (int k = 0; k < 16; k++) pkR[16*(size_t) s + k] = (real) pk[k];
+    }
+    for (int k = 0; k < 16; k++) sphD[16*(size_t) s + k] = a.sph[k];
+    for (int k = 0; k < 6; k++) alphaLab[6*(size_t) s + k] = a.alpha[k];
+    aniso[s] = a.aniso;
+    double x = poswOrig[3*o], y = poswOrig[3*o+1], z = poswOrig[3*o+2];
+    posS[s] = make_double4(x, y, z, 0.0);
+    posF[s] = make_float4((float) x, (float) y, (float) z, 0.f);
+    dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
+    typename Real4<real>::type m;
+    m.x = 0; m.y = 0; m.z = 0; m.w = (real) pp.damp[o];
+    mud[s] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 2: neighbour list (one warp per sorted atom; pass 0 counts, pass 1 fills)
+// ---------------------------------------------------------------------------------------------------
+// A cheap FP32 test settles every candidate that is not within 1e-4 nm of the cutoff sphere; the few
+// that are get the reference's own FP64 test on the raw positions, so the pair set is exactly
+// { i<j : |minimg(r_j - r_i)|^2 <= rc^2 } as decided by MPIDReferencePmeForce (:2829, :4178, :4350).
+// Pairs with a covalent scale (1-2, 1-3, 1-4) are left out: they live in the static special list.
+template <bool FILL>
+__global__ void k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __restrict__ posOrig,
+                                const int* __restrict__ order, const int* __restrict__ sortedKey, const int* __restrict__ cellStart,
+                                const int* __restrict__ spStart, const int* __restrict__ spPartner,
+                                unsigned* __restrict__ fullCount, unsigned* __restrict__ halfCount,
+                                const unsigned* __restrict__ fullStart, const unsigned* __restrict__ halfStart,
+                                unsigned* __restrict__ nbr, unsigned* __restrict__ pairI, unsigned* __restrict__ pairJ) {
+    const int lane = threadIdx.x & 31;
+    const int i = P.rowBegin + (blockIdx.x*blockDim.x + threadIdx.x)/32;
+    if (i >= P.rowEnd) return;
+    const float4 pi = posF[i];
+    const int oi = order[i];
+    const int sp0 = spStart[oi], sp1 = spStart[oi+1];
+    const bool pme = P.method == PME;
+    int cx = 0, cy = 0, cz = 0;
+    if (pme) {
+        int key = sortedKey[i];
+        cz = key % P.ncell[2]; key /= P.ncell[2];
+        cy = key % P.ncell[1]; cx = key / P.ncell[1];
+    }
+    const float rcLo = (float) P.cutoff - 1.0e-4f, rcHi = (float) P.cutoff + 1.0e-4f;
+    const float rcLo2 = rcLo > 0.f ? rcLo*rcLo : 0.f, rcHi2 = rcHi*rcHi;
+    const float rax = (float) P.box.ra[0], rby = (float) P.box.rb[1], rcz = (float) P.box.rc[2];
+    const float ax = (float) P.box.a[0], bx = (float) P.box.b[0], by = (float) P.box.b[1];
+    const float ccx = (float) P.box.c[0], ccy = (float) P.box.c[1], ccz = (float) P.box.c[2];
+    unsigned nFull = 0, nHalf = 0;
+    unsigned baseFull = 0, baseHalf = 0;
+    if (FILL) { baseFull = fullStart[i - P.rowBegin]; baseHalf = halfStart[i - P.rowBegin]; }
+    const int rx = (pme && P.ncell[0] > 1) ? 1 : 0, ry = (pme && P.ncell[1] > 1) ? 1 : 0, rz = (pme && P.ncell[2] > 1) ? 1 : 0;
+    for (int dx = -rx; dx <= rx; dx++) {
+        int X = cx + dx; X += (X < 0) ? P.ncell[0] : 0; X -= (X >= P.ncell[0]) ? P.ncell[0] : 0;
+        for (int dy = -ry; dy <= ry; dy++) {
+            int Y = cy + dy; Y += (Y < 0) ? P.ncell[1] : 0; Y -= (Y >= P.ncell[1]) ? P.ncell[1] : 0;
+            for (int dz = -rz; dz <= rz; dz++) {
+                int Z = cz + dz; Z += (Z < 0) ? P.ncell[2] : 0; Z -= (Z >= P.ncell[2]) ? P.ncell[2] : 0;
+                const int c = (X*P.ncell[1] + Y)*P.ncell[2] + Z;
+                const int jb = cellStart[c], je = cellStart[c+1];
+                for (int j0 = jb; j0 < je; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool in = (j < je) && (j != i);
+                    unsigned code = 13;
+                    if (in && pme) {
+                        float4 pj = posF[j];
+                        float ddx = pj.x - pi.x, ddy = pj.y - pi.y, ddz = pj.z - pi.z;
+                        float sz = floorf(ddz*rcz + 0.5f);
+                        ddx -= ccx*sz; ddy -= ccy*sz; ddz -= ccz*sz;
+                        float sy = floorf(ddy*rby + 0.5f);
+                        ddx -= bx*sy; ddy -= by*sy;
+                        float sx = floorf(ddx*rax + 0.5f);
+                        ddx -= ax*sx;
+                        float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
+                        code = (unsigned) (((int) sx + 1)*9 + ((int) sy + 1)*3 + ((int) sz + 1));
+                        if (r2 > rcHi2) in = false;
+                        else if (r2 >= rcLo2) {
+                            // borderline: the oracle's test, bit for bit, on the raw positions
+                            int oj = order[j];
+                            int lo = min(oi, oj), hi = max(oi, oj);
+                            double ex = posOrig[3*hi] - posOrig[3*lo], ey = posOrig[3*hi+1] - posOrig[3*lo+1], ez = posOrig[3*hi+2] - posOrig[3*lo+2];
+                            periodicDelta(P.box, ex, ey, ez);
+                            in = !(dist2Exact(ex, ey, ez) > P.cutoff2);
+                        }
+                        if (code > 26u) in = false;   // cannot happen for wrapped positions; keeps the table index safe
+                    }
+                    if (in && sp1 > sp0) {
+                        int oj = order[j];
+                        for (int k = sp0; k < sp1; k++) if (spPartner[k] == oj) in = false;
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, in);
+                    const bool upper = in && (j > i);
+                    const unsigned maskH = __ballot_sync(0xffffffffu, upper);
+                    if (FILL) {
+                        const unsigned lt = (1u << lane) - 1u;
+                        if (in) nbr[baseFull + nFull + __popc(mask & lt)] = (unsigned) j | (code << MPID_CODE_SHIFT);
+                        if (upper) {
+                            unsigned p = baseHalf + nHalf + __popc(maskH & lt);
+                            pairI[p] = (unsigned) i;
+                            pairJ[p] = (unsigned) j | (code << MPID_CODE_SHIFT);
+                        }
+                    }
+                    nFull += __popc(mask);
+                    nHalf += __popc(maskH);
+                }
+            }
+        }
+    }
+    if (!FILL && lane == 0) { fullCount[i - P.rowBegin] = nFull; halfCount[i - P.rowBegin] = nHalf; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 3: real-space fields, gather over the full neighbour list (8 lanes per atom, no atomics)
+// ---------------------------------------------------------------------------------------------------
+#define MPID_LANES 8
+
+template <typename real>
+__device__ __forceinline__ void pairDelta(const DevParams& P, const double4& pi, const double4& pj, unsigned code,
+                                          real& dx, real& dy, real& dz) {
+    dx = (real) ((pj.x - pi.x) - P.shift[code][0]);
+    dy = (real) ((pj.y - pi.y) - P.shift[code][1]);
+    dz = (real) ((pj.z - pi.z) - P.shift[code][2]);
+}
+
+// Permanent-multipole field of the ordinary pairs.   reference stage: :911-934 + :2812-2920
+template <typename real, bool EWALD>
+__global__ void __launch_bounds__(256)
+k_fixed_field(DevParams P, const double4* __restrict__ posS, const real* __restrict__ cart,
+              const typename Real4<real>::type* __restrict__ mud,
+              const unsigned* __restrict__ nbrStart, const unsigned* __restrict__ nbr, double* __restrict__ field) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int i = P.rowBegin + t/MPID_LANES;
+    const int sub = t % MPID_LANES;
+    double ex = 0, ey = 0, ez = 0;
+    if (i < P.rowEnd) {
+        const double4 pi = posS[i];
+        const real dampI = mud[i].w;
+        const unsigned kb = nbrStart[i - P.rowBegin], ke = nbrStart[i - P.rowBegin + 1];
+        for (unsigned k = kb + sub; k < ke; k += MPID_LANES) {
+            const unsigned e = nbr[k];
+            const unsigned j = e & MPID_JMASK;
+            real dx, dy, dz;
+            pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
+            const real r2 = dx*dx + dy*dy + dz*dz;
+            const real r = t_sqrt(r2);
+            real tc[4], c[4];
+            tholeComplements<real>(dampI, mud[j].w, real(0), (real) P.defaultThole, false, r, tc);
+            fieldCoefficients<real, EWALD>(r, (real) P.alpha, real(1), tc, 4, c);
+            real m[20];
+            const typename Real4<real>::type* src = reinterpret_cast<const typename Real4<real>::type*>(cart + 20*(size_t) j);
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                typename Real4<real>::type v = src[q];
+                m[4*q] = v.x; m[4*q+1] = v.y; m[4*q+2] = v.z; m[4*q+3] = v.w;
+            }
+            real fx = 0, fy = 0, fz = 0;
+            fixedFieldDirected<real>(m, dx, dy, dz, c, fx, fy, fz);
+            ex += fx; ey += fy; ez += fz;
+        }
+    }
+#pragma unroll
+    for (int off = MPID_LANES/2; off > 0; off >>= 1) {
+        ex += __shfl_xor_sync(0xffffffffu, ex, off);
+        ey += __shfl_xor_sync(0xffffffffu, ey, off);
+        ez += __shfl_xor_sync(0xffffffffu, ez, off);
+    }
+    if (i < P.rowEnd && sub == 0) { field[3*(size_t) i] = ex; field[3*(size_t) i+1] = ey; field[3*(size_t) i+2] = ez; }
+}
+
+// Field (and, for the extrapolated solver, field gradient) of the induced dipoles, ordinary pairs.
+//   reference stage: :4084-4088 + :4161-4281 (PME), :1037-1048 + :962-1035 (no cutoff)
+template <typename real, bool EWALD, bool GRAD>
+__global__ void __launch_bounds__(256)
+k_induced_field(DevParams P, const double4* __restrict__ posS, const typename Real4<real>::type* __restrict__ mud,
+                const unsigned* __restrict__ nbrStart, const unsigned* __restrict__ nbr,
+                double* __restrict__ field, double* __restrict__ grad) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int i = P.rowBegin + t/MPID_LANES;
+    const int sub = t % MPID_LANES;
+    double ex = 0, ey = 0, ez = 0;
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    if (i < P.rowEnd) {
+        const double4 pi = posS[i];
+        const real dampI = mud[i].w;
+        const unsigned kb = nbrStart[i - P.rowBegin], ke = nbrStart[i - P.rowBegin + 1];
+        for (unsigned k = kb + sub; k < ke; k += MPID_LANES) {
+            const unsigned e = nbr[k];
+            const unsigned j = e & MPID_JMASK;
+            real dx, dy, dz;
+            pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
+            const typename Real4<real>::type mj = mud[j];
+            const real r2 = dx*dx + dy*dy + dz*dz;
+            const real r = t_sqrt(r2);
+            real tc[4], c[4];
+            tholeComplements<real>(dampI, mj.w, real(0), (real) P.defaultThole, false, r, tc);
+            fieldCoefficients<real, EWALD>(r, (real) P.alpha, real(1), tc, GRAD ? 3 : 2, c);
+            real fx = 0, fy = 0, fz = 0;
+            inducedFieldDirected<real>(mj.x, mj.y, mj.z, dx, dy, dz, c, fx, fy, fz);
+            ex += fx; ey += fy; ez += fz;
+            if (GRAD) {
+                real gg[6] = {0, 0, 0, 0, 0, 0};
+                inducedFieldGradientDirected<real>(mj.x, mj.y, mj.z, dx, dy, dz, c, gg);
+#pragma unroll
+                for (int q = 0; q < 6; q++) g[q] += gg[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int off = MPID_LANES/2; off > 0; off >>= 1) {
+        ex += __shfl_xor_sync(0xffffffffu, ex, off);
+        ey += __shfl_xor_sync(0xffffffffu, ey, off);
+        ez += __shfl_xor_sync(0xffffffffu, ez, off);
+        if (GRAD) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) g[q] += __shfl_xor_sync(0xffffffffu, g[q], off);
+        }
+    }
+    if (i < P.rowEnd && sub == 0) {
+        field[3*(size_t) i] = ex; field[3*(size_t) i+1] = ey; field[3*(size_t) i+2] = ez;
+        if (GRAD) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) grad[6*(size_t) i + q] += g[q];
+        }
+    }
+}
+
+// Covalently scaled pairs (1-2, 1-3, 1-4): always FP64, exact reference cutoff test, one thread per
+// atom over its (static) partner list, added on top of what the gather kernels wrote.
+//   MODE 0: permanent field   MODE 1: induced field   MODE 2: induced field + gradient
+template <int MODE>
+__global__ void k_special_field(DevParams P, const int* __restrict__ order, const int* __restrict__ inv,
+                                const double* __restrict__ posOrig, const int* __restrict__ spStart,
+                                const int* __restrict__ spPartner, const int* __restrict__ spClass,
+                                const double* __restrict__ cartD, const double2* __restrict__ dampTholeD,
+                                const double* __restrict__ mu, double* __restrict__ field, double* __restrict__ grad) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.rowEnd) return;
+    const int o = order[s];
+    const int k0 = spStart[o], k1 = spStart[o+1];
+    if (k1 == k0) return;
+    double ex = 0, ey = 0, ez = 0, g[6] = {0, 0, 0, 0, 0, 0};
+    const double2 dtI = dampTholeD[s];
+    for (int k = k0; k < k1; k++) {
+        const int oj = spPartner[k];
+        const int cls = spClass[k];
+        const int lo = min(o, oj), hi = max(o, oj);
+        double dx = posOrig[3*hi] - posOrig[3*lo], dy = posOrig[3*hi+1] - posOrig[3*lo+1], dz = posOrig[3*hi+2] - posOrig[3*lo+2];
+        if (P.method == PME) periodicDelta(P.box, dx, dy, dz);
+        const double r2 = dist2Exact(dx, dy, dz);
+        if (P.method == PME && r2 > P.cutoff2) continue;
+        if (o == hi) { dx = -dx; dy = -dy; dz = -dz; }      // d = r_other - r_me
+        const int sj = inv[oj];
+        const double2 dtJ = dampTholeD[sj];
+        const double scale = cls == 1 ? 0.0 : P.scale14;
+        const double r = sqrt(r2);
+        double tc[4], c[4];
+        tholeComplements<double>(dtI.x, dtJ.x, dtI.y + dtJ.y, P.defaultThole, scale == 0.0, r, tc);
+        if (MODE == 0) {
+            if (P.method == PME) fieldCoefficients<double, true>(r, P.alpha, scale, tc, 4, c);
+            else fieldCoefficients<double, false>(r, 0.0, scale, tc, 4, c);
+            fixedFieldDirected<double>(cartD + 20*(size_t) sj, dx, dy, dz, c, ex, ey, ez);
+        } else {
+            if (P.method == PME) fieldCoefficients<double, true>(r, P.alpha, 1.0, tc, 3, c);
+            else fieldCoefficients<double, false>(r, 0.0, 1.0, tc, 3, c);
+            const double mx = mu[3*(size_t) sj], my = mu[3*(size_t) sj+1], mz = mu[3*(size_t) sj+2];
+            inducedFieldDirected<double>(mx, my, mz, dx, dy, dz, c, ex, ey, ez);
+            if (MODE == 2) inducedFieldGradientDirected<double>(mx, my, mz, dx, dy, dz, c, g);
+        }
+    }
+    field[3*(size_t) s] += ex; field[3*(size_t) s+1] += ey; field[3*(size_t) s+2] += ez;
+    if (MODE == 2) for (int q = 0; q < 6; q++) grad[6*(size_t) s + q] += g[q];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 4: pair energy / force / torque over the i-major half list (one thread per pair)
+// ---------------------------------------------------------------------------------------------------
+//   reference stage: :4932-4946 + :4335-4920 (PME), :2140-2158 + :1331-1893 (no cutoff)
+template <typename real, bool EWALD, bool MUTUAL>
+__global__ void __launch_bounds__(128)
+k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ pairI, const unsigned* __restrict__ pairJ,
+                 const double4* __restrict__ posS, const real* __restrict__ pk, const typename Real4<real>::type* __restrict__ mud,
+                 const int* __restrict__ aniso,
+                 unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque, unsigned long long* __restrict__ energy) {
+    const long long p = (long long) blockIdx.x*blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int i = -1 - lane;      // distinct dummies so idle lanes never merge with a real segment
+    unsigned j = 0;
+    double e = 0;
+    real f[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tj[3] = {0, 0, 0};
+    const bool active = p < numPairs;
+    if (active) {
+        i = (int) pairI[p];
+        const unsigned ej = pairJ[p];
+        j = ej & MPID_JMASK;
+        real dx, dy, dz;
+        pairDelta<real>(P, posS[i], posS[j], ej >> MPID_CODE_SHIFT, dx, dy, dz);
+        real qi[16], qj[16];
+        typedef typename Real4<real>::type R4;
+        const R4* si = reinterpret_cast<const R4*>(pk + 16*(size_t) i);
+        const R4* sj = reinterpret_cast<const R4*>(pk + 16*(size_t) j);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            R4 a = si[q], b = sj[q];
+            qi[4*q] = a.x; qi[4*q+1] = a.y; qi[4*q+2] = a.z; qi[4*q+3] = a.w;
+            qj[4*q] = b.x; qj[4*q+1] = b.y; qj[4*q+2] = b.z; qj[4*q+3] = b.w;
+        }
+        const R4 mi = mud[i], mj = mud[j];
+        real uI[3] = {mi.x, mi.y, mi.z}, uJ[3] = {mj.x, mj.y, mj.z};
+        const real r2 = dx*dx + dy*dy + dz*dz;
+        e = (double) pairElectrostatics<real, EWALD, MUTUAL>(qi, qj, uI, uJ, mi.w, mj.w, real(0), real(0), aniso[i] != 0, aniso[j] != 0,
+                                                           dx, dy, dz, r2, (real) P.alpha, (real) P.defaultThole, real(1), real(1), f, ti, tj);
+    }
+    // j side: scattered fixed-point atomics
+    if (active) {
+        atomicAddFixed(&force[3*(size_t) j], (double) f[0]); atomicAddFixed(&force[3*(size_t) j+1], (double) f[1]); atomicAddFixed(&force[3*(size_t) j+2], (double) f[2]);
+        atomicAddFixed(&torque[3*(size_t) j], (double) tj[0]); atomicAddFixed(&torque[3*(size_t) j+1], (double) tj[1]); atomicAddFixed(&torque[3*(size_t) j+2], (double) tj[2]);
+    }
+    // i side: pairs of one i are contiguous, so a segmented warp reduction leaves one atomic per run
+    double v[6] = {-(double) f[0], -(double) f[1], -(double) f[2], (double) ti[0], (double) ti[1], (double) ti[2]};
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int io = __shfl_down_sync(0xffffffffu, i, off);
+        const bool take = (lane + off < 32) && (io == i);
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const double w = __shfl_down_sync(0xffffffffu, v[q], off);
+            if (take) v[q] += w;
+        }
+    }
+    const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
+    if (active && (lane == 0 || iprev != i)) {
+        atomicAddFixed(&force[3*(size_t) i], v[0]); atomicAddFixed(&force[3*(size_t) i+1], v[1]); atomicAddFixed(&force[3*(size_t) i+2], v[2]);
+        atomicAddFixed(&torque[3*(size_t) i], v[3]); atomicAddFixed(&torque[3*(size_t) i+1], v[4]); atomicAddFixed(&torque[3*(size_t) i+2], v[5]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if (lane == 0 && e != 0.0) atomicAddFixed(energy, e);
+}
+
+// Covalently scaled pairs: FP64, one thread per static special pair (original indices lo < hi).
+template <bool MUTUAL>
+__global__ void k_special_electrostatics(DevParams P, int numSpecial, const int* __restrict__ spPairLo, const int* __restrict__ spPairHi,
+                                         const int* __restrict__ spPairClass, const int* __restrict__ inv,
+                                         const double* __restrict__ posOrig, const double* __restrict__ pkD,
+                                         const double2* __restrict__ dampTholeD, const double* __restrict__ mu, const int* __restrict__ aniso,
+                                         unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque,
+                                         unsigned long long* __restrict__ energy) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= numSpecial) return;
+    if ((k % P.numRanks) != P.rank) return;
+    const int lo = spPairLo[k], hi = spPairHi[k];
+    double dx = posOrig[3*hi] - posOrig[3*lo], dy = posOrig[3*hi+1] - posOrig[3*lo+1], dz = posOrig[3*hi+2] - posOrig[3*lo+2];
+    if (P.method == PME) periodicDelta(P.box, dx, dy, dz);
+    const double r2 = dist2Exact(dx, dy, dz);
+    if (P.method == PME && r2 > P.cutoff2) return;
+    const int si = inv[lo], sj = inv[hi];
+    const double scale = spPairClass[k] == 1 ? 0.0 : P.scale14;
+    const double2 dtI = dampTholeD[si], dtJ = dampTholeD[sj];
+    double f[3], ti[3], tj[3], e;
+    if (P.method == PME)
+        e = pairElectrostatics<double, true, MUTUAL>(pkD + 16*(size_t) si, pkD + 16*(size_t) sj, mu + 3*(size_t) si, mu + 3*(size_t) sj,
+                dtI.x, dtJ.x, dtI.y, dtJ.y, aniso[si] != 0, aniso[sj] != 0, dx, dy, dz, r2, P.alpha, P.defaultThole, scale, scale, f, ti, tj);
+    else
+        e = pairElectrostatics<double, false, MUTUAL>(pkD + 16*(size_t) si, pkD + 16*(size_t) sj, mu + 3*(size_t) si, mu + 3*(size_t) sj,
+                dtI.x, dtJ.x, dtI.y, dtJ.y, aniso[si] != 0, aniso[sj] != 0, dx, dy, dz, r2, 0.0, P.defaultThole, scale, scale, f, ti, tj);
+    for (int q = 0; q < 3; q++) {
+        atomicAddFixed(&force[3*(size_t) si + q], -f[q]);
+        atomicAddFixed(&force[3*(size_t) sj + q], f[q]);
+        atomicAddFixed(&torque[3*(size_t) si + q], ti[q]);
+        atomicAddFixed(&torque[3*(size_t) sj + q], tj[q]);
+    }
+    atomicAddFixed(energy, e);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 5: PME
+// ---------------------------------------------------------------------------------------------------
+// Scaled-fractional multipoles of the permanent moments (20 per atom).  reference: :3077-3169
+template <typename real>
+__global__ void k_fractional_multipoles(DevParams P, const real* __restrict__ cart, real* __restrict__ frac) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    real m[20], f[20];
+    for (int k = 0; k < 20; k++) m[k] = cart[20*(size_t) s + k];
+    multipolesToFractional<real>(P.geom.A, m, f);
+    for (int k = 0; k < 20; k++) frac[20*(size_t) s + k] = f[k];
+}
+
+// B-spline spreading: 6 threads per atom (one per x plane), 36 atomic adds each.
+//   reference: spreadFixedMultipolesOntoGrid (:3269-3327), spreadInducedDipolesOnGrid (:3532-3573)
+template <typename real, bool FIXED>
+__global__ void __launch_bounds__(192)
+k_spread(DevParams P, const double4* __restrict__ posS, const real* __restrict__ frac, const double* __restrict__ mu,
+         real* __restrict__ grid) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int s = P.rowBegin + t/6;
+    const int ix = t % 6;
+    if (s >= P.rowEnd) return;
+    const double4 p = posS[s];
+    int ig[3]; double w[3];
+    pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
+    real tx[6][5], ty[6][5], tz[6][5];
+    bsplineWeights<real>((real) w[0], tx);
+    bsplineWeights<real>((real) w[1], ty);
+    bsplineWeights<real>((real) w[2], tz);
+    real f[20];
+    if (FIXED) {
+        for (int k = 0; k < 20; k++) f[k] = frac[20*(size_t) s + k];
+    } else {
+        const double mx = mu[3*(size_t) s], my = mu[3*(size_t) s+1], mz = mu[3*(size_t) s+2];
+        f[0] = 0;
+        for (int k = 0; k < 3; k++) f[1+k] = (real) (P.geom.A[k][0]*mx + P.geom.A[k][1]*my + P.geom.A[k][2]*mz);
+    }
+    const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2];
+    int x = ig[0] + ix; x -= (x >= nx) ? nx : 0;
+    real txr[5];
+    for (int k = 0; k < 5; k++) txr[k] = tx[0][k];
+    for (int a = 1; a < 6; a++) if (a == ix) for (int k = 0; k < 5; k++) txr[k] = tx[a][k];
+#pragma unroll
+    for (int iy = 0; iy < 6; iy++) {
+        int y = ig[1] + iy; y -= (y >= ny) ? ny : 0;
+        real* row = grid + ((size_t) x*ny + y)*nz;
+#pragma unroll
+        for (int iz = 0; iz < 6; iz++) {
+            int z = ig[2] + iz; z -= (z >= nz) ? nz : 0;
+            atomicAdd(row + z, spreadTerm<real, FIXED>(f, txr, ty[iy], tz[iz]));
+        }
+    }
+}
+
+// Reciprocal convolution on the half-complex grid.   reference: performMPIDReciprocalConvolution (:3329-3366)
+template <typename cplx, typename real>
+__global__ void k_convolution(size_t count, const real* __restrict__ eterm, cplx* __restrict__ g) {
+    const size_t k = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const real e = eterm[k];
+    cplx v = g[k];
+    v.x *= e; v.y *= e;
+    g[k] = v;
+}
+
+// eterm[kx][ky][kz<=nz/2] = exp(-pi^2 m^2/alpha^2) / (pi V m^2 Bx By Bz), zero at the origin
+template <typename real>
+__global__ void k_eterm_table(DevParams P, const double* __restrict__ modX, const double* __restrict__ modY,
+                              const double* __restrict__ modZ, real* __restrict__ eterm) {
+    const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2], nzc = nz/2 + 1;
+    const size_t k = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= (size_t) nx*ny*nzc) return;
+    const int kz = (int) (k % nzc);
+    const int ky = (int) ((k / nzc) % ny);
+    const int kx = (int) (k / ((size_t) nzc*ny));
+    if (kx == 0 && ky == 0 && kz == 0) { eterm[k] = 0; return; }
+    const int mx = (kx < (nx+1)/2) ? kx : kx - nx;
+    const int my = (ky < (ny+1)/2) ? ky : ky - ny;
+    const int mz = (kz < (nz+1)/2) ? kz : kz - nz;
+    const double hx = mx*P.box.ra[0];
+    const double hy = mx*P.box.rb[0] + my*P.box.rb[1];
+    const double hz = mx*P.box.rc[0] + my*P.box.rc[1] + mz*P.box.rc[2];
+    const double m2 = hx*hx + hy*hy + hz*hz;
+    const double expFactor = MPID_PI*MPID_PI/(P.alpha*P.alpha);
+    const double scaleFactor = 1.0/(MPID_PI*P.box.a[0]*P.box.b[1]*P.box.c[2]);
+    eterm[k] = (real) (scaleFactor*exp(-expFactor*m2)/(m2*modX[kx]*modY[ky]*modZ[kz]));
+}
+
+// Potential derivatives at the atoms up to total order LEVEL (4 -> all 35), SoA output phi[idx*n + s].
+//   reference: computeFixedPotentialFromGrid (:3368-3530), computeInducedPotentialFromGrid (:3575-3737)
+template <typename real, int LEVEL>
+__global__ void __launch_bounds__(128)
+k_gather(DevParams P, const double4* __restrict__ posS, const real* __restrict__ grid, real* __restrict__ phi) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.rowEnd) return;
+    const double4 p = posS[s];
+    int ig[3]; double w[3];
+    pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
+    real tx[6][5], ty[6][5], tz[6][5];
+    bsplineWeights<real>((real) w[0], tx);
+    bsplineWeights<real>((real) w[1], ty);
+    bsplineWeights<real>((real) w[2], tz);
+    const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2];
+    constexpr int NV = LEVEL + 1;
+    // acc[t][u][v] with t+u+v <= LEVEL; built by successive contraction z -> y -> x
+    real acc[NV][NV][NV];
+#pragma unroll
+    for (int t = 0; t < NV; t++)
+#pragma unroll
+        for (int u = 0; u < NV; u++)
+#pragma unroll
+            for (int v = 0; v < NV; v++) acc[t][u][v] = 0;
+#pragma unroll
+    for (int ix = 0; ix < 6; ix++) {
+        int x = ig[0] + ix; x -= (x >= nx) ? nx : 0;
+        real yz[NV][NV];
+#pragma unroll
+        for (int u = 0; u < NV; u++)
+#pragma unroll
+            for (int v = 0; v < NV; v++) yz[u][v] = 0;
+#pragma unroll
+        for (int iy = 0; iy < 6; iy++) {
+            int y = ig[1] + iy; y -= (y >= ny) ? ny : 0;
+            const real* row = grid + ((size_t) x*ny + y)*nz;
+            real zs[NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++) zs[v] = 0;
+#pragma unroll
+            for (int iz = 0; iz < 6; iz++) {
+                int z = ig[2] + iz; z -= (z >= nz) ? nz : 0;
+                const real q = row[z];
+#pragma unroll
+                for (int v = 0; v < NV; v++) zs[v] += q*tz[iz][v];
+            }
+#pragma unroll
+            for (int u = 0; u < NV; u++)
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+                    if (u + v <= LEVEL) yz[u][v] += zs[v]*ty[iy][u];
+        }
+#pragma unroll
+        for (int t = 0; t < NV; t++)
+#pragma unroll
+            for (int u = 0; u < NV; u++)
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+                    if (t + u + v <= LEVEL) acc[t][u][v] += yz[u][v]*tx[ix][t];
+    }
+#pragma unroll
+    for (int t = 0; t < NV; t++)
+#pragma unroll
+        for (int u = 0; u < NV; u++)
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                if (t + u + v <= LEVEL) phi[(size_t) phiIndex(t, u, v)*P.n + s] = acc[t][u][v];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 6: per-atom solver arithmetic
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void applyAlphaLab(const double* a, double fx, double fy, double fz, double& ox, double& oy, double& oz) {
+    ox = a[0]*fx + a[1]*fy + a[2]*fz;
+    oy = a[1]*fx + a[3]*fy + a[4]*fz;
+    oz = a[2]*fx + a[4]*fy + a[5]*fz;
+}
+
+template <typename real>
+__device__ __forceinline__ void reciprocalFieldOf(const DevParams& P, const real* __restrict__ phi, int s, double& fx, double& fy, double& fz) {
+    const double p1 = phi[(size_t) 1*P.n + s], p2 = phi[(size_t) 2*P.n + s], p3 = phi[(size_t) 3*P.n + s];
+    fx = -(p1*P.geom.A[0][0] + p2*P.geom.A[1][0] + p3*P.geom.A[2][0]);
+    fy = -(p1*P.geom.A[0][1] + p2*P.geom.A[1][1] + p3*P.geom.A[2][1]);
+    fz = -(p1*P.geom.A[0][2] + p2*P.geom.A[1][2] + p3*P.geom.A[2][2]);
+}
+
+// E_fixed += reciprocal + self for the rows this rank owns   (:2922-2949)
+template <typename real>
+__global__ void k_fixed_recip(DevParams P, const real* __restrict__ phi, const double* __restrict__ cartD, double* __restrict__ field) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.rowEnd) return;
+    if (P.method != PME) return;
+    double rx, ry, rz;
+    reciprocalFieldOf<real>(P, phi, s, rx, ry, rz);
+    field[3*(size_t) s]   += rx + P.selfFieldTerm*cartD[20*(size_t) s+1];
+    field[3*(size_t) s+1] += ry + P.selfFieldTerm*cartD[20*(size_t) s+2];
+    field[3*(size_t) s+2] += rz + P.selfFieldTerm*cartD[20*(size_t) s+3];
+}
+// efix = alpha.E_fixed ; mu = efix       (:1305-1316, :936-946)
+template <typename real>
+__global__ void k_fixed_mu(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ field,
+                           double* __restrict__ efix, double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    double ox, oy, oz;
+    applyAlphaLab(alphaLab + 6*(size_t) s, field[3*(size_t) s], field[3*(size_t) s+1], field[3*(size_t) s+2], ox, oy, oz);
+    efix[3*(size_t) s] = ox; efix[3*(size_t) s+1] = oy; efix[3*(size_t) s+2] = oz;
+    mu[3*(size_t) s] = ox; mu[3*(size_t) s+1] = oy; mu[3*(size_t) s+2] = oz;
+    typename Real4<real>::type m = mud[s];
+    m.x = (real) ox; m.y = (real) oy; m.z = (real) oz;
+    mud[s] = m;
+}
+
+// Induced field: add the reciprocal part, the self term and (GRAD) the reciprocal field gradient.
+//   reference: :4046-4058, :4094-4129, :4133-4140
+template <typename real, bool GRAD>
+__global__ void k_induced_finish(DevParams P, const real* __restrict__ phidp, const double* __restrict__ mu,
+                                 double* __restrict__ field, double* __restrict__ grad) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.rowEnd) return;
+    if (P.method != PME) return;
+    double rx, ry, rz;
+    reciprocalFieldOf<real>(P, phidp, s, rx, ry, rz);
+    field[3*(size_t) s]   += rx + P.selfFieldTerm*mu[3*(size_t) s];
+    field[3*(size_t) s+1] += ry + P.selfFieldTerm*mu[3*(size_t) s+1];
+    field[3*(size_t) s+2] += rz + P.selfFieldTerm*mu[3*(size_t) s+2];
+    if (GRAD) {
+        const size_t n = P.n;
+        const double pxx = phidp[4*n + s], pyy = phidp[5*n + s], pzz = phidp[6*n + s];
+        const double pxy = phidp[7*n + s], pxz = phidp[8*n + s], pyz = phidp[9*n + s];
+        const double E[3][3] = {{pxx, pxy, pxz}, {pxy, pyy, pyz}, {pxz, pyz, pzz}};
+        const int gi[6] = {0, 1, 2, 0, 0, 1}, gj[6] = {0, 1, 2, 1, 2, 2};
+        for (int c = 0; c < 6; c++) {
+            double sum = 0;
+            for (int k = 0; k < 3; k++)
+                for (int l = 0; l < 3; l++) sum += P.geom.A[k][gi[c]]*E[k][l]*P.geom.A[l][gj[c]];
+            grad[6*(size_t) s + c] -= sum;
+        }
+    }
+}
+
+// DIIS bookkeeping (:1195-1218): newDip = efix + alpha.E_ind, err = newDip - mu, both into history slot.
+__global__ void k_diis_record(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ efix,
+                              const double* __restrict__ ifield, const double* __restrict__ mu,
+                              double* __restrict__ histDip, double* __restrict__ histErr) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    double ox, oy, oz;
+    applyAlphaLab(alphaLab + 6*(size_t) s, ifield[3*(size_t) s], ifield[3*(size_t) s+1], ifield[3*(size_t) s+2], ox, oy, oz);
+    const double nx = efix[3*(size_t) s] + ox, ny = efix[3*(size_t) s+1] + oy, nz = efix[3*(size_t) s+2] + oz;
+    histDip[3*(size_t) s] = nx; histDip[3*(size_t) s+1] = ny; histDip[3*(size_t) s+2] = nz;
+    histErr[3*(size_t) s] = nx - mu[3*(size_t) s]; histErr[3*(size_t) s+1] = ny - mu[3*(size_t) s+1]; histErr[3*(size_t) s+2] = nz - mu[3*(size_t) s+2];
+}
+
+// dots[k] = <vec, hist_k> for k < m : fixed block partition + ordered second pass => deterministic
+struct VecList { const double* v[MPID_MAX_HISTORY + 1]; };
+__global__ void __launch_bounds__(256)
+k_dots_partial(size_t len, int m, const double* __restrict__ vec, VecList hist, double* __restrict__ partial) {
+    __shared__ double sh[256/32][MPID_MAX_HISTORY + 1];
+    double acc[MPID_MAX_HISTORY + 1];
+    for (int k = 0; k < m; k++) acc[k] = 0;
+    for (size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x; idx < len; idx += (size_t) gridDim.x*blockDim.x) {
+        const double a = vec[idx];
+        for (int k = 0; k < m; k++) acc[k] += a*hist.v[k][idx];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = 0; k < m; k++) {
+        double v = acc[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sh[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < m) {
+        double v = 0;
+        for (int w = 0; w < 256/32; w++) v += sh[w][threadIdx.x];
+        partial[(size_t) blockIdx.x*(MPID_MAX_HISTORY + 1) + threadIdx.x] = v;
+    }
+}
+__global__ void k_dots_final(int numBlocks, int m, const double* __restrict__ partial, double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= m) return;
+    double v = 0;
+    for (int b = 0; b < numBlocks; b++) v += partial[(size_t) b*(MPID_MAX_HISTORY + 1) + k];
+    out[k] = v;
+}
+
+// mu = sum_k coef[k] * vec_k   (DIIS extrapolation :1240-1249, OPT combination :1172-1177); repacks mud
+struct CoefList { double c[MPID_MAX_HISTORY + 1]; };
+template <typename real>
+__global__ void k_combine(int n, int m, VecList vecs, CoefList coef, double* __restrict__ mu,
+                          typename Real4<real>::type* __restrict__ mud) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double x = 0, y = 0, z = 0;
+    for (int k = 0; k < m; k++) {
+        const double c = coef.c[k];
+        x += c*vecs.v[k][3*(size_t) s]; y += c*vecs.v[k][3*(size_t) s+1]; z += c*vecs.v[k][3*(size_t) s+2];
+    }
+    mu[3*(size_t) s] = x; mu[3*(size_t) s+1] = y; mu[3*(size_t) s+2] = z;
+    typename Real4<real>::type v = mud[s];
+    v.x = (real) x; v.y = (real) y; v.z = (real) z;
+    mud[s] = v;
+}
+
+// OPT recursion step (:1149-1167): mu = alpha.E_ind ; store mu, field (gradient is stored by the caller's buffer)
+template <typename real>
+__global__ void k_opt_step(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ ifield,
+                           double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud,
+                           double* __restrict__ ptDip, double* __restrict__ ptField) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    double ox, oy, oz;
+    const double fx = ifield[3*(size_t) s], fy = ifield[3*(size_t) s+1], fz = ifield[3*(size_t) s+2];
+    applyAlphaLab(alphaLab + 6*(size_t) s, fx, fy, fz, ox, oy, oz);
+    mu[3*(size_t) s] = ox; mu[3*(size_t) s+1] = oy; mu[3*(size_t) s+2] = oz;
+    ptDip[3*(size_t) s] = ox; ptDip[3*(size_t) s+1] = oy; ptDip[3*(size_t) s+2] = oz;
+    ptField[3*(size_t) s] = fx; ptField[3*(size_t) s+1] = fy; ptField[3*(size_t) s+2] = fz;
+    typename Real4<real>::type v = mud[s];
+    v.x = (real) ox; v.y = (real) oy; v.z = (real) oz;
+    mud[s] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 7: reciprocal-space energy/force/torque, self terms, OPT response, torque mapping, output
+// ---------------------------------------------------------------------------------------------------
+//   reference: :3739-3866, :3871-4024, :4283-4333
+template <typename real>
+__global__ void __launch_bounds__(128)
+k_reciprocal_terms(DevParams P, const real* __restrict__ phi, const real* __restrict__ phidp, const double* __restrict__ cartD,
+                   const double* __restrict__ sphD, const double* __restrict__ mu, const int* __restrict__ aniso,
+                   unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque, unsigned long long* __restrict__ energy) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    double e = 0;
+    if (s < P.rowEnd) {
+        const size_t n = P.n;
+        const double ke = MPID_ELECTRIC;
+        const bool mutual = P.polarization == Mutual;
+        double c[20], frac[20], find[4], p[35], pd[35], m[20], cp[20], tq[3];
+        for (int k = 0; k < 20; k++) c[k] = cartD[20*(size_t) s + k];
+        for (int k = 0; k < 35; k++) { p[k] = phi[k*n + s]; pd[k] = phidp[k*n + s]; }
+        const double ux = mu[3*(size_t) s], uy = mu[3*(size_t) s+1], uz = mu[3*(size_t) s+2];
+        multipolesToFractional<double>(P.geom.A, c, frac);
+        find[0] = 0;
+        for (int k = 0; k < 3; k++) find[1+k] = P.geom.A[k][0]*ux + P.geom.A[k][1]*uy + P.geom.A[k][2]*uz;
+        const bool an = aniso[s] != 0;
+        double tx = 0, ty = 0, tz = 0;
+        // induced part
+        const bool addU = mutual && an;
+        torqueMultipoles<double>(c, addU ? ux : 0.0, addU ? uy : 0.0, addU ? uz : 0.0, m);
+        potentialToCartesian<double>(P.geom.A, pd, cp);
+        reciprocalTorque<double>(m, cp, tq);
+        tx += ke*tq[0]; ty += ke*tq[1]; tz += ke*tq[2];
+        double eInd = 2.0*(find[1]*p[1] + find[2]*p[2] + find[3]*p[3]);
+        double f[3];
+        for (int d = 0; d < 3; d++) {
+            const int dt = d == 0, du = d == 1, dv = d == 2;
+            double v = 2.0*contractFractional<double>(find, 4, p, dt, du, dv);
+            if (mutual) v += 2.0*contractFractional<double>(find, 4, pd, dt, du, dv);
+            v += 2.0*contractFractional<double>(frac, 20, pd, dt, du, dv);
+            f[d] = 0.5*ke*v;
+        }
+        // permanent part
+        torqueMultipoles<double>(c, an ? ux : 0.0, an ? uy : 0.0, an ? uz : 0.0, m);
+        potentialToCartesian<double>(P.geom.A, p, cp);
+        reciprocalTorque<double>(m, cp, tq);
+        tx += ke*tq[0]; ty += ke*tq[1]; tz += ke*tq[2];
+        const double ePerm = contractFractional<double>(frac, 20, p, 0, 0, 0);
+        for (int d = 0; d < 3; d++) f[d] += ke*contractFractional<double>(frac, 20, p, d == 0, d == 1, d == 2);
+        double Fx = -(f[0]*P.geom.A[0][0] + f[1]*P.geom.A[1][0] + f[2]*P.geom.A[2][0]);
+        double Fy = -(f[0]*P.geom.A[0][1] + f[1]*P.geom.A[1][1] + f[2]*P.geom.A[2][1]);
+        double Fz = -(f[0]*P.geom.A[0][2] + f[1]*P.geom.A[1][2] + f[2]*P.geom.A[2][2]);
+        // self torque on isotropic sites
+        if (!an) {
+            const double term = (2.0/3.0)*ke*P.alpha*P.alpha*P.alpha/MPID_SQRT_PI;
+            const double dx = c[1], dy = c[2], dz = c[3];
+            tx += term*2.0*(dy*uz - dz*uy); ty += term*2.0*(dz*ux - dx*uz); tz += term*2.0*(dx*uy - dy*ux);
+        }
+        // self energy
+        const double* sp = sphD + 16*(size_t) s;
+        double qii = 0, oii = 0;
+        for (int k = 4; k < 9; k++) qii += sp[k]*sp[k];
+        for (int k = 9; k < 16; k++) oii += sp[k]*sp[k];
+        const double cii = sp[0]*sp[0];
+        const double dii = sp[2]*(sp[2] + ux) + sp[3]*(sp[3] + uy) + sp[1]*(sp[1] + uz);
+        const double a2 = P.alpha*P.alpha;
+        e = 0.25*ke*eInd + 0.5*ke*ePerm
+          - P.alpha*ke/MPID_SQRT_PI*(cii + (2.0/3.0)*a2*dii + (4.0/15.0)*a2*a2*qii + (8.0/105.0)*a2*a2*a2*oii);
+        atomicAddFixed(&force[3*(size_t) s], Fx); atomicAddFixed(&force[3*(size_t) s+1], Fy); atomicAddFixed(&force[3*(size_t) s+2], Fz);
+        atomicAddFixed(&torque[3*(size_t) s], tx); atomicAddFixed(&torque[3*(size_t) s+1], ty); atomicAddFixed(&torque[3*(size_t) s+2], tz);
+    }
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAddFixed(energy, e);
+}
+
+// OPT dipole-response force and torque (:4956-4984, :2160-2188)
+struct OptLists { const double* dip[8]; const double* field[8]; const double* grad[8]; double part[8]; int K; };
+__global__ void k_opt_force(DevParams P, OptLists L, const int* __restrict__ aniso,
+                            unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.rowEnd) return;
+    const double ke = MPID_ELECTRIC;
+    double fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0;
+    const bool an = aniso[s] != 0;
+    for (int l = 0; l < L.K-1; l++)
+        for (int m = 0; m < L.K-1-l; m++) {
+            const double p = L.part[l+m+1];
+            if (fabs(p) < 1e-6) continue;
+            const double* u = L.dip[l] + 3*(size_t) s;
+            const double* g = L.grad[m] + 6*(size_t) s;
+            fx += p*ke*(u[0]*g[0] + u[1]*g[3] + u[2]*g[4]);
+            fy += p*ke*(u[0]*g[3] + u[1]*g[1] + u[2]*g[5]);
+            fz += p*ke*(u[0]*g[4] + u[1]*g[5] + u[2]*g[2]);
+            if (an) {
+                const double* fl = L.field[m] + 3*(size_t) s;
+                tx += p*ke*(u[1]*fl[2] - u[2]*fl[1]);
+                ty += p*ke*(u[2]*fl[0] - u[0]*fl[2]);
+                tz += p*ke*(u[0]*fl[1] - u[1]*fl[0]);
+            }
+        }
+    atomicAddFixed(&force[3*(size_t) s], fx); atomicAddFixed(&force[3*(size_t) s+1], fy); atomicAddFixed(&force[3*(size_t) s+2], fz);
+    if (an) { atomicAddFixed(&torque[3*(size_t) s], tx); atomicAddFixed(&torque[3*(size_t) s+1], ty); atomicAddFixed(&torque[3*(size_t) s+2], tz); }
+}
+
+// torque -> forces on the frame atoms (:2112-2131, :1895-2110); one thread per sorted atom
+__global__ void k_torque_to_force(DevParams P, ParticleParams pp, const int* __restrict__ order, const int* __restrict__ inv,
+                                  const double* __restrict__ posOrig, const unsigned long long* __restrict__ torque,
+                                  unsigned long long* __restrict__ force) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    const int o = order[s];
+    const int axis = pp.axis[o];
+    if (axis == NoAxisType) return;
+    const int az = pp.atomZ[o], ax = pp.atomX[o], ay = pp.atomY[o];
+    if (az < 0) return;
+    const double tq[3] = {fixedToDouble(torque[3*(size_t) s]), fixedToDouble(torque[3*(size_t) s+1]), fixedToDouble(torque[3*(size_t) s+2])};
+    const double* pi = posOrig + 3*o;
+    const double* pz = posOrig + 3*az;
+    const double* px = ax >= 0 ? posOrig + 3*ax : pz;
+    const double* py = ay >= 0 ? posOrig + 3*ay : pz;
+    double fI[3], fZ[3], fX[3], fY[3];
+    torqueToForce(axis, pi, pz, px, py, ay >= 0, tq, fI, fZ, fX, fY);
+    const int sz = inv[az];
+    for (int k = 0; k < 3; k++) {
+        atomicAddFixed(&force[3*(size_t) s + k], fI[k]);
+        atomicAddFixed(&force[3*(size_t) sz + k], fZ[k]);
+    }
+    if (ax >= 0) { const int sx = inv[ax]; for (int k = 0; k < 3; k++) atomicAddFixed(&force[3*(size_t) sx + k], fX[k]); }
+    if (ay >= 0) { const int sy = inv[ay]; for (int k = 0; k < 3; k++) atomicAddFixed(&force[3*(size_t) sy + k], fY[k]); }
+}
+
+// forcesOrig[o] += fixed-point force of the sorted slot
+__global__ void k_output_forces(int n, const int* __restrict__ order, const unsigned long long* __restrict__ force, double* __restrict__ forcesOrig) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int o = order[s];
+    forcesOrig[3*(size_t) o]   += fixedToDouble(force[3*(size_t) s]);
+    forcesOrig[3*(size_t) o+1] += fixedToDouble(force[3*(size_t) s+1]);
+    forcesOrig[3*(size_t) o+2] += fixedToDouble(force[3*(size_t) s+2]);
+}
+
+// out[o] = vec[s] (3 components), optionally adding the lab permanent dipole
+__global__ void k_unsort_vec3(int n, const int* __restrict__ order, const double* __restrict__ vec, const double* __restrict__ cartD,
+                              int which, double* __restrict__ out) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int o = order[s];
+    for (int k = 0; k < 3; k++) {
+        double v = 0;
+        if (which == 0 || which == 2) v += vec[3*(size_t) s + k];
+        if (which == 1 || which == 2) v += cartD[20*(size_t) s + 1 + k];
+        out[3*(size_t) o + k] = v;
+    }
+}
+
+} // namespace mpid
+#endif

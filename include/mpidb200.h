@@ -92,6 +92,10 @@ int mpidb200_execute(mpidb200_handle h, const double* positions, int include_for
 int mpidb200_execute_device(mpidb200_handle h, const double* d_positions, int include_forces, int include_energy,
                             double* energy, double* d_forces);
 
+/* Run the engine on a caller-owned CUDA stream (e.g. the host framework's current stream) instead of its
+ * own; pass NULL to return to the private stream.  The caller keeps ownership. */
+int mpidb200_set_stream(mpidb200_handle h, void* cuda_stream);
+
 /* replaces getInducedDipoles / getLabFramePermanentDipoles / getTotalDipoles (mpidKernels.h:79-84):
  * evaluate at `positions` and return double[3N].  which: 0 induced, 1 lab-frame permanent, 2 total */
 int mpidb200_get_dipoles(mpidb200_handle h, const double* positions, int which, double* out);
@@ -111,18 +115,23 @@ int mpidb200_get_pme_parameters(mpidb200_handle h, double* alpha, int* nx, int* 
 /* Solver and timing statistics of the last execute: iterations, final epsilon, and CUDA-event
  * milliseconds per stage (see MPIDB200_STAGE_*). */
 enum {
-    MPIDB200_STAGE_NEIGHBOR = 0,   /* sort + lab frames + neighbour list       */
-    MPIDB200_STAGE_FIXED_PME,      /* spread/FFT/convolution/gather, permanent */
-    MPIDB200_STAGE_FIXED_REAL,     /* real-space permanent field               */
-    MPIDB200_STAGE_INDUCED_PME,    /* all induced reciprocal passes            */
-    MPIDB200_STAGE_INDUCED_REAL,   /* all induced real-space passes            */
-    MPIDB200_STAGE_SOLVER,         /* DIIS/CG/OPT vector work + collectives    */
-    MPIDB200_STAGE_ELECTROSTATICS, /* pair energy/force/torque                 */
-    MPIDB200_STAGE_FINISH,         /* reciprocal terms, torque mapping, output */
+    MPIDB200_STAGE_SORT = 0,       /* wrap, cell sort, lab-frame moments                     */
+    MPIDB200_STAGE_NLIST,          /* neighbour-list count + scan + fill                     */
+    MPIDB200_STAGE_FIXED_SPREAD,   /* permanent multipoles -> grid (incl. grid clear)        */
+    MPIDB200_STAGE_FFT,            /* every R2C FFT + convolution + C2R FFT of the call      */
+    MPIDB200_STAGE_FIXED_GATHER,   /* 35 potential derivatives of the permanent grid         */
+    MPIDB200_STAGE_FIXED_REAL,     /* real-space permanent field (+ mu = alpha.E)            */
+    MPIDB200_STAGE_IND_SPREAD,     /* induced dipoles -> grid, all passes                    */
+    MPIDB200_STAGE_IND_GATHER,     /* induced potential derivatives, all passes              */
+    MPIDB200_STAGE_IND_REAL,       /* real-space induced field, all passes (+ collectives)   */
+    MPIDB200_STAGE_SOLVER,         /* DIIS / OPT vector work and its host round trips        */
+    MPIDB200_STAGE_ELECTROSTATICS, /* pair energy / force / torque                           */
+    MPIDB200_STAGE_FINISH,         /* reciprocal terms, torque mapping, output               */
     MPIDB200_NUM_STAGES
 };
 int mpidb200_get_stats(mpidb200_handle h, int* iterations, double* epsilon, double* stage_ms, long long* num_pairs);
-/* enable per-stage CUDA-event timing (adds synchronisations; off by default) */
+/* per-stage CUDA-event timing: events are recorded on the engine's stream around each stage and read
+ * after the call's final synchronisation (no extra synchronisation is added); off by default */
 int mpidb200_set_profiling(mpidb200_handle h, int enabled);
 /* number of kernel launches issued by the last execute */
 long long mpidb200_last_launch_count(mpidb200_handle h);

@@ -32,11 +32,14 @@ class _Config(ctypes.Structure):
                 ("frameless_alpha_fix", ctypes.c_int)]
 
 
+STAGE_NAMES = ["sort", "nlist", "fixed_spread", "fft", "fixed_gather", "fixed_real", "ind_spread", "ind_gather", "ind_real",
+               "solver", "electrostatics", "finish"]
+
 EXPORTS = ["mpidb200_last_error", "mpidb200_default_config", "mpidb200_create", "mpidb200_destroy", "mpidb200_set_particles",
            "mpidb200_set_covalent_maps", "mpidb200_set_box", "mpidb200_execute", "mpidb200_execute_device",
            "mpidb200_get_dipoles", "mpidb200_get_system_multipole_moments", "mpidb200_get_electrostatic_potential",
            "mpidb200_get_pme_parameters", "mpidb200_get_stats", "mpidb200_set_profiling", "mpidb200_last_launch_count",
-           "mpidb200_get_pair_list", "mpidb200_nccl_unique_id", "mpidb200_comm_init"]
+           "mpidb200_get_pair_list", "mpidb200_nccl_unique_id", "mpidb200_comm_init", "mpidb200_set_stream"]
 
 
 def load_library():
@@ -409,9 +412,9 @@ class MPIDB200Kernel:
         self._check(self._lib.mpidb200_set_profiling(self._h, ctypes.c_int(1 if enabled else 0)))
 
     def getStats(self):
-        it = ctypes.c_int(); eps = ctypes.c_double(); ms = (ctypes.c_double*8)(); pairs = ctypes.c_longlong()
+        it = ctypes.c_int(); eps = ctypes.c_double(); ms = (ctypes.c_double*16)(); pairs = ctypes.c_longlong()
         self._check(self._lib.mpidb200_get_stats(self._h, ctypes.byref(it), ctypes.byref(eps), ms, ctypes.byref(pairs)))
-        names = ["neighbor", "fixed_pme", "fixed_real", "induced_pme", "induced_real", "solver", "electrostatics", "finish"]
+        names = STAGE_NAMES
         return dict(iterations=it.value, epsilon=eps.value, pairs=pairs.value,
                     stage_ms={k: ms[i] for i, k in enumerate(names)},
                     launches=int(self._lib.mpidb200_last_launch_count(self._h)))
@@ -424,6 +427,10 @@ class MPIDB200Kernel:
         self._check(self._lib.mpidb200_get_pair_list(self._h, ctypes.c_longlong(m), _ip(pi), _ip(pj), _ip(pc), ctypes.byref(cnt)))
         k = cnt.value
         return pi[:k], pj[:k], pc[:k]
+
+    def setStream(self, cuda_stream):
+        """cuda_stream: raw cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream), or None."""
+        self._check(self._lib.mpidb200_set_stream(self._h, ctypes.c_void_p(cuda_stream if cuda_stream else None)))
 
     def commInit(self, rank, numRanks, uniqueId):
         buf = (ctypes.c_ubyte*128).from_buffer_copy(bytes(uniqueId))

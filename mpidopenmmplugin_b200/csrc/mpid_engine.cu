@@ -91,6 +91,7 @@ struct EngineBase {
     virtual void getStats(int* it, double* eps, double* ms, long long* pairs) = 0;
     virtual long long getPairList(long long cap, int* pi, int* pj, int* pc) = 0;
     virtual void commInit(int rank, int nranks, const unsigned char* id) = 0;
+    virtual void setStream(void* st) = 0;
     virtual void systemMoments(const double* pos, const double* masses, double* out13) = 0;
     virtual void potential(const double* pos, int npts, const double* pts, double* out) = 0;
     bool profiling = false;
@@ -119,7 +120,7 @@ struct Engine : public EngineBase {
     typedef typename FftTraits<real>::cplx cplx;
     mpidb200_config cfg;
     int n;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, ownStream = nullptr;
     bool haveParticles = false, haveBox = false, pmeReady = false;
     // host copies
     std::vector<double> hCharge, hDipole, hQuad, hOct, hThole, hAlpha, hDamp;
@@ -156,17 +157,15 @@ struct Engine : public EngineBase {
     double* hPinnedPos = nullptr; size_t hPinnedPosCap = 0;
     // statistics
     int lastIterations = 0; double lastEps = 0; double stageMs[MPIDB200_NUM_STAGES]; long long lastPairs = 0, lastFull = 0;
-    cudaEvent_t evA = nullptr, evB = nullptr;
     // multi-GPU
     void* comm = nullptr; int rank = 0, numRanks = 1;
     std::vector<double> hLastMu;
 
     explicit Engine(const mpidb200_config& c) : cfg(c), n(c.num_particles) {
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
+        stream = ownStream;
         CUDA_CHECK(cudaMallocHost((void**) &hPinned, 256*sizeof(double)));
-        CUDA_CHECK(cudaEventCreate(&evA));
-        CUDA_CHECK(cudaEventCreate(&evB));
         memset(&P, 0, sizeof(P));
         memset(stageMs, 0, sizeof(stageMs));
         if (cfg.nonbonded_method == MPIDB200_NOCUTOFF) {
@@ -180,9 +179,14 @@ struct Engine : public EngineBase {
         if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); }
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
-        if (evA) cudaEventDestroy(evA);
-        if (evB) cudaEventDestroy(evB);
-        if (stream) cudaStreamDestroy(stream);
+        for (cudaEvent_t e : evPool) cudaEventDestroy(e);
+        if (ownStream) cudaStreamDestroy(ownStream);
+    }
+    void setStream(void* st) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        stream = st ? (cudaStream_t) st : ownStream;
+        if (plansMade) { CUFFT_CHECK(cufftSetStream(planF, stream)); CUFFT_CHECK(cufftSetStream(planB, stream)); }
     }
 
 #define LAUNCH(kernel, gridDim, blockDim, ...) do { kernel<<<(gridDim), (blockDim), 0, stream>>>(__VA_ARGS__); launches++; \
@@ -372,21 +376,36 @@ struct Engine : public EngineBase {
         haveBox = true;
     }
 
-    // ---- timing helpers ------------------------------------------------------------------------------
-    int curStage = -1;
+    // ---- timing helpers: event pairs recorded on the stream, read back after the final sync ----------
+    std::vector<cudaEvent_t> evPool;
+    std::vector<int> evStage;
+    int evUsed = 0, curStage = -1;
     void stageBegin(int st) {
         if (!profiling) return;
+        if (2*(evUsed + 1) > (int) evPool.size()) {
+            cudaEvent_t a, b;
+            CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+            evPool.push_back(a); evPool.push_back(b); evStage.push_back(st);
+        }
+        evStage[evUsed] = st;
         curStage = st;
-        CUDA_CHECK(cudaEventRecord(evA, stream));
+        CUDA_CHECK(cudaEventRecord(evPool[2*evUsed], stream));
     }
     void stageEnd() {
         if (!profiling || curStage < 0) return;
-        CUDA_CHECK(cudaEventRecord(evB, stream));
-        CUDA_CHECK(cudaEventSynchronize(evB));
-        float ms = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, evA, evB));
-        stageMs[curStage] += ms;
+        CUDA_CHECK(cudaEventRecord(evPool[2*evUsed + 1], stream));
+        evUsed++;
         curStage = -1;
+    }
+    void collectTimings() {
+        if (!profiling) return;
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int k = 0; k < evUsed; k++) {
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, evPool[2*k], evPool[2*k+1]));
+            stageMs[evStage[k]] += ms;
+        }
+        evUsed = 0;
     }
 
     void allReduce(void* buf, size_t count, int dtype) {
@@ -435,7 +454,9 @@ struct Engine : public EngineBase {
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
         LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
                dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p);
+        stageEnd();
         // neighbour list: count, scan, fill
+        stageBegin(MPIDB200_STAGE_NLIST);
         int rows = P.rowEnd - P.rowBegin;
         dFullCount.ensure((size_t) rows + 1); dHalfCount.ensure((size_t) rows + 1); dFullStart.ensure((size_t) rows + 1); dHalfStart.ensure((size_t) rows + 1);
         CUDA_CHECK(cudaMemsetAsync(dFullCount.p, 0, ((size_t) rows + 1)*sizeof(unsigned), stream));
@@ -463,11 +484,13 @@ struct Engine : public EngineBase {
 
     void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
         size_t GC = (size_t) grid[0]*grid[1]*(grid[2]/2 + 1);
+        stageBegin(MPIDB200_STAGE_FFT);
         if (numRanks > 1) allReduce(dGrid.p, (size_t) grid[0]*grid[1]*grid[2], sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64);
         CUFFT_CHECK(FftTraits<real>::fwd(planF, dGrid.p, dGridC.p));
         LAUNCH((k_convolution<cplx, real>), blocksFor((long long) GC, 256), 256, GC, dEterm.p, dGridC.p);
         CUFFT_CHECK(FftTraits<real>::bwd(planB, dGridC.p, dGrid.p));
         launches += 2;
+        stageEnd();
     }
 
     real* cartR() { return sizeof(real) == sizeof(double) ? (real*) dCartD.p : dCartR.p; }
@@ -480,12 +503,14 @@ struct Engine : public EngineBase {
         dField.ensure(3*(size_t) n); dEfix.ensure(3*(size_t) n); dMu.ensure(3*(size_t) n);
         dPhi.ensure(35*(size_t) n); dPhidp.ensure(35*(size_t) n);
         if (pme) {
-            stageBegin(MPIDB200_STAGE_FIXED_PME);
+            stageBegin(MPIDB200_STAGE_FIXED_SPREAD);
             dFrac.ensure(20*(size_t) n);
             LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
             CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), stream));
             if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
+            stageEnd();
             reciprocalPass();
+            stageBegin(MPIDB200_STAGE_FIXED_GATHER);
             if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhi.p);
             stageEnd();
         }
@@ -512,10 +537,12 @@ struct Engine : public EngineBase {
         size_t G = (size_t) grid[0]*grid[1]*grid[2];
         dIfield.ensure(3*(size_t) n);
         if (pme) {
-            stageBegin(MPIDB200_STAGE_INDUCED_PME);
+            stageBegin(MPIDB200_STAGE_IND_SPREAD);
             CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), stream));
             if (rows > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, (const real*) nullptr, dMu.p, dGrid.p);
+            stageEnd();
             reciprocalPass();
+            stageBegin(MPIDB200_STAGE_IND_GATHER);
             if (rows > 0) {
                 if (level == 1) LAUNCH((k_gather<real, 1>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
                 else if (level == 2) LAUNCH((k_gather<real, 2>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
@@ -524,7 +551,7 @@ struct Engine : public EngineBase {
             stageEnd();
         }
         if (!realSpace) return;
-        stageBegin(MPIDB200_STAGE_INDUCED_REAL);
+        stageBegin(MPIDB200_STAGE_IND_REAL);
         if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dIfield.p, 0, 3*(size_t) n*sizeof(double), stream));
         if (rows > 0) {
             const int nb = blocksFor((long long) rows*MPID_LANES, 256);
@@ -670,7 +697,7 @@ struct Engine : public EngineBase {
         memset(stageMs, 0, sizeof(stageMs));
         const bool pme = P.method == PME;
         P.numRanks = numRanks; P.rank = rank;
-        stageBegin(MPIDB200_STAGE_NEIGHBOR);
+        stageBegin(MPIDB200_STAGE_SORT);
         buildNeighbors(dPosIn);
         dForce.ensure(3*(size_t) n); dTorque.ensure(3*(size_t) n); dEnergy.ensure(2);
         CUDA_CHECK(cudaMemsetAsync(dForce.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
@@ -688,14 +715,14 @@ struct Engine : public EngineBase {
             solveMutualDiis(dPosIn);
             if (pme && !dipolesOnly && rows > 0) {
                 // the converged dipoles' reciprocal potential is still on the grid: fetch all 35 derivatives
-                stageBegin(MPIDB200_STAGE_INDUCED_PME);
+                stageBegin(MPIDB200_STAGE_IND_GATHER);
                 LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
                 stageEnd();
             }
         } else {
             solveExtrapolated(dPosIn);
         }
-        if (dipolesOnly) return;
+        if (dipolesOnly) { collectTimings(); return; }
 
         stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
         const bool mutual = P.polarization == Mutual;
@@ -739,8 +766,9 @@ struct Engine : public EngineBase {
         }
         unsigned long long* he = (unsigned long long*) hPinned;
         CUDA_CHECK(cudaMemcpyAsync(he, dEnergy.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
         stageEnd();
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        collectTimings();
         if (energy) *energy = includeEnergy ? (double) ((long long) he[0])*(1.0/MPID_FIXED_SCALE) : 0.0;
     }
 
@@ -985,6 +1013,9 @@ int mpidb200_set_profiling(mpidb200_handle h, int enabled) {
 long long mpidb200_last_launch_count(mpidb200_handle h) { return asEngine(h)->launches; }
 int mpidb200_get_pair_list(mpidb200_handle h, long long capacity, int* pairs_i, int* pairs_j, int* pair_class, long long* count) {
     return guarded([&] { *count = asEngine(h)->getPairList(capacity, pairs_i, pairs_j, pair_class); });
+}
+int mpidb200_set_stream(mpidb200_handle h, void* cuda_stream) {
+    return guarded([&] { asEngine(h)->setStream(cuda_stream); });
 }
 int mpidb200_nccl_unique_id(unsigned char* out128) {
     return guarded([&] {

@@ -479,13 +479,21 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
                              T* force, T* tqI, T* tqJ) {
     const T r = t_sqrt(r2);
     const T rInv = T(1)/r;
-    // pair frame.  Any x axis perpendicular to Z gives the same energy, force and torques, so pick the
-    // lab axis least aligned with Z (the reference uses x unless the pair is parallel to it, :650-681).
+    // pair frame (formQIRotationMatrix, :650-681): x axis = lab x made orthogonal to Z, or lab y when the
+    // pair lies exactly along x.  The choice matters: the reference's induced-induced z-torque term on
+    // anisotropic sites (:4877-4878) is not invariant under rotations about Z, so parity needs the same
+    // axis.  1 - Zx^2 is formed as Zy^2 + Zz^2 so nearly x-aligned pairs stay accurate in FP32.
     V3<T> Z = mk<T>(dx*rInv, dy*rInv, dz*rInv);
-    V3<T> X = (t_abs(Z.x) < T(0.8)) ? mk<T>(T(1), T(0), T(0)) : mk<T>(T(0), T(1), T(0));
-    T zx = dot(Z, X);
-    X = X - Z*zx;
-    normalize(X);
+    V3<T> X;
+    if (dy != T(0) || dz != T(0)) {
+        T s2 = Z.y*Z.y + Z.z*Z.z;
+        T sInv = T(1)/t_sqrt(s2);
+        X = mk<T>(s2*sInv, -Z.x*Z.y*sInv, -Z.x*Z.z*sInv);
+    } else {
+        T s2 = Z.x*Z.x + Z.z*Z.z;
+        T sInv = T(1)/t_sqrt(s2);
+        X = mk<T>(-Z.x*Z.y*sInv, s2*sInv, -Z.y*Z.z*sInv);
+    }
     V3<T> Y = cross(Z, X);
 
     T QI[16], QJ[16];

@@ -127,3 +127,59 @@ def methanol_dimer(method, polarization):
     s.alpha = 4.5
     s.grid = (64, 64, 64)
     return s
+
+
+# ---------------------------------------------------------------------------------------------------
+# the oracle's pair set, restated with numpy for the bit-exactness tests
+# ---------------------------------------------------------------------------------------------------
+def pair_classes(s):
+    """{(i,j): class} for i<j from the covalent maps, exactly as setupScaleMaps
+    (MPIDReferenceForce.cpp:190-225): 1 = scale 0 (1-2, 1-3), 2 = 1-4, later lists override earlier ones."""
+    off, idx = s.cov_csr()
+    n = s.n
+    out = {}
+    for t in range(4):
+        for i in range(n):
+            for j in idx[off[t*(n+1)+i]:off[t*(n+1)+i+1]]:
+                j = int(j)
+                if j <= i:
+                    continue
+                out[(i, j)] = 1 if t < 2 else (2 if t == 2 else 0)
+    return {k: v for k, v in out.items() if v != 0}
+
+
+def min_image(s, d):
+    """getPeriodicDelta (MPIDReferenceForce.cpp:2671-2676) with separate multiply and add roundings."""
+    d = d.copy()
+    a, b, c = s.box[0], s.box[1], s.box[2]
+    det = a[0]*b[1]*c[2]
+    rc2 = (a[0]*b[1])*(1.0/det)
+    rb1 = (a[0]*c[2])*(1.0/det)
+    ra0 = (b[1]*c[2])*(1.0/det)
+    k = np.floor(d[:, 2]*rc2 + 0.5)
+    d -= k[:, None]*c[None, :]
+    k = np.floor(d[:, 1]*rb1 + 0.5)
+    d -= k[:, None]*b[None, :]
+    k = np.floor(d[:, 0]*ra0 + 0.5)
+    d -= k[:, None]*a[None, :]
+    return d
+
+
+def pair_set_reference(s, chunk=512):
+    """[(i, j, class)] with i<j and |minimg(r_j - r_i)|^2 <= rc^2 in FP64 (all pairs when no cutoff)."""
+    cls = pair_classes(s)
+    n = s.n
+    out = []
+    rc2 = s.cutoff*s.cutoff
+    for i0 in range(0, n, chunk):
+        i1 = min(n, i0 + chunk)
+        d = s.pos[None, :, :] - s.pos[i0:i1, None, :]
+        if s.method == 1:
+            d = min_image(s, d.reshape(-1, 3)).reshape(i1 - i0, n, 3)
+        r2 = d[:, :, 0]*d[:, :, 0] + d[:, :, 1]*d[:, :, 1] + d[:, :, 2]*d[:, :, 2]
+        ok = (r2 <= rc2) if s.method == 1 else np.ones_like(r2, dtype=bool)
+        ii, jj = np.nonzero(ok)
+        for a, b in zip(ii + i0, jj):
+            if a < b:
+                out.append((int(a), int(b), cls.get((int(a), int(b)), 0)))
+    return out

@@ -1,0 +1,286 @@
+"""Parity of the CUDA engine (through the C ABI) with the oracle.  Tolerances (north star): relative force
+error 1e-5 in mixed precision, 1e-8 in double; neighbour list / exclusion classes bit-exact."""
+import numpy as np
+import pytest
+
+from _common import (Oracle, load_fixture, make_kernel, methanol_dimer, pair_set_reference, rel_err, water_box, water_dimer)
+from mpidopenmmplugin_b200 import MPIDB200Error, MPIDForce, MPIDB200Kernel
+from mpidopenmmplugin_b200.workloads import ANISO_ALPHA_O
+from test_oracle_golden import GOLDEN, MAKERS, assert_equal_tol
+
+pytestmark = pytest.mark.gpu
+
+FTOL = {"mixed": 1e-5, "double": 1e-8}
+# mutual polarization: both sides iterate to eps (1e-8/1e-9 in the reference's tests) with different linear
+# solvers for the DIIS step, so the converged dipoles agree to ~eps, not to round-off
+MU_TOL_MUTUAL = 2e-6
+
+
+def run(s, prec):
+    k = make_kernel(s, precision=prec)
+    f = np.zeros((s.n, 3))
+    e = k.execute(s.pos, True, True, f)
+    mu = k.getInducedDipoles(s.pos)
+    return k, e, f, mu
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+@pytest.mark.parametrize("key", sorted(GOLDEN.keys()))
+def test_reference_golden_configurations(key, prec):
+    name, method, pol = key
+    s = MAKERS[name](method, pol)
+    k, e, f, mu = run(s, prec)
+    assert_equal_tol(GOLDEN[key], e, 1e-4)                 # the reference's own assertion
+    o = Oracle(s)
+    e0, f0 = o.execute()
+    mu0 = o.dipoles(0)
+    ftol = FTOL[prec] if pol != 0 else max(FTOL[prec], 5e-7)
+    assert rel_err(f, f0) < ftol
+    assert rel_err(mu, mu0) < (MU_TOL_MUTUAL if pol == 0 else 10*FTOL[prec])
+    assert abs(e - e0) <= (1e-5 if prec == "mixed" else 1e-8)*max(1.0, abs(e0))
+    if pol == 0:
+        assert k.getStats()["epsilon"] < s.epsilon
+    k.close()
+
+
+@pytest.mark.parametrize("scale,expected", [(1.0, -1389.35), (0.5, -694.675), (0.0, 0.0)])
+@pytest.mark.parametrize("method", [0, 1])
+def test_14_scaling(scale, expected, method):
+    """test14ScalingNoCutoff / test14ScalingPME (TestReferenceMPIDForce.cpp:1603-1699)."""
+    s = load_fixture("charge_square")
+    s.method = method
+    s.polarization = 1
+    s.scale14 = scale
+    if method == 1:
+        s.box = np.diag([2.0]*3); s.cutoff = 0.7; s.alpha = 0.001; s.grid = (64, 64, 64)
+    k, e, f, mu = run(s, "double")
+    e0, f0 = Oracle(s).execute()
+    assert abs(e - e0) < 1e-6*max(1.0, abs(e0))
+    if method == 0:
+        assert abs(e - expected) < 1e-2
+    assert np.abs(f - f0).max() < 1e-6*max(1.0, np.abs(f0).max())
+    k.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+@pytest.mark.parametrize("pol,eps", [(1, 1e-5), (2, 1e-5), (0, 1e-7)])
+def test_waterbox_996(pol, eps, prec):
+    """examples/waterbox coordinates, SWM6, PME alpha=3.2853, 32^3, rc=0.8 nm (BASELINE config 3)."""
+    s = water_box((1, 1, 1), polarization=pol, epsilon=eps)
+    k, e, f, mu = run(s, prec)
+    o = Oracle(s)
+    e0, f0 = o.execute()
+    mu0 = o.dipoles(0)
+    assert rel_err(f, f0) < FTOL[prec]
+    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else (1e-6 if pol == 0 else 1e-9))
+    assert abs(e - e0) < (1e-5 if prec == "mixed" else 1e-8)*abs(e0)
+    per_atom = np.linalg.norm(f - f0, axis=1)/np.sqrt(np.mean(np.sum(f0*f0, axis=1)))
+    assert per_atom.max() < 20*FTOL[prec]
+    k.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_anisotropic_mutual_waterbox(prec):
+    s = water_box((1, 1, 1), polarization=0, epsilon=1e-7, anisotropic=True)
+    k, e, f, mu = run(s, prec)
+    e0, f0 = Oracle(s).execute()
+    assert rel_err(f, f0) < FTOL[prec]*(1 if prec == "mixed" else 10)
+    k.close()
+
+
+def test_pair_list_is_bit_exact_waterbox():
+    s = water_box((1, 1, 1), polarization=1)
+    k, e, f, mu = run(s, "mixed")
+    pi, pj, pc = k.getPairList()
+    got = set(zip(pi.tolist(), pj.tolist(), pc.tolist()))
+    ref = set(pair_set_reference(s))
+    assert len(got) == len(pi)                  # no duplicates
+    assert got == ref
+    assert len(ref) == 312265                   # pair count measured on the reference
+    k.close()
+
+
+def test_pair_list_boundary_cases():
+    """Pairs placed within a few ulps of the cutoff sphere, across periodic images, must be classified exactly
+    like the oracle's FP64 test r2 > rc2 -> skip."""
+    rng = np.random.default_rng(7)
+    n = 600
+    s = load_fixture("charge_square")
+    from _common import System
+    t = System(n)
+    t.method = 1; t.polarization = 1; t.cutoff = 0.9; t.alpha = 3.0; t.grid = (24, 24, 24)
+    L = 2.7
+    t.box = np.diag([L, L, L])
+    t.charges[:] = rng.normal(size=n)*0.1
+    t.charges -= t.charges.mean()
+    pos = rng.uniform(-3*L, 3*L, size=(n, 3))       # deliberately unwrapped
+    # make half of the atoms sit at (almost) exactly the cutoff from a partner
+    for a in range(0, n - 1, 2):
+        v = rng.normal(size=3); v /= np.linalg.norm(v)
+        r = t.cutoff*(1.0 + rng.integers(-3, 4)*2.2e-16)
+        img = rng.integers(-2, 3, size=3)*L
+        pos[a+1] = pos[a] + v*r + img
+    t.pos = pos
+    k = make_kernel(t, precision="mixed")
+    f = np.zeros((n, 3))
+    k.execute(t.pos, True, True, f)
+    pi, pj, pc = k.getPairList()
+    got = set(zip(pi.tolist(), pj.tolist(), pc.tolist()))
+    ref = set(pair_set_reference(t))
+    assert got == ref
+    e0, f0 = Oracle(t).execute()
+    assert rel_err(f, f0) < 1e-5
+    k.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_all_axis_types_and_triclinic_box(prec):
+    """ZBisect, ThreeFold, ZOnly, NoAxisType and chirality flips are not covered by the reference's fixtures;
+    the compiled oracle is the authority.  Random but traceless moments on 125 'molecules' of 4 atoms in a
+    reduced triclinic box."""
+    rng = np.random.default_rng(11)
+    from _common import System
+    nm = 125
+    n = 4*nm
+    s = System(n)
+    s.method = 1; s.polarization = 0; s.cutoff = 0.8; s.alpha = 3.5; s.grid = (30, 30, 30); s.epsilon = 1e-8; s.max_iter = 200
+    s.default_thole = 4.0; s.scale14 = 0.6
+    L = 2.4
+    s.box = np.array([[L, 0, 0], [0.3, L, 0], [-0.25, 0.35, L]])
+    base = np.array([[0, 0, 0], [0.1, 0, 0], [-0.03, 0.095, 0], [-0.03, -0.05, 0.085]])
+    s.covalent = [[[] for _ in range(8)] for _ in range(n)]
+    grid_pts = [(i, j, k) for i in range(5) for j in range(5) for k in range(5)]
+    for m in range(nm):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        frac = (np.array(grid_pts[m]) + 0.5)/5.0
+        origin = frac @ s.box + rng.normal(scale=0.02, size=3)
+        for a in range(4):
+            i = 4*m + a
+            s.pos[i] = origin + base[a] @ q.T
+            s.charges[i] = rng.normal()*0.3
+            s.dipoles[i] = rng.normal(size=3)*0.01
+            qq = rng.normal(size=(3, 3))*0.001; qq = 0.5*(qq + qq.T); qq -= np.eye(3)*np.trace(qq)/3
+            s.quadrupoles[i] = [qq[0, 0], qq[0, 1], qq[1, 1], qq[0, 2], qq[1, 2], qq[2, 2]]
+            o3 = rng.normal(size=(3, 3, 3))*1e-4
+            o3 = sum(np.transpose(o3, p) for p in [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)])/6
+            tr = np.einsum("iij->j", o3)
+            for x in range(3):
+                for y in range(3):
+                    for z in range(3):
+                        o3[x, y, z] -= ((x == y)*tr[z] + (x == z)*tr[y] + (y == z)*tr[x])/5
+            s.octopoles[i] = [o3[0, 0, 0], o3[0, 0, 1], o3[0, 1, 1], o3[1, 1, 1], o3[0, 0, 2], o3[0, 1, 2], o3[1, 1, 2], o3[0, 2, 2], o3[1, 2, 2], o3[2, 2, 2]]
+            s.tholes[i] = 1.0 + rng.uniform()
+            s.alphas[i] = 0.0008*(1 + 0.4*rng.uniform(size=3)) if a != 3 else [0.0006]*3
+        c = 4*m
+        kinds = [MPIDForce.ZBisect, MPIDForce.ThreeFold, MPIDForce.ZThenX, MPIDForce.ZOnly, MPIDForce.Bisector, MPIDForce.NoAxisType]
+        kind = kinds[m % 6]
+        s.axis[c] = kind
+        if kind == MPIDForce.NoAxisType:
+            pass
+        elif kind == MPIDForce.ZOnly:
+            s.atomZ[c] = c+1
+        elif kind in (MPIDForce.ZBisect, MPIDForce.ThreeFold):
+            s.atomZ[c], s.atomX[c], s.atomY[c] = c+1, c+2, c+3
+        else:
+            s.atomZ[c], s.atomX[c] = c+1, c+2
+            if kind == MPIDForce.ZThenX and m % 2 == 0:
+                s.atomY[c] = c+3                       # chirality check path
+        for a in (1, 2, 3):
+            s.axis[c+a] = MPIDForce.ZThenX; s.atomZ[c+a] = c; s.atomX[c+a] = c + (a % 3) + 1
+        for a in range(4):
+            s.covalent[c+a][0] = [c+b for b in range(4) if (a == 0) != (b == 0)]            # 1-2: centre <-> ligands
+            s.covalent[c+a][1] = [c+b for b in range(1, 4) if a != 0 and b != a]             # 1-3: ligand <-> ligand
+        if m + 1 < nm:                                                                       # a few 1-4 / 1-5 relations across molecules
+            s.covalent[c+1][2] = [c+5]
+            s.covalent[c+2][3] = [c+6]
+    k, e, f, mu = run(s, prec)
+    o = Oracle(s)
+    e0, f0 = o.execute()
+    mu0 = o.dipoles(0)
+    assert rel_err(f, f0) < FTOL[prec]*(1 if prec == "mixed" else 30)
+    assert rel_err(mu, mu0) < 1e-5
+    assert abs(e - e0) < (1e-5 if prec == "mixed" else 1e-8)*max(1.0, abs(e0))
+    pi, pj, pc = k.getPairList()
+    assert set(zip(pi.tolist(), pj.tolist(), pc.tolist())) == set(pair_set_reference(s))
+    k.close()
+
+
+def test_frameless_atoms_have_zero_polarizability():
+    """NoAxisType atoms without a z anchor keep a zero lab-frame polarizability on the Reference
+    platform, so a charges-only system has mu == 0; the opt-in fix restores alpha_lab = diag(alpha)."""
+    s = water_box((1, 1, 1), polarization=1)
+    s.dipoles[:] = 0; s.quadrupoles[:] = 0; s.octopoles[:] = 0
+    s.axis[:] = MPIDForce.NoAxisType; s.atomZ[:] = -1; s.atomX[:] = -1
+    k, e, f, mu = run(s, "double")
+    e0, f0 = Oracle(s).execute()
+    assert np.abs(mu).max() == 0.0
+    assert abs(e - e0) < 1e-8*abs(e0) and rel_err(f, f0) < 1e-8
+    k.close()
+
+
+def test_queries_and_errors():
+    s = water_box((1, 1, 1), polarization=0, epsilon=1e-7)
+    k = make_kernel(s, precision="double")
+    o = Oracle(s)
+    assert k.getPMEParameters() == (3.2853, 32, 32, 32) == o.pme_parameters()
+    assert rel_err(k.getLabFramePermanentDipoles(s.pos), o.dipoles(1)) < 1e-12
+    assert rel_err(k.getTotalDipoles(s.pos), o.dipoles(2)) < 1e-6
+    masses = np.tile([15.999, 1.008, 1.008], s.n//3)
+    mom = k.getSystemMultipoleMoments(s.pos, masses)
+    # the oracle driver builds its System with unit masses
+    mom1 = k.getSystemMultipoleMoments(s.pos, np.ones(s.n))
+    assert np.allclose(mom1, o.system_moments(), rtol=1e-6, atol=1e-6)
+    assert mom.shape == (13,)
+    # forces are accumulated, not overwritten (MPIDReferenceKernels.cpp:229-238)
+    f = np.ones((s.n, 3))
+    k.execute(s.pos, True, True, f)
+    g = np.zeros((s.n, 3))
+    k.execute(s.pos, True, True, g)
+    assert np.allclose(f - 1.0, g, rtol=0, atol=1e-9)
+    # box smaller than twice the cutoff (MPIDReferenceKernels.cpp:193-197)
+    with pytest.raises(MPIDB200Error, match="less than twice the nonbonded cutoff"):
+        k.setPeriodicBoxVectors(np.diag([1.5, 3.0, 3.0]))
+    k.close()
+    # non-convergence raises like the Reference platform (MPIDReferenceForce.cpp:2229-2235)
+    t = water_box((1, 1, 1), polarization=0, epsilon=1e-12)
+    t.max_iter = 2
+    k = make_kernel(t, precision="double")
+    with pytest.raises(MPIDB200Error, match="did not converge"):
+        k.execute(t.pos, True, True, np.zeros((t.n, 3)))
+    k.close()
+    with pytest.raises(MPIDB200Error, match="not using PME"):
+        u = load_fixture("water_dimer"); u.method = 0
+        make_kernel(u).getPMEParameters()
+
+
+def test_automatic_pme_parameters():
+    """alpha/grid derived from the error tolerance (NonbondedForceImpl::calcPMEParameters, call site
+    MPIDReferenceKernels.cpp:161-170): alpha = sqrt(-ln(2 tol))/rc, n = ceil(2 alpha L/(3 tol^(1/5)))."""
+    s = water_box((1, 1, 1), polarization=1)
+    s.alpha = 0.0; s.grid = (0, 0, 0); s.ewald_tol = 5e-4
+    k = make_kernel(s, precision="double")
+    a, nx, ny, nz = k.getPMEParameters()
+    assert abs(a - np.sqrt(-np.log(2*5e-4))/0.8) < 1e-12 and abs(a - 3.2853) < 1e-3
+    assert (nx, ny, nz) == (32, 32, 32)
+    k.close()
+
+
+def test_mpidforce_object_path_matches_flat_path():
+    s = water_dimer(1, 0)
+    f = s.to_force()
+    k = MPIDB200Kernel(precision="double")
+    k.initialize(s.n, f, s.box)
+    assert MPIDB200Kernel.Name() == "CalcMPIDForce"
+    frc = np.zeros((s.n, 3))
+    e = k.execute(s.pos, True, True, frc)
+    assert_equal_tol(-2.533082539, e, 1e-6)
+    # updateParametersInContext: scale every charge and re-evaluate against a fresh oracle
+    for i in range(s.n):
+        p = list(f.getMultipoleParameters(i)); p[0] *= 0.9
+        f.setMultipoleParameters(i, *p)
+    f.updateParametersInContext(k)
+    t = s.copy(); t.charges *= 0.9
+    e1 = k.execute(s.pos, False, True)
+    e0, _ = Oracle(t).execute()
+    assert abs(e1 - e0) < 1e-8*abs(e0)
+    k.close()

@@ -121,6 +121,9 @@ struct Engine : public EngineBase {
     mpidb200_config cfg;
     int n;
     cudaStream_t stream = nullptr, ownStream = nullptr;
+    cudaStream_t stream2 = nullptr;     // reciprocal-space work runs here, concurrently with the real-space kernels
+    cudaStream_t cur = nullptr;         // stream the LAUNCH macro / stage timers currently target
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool haveParticles = false, haveBox = false, pmeReady = false;
     // host copies
     std::vector<double> hCharge, hDipole, hQuad, hOct, hThole, hAlpha, hDamp;
@@ -143,7 +146,8 @@ struct Engine : public EngineBase {
     DevBuf<int> dAniso;
     DevBuf<double2> dDampThole;
     DevBuf<real4> dMud;
-    DevBuf<unsigned> dFullCount, dHalfCount, dFullStart, dHalfStart, dNbr, dPairI, dPairJ;
+    DevBuf<unsigned> dCounts, dHalfCount, dHalfStart, dMaxCount, dNbr, dPairI, dPairJ;
+    int nbrCap = 0;
     DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
     DevBuf<unsigned long long> dForce, dTorque, dEnergy;
     DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp;
@@ -165,6 +169,10 @@ struct Engine : public EngineBase {
         CUDA_CHECK(cudaSetDevice(cfg.device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
         stream = ownStream;
+        cur = stream;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
         CUDA_CHECK(cudaMallocHost((void**) &hPinned, 256*sizeof(double)));
         memset(&P, 0, sizeof(P));
         memset(stageMs, 0, sizeof(stageMs));
@@ -180,16 +188,40 @@ struct Engine : public EngineBase {
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
         for (cudaEvent_t e : evPool) cudaEventDestroy(e);
+        if (evFork) cudaEventDestroy(evFork);
+        if (evJoin) cudaEventDestroy(evJoin);
+        if (stream2) cudaStreamDestroy(stream2);
         if (ownStream) cudaStreamDestroy(ownStream);
+    }
+    // Reciprocal space is independent of the real-space pair kernels until their results are combined, and
+    // neither fills the GPU on its own at these sizes: fork it onto stream2 (single rank only -- with NCCL the
+    // grid all-reduce must stay ordered with the field all-reduce on one stream).
+    bool overlapPme() const { return numRanks == 1; }
+    cudaStream_t pmeStream() const { return overlapPme() ? stream2 : stream; }
+    void forkPme() {
+        if (!overlapPme()) return;
+        CUDA_CHECK(cudaEventRecord(evFork, stream));
+        CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
+        cur = stream2;
+    }
+    void backToMain() { cur = stream; }
+    void joinPme() {
+        if (!overlapPme()) return;
+        CUDA_CHECK(cudaEventRecord(evJoin, stream2));
+        CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin, 0));
+    }
+    void setPlanStreams() {
+        if (plansMade) { CUFFT_CHECK(cufftSetStream(planF, pmeStream())); CUFFT_CHECK(cufftSetStream(planB, pmeStream())); }
     }
     void setStream(void* st) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
         CUDA_CHECK(cudaStreamSynchronize(stream));
         stream = st ? (cudaStream_t) st : ownStream;
-        if (plansMade) { CUFFT_CHECK(cufftSetStream(planF, stream)); CUFFT_CHECK(cufftSetStream(planB, stream)); }
+        cur = stream;
+        setPlanStreams();
     }
 
-#define LAUNCH(kernel, gridDim, blockDim, ...) do { kernel<<<(gridDim), (blockDim), 0, stream>>>(__VA_ARGS__); launches++; \
+#define LAUNCH(kernel, gridDim, blockDim, ...) do { kernel<<<(gridDim), (blockDim), 0, cur>>>(__VA_ARGS__); launches++; \
         cudaError_t le__ = cudaGetLastError(); if (le__ != cudaSuccess) throw CudaError(std::string("launch of " #kernel " failed: ") + cudaGetErrorString(le__)); } while (0)
 
     // ---- parameters --------------------------------------------------------------------------------
@@ -324,6 +356,7 @@ struct Engine : public EngineBase {
         }
         if (!pme) {
             P.ncell[0] = P.ncell[1] = P.ncell[2] = 1;
+            P.reach[0] = P.reach[1] = P.reach[2] = 0;
             P.alpha = 0; P.selfFieldTerm = 0;
             P.grid[0] = P.grid[1] = P.grid[2] = 0;
             haveBox = true;
@@ -352,20 +385,20 @@ struct Engine : public EngineBase {
         double w[3] = {vol/sqrt(bxc[0]*bxc[0] + bxc[1]*bxc[1] + bxc[2]*bxc[2]), vol/sqrt(cxa[0]*cxa[0] + cxa[1]*cxa[1] + cxa[2]*cxa[2]),
                        vol/sqrt(axb[0]*axb[0] + axb[1]*axb[1] + axb[2]*axb[2])};
         for (int d = 0; d < 3; d++) {
-            int nc = (int) floor(w[d]/(cfg.cutoff*1.0001));
-            if (nc < 3) nc = 1;
-            nc = std::min(nc, 1024);
-            P.ncell[d] = nc;
+            int n2 = (int) floor(w[d]/(0.5*cfg.cutoff*1.0001)), n1 = (int) floor(w[d]/(cfg.cutoff*1.0001));
+            if (n2 >= 5) { P.ncell[d] = std::min(n2, 1024); P.reach[d] = 2; }
+            else if (n1 >= 3) { P.ncell[d] = n1; P.reach[d] = 1; }
+            else { P.ncell[d] = 1; P.reach[d] = 0; }
         }
+        nbrCap = 0;
         // FFT plans + convolution table
         size_t G = (size_t) g[0]*g[1]*g[2], GC = (size_t) g[0]*g[1]*(g[2]/2 + 1);
         if (gridChanged || !plansMade) {
             if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); plansMade = false; }
             CUFFT_CHECK(cufftPlan3d(&planF, g[0], g[1], g[2], FftTraits<real>::fwdType));
             CUFFT_CHECK(cufftPlan3d(&planB, g[0], g[1], g[2], FftTraits<real>::bwdType));
-            CUFFT_CHECK(cufftSetStream(planF, stream));
-            CUFFT_CHECK(cufftSetStream(planB, stream));
             plansMade = true;
+            setPlanStreams();
             std::vector<double> mx, my, mz;
             bsplineModuli(g[0], mx); bsplineModuli(g[1], my); bsplineModuli(g[2], mz);
             dModX.upload(mx, stream); dModY.upload(my, stream); dModZ.upload(mz, stream);
@@ -389,11 +422,11 @@ struct Engine : public EngineBase {
         }
         evStage[evUsed] = st;
         curStage = st;
-        CUDA_CHECK(cudaEventRecord(evPool[2*evUsed], stream));
+        CUDA_CHECK(cudaEventRecord(evPool[2*evUsed], cur));
     }
     void stageEnd() {
         if (!profiling || curStage < 0) return;
-        CUDA_CHECK(cudaEventRecord(evPool[2*evUsed + 1], stream));
+        CUDA_CHECK(cudaEventRecord(evPool[2*evUsed + 1], cur));
         evUsed++;
         curStage = -1;
     }
@@ -410,7 +443,7 @@ struct Engine : public EngineBase {
 
     void allReduce(void* buf, size_t count, int dtype) {
         if (numRanks <= 1) return;
-        int rc = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, comm, stream);
+        int rc = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, comm, cur);
         if (rc != 0) throw CudaError(std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     }
 
@@ -455,31 +488,44 @@ struct Engine : public EngineBase {
         LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
                dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p);
         stageEnd();
-        // neighbour list: count, scan, fill
+        // neighbour list: single pass into per-atom runs, then the flat half list for the energy kernel
         stageBegin(MPIDB200_STAGE_NLIST);
         int rows = P.rowEnd - P.rowBegin;
-        dFullCount.ensure((size_t) rows + 1); dHalfCount.ensure((size_t) rows + 1); dFullStart.ensure((size_t) rows + 1); dHalfStart.ensure((size_t) rows + 1);
-        CUDA_CHECK(cudaMemsetAsync(dFullCount.p, 0, ((size_t) rows + 1)*sizeof(unsigned), stream));
-        CUDA_CHECK(cudaMemsetAsync(dHalfCount.p, 0, ((size_t) rows + 1)*sizeof(unsigned), stream));
-        if (rows > 0)
-            LAUNCH((k_neighbor_list<false>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
-                   dSpStart.p, dSpPartner.p, dFullCount.p, dHalfCount.p, (const unsigned*) nullptr, (const unsigned*) nullptr,
-                   (unsigned*) nullptr, (unsigned*) nullptr, (unsigned*) nullptr);
-        size_t tempBytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dFullCount.p, dFullStart.p, rows + 1, stream);
-        dScanTemp.ensure(tempBytes + 16);
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dFullCount.p, dFullStart.p, rows + 1, stream));
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dHalfCount.p, dHalfStart.p, rows + 1, stream));
-        launches += 2;
-        unsigned* totals = (unsigned*) hPinned;
-        CUDA_CHECK(cudaMemcpyAsync(&totals[0], dFullStart.p + rows, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaMemcpyAsync(&totals[1], dHalfStart.p + rows, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        lastFull = totals[0]; lastPairs = totals[1];
-        dNbr.ensure((size_t) lastFull + 1); dPairI.ensure((size_t) lastPairs + 1); dPairJ.ensure((size_t) lastPairs + 1);
-        if (rows > 0)
-            LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
-                   dSpStart.p, dSpPartner.p, (unsigned*) nullptr, (unsigned*) nullptr, dFullStart.p, dHalfStart.p, dNbr.p, dPairI.p, dPairJ.p);
+        dCounts.ensure(2*(size_t) rows + 2); dHalfCount.ensure((size_t) rows + 1); dHalfStart.ensure((size_t) rows + 1); dMaxCount.ensure(2);
+        if (nbrCap == 0) {
+            // first guess: 1.35 x the mean number of neighbours at this density (+ slack); grown on demand
+            double expected = P.method == PME ? (4.0/3.0)*MPID_PI*cfg.cutoff*cfg.cutoff*cfg.cutoff*n/(boxA[0]*boxB[1]*boxC[2]) : (double) n;
+            nbrCap = P.method == PME ? (int) (1.35*expected) + 48 : n;
+            nbrCap = std::min(std::max(nbrCap, 32), std::max(n, 32));
+        }
+        const bool roundMode = P.method != PME || P.reach[0] == 0 || P.reach[1] == 0 || P.reach[2] == 0;
+        for (int attempt = 0; ; attempt++) {
+            P.nbrCap = nbrCap;
+            dNbr.ensure((size_t) std::max(rows, 1)*nbrCap);
+            CUDA_CHECK(cudaMemsetAsync(dMaxCount.p, 0, 2*sizeof(unsigned), stream));
+            if (rows > 0) {
+                if (roundMode) LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
+                                      dSpStart.p, dSpPartner.p, dNbr.p, dCounts.p, dMaxCount.p);
+                else LAUNCH((k_neighbor_list<false>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
+                            dSpStart.p, dSpPartner.p, dNbr.p, dCounts.p, dMaxCount.p);
+            }
+            LAUNCH(k_half_counts, blocksFor(rows + 1, B), B, rows, dCounts.p, dHalfCount.p);
+            size_t tempBytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dHalfCount.p, dHalfStart.p, rows + 1, stream);
+            dScanTemp.ensure(tempBytes + 16);
+            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dHalfCount.p, dHalfStart.p, rows + 1, stream));
+            launches += 1;
+            unsigned* totals = (unsigned*) hPinned;
+            CUDA_CHECK(cudaMemcpyAsync(&totals[0], dMaxCount.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&totals[1], dHalfStart.p + rows, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            if ((int) totals[0] <= nbrCap) { lastPairs = totals[1]; break; }
+            if (attempt > 3) throw std::runtime_error("mpidb200: neighbour list capacity could not be established");
+            nbrCap = (int) (totals[0]*1.2) + 16;       // rare: density fluctuation beyond the guess
+        }
+        dPairI.ensure((size_t) lastPairs + 1); dPairJ.ensure((size_t) lastPairs + 1);
+        if (rows > 0 && lastPairs > 0)
+            LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dHalfStart.p, dPairI.p, dPairJ.p);
     }
 
     void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
@@ -503,27 +549,30 @@ struct Engine : public EngineBase {
         dField.ensure(3*(size_t) n); dEfix.ensure(3*(size_t) n); dMu.ensure(3*(size_t) n);
         dPhi.ensure(35*(size_t) n); dPhidp.ensure(35*(size_t) n);
         if (pme) {
+            forkPme();
             stageBegin(MPIDB200_STAGE_FIXED_SPREAD);
             dFrac.ensure(20*(size_t) n);
             LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
-            CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), stream));
+            CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
             if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
             stageEnd();
             reciprocalPass();
             stageBegin(MPIDB200_STAGE_FIXED_GATHER);
             if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhi.p);
             stageEnd();
+            backToMain();
         }
         stageBegin(MPIDB200_STAGE_FIXED_REAL);
-        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), stream));
+        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
         if (rows > 0) {
-            if (pme) LAUNCH((k_fixed_field<real, true>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dFullStart.p, dNbr.p, dField.p);
-            else LAUNCH((k_fixed_field<real, false>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dFullStart.p, dNbr.p, dField.p);
+            if (pme) LAUNCH((k_fixed_field<real, true>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
+            else LAUNCH((k_fixed_field<real, false>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
             if (!hSpPartner.empty())
                 LAUNCH((k_special_field<0>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
                        dCartD.p, dDampThole.p, (const double*) nullptr, dField.p, (double*) nullptr);
-            if (pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
         }
+        if (pme) joinPme();
+        if (rows > 0 && pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
         allReduce(dField.p, 3*(size_t) n, NCCL_FLOAT64);
         LAUNCH((k_fixed_mu<real>), blocksFor(n, 256), 256, P, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
         stageEnd();
@@ -537,8 +586,9 @@ struct Engine : public EngineBase {
         size_t G = (size_t) grid[0]*grid[1]*grid[2];
         dIfield.ensure(3*(size_t) n);
         if (pme) {
+            forkPme();
             stageBegin(MPIDB200_STAGE_IND_SPREAD);
-            CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), stream));
+            CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
             if (rows > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, (const real*) nullptr, dMu.p, dGrid.p);
             stageEnd();
             reciprocalPass();
@@ -549,18 +599,19 @@ struct Engine : public EngineBase {
                 else LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
             }
             stageEnd();
+            backToMain();
         }
-        if (!realSpace) return;
+        if (!realSpace) { if (pme) joinPme(); return; }
         stageBegin(MPIDB200_STAGE_IND_REAL);
-        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dIfield.p, 0, 3*(size_t) n*sizeof(double), stream));
+        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dIfield.p, 0, 3*(size_t) n*sizeof(double), cur));
         if (rows > 0) {
             const int nb = blocksFor((long long) rows*MPID_LANES, 256);
             if (grad) {
-                if (pme) LAUNCH((k_induced_field<real, true, true>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, grad);
-                else LAUNCH((k_induced_field<real, false, true>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, grad);
+                if (pme) LAUNCH((k_induced_field<real, true, true>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, grad);
+                else LAUNCH((k_induced_field<real, false, true>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, grad);
             } else {
-                if (pme) LAUNCH((k_induced_field<real, true, false>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, (double*) nullptr);
-                else LAUNCH((k_induced_field<real, false, false>), nb, 256, P, dPosS.p, dMud.p, dFullStart.p, dNbr.p, dIfield.p, (double*) nullptr);
+                if (pme) LAUNCH((k_induced_field<real, true, false>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, (double*) nullptr);
+                else LAUNCH((k_induced_field<real, false, false>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, (double*) nullptr);
             }
             if (!hSpPartner.empty()) {
                 if (grad) LAUNCH((k_special_field<2>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
@@ -568,10 +619,11 @@ struct Engine : public EngineBase {
                 else LAUNCH((k_special_field<1>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
                             dCartD.p, dDampThole.p, dMu.p, dIfield.p, (double*) nullptr);
             }
-            if (pme) {
-                if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, grad);
-                else LAUNCH((k_induced_finish<real, false>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
-            }
+        }
+        if (pme) joinPme();
+        if (rows > 0 && pme) {
+            if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, grad);
+            else LAUNCH((k_induced_finish<real, false>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
         }
         // the per-iteration collective of the partitioned solver: partial induced fields -> full field
         allReduce(dIfield.p, 3*(size_t) n, NCCL_FLOAT64);
@@ -922,6 +974,7 @@ struct Engine : public EngineBase {
         if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
         rank = rk; numRanks = nr;
         P.rank = rk; P.numRanks = nr;
+        setPlanStreams();
     }
 };
 

@@ -6,7 +6,7 @@
 //   posF      float4   same, single precision                    -- neighbour-list pre-test only
 //   cart      real[20] lab Cartesian moments   q d(3) Q(6) O(10) -- permanent-field kernel, PME spread
 //   pk        real[16] packed traceless moments (packPairMoments) -- energy kernel
-//   mud       real4    (mu_x, mu_y, mu_z, damping factor)        -- induced-field and energy kernels
+//   mud       real4    (mu_x, mu_y, mu_z, 1/damping factor or 0) -- induced-field and energy kernels
 //   field/... double   accumulators written by exactly one thread per atom (no atomics)
 //   force/torque/energy  64-bit fixed point (2^32), atomics, order independent => deterministic
 // Neighbour list: full CSR list for the gather-style field kernels, flat i-major half list for the
@@ -28,6 +28,8 @@ struct DevParams {
     int n;
     int method, polarization;
     int ncell[3];
+    int reach[3];                // neighbour cells scanned on each side per dimension (0: single cell)
+    int nbrCap;                  // per-atom capacity of the neighbour list
     int grid[3];
     int numRanks, rank;          // multi-GPU row partition
     int rowBegin, rowEnd;        // sorted-atom range owned by this rank
@@ -149,33 +151,39 @@ __global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, co
     posF[s] = make_float4((float) x, (float) y, (float) z, 0.f);
     dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
     typename Real4<real>::type m;
-    m.x = 0; m.y = 0; m.z = 0; m.w = (real) pp.damp[o];
+    m.x = 0; m.y = 0; m.z = 0; m.w = pp.damp[o] != 0.0 ? (real) (1.0/pp.damp[o]) : real(0);   // inverse damping factor
     mud[s] = m;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Stage 2: neighbour list (one warp per sorted atom; pass 0 counts, pass 1 fills)
+// Stage 2: neighbour list (one warp per sorted atom, single pass)
 // ---------------------------------------------------------------------------------------------------
+// Layout: atom i owns nbr[i*cap .. (i+1)*cap).  Neighbours with a higher sorted index ("upper") are
+// packed from the front, the others from the back, so the front run doubles as the half list of the
+// energy kernel and the field kernels walk both runs.  counts[2*i] = upper, counts[2*i+1] = lower.
 // A cheap FP32 test settles every candidate that is not within 1e-4 nm of the cutoff sphere; the few
 // that are get the reference's own FP64 test on the raw positions, so the pair set is exactly
 // { i<j : |minimg(r_j - r_i)|^2 <= rc^2 } as decided by MPIDReferencePmeForce (:2829, :4178, :4350).
 // Pairs with a covalent scale (1-2, 1-3, 1-4) are left out: they live in the static special list.
-template <bool FILL>
-__global__ void k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __restrict__ posOrig,
-                                const int* __restrict__ order, const int* __restrict__ sortedKey, const int* __restrict__ cellStart,
-                                const int* __restrict__ spStart, const int* __restrict__ spPartner,
-                                unsigned* __restrict__ fullCount, unsigned* __restrict__ halfCount,
-                                const unsigned* __restrict__ fullStart, const unsigned* __restrict__ halfStart,
-                                unsigned* __restrict__ nbr, unsigned* __restrict__ pairI, unsigned* __restrict__ pairJ) {
+// ROUND = false: every periodic dimension has >= 2*reach+1 cells, so the image of a neighbour cell is
+// known from the cell wrap and no per-candidate rounding is needed.  ROUND = true: generic path
+// (small boxes, no-cutoff all-pairs) with a per-candidate minimum-image search.
+template <bool ROUND>
+__global__ void __launch_bounds__(256)
+k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __restrict__ posOrig,
+                const int* __restrict__ order, const int* __restrict__ sortedKey, const int* __restrict__ cellStart,
+                const int* __restrict__ spStart, const int* __restrict__ spPartner,
+                unsigned* __restrict__ nbr, unsigned* __restrict__ counts, unsigned* __restrict__ maxCount) {
     const int lane = threadIdx.x & 31;
-    const int i = P.rowBegin + (blockIdx.x*blockDim.x + threadIdx.x)/32;
+    const int row = (blockIdx.x*blockDim.x + threadIdx.x)/32;
+    const int i = P.rowBegin + row;
     if (i >= P.rowEnd) return;
     const float4 pi = posF[i];
     const int oi = order[i];
     const int sp0 = spStart[oi], sp1 = spStart[oi+1];
     const bool pme = P.method == PME;
     int cx = 0, cy = 0, cz = 0;
-    if (pme) {
+    {
         int key = sortedKey[i];
         cz = key % P.ncell[2]; key /= P.ncell[2];
         cy = key % P.ncell[1]; cx = key / P.ncell[1];
@@ -185,38 +193,51 @@ __global__ void k_neighbor_list(DevParams P, const float4* __restrict__ posF, co
     const float rax = (float) P.box.ra[0], rby = (float) P.box.rb[1], rcz = (float) P.box.rc[2];
     const float ax = (float) P.box.a[0], bx = (float) P.box.b[0], by = (float) P.box.b[1];
     const float ccx = (float) P.box.c[0], ccy = (float) P.box.c[1], ccz = (float) P.box.c[2];
-    unsigned nFull = 0, nHalf = 0;
-    unsigned baseFull = 0, baseHalf = 0;
-    if (FILL) { baseFull = fullStart[i - P.rowBegin]; baseHalf = halfStart[i - P.rowBegin]; }
-    const int rx = (pme && P.ncell[0] > 1) ? 1 : 0, ry = (pme && P.ncell[1] > 1) ? 1 : 0, rz = (pme && P.ncell[2] > 1) ? 1 : 0;
-    for (int dx = -rx; dx <= rx; dx++) {
-        int X = cx + dx; X += (X < 0) ? P.ncell[0] : 0; X -= (X >= P.ncell[0]) ? P.ncell[0] : 0;
-        for (int dy = -ry; dy <= ry; dy++) {
-            int Y = cy + dy; Y += (Y < 0) ? P.ncell[1] : 0; Y -= (Y >= P.ncell[1]) ? P.ncell[1] : 0;
-            for (int dz = -rz; dz <= rz; dz++) {
-                int Z = cz + dz; Z += (Z < 0) ? P.ncell[2] : 0; Z -= (Z >= P.ncell[2]) ? P.ncell[2] : 0;
-                const int c = (X*P.ncell[1] + Y)*P.ncell[2] + Z;
-                const int jb = cellStart[c], je = cellStart[c+1];
+    const unsigned cap = (unsigned) P.nbrCap;
+    unsigned* base = nbr + (size_t) row*cap;
+    unsigned nUp = 0, nLow = 0;
+    const int Rx = P.reach[0], Ry = P.reach[1], Rz = P.reach[2];
+    for (int dx = -Rx; dx <= Rx; dx++) {
+        int X = cx + dx, wx = 0;
+        if (X < 0) { X += P.ncell[0]; wx = -1; } else if (X >= P.ncell[0]) { X -= P.ncell[0]; wx = 1; }
+        for (int dy = -Ry; dy <= Ry; dy++) {
+            int Y = cy + dy, wy = 0;
+            if (Y < 0) { Y += P.ncell[1]; wy = -1; } else if (Y >= P.ncell[1]) { Y -= P.ncell[1]; wy = 1; }
+            const int colBase = (X*P.ncell[1] + Y)*P.ncell[2];
+            // the z cells cz-Rz .. cz+Rz are contiguous in the sorted order except where they wrap
+            for (int seg = 0; seg < 3; seg++) {
+                int z0, z1, wz;
+                if (seg == 0) { z0 = max(cz - Rz, 0); z1 = min(cz + Rz, P.ncell[2] - 1); wz = 0; }
+                else if (seg == 1) { if (cz - Rz >= 0) continue; z0 = cz - Rz + P.ncell[2]; z1 = P.ncell[2] - 1; wz = -1; }
+                else { if (cz + Rz < P.ncell[2]) continue; z0 = 0; z1 = cz + Rz - P.ncell[2]; wz = 1; }
+                const int jb = cellStart[colBase + z0], je = cellStart[colBase + z1 + 1];
+                // image of the neighbour cell: r_j(image) = r_j + wx a + wy b + wz c
+                const float shx = wx*ax + wy*bx + wz*ccx, shy = wy*by + wz*ccy, shz = wz*ccz;
+                const unsigned segCode = (unsigned) ((1 - wx)*9 + (1 - wy)*3 + (1 - wz));
                 for (int j0 = jb; j0 < je; j0 += 32) {
                     const int j = j0 + lane;
                     bool in = (j < je) && (j != i);
-                    unsigned code = 13;
+                    unsigned code = segCode;
                     if (in && pme) {
-                        float4 pj = posF[j];
+                        const float4 pj = posF[j];
                         float ddx = pj.x - pi.x, ddy = pj.y - pi.y, ddz = pj.z - pi.z;
-                        float sz = floorf(ddz*rcz + 0.5f);
-                        ddx -= ccx*sz; ddy -= ccy*sz; ddz -= ccz*sz;
-                        float sy = floorf(ddy*rby + 0.5f);
-                        ddx -= bx*sy; ddy -= by*sy;
-                        float sx = floorf(ddx*rax + 0.5f);
-                        ddx -= ax*sx;
-                        float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
-                        code = (unsigned) (((int) sx + 1)*9 + ((int) sy + 1)*3 + ((int) sz + 1));
+                        if (ROUND) {
+                            float sz = floorf(ddz*rcz + 0.5f);
+                            ddx -= ccx*sz; ddy -= ccy*sz; ddz -= ccz*sz;
+                            float sy = floorf(ddy*rby + 0.5f);
+                            ddx -= bx*sy; ddy -= by*sy;
+                            float sx = floorf(ddx*rax + 0.5f);
+                            ddx -= ax*sx;
+                            code = (unsigned) (((int) sx + 1)*9 + ((int) sy + 1)*3 + ((int) sz + 1));
+                        } else {
+                            ddx += shx; ddy += shy; ddz += shz;
+                        }
+                        const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
                         if (r2 > rcHi2) in = false;
                         else if (r2 >= rcLo2) {
                             // borderline: the oracle's test, bit for bit, on the raw positions
-                            int oj = order[j];
-                            int lo = min(oi, oj), hi = max(oi, oj);
+                            const int oj = order[j];
+                            const int lo = min(oi, oj), hi = max(oi, oj);
                             double ex = posOrig[3*hi] - posOrig[3*lo], ey = posOrig[3*hi+1] - posOrig[3*lo+1], ez = posOrig[3*hi+2] - posOrig[3*lo+2];
                             periodicDelta(P.box, ex, ey, ez);
                             in = !(dist2Exact(ex, ey, ez) > P.cutoff2);
@@ -224,28 +245,48 @@ __global__ void k_neighbor_list(DevParams P, const float4* __restrict__ posF, co
                         if (code > 26u) in = false;   // cannot happen for wrapped positions; keeps the table index safe
                     }
                     if (in && sp1 > sp0) {
-                        int oj = order[j];
+                        const int oj = order[j];
                         for (int k = sp0; k < sp1; k++) if (spPartner[k] == oj) in = false;
                     }
-                    const unsigned mask = __ballot_sync(0xffffffffu, in);
                     const bool upper = in && (j > i);
-                    const unsigned maskH = __ballot_sync(0xffffffffu, upper);
-                    if (FILL) {
+                    const unsigned maskU = __ballot_sync(0xffffffffu, upper);
+                    const unsigned maskL = __ballot_sync(0xffffffffu, in && !upper);
+                    const unsigned cu = __popc(maskU), cl = __popc(maskL);
+                    if (nUp + nLow + cu + cl <= cap) {
                         const unsigned lt = (1u << lane) - 1u;
-                        if (in) nbr[baseFull + nFull + __popc(mask & lt)] = (unsigned) j | (code << MPID_CODE_SHIFT);
-                        if (upper) {
-                            unsigned p = baseHalf + nHalf + __popc(maskH & lt);
-                            pairI[p] = (unsigned) i;
-                            pairJ[p] = (unsigned) j | (code << MPID_CODE_SHIFT);
-                        }
+                        const unsigned entry = (unsigned) j | (code << MPID_CODE_SHIFT);
+                        if (upper) base[nUp + __popc(maskU & lt)] = entry;
+                        else if (in) base[cap - 1 - (nLow + __popc(maskL & lt))] = entry;
                     }
-                    nFull += __popc(mask);
-                    nHalf += __popc(maskH);
+                    nUp += cu; nLow += cl;
                 }
             }
         }
     }
-    if (!FILL && lane == 0) { fullCount[i - P.rowBegin] = nFull; halfCount[i - P.rowBegin] = nHalf; }
+    if (lane == 0) {
+        counts[2*(size_t) row] = nUp; counts[2*(size_t) row + 1] = nLow;
+        atomicMax(maxCount, nUp + nLow);
+    }
+}
+
+// upper counts -> (halfCount) for the scan that places each atom's run in the flat half list
+__global__ void k_half_counts(int rows, const unsigned* __restrict__ counts, unsigned* __restrict__ halfCount) {
+    const int r = blockIdx.x*blockDim.x + threadIdx.x;
+    if (r <= rows) halfCount[r] = r < rows ? counts[2*(size_t) r] : 0u;
+}
+// flat i-major half list for the energy kernel (one warp per atom copies its upper run)
+__global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, const unsigned* __restrict__ counts,
+                               const unsigned* __restrict__ halfStart, unsigned* __restrict__ pairI, unsigned* __restrict__ pairJ) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x*blockDim.x + threadIdx.x)/32;
+    if (row >= P.rowEnd - P.rowBegin) return;
+    const unsigned nUp = counts[2*(size_t) row];
+    const unsigned dst = halfStart[row];
+    const unsigned* base = nbr + (size_t) row*P.nbrCap;
+    for (unsigned k = lane; k < nUp; k += 32) {
+        pairI[dst + k] = (unsigned) (P.rowBegin + row);
+        pairJ[dst + k] = base[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -266,25 +307,24 @@ template <typename real, bool EWALD>
 __global__ void __launch_bounds__(256)
 k_fixed_field(DevParams P, const double4* __restrict__ posS, const real* __restrict__ cart,
               const typename Real4<real>::type* __restrict__ mud,
-              const unsigned* __restrict__ nbrStart, const unsigned* __restrict__ nbr, double* __restrict__ field) {
+              const unsigned* __restrict__ counts, const unsigned* __restrict__ nbr, double* __restrict__ field) {
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int i = P.rowBegin + t/MPID_LANES;
     const int sub = t % MPID_LANES;
     double ex = 0, ey = 0, ez = 0;
     if (i < P.rowEnd) {
         const double4 pi = posS[i];
-        const real dampI = mud[i].w;
-        const unsigned kb = nbrStart[i - P.rowBegin], ke = nbrStart[i - P.rowBegin + 1];
-        for (unsigned k = kb + sub; k < ke; k += MPID_LANES) {
-            const unsigned e = nbr[k];
+        const real invDampI = mud[i].w;
+        const unsigned nUp = counts[2*(size_t) (i - P.rowBegin)], nAll = nUp + counts[2*(size_t) (i - P.rowBegin) + 1];
+        const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        for (unsigned k = sub; k < nAll; k += MPID_LANES) {
+            const unsigned e = k < nUp ? base[k] : base[P.nbrCap - 1 - (k - nUp)];
             const unsigned j = e & MPID_JMASK;
             real dx, dy, dz;
             pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
             const real r2 = dx*dx + dy*dy + dz*dz;
-            const real r = t_sqrt(r2);
-            real tc[4], c[4];
-            tholeComplements<real>(dampI, mud[j].w, real(0), (real) P.defaultThole, false, r, tc);
-            fieldCoefficients<real, EWALD>(r, (real) P.alpha, real(1), tc, 4, c);
+            real c[4];
+            fieldCoefficientsOrdinary<real, EWALD, 4>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mud[j].w, c);
             real m[20];
             const typename Real4<real>::type* src = reinterpret_cast<const typename Real4<real>::type*>(cart + 20*(size_t) j);
 #pragma unroll
@@ -311,7 +351,7 @@ k_fixed_field(DevParams P, const double4* __restrict__ posS, const real* __restr
 template <typename real, bool EWALD, bool GRAD>
 __global__ void __launch_bounds__(256)
 k_induced_field(DevParams P, const double4* __restrict__ posS, const typename Real4<real>::type* __restrict__ mud,
-                const unsigned* __restrict__ nbrStart, const unsigned* __restrict__ nbr,
+                const unsigned* __restrict__ counts, const unsigned* __restrict__ nbr,
                 double* __restrict__ field, double* __restrict__ grad) {
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int i = P.rowBegin + t/MPID_LANES;
@@ -320,19 +360,18 @@ k_induced_field(DevParams P, const double4* __restrict__ posS, const typename Re
     double g[6] = {0, 0, 0, 0, 0, 0};
     if (i < P.rowEnd) {
         const double4 pi = posS[i];
-        const real dampI = mud[i].w;
-        const unsigned kb = nbrStart[i - P.rowBegin], ke = nbrStart[i - P.rowBegin + 1];
-        for (unsigned k = kb + sub; k < ke; k += MPID_LANES) {
-            const unsigned e = nbr[k];
+        const real invDampI = mud[i].w;
+        const unsigned nUp = counts[2*(size_t) (i - P.rowBegin)], nAll = nUp + counts[2*(size_t) (i - P.rowBegin) + 1];
+        const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        for (unsigned k = sub; k < nAll; k += MPID_LANES) {
+            const unsigned e = k < nUp ? base[k] : base[P.nbrCap - 1 - (k - nUp)];
             const unsigned j = e & MPID_JMASK;
             real dx, dy, dz;
             pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
             const typename Real4<real>::type mj = mud[j];
             const real r2 = dx*dx + dy*dy + dz*dz;
-            const real r = t_sqrt(r2);
-            real tc[4], c[4];
-            tholeComplements<real>(dampI, mj.w, real(0), (real) P.defaultThole, false, r, tc);
-            fieldCoefficients<real, EWALD>(r, (real) P.alpha, real(1), tc, GRAD ? 3 : 2, c);
+            real c[4];
+            fieldCoefficientsOrdinary<real, EWALD, (GRAD ? 3 : 2)>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mj.w, c);
             real fx = 0, fy = 0, fz = 0;
             inducedFieldDirected<real>(mj.x, mj.y, mj.z, dx, dy, dz, c, fx, fy, fz);
             ex += fx; ey += fy; ez += fz;
@@ -446,7 +485,8 @@ k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ p
         const R4 mi = mud[i], mj = mud[j];
         real uI[3] = {mi.x, mi.y, mi.z}, uJ[3] = {mj.x, mj.y, mj.z};
         const real r2 = dx*dx + dy*dy + dz*dz;
-        e = (double) pairElectrostatics<real, EWALD, MUTUAL>(qi, qj, uI, uJ, mi.w, mj.w, real(0), real(0), aniso[i] != 0, aniso[j] != 0,
+        const real dampI = mi.w != real(0) ? real(1)/mi.w : real(0), dampJ = mj.w != real(0) ? real(1)/mj.w : real(0);
+        e = (double) pairElectrostatics<real, EWALD, MUTUAL>(qi, qj, uI, uJ, dampI, dampJ, real(0), real(0), aniso[i] != 0, aniso[j] != 0,
                                                            dx, dy, dz, r2, (real) P.alpha, (real) P.defaultThole, real(1), real(1), f, ti, tj);
     }
     // j side: scattered fixed-point atomics

@@ -67,6 +67,55 @@ MPID_HD double t_sqrt(double x) { return sqrt(x); }
 MPID_HD float  t_abs(float x)  { return fabsf(x); }
 MPID_HD double t_abs(double x) { return fabs(x); }
 
+// ---- fast single-precision primitives for the field kernels (the double overloads stay exact) ---------
+// On the device these map to MUFU.RSQ / MUFU.EX2 / MUFU.RCP; the host build uses libm so the unit tests
+// exercise the same formulas.
+MPID_HD float t_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f/sqrtf(x);
+#endif
+}
+MPID_HD double t_rsqrt(double x) { return 1.0/sqrt(x); }
+MPID_HD float t_expneg(float x) {     // exp(x) for x <= 0; relative error ~ |x| * 1e-7
+#if defined(__CUDA_ARCH__)
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
+MPID_HD double t_expneg(double x) { return exp(x); }
+MPID_HD float t_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f/x;
+#endif
+}
+MPID_HD double t_rcp(double x) { return 1.0/x; }
+// erfc(x) for x >= 0 given ex = exp(-x*x): erfc(x) = ex * erfcx(x), erfcx as a degree-10 polynomial in
+// t = 1/(1 + 0.75 x) fitted on [0,4] (max relative error 2.7e-7 including FP32 Horner rounding).
+MPID_HD float t_erfc_ex(float x, float ex) {
+    if (x < 4.0f) {
+        const float t = t_rcp(1.0f + 0.75f*x);
+        float p = -9.0269587385e-02f;
+        p = p*t + 5.4411171075e-01f;
+        p = p*t - 1.3480634979e+00f;
+        p = p*t + 1.6405107015e+00f;
+        p = p*t - 7.4142197215e-01f;
+        p = p*t - 3.4753290535e-01f;
+        p = p*t + 2.5065307994e-01f;
+        p = p*t + 2.3229455381e-01f;
+        p = p*t + 4.3818957598e-01f;
+        p = p*t + 4.2144743440e-01f;
+        p = p*t + 8.0885749310e-05f;
+        return p*ex;
+    }
+    return erfcf(x);
+}
+MPID_HD double t_erfc_ex(double x, double) { return erfc(x); }
+
 // ---- periodic box ---------------------------------------------------------------------------------
 // Box vectors a=(ax,0,0), b=(bx,by,0), c=(cx,cy,cz) and the reciprocal vectors of
 // MPIDReferencePmeForce::setPeriodicBoxSize (:2618-2636).
@@ -333,11 +382,11 @@ template <typename T> MPID_HD void tholeComplements(T dampI, T dampJ, T tholeSum
             T ex = t_exp(-au);
             T au2 = au*au, au3 = au2*au, au4 = au3*au, au5 = au4*au;
             T p3 = T(1) + au + T(0.5)*au2;
-            T p5 = p3 + au3/T(6);
+            T p5 = p3 + au3*T(1.0/6.0);
             e[0] = ex*p3;
             e[1] = ex*p5;
-            e[2] = ex*(p5 + au4/T(30));
-            e[3] = ex*(p5 + T(4)*au4/T(105) + au5/T(210));
+            e[2] = ex*(p5 + au4*T(1.0/30.0));
+            e[3] = ex*(p5 + au4*T(4.0/105.0) + au5*T(1.0/210.0));
         }
     }
 }
@@ -367,6 +416,54 @@ template <typename T, bool EWALD> MPID_HD void fieldCoefficients(T r, T alphaEwa
             c[k] = bn - oneMinus*bare;
         } else {
             c[k] = (T(1) - oneMinus)*bare;
+        }
+        fac += T(2);
+    }
+}
+
+// The same coefficients for an ORDINARY pair (d/p/u-scale = 1, default Thole width), from r^2, arranged
+// for the hot field kernels: one rsqrt, one exp shared between erfc and the Gaussian terms, no divisions,
+// and a branch-free Thole part (invDamp = 1/(damp_i damp_j), or 0 when either site is undamped).
+//   c_k = bn_k - e_k (2k-1)!!/r^(2k+1)  (PME)      c_k = (1 - e_k) (2k-1)!!/r^(2k+1)  (no cutoff)
+template <typename T, bool EWALD, int NK>
+MPID_HD void fieldCoefficientsOrdinary(T r2, T alphaEwald, T defaultThole, T invDamp, T* c) {
+    const T rinv = t_rsqrt(r2);
+    const T r = r2*rinv, rinv2 = rinv*rinv;
+    // Thole complements e_k = exp(-au) poly_k(au); au >= 50 (or undamped) -> 0  (:2693-2701)
+    T e[4] = {T(0), T(0), T(0), T(0)};
+    {
+        const T au = defaultThole*r*invDamp;
+        const bool damped = (invDamp != T(0)) && (au < T(50));
+        const T ex = damped ? t_expneg(-au) : T(0);
+        const T au2 = au*au, au3 = au2*au;
+        const T p3 = T(1) + au + T(0.5)*au2;
+        const T p5 = p3 + au3*T(1.0/6.0);
+        e[0] = ex*p3;
+        e[1] = ex*p5;
+        if (NK > 2) e[2] = ex*(p5 + au2*au2*T(1.0/30.0));
+        if (NK > 3) e[3] = ex*(p5 + au2*au2*(T(4.0/105.0) + au*T(1.0/210.0)));
+    }
+    T bare = rinv;
+    T bn = T(0), ex2 = T(0), a2n = T(0), alsq2 = T(0);
+    if (EWALD) {
+        const T x = alphaEwald*r;
+        ex2 = t_expneg(-(x*x));
+        bn = t_erfc_ex(x, ex2)*rinv;
+        alsq2 = T(2)*alphaEwald*alphaEwald;
+        a2n = T(1.0/MPID_SQRT_PI)/alphaEwald;
+    }
+    T fac = T(1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < NK; k++) {
+        bare = bare*fac*rinv2;
+        if (EWALD) {
+            a2n *= alsq2;
+            bn = (fac*bn + a2n*ex2)*rinv2;
+            c[k] = bn - e[k]*bare;
+        } else {
+            c[k] = (T(1) - e[k])*bare;
         }
         fac += T(2);
     }
@@ -516,7 +613,7 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
     if (EWALD) {
         T x = alphaEwald*r;
         x2 = x*x;
-        T X0 = T(2)*t_exp(-x2)/T(MPID_SQRT_PI);
+        T X0 = T(2.0/MPID_SQRT_PI)*t_exp(-x2);
         T xX = x*X0;
         x3X = xX*x2; x5X = x3X*x2; x7X = x5X*x2; x9X = x7X*x2;
         B1 = (mScale - T(1)) + t_erfc(x);
@@ -539,22 +636,22 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
             T ex = t_exp(-au);
             T au2 = au*au, au3 = au2*au, au4 = au3*au, au5 = au4*au, au6 = au5*au;
             T p2 = T(1) + au + T(0.5)*au2;
-            T p3 = p2 + au3/T(6);
-            T p4 = p3 + au4/T(24);
+            T p3 = p2 + au3*T(1.0/6.0);
+            T p4 = p3 + au4*T(1.0/24.0);
             tc_c  = ex*p2;
-            tc_d0 = ex*(p2 + au3/T(4));
+            tc_d0 = ex*(p2 + au3*T(0.25));
             tc_d1 = ex*p2;
-            tc_q0 = ex*(p3 + au4/T(18));
+            tc_q0 = ex*(p3 + au4*T(1.0/18.0));
             tc_q1 = ex*p3;
-            tc_o0 = ex*(p4 + au5/T(120));
-            tc_o1 = ex*(p3 + au4/T(30));
-            dc_c  = ex*(p2 + au3/T(4));
-            dc_d0 = ex*(p3 + au4/T(12));
+            tc_o0 = ex*(p4 + au5*T(1.0/120.0));
+            tc_o1 = ex*(p3 + au4*T(1.0/30.0));
+            dc_c  = ex*(p2 + au3*T(0.25));
+            dc_d0 = ex*(p3 + au4*T(1.0/12.0));
             dc_d1 = ex*p3;
-            dc_q0 = ex*(p4 + au5/T(72));
+            dc_q0 = ex*(p4 + au5*T(1.0/72.0));
             dc_q1 = ex*p4;
-            dc_o0 = ex*(p4 + au5/T(120) + au6/T(600));
-            dc_o1 = ex*(p3 + au4/T(25) + au5/T(150));
+            dc_o0 = ex*(p4 + au5*T(1.0/120.0) + au6*T(1.0/600.0));
+            dc_o1 = ex*(p3 + au4*T(0.04) + au5*T(1.0/150.0));
         }
     }
     // (pScale*thole + bVec[k]) = (pScale - mScale) + B_k - pScale*tc ; uScale == 1 for the U-U block

@@ -193,9 +193,15 @@ template <typename T> struct Emul {
             T scale = T(classScale(cls));
             T r = t_sqrt(T(r2));
             T e[4], c[4];
+            if (cls == 0) {      // ordinary pair: the hot-kernel formulation
+                T inv = (S.damp[i] != 0 && S.damp[j] != 0) ? T(1.0/S.damp[i])*T(1.0/S.damp[j]) : T(0);
+                if (S.method == PME) fieldCoefficientsOrdinary<T, true, 4>(T(r2), T(S.alpha), T(S.defaultThole), inv, c);
+                else fieldCoefficientsOrdinary<T, false, 4>(T(r2), T(0), T(S.defaultThole), inv, c);
+            } else {
             tholeComplements<T>(T(S.damp[i]), T(S.damp[j]), T(S.thole[i] + S.thole[j]), T(S.defaultThole), scale == T(0), r, e);
             if (S.method == PME) fieldCoefficients<T, true>(r, T(S.alpha), scale, e, 4, c);
             else fieldCoefficients<T, false>(r, T(0), scale, e, 4, c);
+            }
             T ex = 0, ey = 0, ez = 0;
             fixedFieldDirected<T>(&cart[20*j], T(dx), T(dy), T(dz), c, ex, ey, ez);
             field[3*i] += ex; field[3*i+1] += ey; field[3*i+2] += ez;
@@ -213,9 +219,15 @@ template <typename T> struct Emul {
             int cls = pairClass(i, j);
             T r = t_sqrt(T(r2));
             T e[4], c[4];
+            if (cls == 0) {
+                T inv = (S.damp[i] != 0 && S.damp[j] != 0) ? T(1.0/S.damp[i])*T(1.0/S.damp[j]) : T(0);
+                if (S.method == PME) fieldCoefficientsOrdinary<T, true, 3>(T(r2), T(S.alpha), T(S.defaultThole), inv, c);
+                else fieldCoefficientsOrdinary<T, false, 3>(T(r2), T(0), T(S.defaultThole), inv, c);
+            } else {
             tholeComplements<T>(T(S.damp[i]), T(S.damp[j]), T(S.thole[i] + S.thole[j]), T(S.defaultThole), classScale(cls) == 0.0, r, e);
             if (S.method == PME) fieldCoefficients<T, true>(r, T(S.alpha), T(1), e, 3, c);
             else fieldCoefficients<T, false>(r, T(0), T(1), e, 3, c);
+            }
             T ex = 0, ey = 0, ez = 0;
             inducedFieldDirected<T>(T(dip[3*j]), T(dip[3*j+1]), T(dip[3*j+2]), T(dx), T(dy), T(dz), c, ex, ey, ez);
             field[3*i] += ex; field[3*i+1] += ey; field[3*i+2] += ez;

@@ -36,7 +36,8 @@ def test_reference_golden_configurations(key, prec):
     mu0 = o.dipoles(0)
     ftol = FTOL[prec] if pol != 0 else max(FTOL[prec], 5e-7)
     assert rel_err(f, f0) < ftol
-    assert rel_err(mu, mu0) < (MU_TOL_MUTUAL if pol == 0 else 10*FTOL[prec])
+    # FP32 fields at sites where large intramolecular contributions cancel: the north-star bound itself
+    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else (MU_TOL_MUTUAL if pol == 0 else 1e-7))
     assert abs(e - e0) <= (1e-5 if prec == "mixed" else 1e-8)*max(1.0, abs(e0))
     if pol == 0:
         assert k.getStats()["epsilon"] < s.epsilon

@@ -981,13 +981,13 @@ __global__ void k_torque_to_force(DevParams P, ParticleParams pp, const int* __r
     const double* px = ax >= 0 ? posOrig + 3*ax : pz;
     const double* py = ay >= 0 ? posOrig + 3*ay : pz;
     double fI[3], fZ[3], fX[3], fY[3];
-    torqueToForce(axis, pi, pz, px, py, ay >= 0, tq, fI, fZ, fX, fY);
+    torqueToForce(axis, pi, pz, px, py, ax >= 0, ay >= 0, tq, fI, fZ, fX, fY);
     const int sz = inv[az];
     for (int k = 0; k < 3; k++) {
         atomicAddFixed(&force[3*(size_t) s + k], fI[k]);
         atomicAddFixed(&force[3*(size_t) sz + k], fZ[k]);
     }
-    if (ax >= 0) { const int sx = inv[ax]; for (int k = 0; k < 3; k++) atomicAddFixed(&force[3*(size_t) sx + k], fX[k]); }
+    if (ax >= 0 && axis != ZOnly) { const int sx = inv[ax]; for (int k = 0; k < 3; k++) atomicAddFixed(&force[3*(size_t) sx + k], fX[k]); }
     if (ay >= 0) { const int sy = inv[ay]; for (int k = 0; k < 3; k++) atomicAddFixed(&force[3*(size_t) sy + k], fY[k]); }
 }
 

@@ -1014,9 +1014,12 @@ template <typename T> MPID_HD T contractFractional(const T* f, int nk, const T* 
 // Torque -> forces on the frame-defining atoms
 // =====================================================================================================
 // fI/fZ/fX/fY receive the force increments for the atom and its z/x/y anchors.
-//   reference: mapTorqueToForceForParticle (:1895-2110).  For ZOnly the reference reads an undefined
-//   x anchor; like the plugin's CUDA platform we use the lab axis least aligned with u instead.
-MPID_HD void torqueToForce(int axisType, const double* pi, const double* pz, const double* px, const double* py, bool hasY,
+//   reference: mapTorqueToForceForParticle (:1895-2110).  The reference takes the second direction from
+//   particleData[atomX] for every axis type (:2124-2127); for a ZOnly site without an x anchor that is an
+//   out-of-range read, and there -- like the plugin's CUDA platform -- we use the lab axis least aligned
+//   with u.  (The choice only matters when the torque has a component along u, e.g. anisotropic mutual
+//   polarization on a ZOnly site.)
+MPID_HD void torqueToForce(int axisType, const double* pi, const double* pz, const double* px, const double* py, bool hasX, bool hasY,
                            const double* torque, double* fI, double* fZ, double* fX, double* fY) {
     for (int i = 0; i < 3; i++) fI[i] = fZ[i] = fX[i] = fY[i] = 0.0;
     if (axisType == NoAxisType) return;
@@ -1024,7 +1027,7 @@ MPID_HD void torqueToForce(int axisType, const double* pi, const double* pz, con
     V3<double> U = mk(pz[0]-pi[0], pz[1]-pi[1], pz[2]-pi[2]);
     double nU = normalize(U);
     V3<double> V;
-    if (axisType == ZOnly)
+    if (axisType == ZOnly && !hasX)
         V = (fabs(U.x) < 0.866) ? mk(1.0, 0.0, 0.0) : mk(0.0, 1.0, 0.0);
     else
         V = mk(px[0]-pi[0], px[1]-pi[1], px[2]-pi[2]);

@@ -183,3 +183,74 @@ def pair_set_reference(s, chunk=512):
             if a < b:
                 out.append((int(a), int(b), cls.get((int(a), int(b)), 0)))
     return out
+
+
+def random_molecule_box(seed=11, alpha_scale=0.35):
+    """125 four-atom 'molecules' (centre + 3 ligands) with random traceless moments, every axis type
+    (ZBisect, ThreeFold, ZThenX with and without a chirality anchor, ZOnly, Bisector, NoAxisType), anisotropic
+    polarizabilities, 1-2/1-3/1-4/1-5 covalent relations, in a reduced triclinic box."""
+    from mpidopenmmplugin_b200 import MPIDForce
+    rng = np.random.default_rng(seed)
+    nm = 125
+    n = 4*nm
+    s = System(n)
+    s.method = 1; s.polarization = 0; s.cutoff = 0.8; s.alpha = 3.5; s.grid = (30, 30, 30); s.epsilon = 1e-8; s.max_iter = 200
+    s.default_thole = 4.0; s.scale14 = 0.6
+    L = 2.4
+    s.box = np.array([[L, 0, 0], [0.3, L, 0], [-0.25, 0.35, L]])
+    base = np.array([[0, 0, 0], [0.1, 0, 0], [-0.03, 0.095, 0], [-0.03, -0.05, 0.085]])
+    s.covalent = [[[] for _ in range(8)] for _ in range(n)]
+    grid_pts = [(i, j, k) for i in range(5) for j in range(5) for k in range(5)]
+    for m in range(nm):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        frac = (np.array(grid_pts[m]) + 0.5)/5.0
+        origin = frac @ s.box + rng.normal(scale=0.02, size=3)
+        for a in range(4):
+            i = 4*m + a
+            s.pos[i] = origin + base[a] @ q.T
+            s.charges[i] = rng.normal()*0.3
+            s.dipoles[i] = rng.normal(size=3)*0.01
+            qq = rng.normal(size=(3, 3))*0.001; qq = 0.5*(qq + qq.T); qq -= np.eye(3)*np.trace(qq)/3
+            s.quadrupoles[i] = [qq[0, 0], qq[0, 1], qq[1, 1], qq[0, 2], qq[1, 2], qq[2, 2]]
+            o3 = rng.normal(size=(3, 3, 3))*1e-4
+            o3 = sum(np.transpose(o3, p) for p in [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)])/6
+            tr = np.einsum("iij->j", o3)
+            for x in range(3):
+                for y in range(3):
+                    for z in range(3):
+                        o3[x, y, z] -= ((x == y)*tr[z] + (x == z)*tr[y] + (y == z)*tr[x])/5
+            s.octopoles[i] = [o3[0, 0, 0], o3[0, 0, 1], o3[0, 1, 1], o3[1, 1, 1], o3[0, 0, 2], o3[0, 1, 2], o3[1, 1, 2], o3[0, 2, 2], o3[1, 2, 2], o3[2, 2, 2]]
+            s.tholes[i] = 1.0 + rng.uniform()
+            s.alphas[i] = alpha_scale*(0.0008*(1 + 0.4*rng.uniform(size=3)) if a != 3 else np.array([0.0006]*3))
+        c = 4*m
+        kinds = [MPIDForce.ZBisect, MPIDForce.ThreeFold, MPIDForce.ZThenX, MPIDForce.ZOnly, MPIDForce.Bisector, MPIDForce.NoAxisType]
+        kind = kinds[m % 6]
+        s.axis[c] = kind
+        if kind == MPIDForce.NoAxisType:
+            pass
+        elif kind == MPIDForce.ZOnly:
+            # The reference maps a ZOnly site's torque through particleData[atomX] even though ZOnly needs no x
+            # anchor (MPIDReferenceForce.cpp:2124-2127): with atomX = -1 that is an out-of-range read whose value
+            # depends on the heap.  Give it a valid (ignored-by-the-frame) anchor and axially symmetric moments, for
+            # which the mapping does not depend on that direction.
+            s.atomZ[c], s.atomX[c] = c+1, c+2
+            dz, qz, oz = s.dipoles[c][2], s.quadrupoles[c][5], s.octopoles[c][9]
+            s.dipoles[c] = [0, 0, dz]
+            s.quadrupoles[c] = [-0.5*qz, 0, -0.5*qz, 0, 0, qz]
+            s.octopoles[c] = [0, 0, 0, 0, -0.5*oz, 0, -0.5*oz, 0, 0, oz]
+            s.alphas[c] = [s.alphas[c][0], s.alphas[c][0], s.alphas[c][2]]
+        elif kind in (MPIDForce.ZBisect, MPIDForce.ThreeFold):
+            s.atomZ[c], s.atomX[c], s.atomY[c] = c+1, c+2, c+3
+        else:
+            s.atomZ[c], s.atomX[c] = c+1, c+2
+            if kind == MPIDForce.ZThenX and m % 2 == 0:
+                s.atomY[c] = c+3                       # chirality check path
+        for a in (1, 2, 3):
+            s.axis[c+a] = MPIDForce.ZThenX; s.atomZ[c+a] = c; s.atomX[c+a] = c + (a % 3) + 1
+        for a in range(4):
+            s.covalent[c+a][0] = [c+b for b in range(4) if (a == 0) != (b == 0)]            # 1-2: centre <-> ligands
+            s.covalent[c+a][1] = [c+b for b in range(1, 4) if a != 0 and b != a]             # 1-3: ligand <-> ligand
+        if m + 1 < nm:                                                                       # a few 1-4 / 1-5 relations across molecules
+            s.covalent[c+1][2] = [c+5]
+            s.covalent[c+2][3] = [c+6]
+    return s

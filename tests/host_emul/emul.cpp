@@ -475,7 +475,7 @@ template <typename T> struct Emul {
             const double* pz = &S.pos[3*S.az[i]];
             const double* px = S.ax[i] >= 0 ? &S.pos[3*S.ax[i]] : pz;
             const double* py = S.ay[i] >= 0 ? &S.pos[3*S.ay[i]] : pz;
-            torqueToForce(S.axis[i], &S.pos[3*i], pz, px, py, S.ay[i] >= 0, &torque[3*i], fI, fZ, fX, fY);
+            torqueToForce(S.axis[i], &S.pos[3*i], pz, px, py, S.ax[i] >= 0, S.ay[i] >= 0, &torque[3*i], fI, fZ, fX, fY);
             for (int k = 0; k < 3; k++) {
                 forces[3*i+k] += fI[k];
                 forces[3*S.az[i]+k] += fZ[k];

@@ -100,3 +100,15 @@ def test_math_header_anisotropic_mutual_water():
     e, f, mu, it = emul_evaluate(s, use_float=False)
     assert rel_err(f, f0) < 1e-6
     assert abs(e - e0) < 1e-6*abs(e0)
+
+
+def test_math_header_all_axis_types_triclinic():
+    """Every axis type, chirality flips, 1-4/1-5 classes and a reduced triclinic box against the oracle."""
+    from _common import random_molecule_box
+    s = random_molecule_box()
+    s.polarization = 1
+    o = Oracle(s)
+    e0, f0 = o.execute()
+    e, f, mu, it = emul_evaluate(s, use_float=False)
+    assert rel_err(f, f0) < 1e-10 and abs(e - e0) < 1e-10*abs(e0)
+    assert rel_err(mu, o.dipoles(0)) < 1e-10

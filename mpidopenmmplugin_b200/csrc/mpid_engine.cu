@@ -144,6 +144,7 @@ struct Engine : public EngineBase {
     DevBuf<double> dCartD, dPkD, dSphD, dAlphaLab;
     DevBuf<real> dCartR, dPkR;
     DevBuf<int> dAniso;
+    DevBuf<int4> dSpSorted;
     DevBuf<double2> dDampThole;
     DevBuf<real4> dMud;
     DevBuf<unsigned> dCounts, dHalfCount, dHalfStart, dMaxCount, dNbr, dPairI, dPairJ;
@@ -481,12 +482,13 @@ struct Engine : public EngineBase {
         P.rowEnd = (int) ((long long) n*(rank+1)/numRanks);
         // lab frames
         dPosS.ensure(n); dPosF.ensure(n); dCartD.ensure(20*(size_t) n); dPkD.ensure(16*(size_t) n); dSphD.ensure(16*(size_t) n);
-        dAlphaLab.ensure(6*(size_t) n); dAniso.ensure(n); dDampThole.ensure(n); dMud.ensure(n);
+        dAlphaLab.ensure(6*(size_t) n); dAniso.ensure(n); dDampThole.ensure(n); dMud.ensure(n); dSpSorted.ensure(n);
         real* cartR; real* pkR;
         if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
         LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
-               dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p);
+               dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p,
+               dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p);
         stageEnd();
         // neighbour list: single pass into per-atom runs, then the flat half list for the energy kernel
         stageBegin(MPIDB200_STAGE_NLIST);
@@ -505,9 +507,9 @@ struct Engine : public EngineBase {
             CUDA_CHECK(cudaMemsetAsync(dMaxCount.p, 0, 2*sizeof(unsigned), stream));
             if (rows > 0) {
                 if (roundMode) LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
-                                      dSpStart.p, dSpPartner.p, dNbr.p, dCounts.p, dMaxCount.p);
+                                      dSpStart.p, dSpPartner.p, dSpSorted.p, dNbr.p, dCounts.p, dMaxCount.p);
                 else LAUNCH((k_neighbor_list<false>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
-                            dSpStart.p, dSpPartner.p, dNbr.p, dCounts.p, dMaxCount.p);
+                            dSpStart.p, dSpPartner.p, dSpSorted.p, dNbr.p, dCounts.p, dMaxCount.p);
             }
             LAUNCH(k_half_counts, blocksFor(rows + 1, B), B, rows, dCounts.p, dHalfCount.p);
             size_t tempBytes = 0;
@@ -664,7 +666,7 @@ struct Engine : public EngineBase {
         const int nb = 296;   // 2 x 148 SMs
         dDotPartial.ensure((size_t) nb*(MPID_MAX_HISTORY + 1)); dDots.ensure(MPID_MAX_HISTORY + 1);
         LAUNCH(k_dots_partial, nb, 256, 3*(size_t) n, m, vec, list, dDotPartial.p);
-        LAUNCH(k_dots_final, 1, 32, nb, m, dDotPartial.p, dDots.p);
+        LAUNCH(k_dots_final, m, 128, nb, m, dDotPartial.p, dDots.p);
         CUDA_CHECK(cudaMemcpyAsync(hostOut, dDots.p, m*sizeof(double), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
@@ -776,8 +778,20 @@ struct Engine : public EngineBase {
         }
         if (dipolesOnly) { collectTimings(); return; }
 
-        stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
         const bool mutual = P.polarization == Mutual;
+        bool forked = false;
+        if (!hSpLo.empty()) {
+            // FP64 covalent pairs run on the second stream beside the FP32 pair kernel; both accumulate with
+            // order-independent fixed-point atomics
+            const int ns = (int) hSpLo.size();
+            forkPme(); forked = true;
+            if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                               dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+            else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                        dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+            backToMain();
+        }
+        stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
         if (lastPairs > 0) {
             const int nb = blocksFor(lastPairs, 128);
 #define ES_LAUNCH(EW, MU) LAUNCH((k_electrostatics<real, EW, MU>), nb, 128, P, lastPairs, dPairI.p, dPairJ.p, dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p)
@@ -785,14 +799,8 @@ struct Engine : public EngineBase {
             else { if (mutual) ES_LAUNCH(false, true); else ES_LAUNCH(false, false); }
 #undef ES_LAUNCH
         }
-        if (!hSpLo.empty()) {
-            const int ns = (int) hSpLo.size();
-            if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                               dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
-            else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                        dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
-        }
         stageEnd();
+        if (forked) joinPme();
 
         stageBegin(MPIDB200_STAGE_FINISH);
         if (pme && rows > 0)

@@ -116,10 +116,24 @@ __global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, co
                             double4* __restrict__ posS, float4* __restrict__ posF,
                             double* __restrict__ cartD, double* __restrict__ pkD, real* __restrict__ cartR, real* __restrict__ pkR,
                             double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso,
-                            double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud) {
+                            double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud,
+                            const int* __restrict__ inv, const int* __restrict__ spStart, const int* __restrict__ spPartner,
+                            int4* __restrict__ spSorted) {
     int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= P.n) return;
     int o = order[s];
+    {   // sorted indices of up to four covalently scaled partners (x = -2 flags "more than four: use the list")
+        const int k0 = spStart[o], k1 = spStart[o+1];
+        int4 q = make_int4(-1, -1, -1, -1);
+        if (k1 - k0 > 4) q.x = -2;
+        else {
+            if (k1 - k0 > 0) q.x = inv[spPartner[k0]];
+            if (k1 - k0 > 1) q.y = inv[spPartner[k0+1]];
+            if (k1 - k0 > 2) q.z = inv[spPartner[k0+2]];
+            if (k1 - k0 > 3) q.w = inv[spPartner[k0+3]];
+        }
+        spSorted[s] = q;
+    }
     int az = pp.atomZ[o], ax = pp.atomX[o], ay = pp.atomY[o];
     const double* pi = posOrig + 3*o;
     const double* pz = az >= 0 ? posOrig + 3*az : pi;
@@ -172,7 +186,7 @@ template <bool ROUND>
 __global__ void __launch_bounds__(256)
 k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __restrict__ posOrig,
                 const int* __restrict__ order, const int* __restrict__ sortedKey, const int* __restrict__ cellStart,
-                const int* __restrict__ spStart, const int* __restrict__ spPartner,
+                const int* __restrict__ spStart, const int* __restrict__ spPartner, const int4* __restrict__ spSorted,
                 unsigned* __restrict__ nbr, unsigned* __restrict__ counts, unsigned* __restrict__ maxCount) {
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x*blockDim.x + threadIdx.x)/32;
@@ -180,7 +194,10 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
     if (i >= P.rowEnd) return;
     const float4 pi = posF[i];
     const int oi = order[i];
-    const int sp0 = spStart[oi], sp1 = spStart[oi+1];
+    const int4 sp = spSorted[i];
+    const bool spMany = sp.x == -2;
+    int sp0 = 0, sp1 = 0;
+    if (spMany) { sp0 = spStart[oi]; sp1 = spStart[oi+1]; }
     const bool pme = P.method == PME;
     int cx = 0, cy = 0, cz = 0;
     {
@@ -244,7 +261,8 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
                         }
                         if (code > 26u) in = false;   // cannot happen for wrapped positions; keeps the table index safe
                     }
-                    if (in && sp1 > sp0) {
+                    if (j == sp.x || j == sp.y || j == sp.z || j == sp.w) in = false;
+                    if (spMany && in) {
                         const int oj = order[j];
                         for (int k = sp0; k < sp1; k++) if (spPartner[k] == oj) in = false;
                     }
@@ -356,8 +374,9 @@ k_induced_field(DevParams P, const double4* __restrict__ posS, const typename Re
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int i = P.rowBegin + t/MPID_LANES;
     const int sub = t % MPID_LANES;
-    double ex = 0, ey = 0, ez = 0;
-    double g[6] = {0, 0, 0, 0, 0, 0};
+    // per-lane partial sums stay in `real` (<= ~30 terms each); lanes are combined in double below
+    real ax_ = 0, ay_ = 0, az_ = 0;
+    real ga[6] = {0, 0, 0, 0, 0, 0};
     if (i < P.rowEnd) {
         const double4 pi = posS[i];
         const real invDampI = mud[i].w;
@@ -372,17 +391,14 @@ k_induced_field(DevParams P, const double4* __restrict__ posS, const typename Re
             const real r2 = dx*dx + dy*dy + dz*dz;
             real c[4];
             fieldCoefficientsOrdinary<real, EWALD, (GRAD ? 3 : 2)>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mj.w, c);
-            real fx = 0, fy = 0, fz = 0;
-            inducedFieldDirected<real>(mj.x, mj.y, mj.z, dx, dy, dz, c, fx, fy, fz);
-            ex += fx; ey += fy; ez += fz;
-            if (GRAD) {
-                real gg[6] = {0, 0, 0, 0, 0, 0};
-                inducedFieldGradientDirected<real>(mj.x, mj.y, mj.z, dx, dy, dz, c, gg);
-#pragma unroll
-                for (int q = 0; q < 6; q++) g[q] += gg[q];
-            }
+            inducedFieldDirected<real>(mj.x, mj.y, mj.z, dx, dy, dz, c, ax_, ay_, az_);
+            if (GRAD) inducedFieldGradientDirected<real>(mj.x, mj.y, mj.z, dx, dy, dz, c, ga);
         }
     }
+    double ex = ax_, ey = ay_, ez = az_;
+    double g[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) g[q] = ga[q];
 #pragma unroll
     for (int off = MPID_LANES/2; off > 0; off >>= 1) {
         ex += __shfl_xor_sync(0xffffffffu, ex, off);
@@ -565,7 +581,33 @@ __global__ void k_fractional_multipoles(DevParams P, const real* __restrict__ ca
     for (int k = 0; k < 20; k++) frac[20*(size_t) s + k] = f[k];
 }
 
-// B-spline spreading: 6 threads per atom (one per x plane), 36 atomic adds each.
+// Six consecutive grid points of one (x,y) line: vector reductions (red.global.add.v2/v4.f32, sm_90+) where the
+// address allows, so a line costs 2-4 L2 atomic requests instead of 6.
+__device__ __forceinline__ void redLine6(float* p, const float* v) {
+    const unsigned mis = (unsigned) ((reinterpret_cast<size_t>(p) >> 2) & 3);
+    if (mis == 0) {
+        atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(reinterpret_cast<float2*>(p + 4), make_float2(v[4], v[5]));
+    } else if (mis == 2) {
+        atomicAdd(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+        atomicAdd(reinterpret_cast<float4*>(p + 2), make_float4(v[2], v[3], v[4], v[5]));
+    } else if (mis == 1) {
+        atomicAdd(p, v[0]);
+        atomicAdd(reinterpret_cast<float2*>(p + 1), make_float2(v[1], v[2]));
+        atomicAdd(reinterpret_cast<float2*>(p + 3), make_float2(v[3], v[4]));
+        atomicAdd(p + 5, v[5]);
+    } else {
+        atomicAdd(p, v[0]);
+        atomicAdd(reinterpret_cast<float4*>(p + 1), make_float4(v[1], v[2], v[3], v[4]));
+        atomicAdd(p + 5, v[5]);
+    }
+}
+__device__ __forceinline__ void redLine6(double* p, const double* v) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) atomicAdd(p + k, v[k]);
+}
+
+// B-spline spreading: 6 threads per atom (one per x plane), 36 grid points each.
 //   reference: spreadFixedMultipolesOntoGrid (:3269-3327), spreadInducedDipolesOnGrid (:3532-3573)
 template <typename real, bool FIXED>
 __global__ void __launch_bounds__(192)
@@ -599,10 +641,16 @@ k_spread(DevParams P, const double4* __restrict__ posS, const real* __restrict__
     for (int iy = 0; iy < 6; iy++) {
         int y = ig[1] + iy; y -= (y >= ny) ? ny : 0;
         real* row = grid + ((size_t) x*ny + y)*nz;
+        real v[6];
 #pragma unroll
-        for (int iz = 0; iz < 6; iz++) {
-            int z = ig[2] + iz; z -= (z >= nz) ? nz : 0;
-            atomicAdd(row + z, spreadTerm<real, FIXED>(f, txr, ty[iy], tz[iz]));
+        for (int iz = 0; iz < 6; iz++) v[iz] = spreadTerm<real, FIXED>(f, txr, ty[iy], tz[iz]);
+        if (ig[2] + 5 < nz) redLine6(row + ig[2], v);
+        else {
+#pragma unroll
+            for (int iz = 0; iz < 6; iz++) {
+                int z = ig[2] + iz; z -= (z >= nz) ? nz : 0;
+                atomicAdd(row + z, v[iz]);
+            }
         }
     }
 }
@@ -819,12 +867,20 @@ k_dots_partial(size_t len, int m, const double* __restrict__ vec, VecList hist, 
         partial[(size_t) blockIdx.x*(MPID_MAX_HISTORY + 1) + threadIdx.x] = v;
     }
 }
-__global__ void k_dots_final(int numBlocks, int m, const double* __restrict__ partial, double* __restrict__ out) {
-    const int k = threadIdx.x;
-    if (k >= m) return;
+__global__ void __launch_bounds__(128)
+k_dots_final(int numBlocks, int m, const double* __restrict__ partial, double* __restrict__ out) {
+    // block k reduces the per-block partials of dot product k with a fixed-shape tree (deterministic)
+    __shared__ double sh[128];
+    const int k = blockIdx.x;
     double v = 0;
-    for (int b = 0; b < numBlocks; b++) v += partial[(size_t) b*(MPID_MAX_HISTORY + 1) + k];
-    out[k] = v;
+    for (int b = threadIdx.x; b < numBlocks; b += 128) v += partial[(size_t) b*(MPID_MAX_HISTORY + 1) + k];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+        if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && k < m) out[k] = sh[0];
 }
 
 // mu = sum_k coef[k] * vec_k   (DIIS extrapolation :1240-1249, OPT combination :1172-1177); repacks mud

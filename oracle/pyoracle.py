@@ -53,8 +53,19 @@ class Oracle:
         box = np.ascontiguousarray(s.box, dtype=np.float64).reshape(-1)
         coefs = np.ascontiguousarray(s.coefs, dtype=np.float64)
         c = np.ascontiguousarray
+        # The reference maps the torque of every framed site through particleData[atomX]
+        # (MPIDReferenceForce.cpp:2124-2127).  For a ZOnly site without an x anchor that is particleData[-1]: an
+        # out-of-range read whose value depends on the heap (we have seen it produce NaN forces).  ZOnly frames do
+        # not use the x anchor, and for the axially symmetric sites the reference's fixtures use the mapping does not
+        # depend on the direction, so hand the oracle a valid placeholder to make it deterministic.
+        atomX = np.array(s.atomX, dtype=np.int32, copy=True)
+        for i in np.nonzero((np.asarray(s.axis) == 4) & (atomX < 0))[0]:
+            for j in range(s.n):
+                if j != i and j != s.atomZ[i]:
+                    atomX[i] = j
+                    break
         rc = L.mpidref_create(ctypes.c_int(s.n), _dp(c(s.charges)), _dp(c(s.dipoles)), _dp(c(s.quadrupoles)), _dp(c(s.octopoles)),
-                              _ip(c(s.axis)), _ip(c(s.atomZ)), _ip(c(s.atomX)), _ip(c(s.atomY)), _dp(c(s.tholes)), _dp(c(s.alphas)),
+                              _ip(c(s.axis)), _ip(c(s.atomZ)), _ip(atomX), _ip(c(s.atomY)), _dp(c(s.tholes)), _dp(c(s.alphas)),
                               _ip(off), _ip(idx), ctypes.c_int(s.method), ctypes.c_int(s.polarization), ctypes.c_double(s.cutoff),
                               ctypes.c_double(s.alpha), ctypes.c_int(int(s.grid[0])), ctypes.c_int(int(s.grid[1])), ctypes.c_int(int(s.grid[2])),
                               ctypes.c_double(s.ewald_tol), ctypes.c_double(s.default_thole), ctypes.c_double(s.scale14),

@@ -147,8 +147,13 @@ struct Engine : public EngineBase {
     DevBuf<int4> dSpSorted;
     DevBuf<double2> dDampThole;
     DevBuf<real4> dMud;
-    DevBuf<unsigned> dCounts, dHalfCount, dHalfStart, dMaxCount, dNbr, dPairI, dPairJ;
+    DevBuf<uint4> dCounts;
+    DevBuf<unsigned> dTypeCount, dTypeStart, dMaxCount, dNbr, dPairI, dPairJ, dPolNbr, dPolCount;
+    DevBuf<int> dFlagS, dPolFlag, dPolRank, dPolList;
     int nbrCap = 0;
+    int numPolTotal = 0;            // polarizable sites (static: follows from the parameters)
+    int numPol = 0, polBegin = 0;   // polarizable sites among this rank's rows
+    long long typeBegin[5] = {0, 0, 0, 0, 0};   // boundaries of the four pair-class lists inside pairI/pairJ
     DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
     DevBuf<unsigned long long> dForce, dTorque, dEnergy;
     DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp;
@@ -164,6 +169,7 @@ struct Engine : public EngineBase {
     int lastIterations = 0; double lastEps = 0; double stageMs[MPIDB200_NUM_STAGES]; long long lastPairs = 0, lastFull = 0;
     // multi-GPU
     void* comm = nullptr; int rank = 0, numRanks = 1;
+    const double* lastPosDevice = nullptr;
     std::vector<double> hLastMu;
 
     explicit Engine(const mpidb200_config& c) : cfg(c), n(c.num_particles) {
@@ -247,6 +253,12 @@ struct Engine : public EngineBase {
                 throw std::runtime_error("MPIDForce: particle " + std::to_string(i) + " needs a y-axis particle for its axis type");
             // dampingFactor (MPIDReferenceKernels.cpp:123)
             hDamp[i] = pow((hAlpha[3*i] + hAlpha[3*i+1] + hAlpha[3*i+2])/3.0, 1.0/6.0);
+        }
+        numPolTotal = 0;
+        for (int i = 0; i < n; i++) {
+            bool anyAlpha = hAlpha[3*i] != 0.0 || hAlpha[3*i+1] != 0.0 || hAlpha[3*i+2] != 0.0;
+            // a site without a z anchor keeps a zero lab-frame tensor unless the opt-in fix is on
+            if (anyAlpha && (hZ[i] >= 0 || cfg.frameless_alpha_fix)) numPolTotal++;
         }
         dCharge.upload(hCharge, stream); dDipole.upload(hDipole, stream); dQuad.upload(hQuad, stream); dOct.upload(hOct, stream);
         dAxis.upload(hAxis, stream); dZ.upload(hZ, stream); dX.upload(hX, stream); dY.upload(hY, stream);
@@ -483,17 +495,37 @@ struct Engine : public EngineBase {
         // lab frames
         dPosS.ensure(n); dPosF.ensure(n); dCartD.ensure(20*(size_t) n); dPkD.ensure(16*(size_t) n); dSphD.ensure(16*(size_t) n);
         dAlphaLab.ensure(6*(size_t) n); dAniso.ensure(n); dDampThole.ensure(n); dMud.ensure(n); dSpSorted.ensure(n);
+        dFlagS.ensure(n); dPolFlag.ensure((size_t) n + 1); dPolRank.ensure((size_t) n + 1); dPolList.ensure((size_t) n + 1);
         real* cartR; real* pkR;
         if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
         LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
                dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p,
-               dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p);
+               dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p, dFlagS.p);
+        // polarizable rows: rank (exclusive scan of the flag) and compact list
+        LAUNCH(k_pol_flags, blocksFor(n + 1, B), B, n, dFlagS.p, dPolFlag.p);
+        {
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, dPolFlag.p, dPolRank.p, n + 1, stream);
+            dScanTemp.ensure(tb + 16);
+            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tb, dPolFlag.p, dPolRank.p, n + 1, stream));
+            launches += 1;
+        }
+        LAUNCH(k_pol_list, blocksFor(n, B), B, n, dFlagS.p, dPolRank.p, dPolList.p);
+        if (numRanks > 1) {
+            int* pr = (int*) hPinned;
+            CUDA_CHECK(cudaMemcpyAsync(&pr[0], dPolRank.p + P.rowBegin, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&pr[1], dPolRank.p + P.rowEnd, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            polBegin = pr[0]; numPol = pr[1] - pr[0];
+        } else { polBegin = 0; numPol = numPolTotal; }
         stageEnd();
         // neighbour list: single pass into per-atom runs, then the flat half list for the energy kernel
         stageBegin(MPIDB200_STAGE_NLIST);
         int rows = P.rowEnd - P.rowBegin;
-        dCounts.ensure(2*(size_t) rows + 2); dHalfCount.ensure((size_t) rows + 1); dHalfStart.ensure((size_t) rows + 1); dMaxCount.ensure(2);
+        const size_t tlen = 4*((size_t) rows + 1);
+        dCounts.ensure((size_t) rows + 1); dTypeCount.ensure(tlen); dTypeStart.ensure(tlen); dMaxCount.ensure(2);
+        dPolCount.ensure((size_t) numPol + 1);
         if (nbrCap == 0) {
             // first guess: 1.35 x the mean number of neighbours at this density (+ slack); grown on demand
             double expected = P.method == PME ? (4.0/3.0)*MPID_PI*cfg.cutoff*cfg.cutoff*cfg.cutoff*n/(boxA[0]*boxB[1]*boxC[2]) : (double) n;
@@ -501,33 +533,39 @@ struct Engine : public EngineBase {
             nbrCap = std::min(std::max(nbrCap, 32), std::max(n, 32));
         }
         const bool roundMode = P.method != PME || P.reach[0] == 0 || P.reach[1] == 0 || P.reach[2] == 0;
+        unsigned* totals = (unsigned*) hPinned;
         for (int attempt = 0; ; attempt++) {
             P.nbrCap = nbrCap;
             dNbr.ensure((size_t) std::max(rows, 1)*nbrCap);
+            dPolNbr.ensure((size_t) std::max(numPol, 1)*nbrCap);
             CUDA_CHECK(cudaMemsetAsync(dMaxCount.p, 0, 2*sizeof(unsigned), stream));
             if (rows > 0) {
                 if (roundMode) LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
-                                      dSpStart.p, dSpPartner.p, dSpSorted.p, dNbr.p, dCounts.p, dMaxCount.p);
+                                      dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
                 else LAUNCH((k_neighbor_list<false>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
-                            dSpStart.p, dSpPartner.p, dSpSorted.p, dNbr.p, dCounts.p, dMaxCount.p);
+                            dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
             }
-            LAUNCH(k_half_counts, blocksFor(rows + 1, B), B, rows, dCounts.p, dHalfCount.p);
+            // one scan over the four concatenated per-class count arrays gives absolute offsets into pairI/pairJ
+            LAUNCH(k_half_counts, blocksFor(rows + 1, B), B, P, rows, dCounts.p, dFlagS.p, dTypeCount.p);
             size_t tempBytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dHalfCount.p, dHalfStart.p, rows + 1, stream);
+            cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, stream);
             dScanTemp.ensure(tempBytes + 16);
-            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dHalfCount.p, dHalfStart.p, rows + 1, stream));
+            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, stream));
             launches += 1;
-            unsigned* totals = (unsigned*) hPinned;
             CUDA_CHECK(cudaMemcpyAsync(&totals[0], dMaxCount.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaMemcpyAsync(&totals[1], dHalfStart.p + rows, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            for (int t = 0; t < 4; t++)
+                CUDA_CHECK(cudaMemcpyAsync(&totals[1 + t], dTypeStart.p + (size_t) t*(rows + 1), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&totals[5], dTypeStart.p + tlen - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
-            if ((int) totals[0] <= nbrCap) { lastPairs = totals[1]; break; }
+            if ((int) totals[0] <= nbrCap) break;
             if (attempt > 3) throw std::runtime_error("mpidb200: neighbour list capacity could not be established");
             nbrCap = (int) (totals[0]*1.2) + 16;       // rare: density fluctuation beyond the guess
         }
+        for (int t = 0; t < 5; t++) typeBegin[t] = totals[1 + t];
+        lastPairs = typeBegin[4];
         dPairI.ensure((size_t) lastPairs + 1); dPairJ.ensure((size_t) lastPairs + 1);
         if (rows > 0 && lastPairs > 0)
-            LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dHalfStart.p, dPairI.p, dPairJ.p);
+            LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, dPairI.p, dPairJ.p);
     }
 
     void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
@@ -556,22 +594,24 @@ struct Engine : public EngineBase {
             dFrac.ensure(20*(size_t) n);
             LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
             CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
-            if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
+            if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, rows, (const int*) nullptr, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
             stageEnd();
             reciprocalPass();
             stageBegin(MPIDB200_STAGE_FIXED_GATHER);
-            if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhi.p);
+            if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhi.p);
             stageEnd();
             backToMain();
         }
         stageBegin(MPIDB200_STAGE_FIXED_REAL);
-        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
-        if (rows > 0) {
-            if (pme) LAUNCH((k_fixed_field<real, true>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
-            else LAUNCH((k_fixed_field<real, false>), blocksFor((long long) rows*MPID_LANES, 256), 256, P, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
+        // the field is consumed at polarizable sites only; everything else stays zero
+        CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
+        const int* polRows = dPolList.p + polBegin;
+        if (numPol > 0) {
+            if (pme) LAUNCH((k_fixed_field<real, true>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
+            else LAUNCH((k_fixed_field<real, false>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
             if (!hSpPartner.empty())
                 LAUNCH((k_special_field<0>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
-                       dCartD.p, dDampThole.p, (const double*) nullptr, dField.p, (double*) nullptr);
+                       dCartD.p, dDampThole.p, dFlagS.p, (const double*) nullptr, dField.p, (double*) nullptr);
         }
         if (pme) joinPme();
         if (rows > 0 && pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
@@ -587,45 +627,48 @@ struct Engine : public EngineBase {
         const int rows = P.rowEnd - P.rowBegin;
         size_t G = (size_t) grid[0]*grid[1]*grid[2];
         dIfield.ensure(3*(size_t) n);
+        const int* polRows = dPolList.p + polBegin;
         if (pme) {
             forkPme();
             stageBegin(MPIDB200_STAGE_IND_SPREAD);
             CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
-            if (rows > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) rows*6, 192), 192, P, dPosS.p, (const real*) nullptr, dMu.p, dGrid.p);
+            if (numPol > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) numPol*6, 192), 192, P, numPol, polRows, dPosS.p, (const real*) nullptr, dMu.p, dGrid.p);
             stageEnd();
             reciprocalPass();
             stageBegin(MPIDB200_STAGE_IND_GATHER);
-            if (rows > 0) {
-                if (level == 1) LAUNCH((k_gather<real, 1>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
-                else if (level == 2) LAUNCH((k_gather<real, 2>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
-                else LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
+            if (level == 4) {
+                if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhidp.p);
+            } else if (numPol > 0) {
+                // solver iterations need the reciprocal field (and its gradient for OPT) at polarizable sites only
+                if (level == 1) LAUNCH((k_gather<real, 1>), blocksFor(numPol, 128), 128, P, numPol, polRows, dPosS.p, dGrid.p, dPhidp.p);
+                else LAUNCH((k_gather<real, 2>), blocksFor(numPol, 128), 128, P, numPol, polRows, dPosS.p, dGrid.p, dPhidp.p);
             }
             stageEnd();
             backToMain();
         }
         if (!realSpace) { if (pme) joinPme(); return; }
         stageBegin(MPIDB200_STAGE_IND_REAL);
-        if (numRanks > 1) CUDA_CHECK(cudaMemsetAsync(dIfield.p, 0, 3*(size_t) n*sizeof(double), cur));
-        if (rows > 0) {
-            const int nb = blocksFor((long long) rows*MPID_LANES, 256);
+        CUDA_CHECK(cudaMemsetAsync(dIfield.p, 0, 3*(size_t) n*sizeof(double), cur));
+        if (numPol > 0) {
+            const int nb = blocksFor((long long) numPol*MPID_LANES, 256);
             if (grad) {
-                if (pme) LAUNCH((k_induced_field<real, true, true>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, grad);
-                else LAUNCH((k_induced_field<real, false, true>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, grad);
+                if (pme) LAUNCH((k_induced_field<real, true, true>), nb, 256, P, numPol, polRows, dPosS.p, dMud.p, dPolCount.p, dPolNbr.p, dIfield.p, grad);
+                else LAUNCH((k_induced_field<real, false, true>), nb, 256, P, numPol, polRows, dPosS.p, dMud.p, dPolCount.p, dPolNbr.p, dIfield.p, grad);
             } else {
-                if (pme) LAUNCH((k_induced_field<real, true, false>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, (double*) nullptr);
-                else LAUNCH((k_induced_field<real, false, false>), nb, 256, P, dPosS.p, dMud.p, dCounts.p, dNbr.p, dIfield.p, (double*) nullptr);
+                if (pme) LAUNCH((k_induced_field<real, true, false>), nb, 256, P, numPol, polRows, dPosS.p, dMud.p, dPolCount.p, dPolNbr.p, dIfield.p, (double*) nullptr);
+                else LAUNCH((k_induced_field<real, false, false>), nb, 256, P, numPol, polRows, dPosS.p, dMud.p, dPolCount.p, dPolNbr.p, dIfield.p, (double*) nullptr);
             }
             if (!hSpPartner.empty()) {
                 if (grad) LAUNCH((k_special_field<2>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
-                                 dCartD.p, dDampThole.p, dMu.p, dIfield.p, grad);
+                                 dCartD.p, dDampThole.p, dFlagS.p, dMu.p, dIfield.p, grad);
                 else LAUNCH((k_special_field<1>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
-                            dCartD.p, dDampThole.p, dMu.p, dIfield.p, (double*) nullptr);
+                            dCartD.p, dDampThole.p, dFlagS.p, dMu.p, dIfield.p, (double*) nullptr);
             }
         }
         if (pme) joinPme();
-        if (rows > 0 && pme) {
-            if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, grad);
-            else LAUNCH((k_induced_finish<real, false>), blocksFor(rows, 256), 256, P, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
+        if (numPol > 0 && pme) {
+            if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, grad);
+            else LAUNCH((k_induced_finish<real, false>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
         }
         // the per-iteration collective of the partitioned solver: partial induced fields -> full field
         allReduce(dIfield.p, 3*(size_t) n, NCCL_FLOAT64);
@@ -748,6 +791,7 @@ struct Engine : public EngineBase {
         if (!haveBox) throw std::runtime_error("mpidb200: periodic box vectors have not been set");
         CUDA_CHECK(cudaSetDevice(cfg.device));
         launches = 0;
+        lastPosDevice = dPosIn;
         memset(stageMs, 0, sizeof(stageMs));
         const bool pme = P.method == PME;
         P.numRanks = numRanks; P.rank = rank;
@@ -770,7 +814,7 @@ struct Engine : public EngineBase {
             if (pme && !dipolesOnly && rows > 0) {
                 // the converged dipoles' reciprocal potential is still on the grid: fetch all 35 derivatives
                 stageBegin(MPIDB200_STAGE_IND_GATHER);
-                LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, dPosS.p, dGrid.p, dPhidp.p);
+                LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhidp.p);
                 stageEnd();
             }
         } else {
@@ -792,13 +836,15 @@ struct Engine : public EngineBase {
             backToMain();
         }
         stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
-        if (lastPairs > 0) {
-            const int nb = blocksFor(lastPairs, 128);
-#define ES_LAUNCH(EW, MU) LAUNCH((k_electrostatics<real, EW, MU>), nb, 128, P, lastPairs, dPairI.p, dPairJ.p, dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p)
-            if (pme) { if (mutual) ES_LAUNCH(true, true); else ES_LAUNCH(true, false); }
-            else { if (mutual) ES_LAUNCH(false, true); else ES_LAUNCH(false, false); }
+        // four pair classes (full/simple site on either side), each with its own specialised instantiation
+#define ES_LAUNCH(EW, MU, A, B, T) { const long long cnt = typeBegin[T+1] - typeBegin[T]; \
+            if (cnt > 0) LAUNCH((k_electrostatics<real, EW, MU, A, B>), blocksFor(cnt, 128), 128, P, cnt, dPairI.p + typeBegin[T], dPairJ.p + typeBegin[T], \
+                                dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p); }
+#define ES_ALL(EW, MU) { ES_LAUNCH(EW, MU, false, false, 0) ES_LAUNCH(EW, MU, false, true, 1) ES_LAUNCH(EW, MU, true, false, 2) ES_LAUNCH(EW, MU, true, true, 3) }
+        if (pme) { if (mutual) ES_ALL(true, true) else ES_ALL(true, false) }
+        else { if (mutual) ES_ALL(false, true) else ES_ALL(false, false) }
+#undef ES_ALL
 #undef ES_LAUNCH
-        }
         stageEnd();
         if (forked) joinPme();
 
@@ -954,7 +1000,7 @@ struct Engine : public EngineBase {
 
     long long getPairList(long long cap, int* pi, int* pj, int* pc) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        long long total = lastPairs + (long long) hSpLo.size();
+        long long total = lastPairs + (long long) hSpLo.size();   // upper bound
         if (!pi) return total;
         std::vector<unsigned> hi(lastPairs), hj(lastPairs);
         std::vector<int> order(n);
@@ -968,8 +1014,18 @@ struct Engine : public EngineBase {
             int a = order[hi[p]], b = order[hj[p] & MPID_JMASK];
             pi[k] = std::min(a, b); pj[k] = std::max(a, b); pc[k] = 0;
         }
-        // the static covalently scaled pairs (the kernels apply the cutoff test to them at run time)
-        for (size_t s = 0; s < hSpLo.size() && k < cap; s++, k++) { pi[k] = hSpLo[s]; pj[k] = hSpHi[s]; pc[k] = hSpPairClass[s]; }
+        // the static covalently scaled pairs, with the cutoff test their kernels apply at run time
+        std::vector<double> pos(3*(size_t) n);
+        if (lastPosDevice) CUDA_CHECK(cudaMemcpy(pos.data(), lastPosDevice, pos.size()*sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t s = 0; s < hSpLo.size() && k < cap; s++) {
+            int lo = hSpLo[s], hi = hSpHi[s];
+            if (P.method == PME) {
+                double dx = pos[3*hi] - pos[3*lo], dy = pos[3*hi+1] - pos[3*lo+1], dz = pos[3*hi+2] - pos[3*lo+2];
+                periodicDelta(P.box, dx, dy, dz);
+                if (dist2Exact(dx, dy, dz) > P.cutoff2) continue;
+            }
+            pi[k] = lo; pj[k] = hi; pc[k] = hSpPairClass[s]; k++;
+        }
         return k;
     }
 

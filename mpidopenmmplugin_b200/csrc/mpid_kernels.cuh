@@ -118,7 +118,7 @@ __global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, co
                             double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso,
                             double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud,
                             const int* __restrict__ inv, const int* __restrict__ spStart, const int* __restrict__ spPartner,
-                            int4* __restrict__ spSorted) {
+                            int4* __restrict__ spSorted, int* __restrict__ flagS) {
     int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= P.n) return;
     int o = order[s];
@@ -161,12 +161,28 @@ __global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, co
     for (int k = 0; k < 6; k++) alphaLab[6*(size_t) s + k] = a.alpha[k];
     aniso[s] = a.aniso;
     double x = poswOrig[3*o], y = poswOrig[3*o+1], z = poswOrig[3*o+2];
+    // site class: bit 0 = polarizable (non-zero lab polarizability), bit 1 = "simple" (charge only, never polarized)
+    bool pol = false, perm = false;
+    for (int k = 0; k < 6; k++) pol = pol || (a.alpha[k] != 0.0);
+    for (int k = 1; k < 16; k++) perm = perm || (pk[k] != 0.0);
+    const int flag = (pol ? 1 : 0) | ((!pol && !perm) ? 2 : 0);
+    flagS[s] = flag;
     posS[s] = make_double4(x, y, z, 0.0);
-    posF[s] = make_float4((float) x, (float) y, (float) z, 0.f);
+    posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
     dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
     typename Real4<real>::type m;
     m.x = 0; m.y = 0; m.z = 0; m.w = pp.damp[o] != 0.0 ? (real) (1.0/pp.damp[o]) : real(0);   // inverse damping factor
     mud[s] = m;
+}
+
+// polarizable-site bookkeeping: polFlag[s] = flag & 1 (scanned into polRank), polList[polRank[s]] = s
+__global__ void k_pol_flags(int n, const int* __restrict__ flagS, int* __restrict__ polFlag) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s <= n) polFlag[s] = s < n ? (flagS[s] & 1) : 0;
+}
+__global__ void k_pol_list(int n, const int* __restrict__ flagS, const int* __restrict__ polRank, int* __restrict__ polList) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s < n && (flagS[s] & 1)) polList[polRank[s]] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -187,7 +203,10 @@ __global__ void __launch_bounds__(256)
 k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __restrict__ posOrig,
                 const int* __restrict__ order, const int* __restrict__ sortedKey, const int* __restrict__ cellStart,
                 const int* __restrict__ spStart, const int* __restrict__ spPartner, const int4* __restrict__ spSorted,
-                unsigned* __restrict__ nbr, unsigned* __restrict__ counts, unsigned* __restrict__ maxCount) {
+                const int* __restrict__ polRank, int polBegin,
+                unsigned* __restrict__ nbr, uint4* __restrict__ counts, unsigned* __restrict__ polNbr, unsigned* __restrict__ polCount,
+                unsigned* __restrict__ maxCount) {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x*blockDim.x + threadIdx.x)/32;
     const int i = P.rowBegin + row;
@@ -199,7 +218,7 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
     int sp0 = 0, sp1 = 0;
     if (spMany) { sp0 = spStart[oi]; sp1 = spStart[oi+1]; }
     const bool pme = P.method == PME;
-    int cx = 0, cy = 0, cz = 0;
+    int cx, cy, cz;
     {
         int key = sortedKey[i];
         cz = key % P.ncell[2]; key /= P.ncell[2];
@@ -212,98 +231,156 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
     const float ccx = (float) P.box.c[0], ccy = (float) P.box.c[1], ccz = (float) P.box.c[2];
     const unsigned cap = (unsigned) P.nbrCap;
     unsigned* base = nbr + (size_t) row*cap;
-    unsigned nUp = 0, nLow = 0;
+    unsigned nUp = 0, nLow = 0, nUpSimple = 0, nPol = 0;
+    const bool iPol = ((int) pi.w & 1) != 0;
+    unsigned* polBase = polNbr + (iPol ? (size_t) (polRank[i] - polBegin)*cap : 0);
     const int Rx = P.reach[0], Ry = P.reach[1], Rz = P.reach[2];
-    for (int dx = -Rx; dx <= Rx; dx++) {
-        int X = cx + dx, wx = 0;
+    const int wy1 = 2*Ry + 1, ncols = (2*Rx + 1)*wy1;      // <= 25 neighbour columns, one per lane
+    // Lane l describes column l: its (wrapped) cell column and the periodic image that wrap implies.
+    int colBase = 0, wx = 0, wy = 0;
+    if (lane < ncols) {
+        int X = cx + lane/wy1 - Rx, Y = cy + lane % wy1 - Ry;
         if (X < 0) { X += P.ncell[0]; wx = -1; } else if (X >= P.ncell[0]) { X -= P.ncell[0]; wx = 1; }
-        for (int dy = -Ry; dy <= Ry; dy++) {
-            int Y = cy + dy, wy = 0;
-            if (Y < 0) { Y += P.ncell[1]; wy = -1; } else if (Y >= P.ncell[1]) { Y -= P.ncell[1]; wy = 1; }
-            const int colBase = (X*P.ncell[1] + Y)*P.ncell[2];
-            // the z cells cz-Rz .. cz+Rz are contiguous in the sorted order except where they wrap
-            for (int seg = 0; seg < 3; seg++) {
-                int z0, z1, wz;
-                if (seg == 0) { z0 = max(cz - Rz, 0); z1 = min(cz + Rz, P.ncell[2] - 1); wz = 0; }
-                else if (seg == 1) { if (cz - Rz >= 0) continue; z0 = cz - Rz + P.ncell[2]; z1 = P.ncell[2] - 1; wz = -1; }
-                else { if (cz + Rz < P.ncell[2]) continue; z0 = 0; z1 = cz + Rz - P.ncell[2]; wz = 1; }
-                const int jb = cellStart[colBase + z0], je = cellStart[colBase + z1 + 1];
-                // image of the neighbour cell: r_j(image) = r_j + wx a + wy b + wz c
-                const float shx = wx*ax + wy*bx + wz*ccx, shy = wy*by + wz*ccy, shz = wz*ccz;
-                const unsigned segCode = (unsigned) ((1 - wx)*9 + (1 - wy)*3 + (1 - wz));
-                for (int j0 = jb; j0 < je; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool in = (j < je) && (j != i);
-                    unsigned code = segCode;
-                    if (in && pme) {
-                        const float4 pj = posF[j];
-                        float ddx = pj.x - pi.x, ddy = pj.y - pi.y, ddz = pj.z - pi.z;
-                        if (ROUND) {
-                            float sz = floorf(ddz*rcz + 0.5f);
-                            ddx -= ccx*sz; ddy -= ccy*sz; ddz -= ccz*sz;
-                            float sy = floorf(ddy*rby + 0.5f);
-                            ddx -= bx*sy; ddy -= by*sy;
-                            float sx = floorf(ddx*rax + 0.5f);
-                            ddx -= ax*sx;
-                            code = (unsigned) (((int) sx + 1)*9 + ((int) sy + 1)*3 + ((int) sz + 1));
-                        } else {
-                            ddx += shx; ddy += shy; ddz += shz;
-                        }
-                        const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
-                        if (r2 > rcHi2) in = false;
-                        else if (r2 >= rcLo2) {
-                            // borderline: the oracle's test, bit for bit, on the raw positions
-                            const int oj = order[j];
-                            const int lo = min(oi, oj), hi = max(oi, oj);
-                            double ex = posOrig[3*hi] - posOrig[3*lo], ey = posOrig[3*hi+1] - posOrig[3*lo+1], ez = posOrig[3*hi+2] - posOrig[3*lo+2];
-                            periodicDelta(P.box, ex, ey, ez);
-                            in = !(dist2Exact(ex, ey, ez) > P.cutoff2);
-                        }
-                        if (code > 26u) in = false;   // cannot happen for wrapped positions; keeps the table index safe
-                    }
-                    if (j == sp.x || j == sp.y || j == sp.z || j == sp.w) in = false;
-                    if (spMany && in) {
-                        const int oj = order[j];
-                        for (int k = sp0; k < sp1; k++) if (spPartner[k] == oj) in = false;
-                    }
-                    const bool upper = in && (j > i);
-                    const unsigned maskU = __ballot_sync(0xffffffffu, upper);
-                    const unsigned maskL = __ballot_sync(0xffffffffu, in && !upper);
-                    const unsigned cu = __popc(maskU), cl = __popc(maskL);
-                    if (nUp + nLow + cu + cl <= cap) {
-                        const unsigned lt = (1u << lane) - 1u;
-                        const unsigned entry = (unsigned) j | (code << MPID_CODE_SHIFT);
-                        if (upper) base[nUp + __popc(maskU & lt)] = entry;
-                        else if (in) base[cap - 1 - (nLow + __popc(maskL & lt))] = entry;
-                    }
-                    nUp += cu; nLow += cl;
-                }
+        if (Y < 0) { Y += P.ncell[1]; wy = -1; } else if (Y >= P.ncell[1]) { Y -= P.ncell[1]; wy = 1; }
+        colBase = (X*P.ncell[1] + Y)*P.ncell[2];
+    }
+    // Two flat passes over the concatenated candidate ranges of all columns: pass 0 the z cells that need no wrap
+    // (contiguous in the sorted order), pass 1 the wrapped remainder.  Flattening keeps all 32 lanes busy.
+    for (int pass = 0; pass < 2; pass++) {
+        int z0 = 0, z1 = -1, wz = 0;
+        if (pass == 0) { z0 = max(cz - Rz, 0); z1 = min(cz + Rz, P.ncell[2] - 1); }
+        else if (cz - Rz < 0) { z0 = cz - Rz + P.ncell[2]; z1 = P.ncell[2] - 1; wz = -1; }
+        else if (cz + Rz >= P.ncell[2]) { z0 = 0; z1 = cz + Rz - P.ncell[2]; wz = 1; }
+        if (z1 < z0) continue;
+        int jb = 0, len = 0;
+        if (lane < ncols) { jb = cellStart[colBase + z0]; len = cellStart[colBase + z1 + 1] - jb; }
+        // image of the column: r_j(image) = r_j + wx a + wy b + wz c
+        const float shx = wx*ax + wy*bx + wz*ccx, shy = wy*by + wz*ccy, shz = wz*ccz;
+        const unsigned colCode = (unsigned) ((1 - wx)*9 + (1 - wy)*3 + (1 - wz));
+        int end = len;                                   // inclusive scan of the range lengths
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL, end, off);
+            if (lane >= off) end += t;
+        }
+        const int total = __shfl_sync(FULL, end, 31);
+        const int begin = end - len;
+        for (int base0 = 0; base0 < total; base0 += 32) {
+            const int idx = base0 + lane;
+            // r = first lane whose inclusive end exceeds idx
+            int r = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int t = __shfl_sync(FULL, end, r + step - 1);
+                if (t <= idx) r += step;
             }
+            r = min(r, 31);
+            const int rjb = __shfl_sync(FULL, jb, r), rbegin = __shfl_sync(FULL, begin, r);
+            const float rsx = __shfl_sync(FULL, shx, r), rsy = __shfl_sync(FULL, shy, r), rsz = __shfl_sync(FULL, shz, r);
+            unsigned code = __shfl_sync(FULL, colCode, r);
+            const int j = rjb + (idx - rbegin);
+            bool in = (idx < total) && (j != i);
+            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) pj = posF[j];
+            if (in && pme) {
+                float ddx = pj.x - pi.x, ddy = pj.y - pi.y, ddz = pj.z - pi.z;
+                if (ROUND) {
+                    float sz = floorf(ddz*rcz + 0.5f);
+                    ddx -= ccx*sz; ddy -= ccy*sz; ddz -= ccz*sz;
+                    float sy = floorf(ddy*rby + 0.5f);
+                    ddx -= bx*sy; ddy -= by*sy;
+                    float sx = floorf(ddx*rax + 0.5f);
+                    ddx -= ax*sx;
+                    code = (unsigned) (((int) sx + 1)*9 + ((int) sy + 1)*3 + ((int) sz + 1));
+                } else {
+                    ddx += rsx; ddy += rsy; ddz += rsz;
+                }
+                const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
+                if (r2 > rcHi2) in = false;
+                else if (r2 >= rcLo2) {
+                    // borderline: the oracle's test, bit for bit, on the raw positions
+                    const int oj = order[j];
+                    const int lo = min(oi, oj), hi = max(oi, oj);
+                    double ex = posOrig[3*hi] - posOrig[3*lo], ey = posOrig[3*hi+1] - posOrig[3*lo+1], ez = posOrig[3*hi+2] - posOrig[3*lo+2];
+                    periodicDelta(P.box, ex, ey, ez);
+                    in = !(dist2Exact(ex, ey, ez) > P.cutoff2);
+                }
+                if (code > 26u) in = false;   // cannot happen for wrapped positions; keeps the table index safe
+            }
+            if (!pme) code = 13;
+            if (j == sp.x || j == sp.y || j == sp.z || j == sp.w) in = false;
+            if (spMany && in) {
+                const int oj = order[j];
+                for (int k = sp0; k < sp1; k++) if (spPartner[k] == oj) in = false;
+            }
+            const int jflag = (int) pj.w;
+            const bool upper = in && (j > i);
+            const unsigned maskU = __ballot_sync(FULL, upper);
+            const unsigned maskL = __ballot_sync(FULL, in && !upper);
+            const unsigned maskS = __ballot_sync(FULL, upper && (jflag & 2));
+            const unsigned maskP = __ballot_sync(FULL, in && iPol && (jflag & 1));
+            const unsigned cu = __popc(maskU), cl = __popc(maskL);
+            if (nUp + nLow + cu + cl <= cap) {
+                const unsigned lt = (1u << lane) - 1u;
+                const unsigned entry = (unsigned) j | (code << MPID_CODE_SHIFT);
+                if (upper) base[nUp + __popc(maskU & lt)] = entry;
+                else if (in) base[cap - 1 - (nLow + __popc(maskL & lt))] = entry;
+                if (in && iPol && (jflag & 1)) polBase[nPol + __popc(maskP & lt)] = entry;
+            }
+            nUp += cu; nLow += cl; nUpSimple += __popc(maskS); nPol += __popc(maskP);
         }
     }
     if (lane == 0) {
-        counts[2*(size_t) row] = nUp; counts[2*(size_t) row + 1] = nLow;
+        counts[row] = make_uint4(nUp, nLow, nUpSimple, nPol);
+        if (iPol) polCount[polRank[i] - polBegin] = nPol;
         atomicMax(maxCount, nUp + nLow);
     }
 }
 
-// upper counts -> (halfCount) for the scan that places each atom's run in the flat half list
-__global__ void k_half_counts(int rows, const unsigned* __restrict__ counts, unsigned* __restrict__ halfCount) {
+// Pair classes of the energy kernel: type = 2*simple(i) + simple(j).  typeCount[t*(rows+1) + r] = number of
+// upper neighbours of row r that fall in class t (scanned per class to place the runs of the four flat lists).
+__global__ void k_half_counts(DevParams P, int rows, const uint4* __restrict__ counts, const int* __restrict__ flagS,
+                              unsigned* __restrict__ typeCount) {
     const int r = blockIdx.x*blockDim.x + threadIdx.x;
-    if (r <= rows) halfCount[r] = r < rows ? counts[2*(size_t) r] : 0u;
+    if (r > rows) return;
+    unsigned c[4] = {0u, 0u, 0u, 0u};
+    if (r < rows) {
+        const uint4 q = counts[r];
+        const int si = (flagS[P.rowBegin + r] >> 1) & 1;
+        c[2*si] = q.x - q.z;
+        c[2*si + 1] = q.z;
+    }
+    for (int t = 0; t < 4; t++) typeCount[(size_t) t*(rows + 1) + r] = c[t];
 }
-// flat i-major half list for the energy kernel (one warp per atom copies its upper run)
-__global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, const unsigned* __restrict__ counts,
-                               const unsigned* __restrict__ halfStart, unsigned* __restrict__ pairI, unsigned* __restrict__ pairJ) {
+// four flat i-major half lists (one warp per atom distributes its upper run by the class of j)
+__global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, const uint4* __restrict__ counts,
+                               const float4* __restrict__ posF, const unsigned* __restrict__ typeStart, int rows,
+                               unsigned listBase1, unsigned listBase2, unsigned listBase3,
+                               unsigned* __restrict__ pairI, unsigned* __restrict__ pairJ) {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x*blockDim.x + threadIdx.x)/32;
-    if (row >= P.rowEnd - P.rowBegin) return;
-    const unsigned nUp = counts[2*(size_t) row];
-    const unsigned dst = halfStart[row];
+    if (row >= rows) return;
+    const int i = P.rowBegin + row;
+    const unsigned nUp = counts[row].x;
+    const int si = ((int) posF[i].w >> 1) & 1;
+    const unsigned bases[4] = {0u, listBase1, listBase2, listBase3};
+    unsigned dstF = bases[2*si] + typeStart[(size_t) (2*si)*(rows + 1) + row];          // j full
+    unsigned dstS = bases[2*si + 1] + typeStart[(size_t) (2*si + 1)*(rows + 1) + row];  // j simple
     const unsigned* base = nbr + (size_t) row*P.nbrCap;
-    for (unsigned k = lane; k < nUp; k += 32) {
-        pairI[dst + k] = (unsigned) (P.rowBegin + row);
-        pairJ[dst + k] = base[k];
+    for (unsigned k0 = 0; k0 < nUp; k0 += 32) {
+        const unsigned k = k0 + lane;
+        const bool valid = k < nUp;
+        unsigned e = 0; bool sj = false;
+        if (valid) { e = base[k]; sj = (((int) posF[e & MPID_JMASK].w >> 1) & 1) != 0; }
+        const unsigned mF = __ballot_sync(FULL, valid && !sj), mS = __ballot_sync(FULL, valid && sj);
+        const unsigned lt = (1u << lane) - 1u;
+        if (valid) {
+            const unsigned d = sj ? dstS + __popc(mS & lt) : dstF + __popc(mF & lt);
+            pairI[d] = (unsigned) i;
+            pairJ[d] = e;
+        }
+        dstF += __popc(mF); dstS += __popc(mS);
     }
 }
 
@@ -323,17 +400,21 @@ __device__ __forceinline__ void pairDelta(const DevParams& P, const double4& pi,
 // Permanent-multipole field of the ordinary pairs.   reference stage: :911-934 + :2812-2920
 template <typename real, bool EWALD>
 __global__ void __launch_bounds__(256)
-k_fixed_field(DevParams P, const double4* __restrict__ posS, const real* __restrict__ cart,
+k_fixed_field(DevParams P, int numPol, const int* __restrict__ polList, const double4* __restrict__ posS, const real* __restrict__ cart,
               const typename Real4<real>::type* __restrict__ mud,
-              const unsigned* __restrict__ counts, const unsigned* __restrict__ nbr, double* __restrict__ field) {
+              const uint4* __restrict__ counts, const unsigned* __restrict__ nbr, double* __restrict__ field) {
+    // only polarizable sites need the permanent field (mu = alpha.E); polList holds this rank's polarizable rows
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    const int i = P.rowBegin + t/MPID_LANES;
+    const int rp = t/MPID_LANES;
     const int sub = t % MPID_LANES;
+    const bool act = rp < numPol;
+    const int i = act ? polList[rp] : 0;
     double ex = 0, ey = 0, ez = 0;
-    if (i < P.rowEnd) {
+    if (act) {
         const double4 pi = posS[i];
         const real invDampI = mud[i].w;
-        const unsigned nUp = counts[2*(size_t) (i - P.rowBegin)], nAll = nUp + counts[2*(size_t) (i - P.rowBegin) + 1];
+        const uint4 cnt = counts[i - P.rowBegin];
+        const unsigned nUp = cnt.x, nAll = cnt.x + cnt.y;
         const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
         for (unsigned k = sub; k < nAll; k += MPID_LANES) {
             const unsigned e = k < nUp ? base[k] : base[P.nbrCap - 1 - (k - nUp)];
@@ -361,29 +442,34 @@ k_fixed_field(DevParams P, const double4* __restrict__ posS, const real* __restr
         ey += __shfl_xor_sync(0xffffffffu, ey, off);
         ez += __shfl_xor_sync(0xffffffffu, ez, off);
     }
-    if (i < P.rowEnd && sub == 0) { field[3*(size_t) i] = ex; field[3*(size_t) i+1] = ey; field[3*(size_t) i+2] = ez; }
+    if (act && sub == 0) { field[3*(size_t) i] = ex; field[3*(size_t) i+1] = ey; field[3*(size_t) i+2] = ez; }
 }
 
 // Field (and, for the extrapolated solver, field gradient) of the induced dipoles, ordinary pairs.
 //   reference stage: :4084-4088 + :4161-4281 (PME), :1037-1048 + :962-1035 (no cutoff)
 template <typename real, bool EWALD, bool GRAD>
 __global__ void __launch_bounds__(256)
-k_induced_field(DevParams P, const double4* __restrict__ posS, const typename Real4<real>::type* __restrict__ mud,
-                const unsigned* __restrict__ counts, const unsigned* __restrict__ nbr,
+k_induced_field(DevParams P, int numPol, const int* __restrict__ polList, const double4* __restrict__ posS,
+                const typename Real4<real>::type* __restrict__ mud,
+                const unsigned* __restrict__ polCount, const unsigned* __restrict__ polNbr,
                 double* __restrict__ field, double* __restrict__ grad) {
+    // induced dipoles live on polarizable sites only and only polarizable sites use their field, so this kernel
+    // walks the polarizable x polarizable neighbour list (mu = 0 elsewhere contributes exactly nothing)
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    const int i = P.rowBegin + t/MPID_LANES;
+    const int rp = t/MPID_LANES;
     const int sub = t % MPID_LANES;
+    const bool act = rp < numPol;
+    const int i = act ? polList[rp] : 0;
     // per-lane partial sums stay in `real` (<= ~30 terms each); lanes are combined in double below
     real ax_ = 0, ay_ = 0, az_ = 0;
     real ga[6] = {0, 0, 0, 0, 0, 0};
-    if (i < P.rowEnd) {
+    if (act) {
         const double4 pi = posS[i];
         const real invDampI = mud[i].w;
-        const unsigned nUp = counts[2*(size_t) (i - P.rowBegin)], nAll = nUp + counts[2*(size_t) (i - P.rowBegin) + 1];
-        const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        const unsigned nAll = polCount[rp];
+        const unsigned* base = polNbr + (size_t) rp*P.nbrCap;
         for (unsigned k = sub; k < nAll; k += MPID_LANES) {
-            const unsigned e = k < nUp ? base[k] : base[P.nbrCap - 1 - (k - nUp)];
+            const unsigned e = base[k];
             const unsigned j = e & MPID_JMASK;
             real dx, dy, dz;
             pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
@@ -409,7 +495,7 @@ k_induced_field(DevParams P, const double4* __restrict__ posS, const typename Re
             for (int q = 0; q < 6; q++) g[q] += __shfl_xor_sync(0xffffffffu, g[q], off);
         }
     }
-    if (i < P.rowEnd && sub == 0) {
+    if (act && sub == 0) {
         field[3*(size_t) i] = ex; field[3*(size_t) i+1] = ey; field[3*(size_t) i+2] = ez;
         if (GRAD) {
 #pragma unroll
@@ -425,10 +511,11 @@ template <int MODE>
 __global__ void k_special_field(DevParams P, const int* __restrict__ order, const int* __restrict__ inv,
                                 const double* __restrict__ posOrig, const int* __restrict__ spStart,
                                 const int* __restrict__ spPartner, const int* __restrict__ spClass,
-                                const double* __restrict__ cartD, const double2* __restrict__ dampTholeD,
+                                const double* __restrict__ cartD, const double2* __restrict__ dampTholeD, const int* __restrict__ flagS,
                                 const double* __restrict__ mu, double* __restrict__ field, double* __restrict__ grad) {
     const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= P.rowEnd) return;
+    if (!(flagS[s] & 1)) return;            // fields are only consumed at polarizable sites
     const int o = order[s];
     const int k0 = spStart[o], k1 = spStart[o+1];
     if (k1 == k0) return;
@@ -469,7 +556,7 @@ __global__ void k_special_field(DevParams P, const int* __restrict__ order, cons
 // Stage 4: pair energy / force / torque over the i-major half list (one thread per pair)
 // ---------------------------------------------------------------------------------------------------
 //   reference stage: :4932-4946 + :4335-4920 (PME), :2140-2158 + :1331-1893 (no cutoff)
-template <typename real, bool EWALD, bool MUTUAL>
+template <typename real, bool EWALD, bool MUTUAL, bool SI, bool SJ>
 __global__ void __launch_bounds__(128)
 k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ pairI, const unsigned* __restrict__ pairJ,
                  const double4* __restrict__ posS, const real* __restrict__ pk, const typename Real4<real>::type* __restrict__ mud,
@@ -502,13 +589,13 @@ k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ p
         real uI[3] = {mi.x, mi.y, mi.z}, uJ[3] = {mj.x, mj.y, mj.z};
         const real r2 = dx*dx + dy*dy + dz*dz;
         const real dampI = mi.w != real(0) ? real(1)/mi.w : real(0), dampJ = mj.w != real(0) ? real(1)/mj.w : real(0);
-        e = (double) pairElectrostatics<real, EWALD, MUTUAL>(qi, qj, uI, uJ, dampI, dampJ, real(0), real(0), aniso[i] != 0, aniso[j] != 0,
+        e = (double) pairElectrostatics<real, EWALD, MUTUAL, SI, SJ>(qi, qj, uI, uJ, dampI, dampJ, real(0), real(0), aniso[i] != 0, aniso[j] != 0,
                                                            dx, dy, dz, r2, (real) P.alpha, (real) P.defaultThole, real(1), real(1), f, ti, tj);
     }
-    // j side: scattered fixed-point atomics
+    // j side: scattered fixed-point atomics (a simple site feels no torque)
     if (active) {
         atomicAddFixed(&force[3*(size_t) j], (double) f[0]); atomicAddFixed(&force[3*(size_t) j+1], (double) f[1]); atomicAddFixed(&force[3*(size_t) j+2], (double) f[2]);
-        atomicAddFixed(&torque[3*(size_t) j], (double) tj[0]); atomicAddFixed(&torque[3*(size_t) j+1], (double) tj[1]); atomicAddFixed(&torque[3*(size_t) j+2], (double) tj[2]);
+        if (!SJ) { atomicAddFixed(&torque[3*(size_t) j], (double) tj[0]); atomicAddFixed(&torque[3*(size_t) j+1], (double) tj[1]); atomicAddFixed(&torque[3*(size_t) j+2], (double) tj[2]); }
     }
     // i side: pairs of one i are contiguous, so a segmented warp reduction leaves one atomic per run
     double v[6] = {-(double) f[0], -(double) f[1], -(double) f[2], (double) ti[0], (double) ti[1], (double) ti[2]};
@@ -525,7 +612,7 @@ k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ p
     const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
     if (active && (lane == 0 || iprev != i)) {
         atomicAddFixed(&force[3*(size_t) i], v[0]); atomicAddFixed(&force[3*(size_t) i+1], v[1]); atomicAddFixed(&force[3*(size_t) i+2], v[2]);
-        atomicAddFixed(&torque[3*(size_t) i], v[3]); atomicAddFixed(&torque[3*(size_t) i+1], v[4]); atomicAddFixed(&torque[3*(size_t) i+2], v[5]);
+        if (!SI) { atomicAddFixed(&torque[3*(size_t) i], v[3]); atomicAddFixed(&torque[3*(size_t) i+1], v[4]); atomicAddFixed(&torque[3*(size_t) i+2], v[5]); }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
@@ -611,12 +698,13 @@ __device__ __forceinline__ void redLine6(double* p, const double* v) {
 //   reference: spreadFixedMultipolesOntoGrid (:3269-3327), spreadInducedDipolesOnGrid (:3532-3573)
 template <typename real, bool FIXED>
 __global__ void __launch_bounds__(192)
-k_spread(DevParams P, const double4* __restrict__ posS, const real* __restrict__ frac, const double* __restrict__ mu,
-         real* __restrict__ grid) {
+k_spread(DevParams P, int numRows, const int* __restrict__ rowList, const double4* __restrict__ posS, const real* __restrict__ frac,
+         const double* __restrict__ mu, real* __restrict__ grid) {
+    // rowList == nullptr: rows rowBegin .. rowBegin+numRows-1; otherwise the listed (polarizable) rows
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    const int s = P.rowBegin + t/6;
     const int ix = t % 6;
-    if (s >= P.rowEnd) return;
+    if (t/6 >= numRows) return;
+    const int s = rowList ? rowList[t/6] : P.rowBegin + t/6;
     const double4 p = posS[s];
     int ig[3]; double w[3];
     pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
@@ -693,9 +781,11 @@ __global__ void k_eterm_table(DevParams P, const double* __restrict__ modX, cons
 //   reference: computeFixedPotentialFromGrid (:3368-3530), computeInducedPotentialFromGrid (:3575-3737)
 template <typename real, int LEVEL>
 __global__ void __launch_bounds__(128)
-k_gather(DevParams P, const double4* __restrict__ posS, const real* __restrict__ grid, real* __restrict__ phi) {
-    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= P.rowEnd) return;
+k_gather(DevParams P, int numRows, const int* __restrict__ rowList, const double4* __restrict__ posS, const real* __restrict__ grid,
+         real* __restrict__ phi) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= numRows) return;
+    const int s = rowList ? rowList[t] : P.rowBegin + t;
     const double4 p = posS[s];
     int ig[3]; double w[3];
     pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
@@ -805,11 +895,12 @@ __global__ void k_fixed_mu(DevParams P, const double* __restrict__ alphaLab, con
 // Induced field: add the reciprocal part, the self term and (GRAD) the reciprocal field gradient.
 //   reference: :4046-4058, :4094-4129, :4133-4140
 template <typename real, bool GRAD>
-__global__ void k_induced_finish(DevParams P, const real* __restrict__ phidp, const double* __restrict__ mu,
-                                 double* __restrict__ field, double* __restrict__ grad) {
-    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= P.rowEnd) return;
+__global__ void k_induced_finish(DevParams P, int numPol, const int* __restrict__ polList, const real* __restrict__ phidp,
+                                 const double* __restrict__ mu, double* __restrict__ field, double* __restrict__ grad) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= numPol) return;
     if (P.method != PME) return;
+    const int s = polList[t];
     double rx, ry, rz;
     reciprocalFieldOf<real>(P, phidp, s, rx, ry, rz);
     field[3*(size_t) s]   += rx + P.selfFieldTerm*mu[3*(size_t) s];

@@ -569,7 +569,9 @@ struct PairParams {
 // tqI / tqJ are lab-frame torques.  U are the lab-frame induced dipoles.
 //   reference: calculatePmeDirectElectrostaticPairIxn (:4335-4920) and calculateElectrostaticPairIxn
 //   (:1331-1893); the no-cutoff routine is the alpha -> 0 limit (every bVec and X term vanishes).
-template <typename T, bool EWALD, bool MUTUAL>
+// SI / SJ ("simple" site): the atom carries a charge only -- no permanent dipole/quadrupole/octopole and no
+// induced dipole -- so every term that multiplies one of those vanishes identically and is compiled out.
+template <typename T, bool EWALD, bool MUTUAL, bool SI = false, bool SJ = false>
 MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* uJ,
                              T dampI, T dampJ, T tholeI, T tholeJ, bool anisoI, bool anisoJ,
                              T dx, T dy, T dz, T r2, T alphaEwald, T defaultThole, T mScale, T pScale,
@@ -594,13 +596,16 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
     V3<T> Y = cross(Z, X);
 
     T QI[16], QJ[16];
-    momentsToQI<T>(pkI, X, Y, Z, QI);
-    momentsToQI<T>(pkJ, X, Y, Z, QJ);
+    if (SI) { QI[0] = pkI[0]; for (int k = 1; k < 16; k++) QI[k] = T(0); } else momentsToQI<T>(pkI, X, Y, Z, QI);
+    if (SJ) { QJ[0] = pkJ[0]; for (int k = 1; k < 16; k++) QJ[k] = T(0); } else momentsToQI<T>(pkJ, X, Y, Z, QJ);
     // induced dipoles, with the factor 1/2 of the reference folded in (:4381-4401)
-    T UI[3], UJ[3];
-    {
-        V3<T> a = mk<T>(uI[0], uI[1], uI[2]), b = mk<T>(uJ[0], uJ[1], uJ[2]);
+    T UI[3] = {T(0), T(0), T(0)}, UJ[3] = {T(0), T(0), T(0)};
+    if (!SI) {
+        V3<T> a = mk<T>(uI[0], uI[1], uI[2]);
         UI[0] = T(0.5)*dot(Z, a); UI[1] = T(0.5)*dot(X, a); UI[2] = T(0.5)*dot(Y, a);
+    }
+    if (!SJ) {
+        V3<T> b = mk<T>(uJ[0], uJ[1], uJ[2]);
         UJ[0] = T(0.5)*dot(Z, b); UJ[1] = T(0.5)*dot(X, b); UJ[2] = T(0.5)*dot(Y, b);
     }
 
@@ -663,20 +668,29 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
     for (int i = 0; i < 16; i++) { Vij[i] = Vji[i] = VijR[i] = VjiR[i] = T(0); }
     Vijd[0] = Vijd[1] = Vijd[2] = Vjid[0] = Vjid[1] = Vjid[2] = T(0);
 
+    // A term "coef * QJ[k]" exists only if site J has that moment (k == 0, or J not simple); likewise for I and
+    // for the induced dipoles.  The indices are literals, so these tests fold at compile time.
+#define MPID_HASJ(k) (!SJ || (k) == 0)
+#define MPID_HASI(k) (!SI || (k) == 0)
     // same-rank block, component a
-#define MPID_SAME(a, E, D) { Vij[a] += (E)*QJ[a]; Vji[a] += (E)*QI[a]; VijR[a] += (D)*QJ[a]; VjiR[a] += (D)*QI[a]; }
+#define MPID_SAME(a, E, D) { if (MPID_HASJ(a)) { Vij[a] += (E)*QJ[a]; VijR[a] += (D)*QJ[a]; } \
+                             if (MPID_HASI(a)) { Vji[a] += (E)*QI[a]; VjiR[a] += (D)*QI[a]; } }
     // induced dipoles riding on a dipole-dipole block (slot k of the induced dipole)
-#define MPID_SAME_U(a, k, EU, DU) { Vij[a] += (EU)*UJ[k]; Vji[a] += (EU)*UI[k]; VijR[a] += (DU)*UJ[k]; VjiR[a] += (DU)*UI[k]; \
-                                    Vijd[k] += (EU)*QJ[a]; Vjid[k] += (EU)*QI[a]; }
+#define MPID_SAME_U(a, k, EU, DU) { if (!SJ) { Vij[a] += (EU)*UJ[k]; VijR[a] += (DU)*UJ[k]; Vijd[k] += (EU)*QJ[a]; } \
+                                    if (!SI) { Vji[a] += (EU)*UI[k]; VjiR[a] += (DU)*UI[k]; Vjid[k] += (EU)*QI[a]; } }
     // mixed-rank block: a belongs to the lower rank, b to the higher one; S1/S2 are the two parities
-#define MPID_CROSS(a, b, S1, S2, E, D) { Vij[a] += (S1)*(E)*QJ[b]; Vji[b] += (S1)*(E)*QI[a]; Vij[b] += (S2)*(E)*QJ[a]; Vji[a] += (S2)*(E)*QI[b]; \
-                                         VijR[a] += (S1)*(D)*QJ[b]; VjiR[b] += (S1)*(D)*QI[a]; VijR[b] += (S2)*(D)*QJ[a]; VjiR[a] += (S2)*(D)*QI[b]; }
+#define MPID_CROSS(a, b, S1, S2, E, D) { if (MPID_HASJ(b)) { Vij[a] += (S1)*(E)*QJ[b]; VijR[a] += (S1)*(D)*QJ[b]; } \
+                                         if (MPID_HASI(a)) { Vji[b] += (S1)*(E)*QI[a]; VjiR[b] += (S1)*(D)*QI[a]; } \
+                                         if (MPID_HASJ(a)) { Vij[b] += (S2)*(E)*QJ[a]; VijR[b] += (S2)*(D)*QJ[a]; } \
+                                         if (MPID_HASI(b)) { Vji[a] += (S2)*(E)*QI[b]; VjiR[a] += (S2)*(D)*QI[b]; } }
     // induced dipole in the lower-rank slot (dipole-quadrupole, dipole-octopole blocks)
-#define MPID_CROSS_U_LO(b, k, S1, S2, EU, DU) { Vijd[k] += (S1)*(EU)*QJ[b]; Vji[b] += (S1)*(EU)*UI[k]; Vij[b] += (S2)*(EU)*UJ[k]; Vjid[k] += (S2)*(EU)*QI[b]; \
-                                                VjiR[b] += (S1)*(DU)*UI[k]; VijR[b] += (S2)*(DU)*UJ[k]; }
+#define MPID_CROSS_U_LO(b, k, S1, S2, EU, DU) { if (!SI && MPID_HASJ(b)) Vijd[k] += (S1)*(EU)*QJ[b]; \
+                                                if (!SI) { Vji[b] += (S1)*(EU)*UI[k]; VjiR[b] += (S1)*(DU)*UI[k]; } \
+                                                if (!SJ) { Vij[b] += (S2)*(EU)*UJ[k]; VijR[b] += (S2)*(DU)*UJ[k]; } \
+                                                if (!SJ && MPID_HASI(b)) Vjid[k] += (S2)*(EU)*QI[b]; }
     // induced dipole in the higher-rank slot (charge-dipole block)
-#define MPID_CROSS_U_HI(a, k, S1, S2, EU, DU) { Vij[a] += (S1)*(EU)*UJ[k]; Vjid[k] += (S1)*(EU)*QI[a]; Vijd[k] += (S2)*(EU)*QJ[a]; Vji[a] += (S2)*(EU)*UI[k]; \
-                                                VijR[a] += (S1)*(DU)*UJ[k]; VjiR[a] += (S2)*(DU)*UI[k]; }
+#define MPID_CROSS_U_HI(a, k, S1, S2, EU, DU) { if (!SJ) { Vij[a] += (S1)*(EU)*UJ[k]; VijR[a] += (S1)*(DU)*UJ[k]; Vjid[k] += (S1)*(EU)*QI[a]; } \
+                                                if (!SI) { Vijd[k] += (S2)*(EU)*QJ[a]; Vji[a] += (S2)*(EU)*UI[k]; VjiR[a] += (S2)*(DU)*UI[k]; } }
     const T P = T(1), M = T(-1);
     T e, d_, eU, dU;
     // charge-charge
@@ -751,9 +765,8 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
     // ---- energy, radial force and torque intermediates (:4799-4838) ---------------------------------
     T energy = T(0), fIZ = T(0), fJZ = T(0);
     for (int i = 0; i < 16; i++) {
-        energy += QI[i]*Vij[i] + QJ[i]*Vji[i];
-        fIZ += QI[i]*VijR[i];
-        fJZ += QJ[i]*VjiR[i];
+        if (!SI || i == 0) { energy += QI[i]*Vij[i]; fIZ += QI[i]*VijR[i]; }
+        if (!SJ || i == 0) { energy += QJ[i]*Vji[i]; fJZ += QJ[i]*VjiR[i]; }
     }
     energy *= T(0.5);
     const T s3 = T(1.7320508075688772), s6 = T(2.4494897427831779), s52 = T(1.5811388300841898), s32 = T(1.2247448713915890);
@@ -766,13 +779,14 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
         + (s52*(Q)[11] - s32*(Q)[15])*(V)[13] + s32*(Q)[12]*(V)[14] + s32*(Q)[13]*(V)[15] )
 #define MPID_GEN_Z(Q, V) ( -(Q)[3]*(V)[2] + (Q)[2]*(V)[3] - (Q)[6]*(V)[5] + (Q)[5]*(V)[6] - T(2)*(Q)[8]*(V)[7] + T(2)*(Q)[7]*(V)[8] \
         - (Q)[11]*(V)[10] + (Q)[10]*(V)[11] - T(2)*(Q)[13]*(V)[12] + T(2)*(Q)[12]*(V)[13] - T(3)*(Q)[15]*(V)[14] + T(3)*(Q)[14]*(V)[15] )
-    T EIX = MPID_GEN_X(QI, Vij), EIY = MPID_GEN_Y(QI, Vij), EIZ = MPID_GEN_Z(QI, Vij);
-    T EJX = MPID_GEN_X(QJ, Vji), EJY = MPID_GEN_Y(QJ, Vji), EJZ = MPID_GEN_Z(QJ, Vji);
+    T EIX = T(0), EIY = T(0), EIZ = T(0), EJX = T(0), EJY = T(0), EJZ = T(0);
+    if (!SI) { EIX = MPID_GEN_X(QI, Vij); EIY = MPID_GEN_Y(QI, Vij); EIZ = MPID_GEN_Z(QI, Vij); }
+    if (!SJ) { EJX = MPID_GEN_X(QJ, Vji); EJY = MPID_GEN_Y(QJ, Vji); EJZ = MPID_GEN_Z(QJ, Vji); }
     // the same for the induced dipoles against the field of the permanent moments only
     T iEIX = UI[2]*Vijd[0] - UI[0]*Vijd[2], iEJX = UJ[2]*Vjid[0] - UJ[0]*Vjid[2];
     T iEIY = UI[0]*Vijd[1] - UI[1]*Vijd[0], iEJY = UJ[0]*Vjid[1] - UJ[1]*Vjid[0];
     T iEIZ = UI[1]*Vijd[2] - UI[2]*Vijd[1], iEJZ = UJ[1]*Vjid[2] - UJ[2]*Vjid[1];
-    if (MUTUAL) {   // induced-induced coupling (:4860-4881)
+    if (MUTUAL && !SI && !SJ) {   // induced-induced coupling (:4860-4881)
         T eC = T(-8.0/3.0)*ri[3]*(T(3)*MPID_UUB(B3, tc_d0) + x3X);
         T dC = T(2)*ri[4]*(T(6)*MPID_UUB(B3, dc_d0) + T(4)*x5X);
         iEIX += eC*UI[2]*UJ[0]; iEJX += eC*UJ[2]*UI[0];
@@ -797,6 +811,8 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
     return energy;
 #undef MPID_UB
 #undef MPID_UUB
+#undef MPID_HASI
+#undef MPID_HASJ
 #undef MPID_SAME
 #undef MPID_SAME_U
 #undef MPID_CROSS

@@ -372,6 +372,14 @@ template <typename T> struct Emul {
         forces.assign(3*n, 0.0);
         double energy = 0;
         bool mutual = S.polarization == Mutual;
+        // "simple" sites: charge only, never polarized (the specialised instantiations of the pair kernel)
+        std::vector<char> simple(n, 0);
+        for (int i = 0; i < n; i++) {
+            bool s0 = true;
+            for (int k = 1; k < 16; k++) if (pk[16*i+k] != T(0)) s0 = false;
+            for (int k = 0; k < 6; k++) if (S.lab[i].alpha[k] != 0.0) s0 = false;
+            simple[i] = s0;
+        }
         for (int i = 0; i < n; i++) for (int j = i+1; j < n; j++) {
             double dx, dy, dz, r2;
             if (!delta(i, j, dx, dy, dz, r2)) continue;
@@ -379,11 +387,14 @@ template <typename T> struct Emul {
             T sc = T(classScale(cls));
             T uI[3] = {T(mu[3*i]), T(mu[3*i+1]), T(mu[3*i+2])}, uJ[3] = {T(mu[3*j]), T(mu[3*j+1]), T(mu[3*j+2])};
             T f[3], ti[3], tj[3], e;
-#define CALL(EW, MU) e = pairElectrostatics<T, EW, MU>(&pk[16*i], &pk[16*j], uI, uJ, T(S.damp[i]), T(S.damp[j]), T(S.thole[i]), T(S.thole[j]), \
+#define CALL4(EW, MU, A, B) e = pairElectrostatics<T, EW, MU, A, B>(&pk[16*i], &pk[16*j], uI, uJ, T(S.damp[i]), T(S.damp[j]), T(S.thole[i]), T(S.thole[j]), \
                 S.lab[i].aniso != 0, S.lab[j].aniso != 0, T(dx), T(dy), T(dz), T(r2), T(S.alpha), T(S.defaultThole), sc, sc, f, ti, tj)
-            if (S.method == PME) { if (mutual) CALL(true, true); else CALL(true, false); }
-            else { if (mutual) CALL(false, true); else CALL(false, false); }
+#define CALL(EW, MU) { if (simple[i] && simple[j]) CALL4(EW, MU, true, true); else if (simple[i]) CALL4(EW, MU, true, false); \
+                       else if (simple[j]) CALL4(EW, MU, false, true); else CALL4(EW, MU, false, false); }
+            if (S.method == PME) { if (mutual) CALL(true, true) else CALL(true, false) }
+            else { if (mutual) CALL(false, true) else CALL(false, false) }
 #undef CALL
+#undef CALL4
             energy += e;
             for (int k = 0; k < 3; k++) {
                 forces[3*i+k] -= f[k]; forces[3*j+k] += f[k];

@@ -149,11 +149,12 @@ struct Engine : public EngineBase {
     DevBuf<real4> dMud;
     DevBuf<uint4> dCounts;
     DevBuf<unsigned> dTypeCount, dTypeStart, dMaxCount, dNbr, dPairI, dPairJ, dPolNbr, dPolCount;
-    DevBuf<int> dFlagS, dPolFlag, dPolRank, dPolList;
+    DevBuf<int> dFlagS, dPolFlag, dPolRank, dPolList, dSimpleRank, dSimpleList;
+    int numSimpleTotal = 0, numSimple = 0, simpleBegin = 0;
     int nbrCap = 0;
     int numPolTotal = 0;            // polarizable sites (static: follows from the parameters)
     int numPol = 0, polBegin = 0;   // polarizable sites among this rank's rows
-    long long typeBegin[5] = {0, 0, 0, 0, 0};   // boundaries of the four pair-class lists inside pairI/pairJ
+    long long typeBegin[6] = {0, 0, 0, 0, 0, 0};   // boundaries of the four pair-class lists inside pairI/pairJ
     DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
     DevBuf<unsigned long long> dForce, dTorque, dEnergy;
     DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp;
@@ -254,11 +255,17 @@ struct Engine : public EngineBase {
             // dampingFactor (MPIDReferenceKernels.cpp:123)
             hDamp[i] = pow((hAlpha[3*i] + hAlpha[3*i+1] + hAlpha[3*i+2])/3.0, 1.0/6.0);
         }
-        numPolTotal = 0;
+        numPolTotal = 0; numSimpleTotal = 0;
         for (int i = 0; i < n; i++) {
             bool anyAlpha = hAlpha[3*i] != 0.0 || hAlpha[3*i+1] != 0.0 || hAlpha[3*i+2] != 0.0;
             // a site without a z anchor keeps a zero lab-frame tensor unless the opt-in fix is on
-            if (anyAlpha && (hZ[i] >= 0 || cfg.frameless_alpha_fix)) numPolTotal++;
+            bool pol = anyAlpha && (hZ[i] >= 0 || cfg.frameless_alpha_fix);
+            if (pol) numPolTotal++;
+            bool perm = false;
+            for (int k = 0; k < 3; k++) perm = perm || hDipole[3*(size_t) i + k] != 0.0;
+            for (int k = 0; k < 6; k++) perm = perm || hQuad[6*(size_t) i + k] != 0.0;
+            for (int k = 0; k < 10; k++) perm = perm || hOct[10*(size_t) i + k] != 0.0;
+            if (!pol && !perm) numSimpleTotal++;
         }
         dCharge.upload(hCharge, stream); dDipole.upload(hDipole, stream); dQuad.upload(hQuad, stream); dOct.upload(hOct, stream);
         dAxis.upload(hAxis, stream); dZ.upload(hZ, stream); dX.upload(hX, stream); dY.upload(hY, stream);
@@ -496,34 +503,41 @@ struct Engine : public EngineBase {
         dPosS.ensure(n); dPosF.ensure(n); dCartD.ensure(20*(size_t) n); dPkD.ensure(16*(size_t) n); dSphD.ensure(16*(size_t) n);
         dAlphaLab.ensure(6*(size_t) n); dAniso.ensure(n); dDampThole.ensure(n); dMud.ensure(n); dSpSorted.ensure(n);
         dFlagS.ensure(n); dPolFlag.ensure((size_t) n + 1); dPolRank.ensure((size_t) n + 1); dPolList.ensure((size_t) n + 1);
+        dSimpleRank.ensure((size_t) n + 1); dSimpleList.ensure((size_t) n + 1);
         real* cartR; real* pkR;
         if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
         LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
                dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p,
                dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p, dFlagS.p);
-        // polarizable rows: rank (exclusive scan of the flag) and compact list
-        LAUNCH(k_pol_flags, blocksFor(n + 1, B), B, n, dFlagS.p, dPolFlag.p);
-        {
+        // polarizable rows and simple rows: rank (exclusive scan of the class flag) and compact list
+        for (int cls = 0; cls < 2; cls++) {
+            int bit = cls == 0 ? 1 : 2;
+            int* rank = cls == 0 ? dPolRank.p : dSimpleRank.p;
+            int* list = cls == 0 ? dPolList.p : dSimpleList.p;
+            LAUNCH(k_pol_flags, blocksFor(n + 1, B), B, n, bit, dFlagS.p, dPolFlag.p);
             size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, dPolFlag.p, dPolRank.p, n + 1, stream);
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, dPolFlag.p, rank, n + 1, stream);
             dScanTemp.ensure(tb + 16);
-            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tb, dPolFlag.p, dPolRank.p, n + 1, stream));
+            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tb, dPolFlag.p, rank, n + 1, stream));
             launches += 1;
+            LAUNCH(k_pol_list, blocksFor(n, B), B, n, bit, dFlagS.p, rank, list);
         }
-        LAUNCH(k_pol_list, blocksFor(n, B), B, n, dFlagS.p, dPolRank.p, dPolList.p);
         if (numRanks > 1) {
             int* pr = (int*) hPinned;
             CUDA_CHECK(cudaMemcpyAsync(&pr[0], dPolRank.p + P.rowBegin, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaMemcpyAsync(&pr[1], dPolRank.p + P.rowEnd, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&pr[2], dSimpleRank.p + P.rowBegin, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&pr[3], dSimpleRank.p + P.rowEnd, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             polBegin = pr[0]; numPol = pr[1] - pr[0];
-        } else { polBegin = 0; numPol = numPolTotal; }
+            simpleBegin = pr[2]; numSimple = pr[3] - pr[2];
+        } else { polBegin = 0; numPol = numPolTotal; simpleBegin = 0; numSimple = numSimpleTotal; }
         stageEnd();
         // neighbour list: single pass into per-atom runs, then the flat half list for the energy kernel
         stageBegin(MPIDB200_STAGE_NLIST);
         int rows = P.rowEnd - P.rowBegin;
-        const size_t tlen = 4*((size_t) rows + 1);
+        const size_t tlen = 5*((size_t) rows + 1);
         dCounts.ensure((size_t) rows + 1); dTypeCount.ensure(tlen); dTypeStart.ensure(tlen); dMaxCount.ensure(2);
         dPolCount.ensure((size_t) numPol + 1);
         if (nbrCap == 0) {
@@ -542,7 +556,7 @@ struct Engine : public EngineBase {
             if (rows > 0) {
                 if (roundMode) LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
                                       dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
-                else LAUNCH((k_neighbor_list<false>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
+                else LAUNCH(k_neighbor_list_cell, numCells, 256, P, dPosF.p, dPosIn, dOrder.p, dCellStart.p,
                             dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
             }
             // one scan over the four concatenated per-class count arrays gives absolute offsets into pairI/pairJ
@@ -553,18 +567,19 @@ struct Engine : public EngineBase {
             CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, stream));
             launches += 1;
             CUDA_CHECK(cudaMemcpyAsync(&totals[0], dMaxCount.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-            for (int t = 0; t < 4; t++)
+            for (int t = 0; t < 5; t++)
                 CUDA_CHECK(cudaMemcpyAsync(&totals[1 + t], dTypeStart.p + (size_t) t*(rows + 1), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaMemcpyAsync(&totals[5], dTypeStart.p + tlen - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&totals[6], dTypeStart.p + tlen - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             if ((int) totals[0] <= nbrCap) break;
             if (attempt > 3) throw std::runtime_error("mpidb200: neighbour list capacity could not be established");
             nbrCap = (int) (totals[0]*1.2) + 16;       // rare: density fluctuation beyond the guess
         }
         for (int t = 0; t < 5; t++) typeBegin[t] = totals[1 + t];
-        lastPairs = typeBegin[4];
-        dPairI.ensure((size_t) lastPairs + 1); dPairJ.ensure((size_t) lastPairs + 1);
-        if (rows > 0 && lastPairs > 0)
+        lastPairs = totals[6];                       // every ordinary pair (i<j) of this rank's rows
+        const long long flatPairs = typeBegin[4];    // pairs in the flat class lists (simple-simple pairs are gathered instead)
+        dPairI.ensure((size_t) flatPairs + 1); dPairJ.ensure((size_t) flatPairs + 1);
+        if (rows > 0 && flatPairs > 0)
             LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, dPairI.p, dPairJ.p);
     }
 
@@ -836,11 +851,16 @@ struct Engine : public EngineBase {
             backToMain();
         }
         stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
-        // four pair classes (full/simple site on either side), each with its own specialised instantiation
+        if (numSimple > 0) {
+            const int nbS = blocksFor((long long) numSimple*MPID_LANES, 256);
+            if (pme) LAUNCH((k_simple_pairs<real, true>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
+            else LAUNCH((k_simple_pairs<real, false>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
+        }
+        // the remaining pair classes (full/simple site on either side), each with its own specialised instantiation
 #define ES_LAUNCH(EW, MU, A, B, T) { const long long cnt = typeBegin[T+1] - typeBegin[T]; \
             if (cnt > 0) LAUNCH((k_electrostatics<real, EW, MU, A, B>), blocksFor(cnt, 128), 128, P, cnt, dPairI.p + typeBegin[T], dPairJ.p + typeBegin[T], \
                                 dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p); }
-#define ES_ALL(EW, MU) { ES_LAUNCH(EW, MU, false, false, 0) ES_LAUNCH(EW, MU, false, true, 1) ES_LAUNCH(EW, MU, true, false, 2) ES_LAUNCH(EW, MU, true, true, 3) }
+#define ES_ALL(EW, MU) { ES_LAUNCH(EW, MU, false, false, 0) ES_LAUNCH(EW, MU, false, true, 1) ES_LAUNCH(EW, MU, true, false, 2) }
         if (pme) { if (mutual) ES_ALL(true, true) else ES_ALL(true, false) }
         else { if (mutual) ES_ALL(false, true) else ES_ALL(false, false) }
 #undef ES_ALL
@@ -1000,19 +1020,27 @@ struct Engine : public EngineBase {
 
     long long getPairList(long long cap, int* pi, int* pj, int* pc) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        long long total = lastPairs + (long long) hSpLo.size();   // upper bound
+        const int rows = P.rowEnd - P.rowBegin;
+        std::vector<uint4> cnt(std::max(rows, 1));
+        if (rows > 0) CUDA_CHECK(cudaMemcpy(cnt.data(), dCounts.p, rows*sizeof(uint4), cudaMemcpyDeviceToHost));
+        long long upper = 0;
+        for (int r = 0; r < rows; r++) upper += cnt[r].x;
+        long long total = upper + (long long) hSpLo.size();   // upper bound
         if (!pi) return total;
-        std::vector<unsigned> hi(lastPairs), hj(lastPairs);
         std::vector<int> order(n);
-        if (lastPairs) {
-            CUDA_CHECK(cudaMemcpy(hi.data(), dPairI.p, lastPairs*sizeof(unsigned), cudaMemcpyDeviceToHost));
-            CUDA_CHECK(cudaMemcpy(hj.data(), dPairJ.p, lastPairs*sizeof(unsigned), cudaMemcpyDeviceToHost));
-        }
         CUDA_CHECK(cudaMemcpy(order.data(), dOrder.p, n*sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<unsigned> all((size_t) std::max(rows, 1)*nbrCap);
+        CUDA_CHECK(cudaMemcpy(all.data(), dNbr.p, all.size()*sizeof(unsigned), cudaMemcpyDeviceToHost));
         long long k = 0;
-        for (long long p = 0; p < lastPairs && k < cap; p++, k++) {
-            int a = order[hi[p]], b = order[hj[p] & MPID_JMASK];
-            pi[k] = std::min(a, b); pj[k] = std::max(a, b); pc[k] = 0;
+        // ordinary pairs: the "upper" run of every row of the per-atom neighbour list
+        for (int r = 0; r < rows && k < cap; r++) {
+            unsigned nUp = cnt[r].x;
+            const unsigned* run = all.data() + (size_t) r*nbrCap;
+            int a = order[P.rowBegin + r];
+            for (unsigned q = 0; q < nUp && k < cap; q++, k++) {
+                int b = order[run[q] & MPID_JMASK];
+                pi[k] = std::min(a, b); pj[k] = std::max(a, b); pc[k] = 0;
+            }
         }
         // the static covalently scaled pairs, with the cutoff test their kernels apply at run time
         std::vector<double> pos(3*(size_t) n);

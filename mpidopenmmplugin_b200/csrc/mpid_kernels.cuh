@@ -2,7 +2,7 @@
 //
 // Layout conventions (all per-atom arrays are in the SORTED order produced by the cell sort unless a
 // name ends in "Orig"):
-//   posS      double4  wrapped position (x,y,z,unused)           -- pair kernels, PME
+//   posS      double4  wrapped position (x,y,z, site class)      -- pair kernels, PME
 //   posF      float4   same, single precision                    -- neighbour-list pre-test only
 //   cart      real[20] lab Cartesian moments   q d(3) Q(6) O(10) -- permanent-field kernel, PME spread
 //   pk        real[16] packed traceless moments (packPairMoments) -- energy kernel
@@ -167,7 +167,7 @@ __global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, co
     for (int k = 1; k < 16; k++) perm = perm || (pk[k] != 0.0);
     const int flag = (pol ? 1 : 0) | ((!pol && !perm) ? 2 : 0);
     flagS[s] = flag;
-    posS[s] = make_double4(x, y, z, 0.0);
+    posS[s] = make_double4(x, y, z, (double) flag);
     posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
     dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
     typename Real4<real>::type m;
@@ -175,14 +175,14 @@ __global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, co
     mud[s] = m;
 }
 
-// polarizable-site bookkeeping: polFlag[s] = flag & 1 (scanned into polRank), polList[polRank[s]] = s
-__global__ void k_pol_flags(int n, const int* __restrict__ flagS, int* __restrict__ polFlag) {
+// site-class bookkeeping: classFlag[s] = (flag & bit) != 0 (scanned into a rank), classList[rank[s]] = s
+__global__ void k_pol_flags(int n, int bit, const int* __restrict__ flagS, int* __restrict__ classFlag) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s <= n) polFlag[s] = s < n ? (flagS[s] & 1) : 0;
+    if (s <= n) classFlag[s] = (s < n && (flagS[s] & bit)) ? 1 : 0;
 }
-__global__ void k_pol_list(int n, const int* __restrict__ flagS, const int* __restrict__ polRank, int* __restrict__ polList) {
+__global__ void k_pol_list(int n, int bit, const int* __restrict__ flagS, const int* __restrict__ rank, int* __restrict__ classList) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s < n && (flagS[s] & 1)) polList[polRank[s]] = s;
+    if (s < n && (flagS[s] & bit)) classList[rank[s]] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -337,20 +337,164 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
     }
 }
 
+// Shared-memory variant for the regular periodic case (every dimension has >= 2*reach+1 cells): one CTA per
+// cell.  All atoms of a cell share the same candidate set, so the CTA stages the (image-shifted) candidate
+// positions of the neighbouring cells in shared memory once and each warp then scans them for one atom of the
+// cell with full lane utilisation.  Output layout and pair set are identical to k_neighbor_list.
+#define MPID_NL_MAXC 1536
+#define MPID_NL_MAXI 64
+__global__ void __launch_bounds__(256)
+k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double* __restrict__ posOrig,
+                     const int* __restrict__ order, const int* __restrict__ cellStart,
+                     const int* __restrict__ spStart, const int* __restrict__ spPartner, const int4* __restrict__ spSorted,
+                     const int* __restrict__ polRank, int polBegin,
+                     unsigned* __restrict__ nbr, uint4* __restrict__ counts, unsigned* __restrict__ polNbr, unsigned* __restrict__ polCount,
+                     unsigned* __restrict__ maxCount) {
+    __shared__ float4 cand[MPID_NL_MAXC];
+    __shared__ unsigned char cflag[MPID_NL_MAXC];
+    __shared__ int rJb[64], rBegin[65];
+    __shared__ float rShift[64][3];
+    __shared__ unsigned rCode[64];
+    __shared__ unsigned ctr[MPID_NL_MAXI][4];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cell = blockIdx.x;
+    int cz = cell % P.ncell[2], tmp = cell / P.ncell[2];
+    const int cy = tmp % P.ncell[1], cx = tmp / P.ncell[1];
+    const int iBeg = max(cellStart[cell], P.rowBegin), iEnd = min(cellStart[cell+1], P.rowEnd);
+    if (iBeg >= iEnd) return;
+    const int Rx = P.reach[0], Ry = P.reach[1], Rz = P.reach[2];
+    const int wy1 = 2*Ry + 1, ncols = (2*Rx + 1)*wy1;
+    const float ax = (float) P.box.a[0], bx = (float) P.box.b[0], by = (float) P.box.b[1];
+    const float ccx = (float) P.box.c[0], ccy = (float) P.box.c[1], ccz = (float) P.box.c[2];
+    // candidate ranges: (pass 0: z cells that need no wrap, pass 1: wrapped remainder) x neighbour columns
+    if (tid < 64) {
+        int jb = 0, len = 0, wx = 0, wy = 0, wz = 0;
+        const int col = tid % ncols, pass = tid / ncols;
+        if (pass < 2) {
+            int X = cx + col/wy1 - Rx, Y = cy + col % wy1 - Ry;
+            if (X < 0) { X += P.ncell[0]; wx = -1; } else if (X >= P.ncell[0]) { X -= P.ncell[0]; wx = 1; }
+            if (Y < 0) { Y += P.ncell[1]; wy = -1; } else if (Y >= P.ncell[1]) { Y -= P.ncell[1]; wy = 1; }
+            const int colBase = (X*P.ncell[1] + Y)*P.ncell[2];
+            int z0 = 0, z1 = -1;
+            if (pass == 0) { z0 = max(cz - Rz, 0); z1 = min(cz + Rz, P.ncell[2] - 1); }
+            else if (cz - Rz < 0) { z0 = cz - Rz + P.ncell[2]; z1 = P.ncell[2] - 1; wz = -1; }
+            else if (cz + Rz >= P.ncell[2]) { z0 = 0; z1 = cz + Rz - P.ncell[2]; wz = 1; }
+            if (z1 >= z0) { jb = cellStart[colBase + z0]; len = cellStart[colBase + z1 + 1] - jb; }
+        }
+        rJb[tid] = jb;
+        rBegin[tid] = len;                  // lengths for now, scanned below
+        rShift[tid][0] = wx*ax + wy*bx + wz*ccx; rShift[tid][1] = wy*by + wz*ccy; rShift[tid][2] = wz*ccz;
+        rCode[tid] = (unsigned) ((1 - wx)*9 + (1 - wy)*3 + (1 - wz));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int r = 0; r < 64; r++) { const int len = rBegin[r]; rBegin[r] = run; run += len; }
+        rBegin[64] = run;
+    }
+    __syncthreads();
+    const int total = rBegin[64];
+    const float rcLo = (float) P.cutoff - 1.0e-4f, rcHi = (float) P.cutoff + 1.0e-4f;
+    const float rcLo2 = rcLo > 0.f ? rcLo*rcLo : 0.f, rcHi2 = rcHi*rcHi;
+    const unsigned cap = (unsigned) P.nbrCap;
+    for (int ib0 = iBeg; ib0 < iEnd; ib0 += MPID_NL_MAXI) {          // batches of atoms of this cell (normally one)
+        const int ib1 = min(ib0 + MPID_NL_MAXI, iEnd);
+        for (int q = tid; q < MPID_NL_MAXI*4; q += 256) ctr[q >> 2][q & 3] = 0u;
+        for (int chunk0 = 0; chunk0 < total; chunk0 += MPID_NL_MAXC) { // chunks of candidates (normally one)
+            const int cnt = min(MPID_NL_MAXC, total - chunk0);
+            __syncthreads();
+            for (int c = tid; c < cnt; c += 256) {
+                const int g = chunk0 + c;
+                int r = 0;
+#pragma unroll
+                for (int step = 32; step > 0; step >>= 1) if (r + step < 64 && rBegin[r + step] <= g) r += step;
+                const int j = rJb[r] + (g - rBegin[r]);
+                const float4 p = posF[j];
+                cand[c] = make_float4(p.x + rShift[r][0], p.y + rShift[r][1], p.z + rShift[r][2], __uint_as_float((unsigned) j | (rCode[r] << MPID_CODE_SHIFT)));
+                cflag[c] = (unsigned char) (int) p.w;
+            }
+            __syncthreads();
+            for (int i = ib0 + warp; i < ib1; i += 8) {
+                const int row = i - P.rowBegin;
+                const float4 pi = posF[i];
+                const int4 sp = spSorted[i];
+                const bool spMany = sp.x == -2;
+                const int oi = order[i];
+                int sp0 = 0, sp1 = 0;
+                if (spMany) { sp0 = spStart[oi]; sp1 = spStart[oi+1]; }
+                const bool iPol = ((int) pi.w & 1) != 0;
+                unsigned* base = nbr + (size_t) row*cap;
+                unsigned* polBase = polNbr + (iPol ? (size_t) (polRank[i] - polBegin)*cap : 0);
+                unsigned nUp = ctr[i - ib0][0], nLow = ctr[i - ib0][1], nUpSimple = ctr[i - ib0][2], nPol = ctr[i - ib0][3];
+                for (int c0 = 0; c0 < cnt; c0 += 32) {
+                    const int c = c0 + lane;
+                    const bool valid = c < cnt;
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int jflag = 0;
+                    if (valid) { q = cand[c]; jflag = cflag[c]; }
+                    const unsigned entry = __float_as_uint(q.w);
+                    const int j = (int) (entry & MPID_JMASK);
+                    bool in = valid && (j != i);
+                    const float ddx = q.x - pi.x, ddy = q.y - pi.y, ddz = q.z - pi.z;
+                    const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
+                    if (r2 > rcHi2) in = false;
+                    else if (in && r2 >= rcLo2) {
+                        // borderline: the oracle's test, bit for bit, on the raw positions
+                        const int oj = order[j];
+                        const int lo = min(oi, oj), hi = max(oi, oj);
+                        double ex = posOrig[3*hi] - posOrig[3*lo], ey = posOrig[3*hi+1] - posOrig[3*lo+1], ez = posOrig[3*hi+2] - posOrig[3*lo+2];
+                        periodicDelta(P.box, ex, ey, ez);
+                        in = !(dist2Exact(ex, ey, ez) > P.cutoff2);
+                    }
+                    if (j == sp.x || j == sp.y || j == sp.z || j == sp.w) in = false;
+                    if (spMany && in) {
+                        const int oj = order[j];
+                        for (int k = sp0; k < sp1; k++) if (spPartner[k] == oj) in = false;
+                    }
+                    const bool upper = in && (j > i);
+                    const unsigned maskU = __ballot_sync(FULL, upper);
+                    const unsigned maskL = __ballot_sync(FULL, in && !upper);
+                    const unsigned maskS = __ballot_sync(FULL, upper && (jflag & 2));
+                    const unsigned maskP = __ballot_sync(FULL, in && iPol && (jflag & 1));
+                    const unsigned cu = __popc(maskU), cl = __popc(maskL);
+                    if (nUp + nLow + cu + cl <= cap) {
+                        const unsigned lt = (1u << lane) - 1u;
+                        if (upper) base[nUp + __popc(maskU & lt)] = entry;
+                        else if (in) base[cap - 1 - (nLow + __popc(maskL & lt))] = entry;
+                        if (in && iPol && (jflag & 1)) polBase[nPol + __popc(maskP & lt)] = entry;
+                    }
+                    nUp += cu; nLow += cl; nUpSimple += __popc(maskS); nPol += __popc(maskP);
+                }
+                if (lane == 0) {
+                    ctr[i - ib0][0] = nUp; ctr[i - ib0][1] = nLow; ctr[i - ib0][2] = nUpSimple; ctr[i - ib0][3] = nPol;
+                    if (chunk0 + MPID_NL_MAXC >= total) {
+                        counts[row] = make_uint4(nUp, nLow, nUpSimple, nPol);
+                        if (iPol) polCount[polRank[i] - polBegin] = nPol;
+                        atomicMax(maxCount, nUp + nLow);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Pair classes of the energy kernel: type = 2*simple(i) + simple(j).  typeCount[t*(rows+1) + r] = number of
 // upper neighbours of row r that fall in class t (scanned per class to place the runs of the four flat lists).
 __global__ void k_half_counts(DevParams P, int rows, const uint4* __restrict__ counts, const int* __restrict__ flagS,
                               unsigned* __restrict__ typeCount) {
     const int r = blockIdx.x*blockDim.x + threadIdx.x;
     if (r > rows) return;
-    unsigned c[4] = {0u, 0u, 0u, 0u};
+    unsigned c[5] = {0u, 0u, 0u, 0u, 0u};
     if (r < rows) {
         const uint4 q = counts[r];
         const int si = (flagS[P.rowBegin + r] >> 1) & 1;
         c[2*si] = q.x - q.z;
-        c[2*si + 1] = q.z;
+        // simple-simple pairs go to k_simple_pairs (gather, no atomics); class 4 only counts them
+        if (si) c[4] = q.z; else c[1] = q.z;
     }
-    for (int t = 0; t < 4; t++) typeCount[(size_t) t*(rows + 1) + r] = c[t];
+    for (int t = 0; t < 5; t++) typeCount[(size_t) t*(rows + 1) + r] = c[t];
 }
 // four flat i-major half lists (one warp per atom distributes its upper run by the class of j)
 __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, const uint4* __restrict__ counts,
@@ -375,7 +519,7 @@ __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, co
         if (valid) { e = base[k]; sj = (((int) posF[e & MPID_JMASK].w >> 1) & 1) != 0; }
         const unsigned mF = __ballot_sync(FULL, valid && !sj), mS = __ballot_sync(FULL, valid && sj);
         const unsigned lt = (1u << lane) - 1u;
-        if (valid) {
+        if (valid && !(si && sj)) {
             const unsigned d = sj ? dstS + __popc(mS & lt) : dstF + __popc(mF & lt);
             pairI[d] = (unsigned) i;
             pairJ[d] = e;
@@ -617,6 +761,64 @@ k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ p
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
     if (lane == 0 && e != 0.0) atomicAddFixed(energy, e);
+}
+
+// Charge-only x charge-only pairs (e.g. H-H in water): 45 % of all pairs but a few dozen flops each, so the
+// cost of the flat-list kernel would be its atomics.  Instead every simple site gathers over its own full
+// neighbour list (8 lanes per site, each pair is seen from both ends) and takes half of the pair energy.
+//   E = k q_i q_j B1/r,  F_i = -k q_i q_j B2 d/r^3  with  B1 = erfc(ar), B2 = B1 + 2 ar exp(-(ar)^2)/sqrt(pi)   (:4527-4534)
+template <typename real, bool EWALD>
+__global__ void __launch_bounds__(256)
+k_simple_pairs(DevParams P, int numSimple, const int* __restrict__ simpleList, const double4* __restrict__ posS,
+               const real* __restrict__ pk, const uint4* __restrict__ counts, const unsigned* __restrict__ nbr,
+               unsigned long long* __restrict__ force, unsigned long long* __restrict__ energy) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int rs = t/MPID_LANES;
+    const int sub = t % MPID_LANES;
+    const bool act = rs < numSimple;
+    const int i = act ? simpleList[rs] : 0;
+    real fx = 0, fy = 0, fz = 0, en = 0;
+    if (act) {
+        const double4 pi = posS[i];
+        const real qi = pk[16*(size_t) i];
+        const uint4 cnt = counts[i - P.rowBegin];
+        const unsigned nUp = cnt.x, nAll = cnt.x + cnt.y;
+        const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        for (unsigned k = sub; k < nAll; k += MPID_LANES) {
+            const unsigned e = k < nUp ? base[k] : base[P.nbrCap - 1 - (k - nUp)];
+            const unsigned j = e & MPID_JMASK;
+            const double4 pj = posS[j];
+            if (!(((int) pj.w) & 2)) continue;
+            real dx, dy, dz;
+            pairDelta<real>(P, pi, pj, e >> MPID_CODE_SHIFT, dx, dy, dz);
+            const real r2 = dx*dx + dy*dy + dz*dz;
+            const real rinv = t_rsqrt(r2);
+            const real qq = real(MPID_ELECTRIC)*qi*pk[16*(size_t) j];
+            real B1 = real(1), B2 = real(1);
+            if (EWALD) {
+                const real x = (real) P.alpha*r2*rinv;
+                const real ex = t_expneg(-(x*x));
+                B1 = t_erfc_ex(x, ex);
+                B2 = B1 + real(2.0/MPID_SQRT_PI)*x*ex;
+            }
+            en += qq*B1*rinv;
+            const real fr = -qq*B2*rinv*rinv*rinv;      // force on i = fr * d
+            fx += fr*dx; fy += fr*dy; fz += fr*dz;
+        }
+    }
+    double dfx = fx, dfy = fy, dfz = fz, de = 0.5*(double) en;
+#pragma unroll
+    for (int off = MPID_LANES/2; off > 0; off >>= 1) {
+        dfx += __shfl_xor_sync(0xffffffffu, dfx, off);
+        dfy += __shfl_xor_sync(0xffffffffu, dfy, off);
+        dfz += __shfl_xor_sync(0xffffffffu, dfz, off);
+    }
+    if (act && sub == 0) {
+        atomicAddFixed(&force[3*(size_t) i], dfx); atomicAddFixed(&force[3*(size_t) i+1], dfy); atomicAddFixed(&force[3*(size_t) i+2], dfz);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) de += __shfl_xor_sync(0xffffffffu, de, off);
+    if ((threadIdx.x & 31) == 0 && de != 0.0) atomicAddFixed(energy, de);
 }
 
 // Covalently scaled pairs: FP64, one thread per static special pair (original indices lo < hi).

@@ -195,6 +195,7 @@ struct Engine : public EngineBase {
         if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); }
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
+        if (hDiis) cudaFreeHost(hDiis);
         for (cudaEvent_t e : evPool) cudaEventDestroy(e);
         if (evFork) cudaEventDestroy(evFork);
         if (evJoin) cudaEventDestroy(evJoin);
@@ -729,12 +730,24 @@ struct Engine : public EngineBase {
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
-    // convergeInduceDipolesByDIIS (:1182-1252)
+    // convergeInduceDipolesByDIIS (:1182-1252), device resident: error overlaps, convergence test and the DIIS solve
+    // stay on the GPU (k_diis_record_dots / k_diis_solve / k_diis_combine), and every kernel of an iteration is a
+    // no-op once the status block says "done".  The host therefore enqueues `predictedEvals` iterations (the count
+    // the previous evaluation needed) back to back and only then reads the status; beyond that it checks after
+    // every iteration.  Iterations past convergence leave mu untouched, so over-prediction costs time, not accuracy.
+    DevBuf<DiisStatus> dDiis;
+    DiisStatus* hDiis = nullptr;
+    int predictedEvals = 0;
+    const bool syncEveryIteration = getenv("MPIDB200_DIIS_SYNC") != nullptr;   // debugging aid: host check after every iteration
     void solveMutualDiis(const double* dPosIn) {
         const int H = MPID_MAX_HISTORY;
+        const int nb = 296;   // 2 x 148 SMs
         dHistDip.ensure((size_t) H*3*n); dHistErr.ensure((size_t) H*3*n);
+        dDotPartial.ensure((size_t) nb*(MPID_MAX_HISTORY + 1));
+        dDiis.ensure(1);
+        if (!hDiis) CUDA_CHECK(cudaMallocHost((void**) &hDiis, sizeof(DiisStatus)));
+        CUDA_CHECK(cudaMemsetAsync(dDiis.p, 0, sizeof(DiisStatus), stream));
         std::vector<int> slots;                 // history slots in age order
-        std::vector<double> Bm((size_t) H*H, 0.0);
         std::vector<int> freeSlots;
         for (int k = H-1; k >= 0; k--) freeSlots.push_back(k);
         lastIterations = 0; lastEps = 0;
@@ -744,31 +757,34 @@ struct Engine : public EngineBase {
             if ((int) slots.size() == H) {     // drop the oldest (:1232-1236)
                 freeSlots.push_back(slots.front());
                 slots.erase(slots.begin());
-                for (int a = 0; a + 1 < H; a++) for (int b = 0; b + 1 < H; b++) Bm[(size_t) a*H + b] = Bm[(size_t) (a+1)*H + (b+1)];
             }
             int slot = freeSlots.back(); freeSlots.pop_back();
             slots.push_back(slot);
-            int m = (int) slots.size();
+            const int m = (int) slots.size();
             double* hd = dHistDip.p + (size_t) slot*3*n;
             double* he = dHistErr.p + (size_t) slot*3*n;
-            LAUNCH(k_diis_record, blocksFor(n, 256), 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he);
-            VecList list;
-            for (int k = 0; k < m; k++) list.v[k] = dHistErr.p + (size_t) slots[k]*3*n;
-            dots(he, list, m, hPinned + 8);
-            for (int k = 0; k < m; k++) Bm[(size_t) (m-1)*H + k] = Bm[(size_t) k*H + (m-1)] = hPinned[8 + k];
-            double eps = MPID_DEBYE*sqrt(hPinned[8 + m - 1]/n);
-            lastIterations = it; lastEps = eps;
-            bool done = eps < cfg.target_epsilon;
-            if (done || it == cfg.max_iterations) {
-                stageEnd();
-                if (!done) throw std::runtime_error("Induced dipoles did not converge:  iterations=" + std::to_string(it) + " eps=" + std::to_string(eps));
-                return;
+            VecList el, dl; SlotList sl;
+            for (int k = 0; k < m; k++) {
+                el.v[k] = dHistErr.p + (size_t) slots[k]*3*n;
+                dl.v[k] = dHistDip.p + (size_t) slots[k]*3*n;
+                sl.s[k] = slots[k];
             }
-            std::vector<double> coef(m, 1.0);
-            if (m > 1) solveDiis(m, Bm, H, coef);
-            VecList dl; CoefList cl;
-            for (int k = 0; k < m; k++) { dl.v[k] = dHistDip.p + (size_t) slots[k]*3*n; cl.c[k] = coef[k]; }
-            LAUNCH((k_combine<real>), blocksFor(n, 256), 256, n, m, dl, cl, dMu.p, dMud.p);
+            LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p);
+            LAUNCH(k_diis_solve, 1, 512, nb, m, sl, it, n, cfg.target_epsilon, dDotPartial.p, dDiis.p);
+            const bool last = it == cfg.max_iterations;
+            if (!last) LAUNCH((k_diis_combine<real>), blocksFor(n, 256), 256, n, m, dl, dDiis.p, dMu.p, dMud.p);
+            if (it + 1 >= predictedEvals || last || syncEveryIteration) {
+                CUDA_CHECK(cudaMemcpyAsync(hDiis, dDiis.p, 3*sizeof(double), cudaMemcpyDeviceToHost, stream));   // done, iterations, eps
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+                lastIterations = hDiis->iterations; lastEps = hDiis->eps;
+                if (hDiis->done || last) {
+                    stageEnd();
+                    if (!hDiis->done)
+                        throw std::runtime_error("Induced dipoles did not converge:  iterations=" + std::to_string(it) + " eps=" + std::to_string(lastEps));
+                    predictedEvals = lastIterations + 1;
+                    return;
+                }
+            }
             stageEnd();
         }
     }

@@ -341,7 +341,7 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
 // cell.  All atoms of a cell share the same candidate set, so the CTA stages the (image-shifted) candidate
 // positions of the neighbouring cells in shared memory once and each warp then scans them for one atom of the
 // cell with full lane utilisation.  Output layout and pair set are identical to k_neighbor_list.
-#define MPID_NL_MAXC 1536
+#define MPID_NL_MAXC 1280
 #define MPID_NL_MAXI 64
 __global__ void __launch_bounds__(256)
 k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double* __restrict__ posOrig,
@@ -356,6 +356,7 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
     __shared__ float rShift[64][3];
     __shared__ unsigned rCode[64];
     __shared__ unsigned ctr[MPID_NL_MAXI][4];
+    __shared__ unsigned short hitq[8][MPID_NL_MAXC];      // per-warp queue of candidate slots inside the pre-test sphere
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cell = blockIdx.x;
@@ -388,10 +389,17 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
         rCode[tid] = (unsigned) ((1 - wx)*9 + (1 - wy)*3 + (1 - wz));
     }
     __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int r = 0; r < 64; r++) { const int len = rBegin[r]; rBegin[r] = run; run += len; }
-        rBegin[64] = run;
+    if (tid < 32) {       // exclusive scan of the 64 range lengths, two per lane
+        const int l0 = rBegin[2*tid], l1 = rBegin[2*tid + 1];
+        int incl = l0 + l1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, off);
+            if (tid >= off) incl += t;
+        }
+        rBegin[2*tid] = incl - l0 - l1;
+        rBegin[2*tid + 1] = incl - l1;
+        if (tid == 31) rBegin[64] = incl;
     }
     __syncthreads();
     const int total = rBegin[64];
@@ -427,19 +435,35 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
                 unsigned* base = nbr + (size_t) row*cap;
                 unsigned* polBase = polNbr + (iPol ? (size_t) (polRank[i] - polBegin)*cap : 0);
                 unsigned nUp = ctr[i - ib0][0], nLow = ctr[i - ib0][1], nUpSimple = ctr[i - ib0][2], nPol = ctr[i - ib0][3];
+                // phase 1: bare distance pre-test of every candidate; survivors (about a quarter) are queued in order
+                unsigned short* const myq = hitq[warp];
+                int qn = 0;
                 for (int c0 = 0; c0 < cnt; c0 += 32) {
                     const int c = c0 + lane;
-                    const bool valid = c < cnt;
+                    bool hit = false;
+                    if (c < cnt) {
+                        const float4 q = cand[c];
+                        const float ddx = q.x - pi.x, ddy = q.y - pi.y, ddz = q.z - pi.z;
+                        hit = ddx*ddx + ddy*ddy + ddz*ddz <= rcHi2;
+                    }
+                    const unsigned m = __ballot_sync(FULL, hit);
+                    if (hit) myq[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short) c;
+                    qn += __popc(m);
+                }
+                __syncwarp();
+                // phase 2: classify the survivors (self, covalent partners, borderline distances, list membership)
+                for (int h0 = 0; h0 < qn; h0 += 32) {
+                    const int h = h0 + lane;
+                    const bool valid = h < qn;
                     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                     int jflag = 0;
-                    if (valid) { q = cand[c]; jflag = cflag[c]; }
+                    if (valid) { const int c = myq[h]; q = cand[c]; jflag = cflag[c]; }
                     const unsigned entry = __float_as_uint(q.w);
                     const int j = (int) (entry & MPID_JMASK);
                     bool in = valid && (j != i);
                     const float ddx = q.x - pi.x, ddy = q.y - pi.y, ddz = q.z - pi.z;
                     const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
-                    if (r2 > rcHi2) in = false;
-                    else if (in && r2 >= rcLo2) {
+                    if (in && r2 >= rcLo2) {
                         // borderline: the oracle's test, bit for bit, on the raw positions
                         const int oj = order[j];
                         const int lo = min(oi, oj), hi = max(oi, oj);
@@ -466,6 +490,7 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
                     }
                     nUp += cu; nLow += cl; nUpSimple += __popc(maskS); nPol += __popc(maskP);
                 }
+                __syncwarp();
                 if (lane == 0) {
                     ctr[i - ib0][0] = nUp; ctr[i - ib0][1] = nLow; ctr[i - ib0][2] = nUpSimple; ctr[i - ib0][3] = nPol;
                     if (chunk0 + MPID_NL_MAXC >= total) {
@@ -1174,6 +1199,162 @@ k_dots_final(int numBlocks, int m, const double* __restrict__ partial, double* _
         __syncthreads();
     }
     if (threadIdx.x == 0 && k < m) out[k] = sh[0];
+}
+
+// ---- device-resident DIIS ---------------------------------------------------------------------------
+// The mutual solver runs without host round trips: the error-overlap matrix, the convergence test and the
+// small linear solve live on the device, and every kernel of an iteration returns at once when `done` is set,
+// so the host may enqueue several iterations ahead (it predicts the count from the previous evaluation) and only
+// then read the status back.  Extra iterations are no-ops on mu, hence idempotent.
+struct DiisStatus {
+    int done;                     // eps < target reached
+    int iterations;               // index of the iteration that converged / last one run (:1219-1231)
+    double eps;
+    double coef[MPID_MAX_HISTORY + 1];
+    double B[MPID_MAX_HISTORY*MPID_MAX_HISTORY];     // <err_a, err_b>, indexed by history slot
+};
+struct SlotList { int s[MPID_MAX_HISTORY + 1]; };
+
+// newDip = efix + alpha.E_ind, err = newDip - mu into history slot (:1195-1218), fused with the partial dot
+// products <err_new, err_k> over the m vectors of the history (the last one being err_new itself).
+// Fixed block partition + ordered second pass => deterministic.
+__global__ void __launch_bounds__(256)
+k_diis_record_dots(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ efix,
+                   const double* __restrict__ ifield, const double* __restrict__ mu,
+                   double* __restrict__ histDip, double* __restrict__ histErr, int m, VecList errs,
+                   const DiisStatus* __restrict__ status, double* __restrict__ partial) {
+    if (status->done) return;
+    __shared__ double sh[256/32][MPID_MAX_HISTORY + 1];
+    double acc[MPID_MAX_HISTORY + 1];
+    for (int k = 0; k < m; k++) acc[k] = 0;
+    for (int s = blockIdx.x*blockDim.x + threadIdx.x; s < P.n; s += gridDim.x*blockDim.x) {
+        double ox, oy, oz;
+        applyAlphaLab(alphaLab + 6*(size_t) s, ifield[3*(size_t) s], ifield[3*(size_t) s+1], ifield[3*(size_t) s+2], ox, oy, oz);
+        const double nx = efix[3*(size_t) s] + ox, ny = efix[3*(size_t) s+1] + oy, nz = efix[3*(size_t) s+2] + oz;
+        histDip[3*(size_t) s] = nx; histDip[3*(size_t) s+1] = ny; histDip[3*(size_t) s+2] = nz;
+        const double e0 = nx - mu[3*(size_t) s], e1 = ny - mu[3*(size_t) s+1], e2 = nz - mu[3*(size_t) s+2];
+        histErr[3*(size_t) s] = e0; histErr[3*(size_t) s+1] = e1; histErr[3*(size_t) s+2] = e2;
+        for (int k = 0; k < m - 1; k++) {
+            const double* h = errs.v[k] + 3*(size_t) s;
+            acc[k] += e0*h[0] + e1*h[1] + e2*h[2];
+        }
+        acc[m-1] += e0*e0 + e1*e1 + e2*e2;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = 0; k < m; k++) {
+        double v = acc[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sh[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < m) {
+        double v = 0;
+        for (int w = 0; w < 256/32; w++) v += sh[w][threadIdx.x];
+        partial[(size_t) blockIdx.x*(MPID_MAX_HISTORY + 1) + threadIdx.x] = v;
+    }
+}
+
+// One CTA: finish the dot products, update B, test convergence (eps = 48.033324 sqrt(<e,e>/N), :1219) and, if not
+// converged, solve the (m+1)x(m+1) DIIS system (:1254-1291 does it through an SVD) by Gauss-Jordan elimination
+// with partial pivoting, one thread per matrix element.
+__global__ void __launch_bounds__(512)
+k_diis_solve(int numBlocks, int m, SlotList slots, int iteration, int numAtoms, double targetEps,
+             const double* __restrict__ partial, DiisStatus* __restrict__ status) {
+    if (status->done) return;
+    constexpr int H = MPID_MAX_HISTORY, R = MPID_MAX_HISTORY + 1, W = MPID_MAX_HISTORY + 2;
+    __shared__ double red[512];
+    __shared__ double dotv[R];
+    __shared__ double a[R][W];
+    __shared__ int pivRow;
+    __shared__ int converged;
+    const int tid = threadIdx.x;
+    // dot product k is finished by the 20 threads of group k = tid/20, in a fixed order
+    {
+        const int k = tid/20, q = tid % 20;
+        double v = 0;
+        if (k < m) for (int b = q; b < numBlocks; b += 20) v += partial[(size_t) b*R + k];
+        red[tid] = v;
+        __syncthreads();
+        if (k < m && q == 0) {
+            double t = 0;
+            for (int u = 0; u < 20; u++) t += red[tid + u];
+            dotv[k] = t;
+        }
+        __syncthreads();
+    }
+    const int newSlot = slots.s[m-1];
+    if (tid < m) {
+        const int sk = slots.s[tid];
+        status->B[newSlot*H + sk] = dotv[tid];
+        status->B[sk*H + newSlot] = dotv[tid];
+    }
+    if (tid == 0) {
+        const double eps = MPID_DEBYE*sqrt(dotv[m-1]/numAtoms);
+        status->iterations = iteration;
+        status->eps = eps;
+        converged = eps < targetEps ? 1 : 0;
+        if (converged) status->done = 1;
+    }
+    __syncthreads();
+    if (converged) return;
+    if (m == 1) { if (tid == 0) status->coef[0] = 1.0; return; }
+    __threadfence_block();
+    const int rank = m + 1, w = rank + 1;
+    const int r = tid / W, c = tid % W;
+    const bool inside = r < rank && c < w && tid < R*W;
+    if (inside) {
+        double v;
+        if (c == rank) v = r == 0 ? -1.0 : 0.0;
+        else if (r == 0 && c == 0) v = 0.0;
+        else if (r == 0 || c == 0) v = -1.0;
+        else v = status->B[slots.s[r-1]*H + slots.s[c-1]];
+        a[r][c] = v;
+    }
+    __syncthreads();
+    for (int col = 0; col < rank; col++) {
+        if (tid == 0) {
+            int piv = col;
+            for (int q = col + 1; q < rank; q++) if (fabs(a[q][col]) > fabs(a[piv][col])) piv = q;
+            pivRow = piv;
+        }
+        __syncthreads();
+        const int piv = pivRow;
+        // swap rows col <-> piv through registers
+        const bool sw = piv != col && inside && (r == col || r == piv);
+        double other = 0.0;
+        if (sw) other = a[r == col ? piv : col][c];
+        __syncthreads();
+        if (sw) a[r][c] = other;
+        __syncthreads();
+        const double d = a[col][col];
+        double f = 0.0, pc = 0.0;
+        if (inside && r != col && d != 0.0) { f = a[r][col]/d; pc = a[col][c]; }
+        __syncthreads();
+        if (inside && r != col && d != 0.0 && f != 0.0 && c >= col) a[r][c] -= f*pc;
+        __syncthreads();
+    }
+    if (tid < m) {
+        const double d = a[tid+1][tid+1];
+        status->coef[tid] = d != 0.0 ? a[tid+1][rank]/d : 0.0;
+    }
+}
+
+// mu = sum_k coef[k] * histDip_k with the coefficients k_diis_solve left in the status block (:1240-1249)
+template <typename real>
+__global__ void k_diis_combine(int n, int m, VecList vecs, const DiisStatus* __restrict__ status, double* __restrict__ mu,
+                               typename Real4<real>::type* __restrict__ mud) {
+    if (status->done) return;
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double x = 0, y = 0, z = 0;
+    for (int k = 0; k < m; k++) {
+        const double c = status->coef[k];
+        x += c*vecs.v[k][3*(size_t) s]; y += c*vecs.v[k][3*(size_t) s+1]; z += c*vecs.v[k][3*(size_t) s+2];
+    }
+    mu[3*(size_t) s] = x; mu[3*(size_t) s+1] = y; mu[3*(size_t) s+2] = z;
+    typename Real4<real>::type v = mud[s];
+    v.x = (real) x; v.y = (real) y; v.z = (real) z;
+    mud[s] = v;
 }
 
 // mu = sum_k coef[k] * vec_k   (DIIS extrapolation :1240-1249, OPT combination :1172-1177); repacks mud

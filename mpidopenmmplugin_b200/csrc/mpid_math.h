@@ -559,6 +559,38 @@ template <typename T> MPID_HD void momentsToQI(const T* pk, const V3<T>& X, cons
     }
 }
 
+// Torque intermediates of the QI frame: rotation generators about the frame's x, y, z axes acting on the
+// 16-vector Q, contracted with the potential-derivative vector V (:4442-4457, :4816-4838).  VM flags the
+// components of V that can be non-zero; the others are skipped at compile time.
+#define MPID_GEN_TERM(k, expr) if (VM & (1u << (k))) acc += (expr)*V[k];
+template <typename T, unsigned VM> MPID_HD T qiGenX(const T* Q, const T* V) {
+    const T s3 = T(1.7320508075688772), s6 = T(2.4494897427831779), s52 = T(1.5811388300841898), s32 = T(1.2247448713915890);
+    T acc = T(0);
+    MPID_GEN_TERM(1, Q[3]) MPID_GEN_TERM(3, -Q[1])
+    MPID_GEN_TERM(4, s3*Q[6]) MPID_GEN_TERM(5, Q[8]) MPID_GEN_TERM(6, -(s3*Q[4] + Q[7])) MPID_GEN_TERM(7, Q[6]) MPID_GEN_TERM(8, -Q[5])
+    MPID_GEN_TERM(9, s6*Q[11]) MPID_GEN_TERM(10, s52*Q[13]) MPID_GEN_TERM(11, -(s6*Q[9] + s52*Q[12]))
+    MPID_GEN_TERM(12, s52*Q[11] + s32*Q[15]) MPID_GEN_TERM(13, -(s52*Q[10] + s32*Q[14])) MPID_GEN_TERM(14, s32*Q[13]) MPID_GEN_TERM(15, -s32*Q[12])
+    return acc;
+}
+template <typename T, unsigned VM> MPID_HD T qiGenY(const T* Q, const T* V) {
+    const T s3 = T(1.7320508075688772), s6 = T(2.4494897427831779), s52 = T(1.5811388300841898), s32 = T(1.2247448713915890);
+    T acc = T(0);
+    MPID_GEN_TERM(1, -Q[2]) MPID_GEN_TERM(2, Q[1])
+    MPID_GEN_TERM(4, -s3*Q[5]) MPID_GEN_TERM(5, s3*Q[4] - Q[7]) MPID_GEN_TERM(6, -Q[8]) MPID_GEN_TERM(7, Q[5]) MPID_GEN_TERM(8, Q[6])
+    MPID_GEN_TERM(9, -s6*Q[10]) MPID_GEN_TERM(10, s6*Q[9] - s52*Q[12]) MPID_GEN_TERM(11, -s52*Q[13])
+    MPID_GEN_TERM(12, s52*Q[10] - s32*Q[14]) MPID_GEN_TERM(13, s52*Q[11] - s32*Q[15]) MPID_GEN_TERM(14, s32*Q[12]) MPID_GEN_TERM(15, s32*Q[13])
+    return acc;
+}
+template <typename T, unsigned VM> MPID_HD T qiGenZ(const T* Q, const T* V) {
+    T acc = T(0);
+    MPID_GEN_TERM(2, -Q[3]) MPID_GEN_TERM(3, Q[2])
+    MPID_GEN_TERM(5, -Q[6]) MPID_GEN_TERM(6, Q[5]) MPID_GEN_TERM(7, T(-2)*Q[8]) MPID_GEN_TERM(8, T(2)*Q[7])
+    MPID_GEN_TERM(10, -Q[11]) MPID_GEN_TERM(11, Q[10]) MPID_GEN_TERM(12, T(-2)*Q[13]) MPID_GEN_TERM(13, T(2)*Q[12])
+    MPID_GEN_TERM(14, T(-3)*Q[15]) MPID_GEN_TERM(15, T(3)*Q[14])
+    return acc;
+}
+#undef MPID_GEN_TERM
+
 struct PairParams {
     double alphaEwald;
     double defaultThole;
@@ -764,24 +796,19 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
 
     // ---- energy, radial force and torque intermediates (:4799-4838) ---------------------------------
     T energy = T(0), fIZ = T(0), fJZ = T(0);
+    constexpr unsigned VMI = SJ ? 0x213u : 0xFFFFu, VMJ = SI ? 0x213u : 0xFFFFu;   // components of Vij / Vji that can be non-zero
+#pragma unroll
     for (int i = 0; i < 16; i++) {
-        if (!SI || i == 0) { energy += QI[i]*Vij[i]; fIZ += QI[i]*VijR[i]; }
-        if (!SJ || i == 0) { energy += QJ[i]*Vji[i]; fJZ += QJ[i]*VjiR[i]; }
+        if ((!SI || i == 0) && ((VMI >> i) & 1u)) { energy += QI[i]*Vij[i]; fIZ += QI[i]*VijR[i]; }
+        if ((!SJ || i == 0) && ((VMJ >> i) & 1u)) { energy += QJ[i]*Vji[i]; fJZ += QJ[i]*VjiR[i]; }
     }
     energy *= T(0.5);
-    const T s3 = T(1.7320508075688772), s6 = T(2.4494897427831779), s52 = T(1.5811388300841898), s32 = T(1.2247448713915890);
-    // rotation generators about the frame's x, y, z axes acting on the 16-vector, contracted with V
-#define MPID_GEN_X(Q, V) ( (Q)[3]*(V)[1] - (Q)[1]*(V)[3] + s3*(Q)[6]*(V)[4] + (Q)[8]*(V)[5] - (s3*(Q)[4] + (Q)[7])*(V)[6] + (Q)[6]*(V)[7] - (Q)[5]*(V)[8] \
-        + s6*(Q)[11]*(V)[9] + s52*(Q)[13]*(V)[10] - (s6*(Q)[9] + s52*(Q)[12])*(V)[11] + (s52*(Q)[11] + s32*(Q)[15])*(V)[12] \
-        - (s52*(Q)[10] + s32*(Q)[14])*(V)[13] + s32*(Q)[13]*(V)[14] - s32*(Q)[12]*(V)[15] )
-#define MPID_GEN_Y(Q, V) ( -(Q)[2]*(V)[1] + (Q)[1]*(V)[2] - s3*(Q)[5]*(V)[4] + (s3*(Q)[4] - (Q)[7])*(V)[5] - (Q)[8]*(V)[6] + (Q)[5]*(V)[7] + (Q)[6]*(V)[8] \
-        - s6*(Q)[10]*(V)[9] + (s6*(Q)[9] - s52*(Q)[12])*(V)[10] - s52*(Q)[13]*(V)[11] + (s52*(Q)[10] - s32*(Q)[14])*(V)[12] \
-        + (s52*(Q)[11] - s32*(Q)[15])*(V)[13] + s32*(Q)[12]*(V)[14] + s32*(Q)[13]*(V)[15] )
-#define MPID_GEN_Z(Q, V) ( -(Q)[3]*(V)[2] + (Q)[2]*(V)[3] - (Q)[6]*(V)[5] + (Q)[5]*(V)[6] - T(2)*(Q)[8]*(V)[7] + T(2)*(Q)[7]*(V)[8] \
-        - (Q)[11]*(V)[10] + (Q)[10]*(V)[11] - T(2)*(Q)[13]*(V)[12] + T(2)*(Q)[12]*(V)[13] - T(3)*(Q)[15]*(V)[14] + T(3)*(Q)[14]*(V)[15] )
+    // rotation generators about the frame's x, y, z axes acting on the 16-vector, contracted with V (qiGenX/Y/Z);
+    // when the partner is a bare charge only the m = 0 components of V exist (mask 0x213 = {0,1,4,9}), which also
+    // makes the |m| >= 2 components of Q dead code
     T EIX = T(0), EIY = T(0), EIZ = T(0), EJX = T(0), EJY = T(0), EJZ = T(0);
-    if (!SI) { EIX = MPID_GEN_X(QI, Vij); EIY = MPID_GEN_Y(QI, Vij); EIZ = MPID_GEN_Z(QI, Vij); }
-    if (!SJ) { EJX = MPID_GEN_X(QJ, Vji); EJY = MPID_GEN_Y(QJ, Vji); EJZ = MPID_GEN_Z(QJ, Vji); }
+    if (!SI) { EIX = qiGenX<T, VMI>(QI, Vij); EIY = qiGenY<T, VMI>(QI, Vij); EIZ = qiGenZ<T, VMI>(QI, Vij); }
+    if (!SJ) { EJX = qiGenX<T, VMJ>(QJ, Vji); EJY = qiGenY<T, VMJ>(QJ, Vji); EJZ = qiGenZ<T, VMJ>(QJ, Vji); }
     // the same for the induced dipoles against the field of the permanent moments only
     T iEIX = UI[2]*Vijd[0] - UI[0]*Vijd[2], iEJX = UJ[2]*Vjid[0] - UJ[0]*Vjid[2];
     T iEIY = UI[0]*Vijd[1] - UI[1]*Vijd[0], iEJY = UJ[0]*Vjid[1] - UJ[1]*Vjid[0];
@@ -818,9 +845,6 @@ MPID_HD T pairElectrostatics(const T* pkI, const T* pkJ, const T* uI, const T* u
 #undef MPID_CROSS
 #undef MPID_CROSS_U_LO
 #undef MPID_CROSS_U_HI
-#undef MPID_GEN_X
-#undef MPID_GEN_Y
-#undef MPID_GEN_Z
 }
 
 // =====================================================================================================

@@ -101,9 +101,10 @@ void compare(const Input& in, MPIDForce::PolarizationType pol, const char* polNa
     State sb = b200.context->getState(State::Forces | State::Energy);
     report("relative force error", polName, relErr(sb.getForces(), sr.getForces()), tol);
     report("relative energy error", polName, std::fabs(sb.getPotentialEnergy() - sr.getPotentialEnergy())/std::fabs(sr.getPotentialEnergy()), tol);
-    // forces are accumulated into the Context's force array, never overwritten: a second evaluation gives the same State
+    // forces are added to the Context's (zeroed) force array, so a second evaluation gives the same State -- up to the
+    // summation order of the floating-point grid reductions in the PME spread, which is not fixed run to run
     State sb2 = b200.context->getState(State::Forces | State::Energy);
-    report("repeat evaluation force change", polName, relErr(sb2.getForces(), sb.getForces()), 0.0);
+    report("repeat evaluation force change", polName, relErr(sb2.getForces(), sb.getForces()), 0.1*tol);
     std::vector<Vec3> mr, mb;
     ref.force->getInducedDipoles(*ref.context, mr);
     b200.force->getInducedDipoles(*b200.context, mb);

@@ -184,7 +184,8 @@ def test_queries_and_errors():
     k.execute(s.pos, True, True, f)
     g = np.zeros((s.n, 3))
     k.execute(s.pos, True, True, g)
-    assert np.allclose(f - 1.0, g, rtol=0, atol=1e-9)
+    # (double precision; the grid spread's floating-point atomics leave ~1e-13 relative run-to-run noise)
+    assert np.abs(f - 1.0 - g).max() < 1e-10*np.abs(g).max()
     # box smaller than twice the cutoff (MPIDReferenceKernels.cpp:193-197)
     with pytest.raises(MPIDB200Error, match="less than twice the nonbonded cutoff"):
         k.setPeriodicBoxVectors(np.diag([1.5, 3.0, 3.0]))

@@ -36,7 +36,7 @@ def test_96k_box_invariances_and_determinism(prec):
     e2 = k.execute(s.pos, True, True, f2)
     # fixed-point accumulation of forces, torques and energy in the pair stage; the only float atomics are the
     # grid spreads, so run-to-run differences stay at round-off of the grid
-    assert abs(e1 - e2) < 1e-9*abs(e1)
+    assert abs(e1 - e2) < 1e-8*abs(e1)
     assert rel_err(f2, f1) < 1e-6
     # rigid translation by a lattice-incommensurate vector + whole-molecule wrapping into another image
     shift = np.array([0.3711, -1.2345, 7.7777])

@@ -1,0 +1,82 @@
+"""Multi-rank host logic on CPU: two processes, gloo backend (the GPU data path uses NCCL inside the engine)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpidopenmmplugin_b200 import sharding  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1. the unique id made on rank 0 reaches every rank unchanged
+        uid = sharding.broadcast_unique_id(dist, lambda: bytes((7*i + 3) % 256 for i in range(128)))
+        assert uid == bytes((7*i + 3) % 256 for i in range(128))
+        # 2. the row ranges tile [0, n) without gaps or overlap
+        b, e = sharding.row_range(n, rank, world)
+        owned = torch.zeros(n, dtype=torch.int32)
+        owned[b:e] = 1
+        dist.all_reduce(owned)
+        assert int(owned.min()) == 1 and int(owned.max()) == 1
+        # 3. partial sums over the owned rows all-reduce to the full sum (what the engine does with the partial
+        #    induced field on every solver iteration); integers, like the fixed-point force buffers -> exact
+        rng = np.random.default_rng(1234)
+        contrib = rng.integers(-2**40, 2**40, size=(n, 3), dtype=np.int64)       # contribution of row i to atom i
+        partial = torch.zeros((n, 3), dtype=torch.int64)
+        partial[b:e] = torch.from_numpy(contrib[b:e])
+        dist.all_reduce(partial)
+        assert torch.equal(partial, torch.from_numpy(contrib))
+        # 4. every special pair has exactly one owner
+        own = sharding.special_pair_owner(1001, world)
+        mine = torch.from_numpy((own == rank).astype(np.int32))
+        dist.all_reduce(mine)
+        assert int(mine.min()) == 1 and int(mine.max()) == 1
+        # 5. timing reduction = max over ranks
+        mx = sharding.max_over_ranks(dist, [1.0 + rank, 5.0 - rank])
+        assert mx == [float(world), 5.0]
+        out.put((rank, "ok"))
+    except Exception as ex:      # pragma: no cover
+        out.put((rank, "FAIL: %r" % (ex,)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [2988, 95617])
+def test_two_rank_partition_and_plumbing(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_collective_inventory_matches_the_engine():
+    """Mutual, PME, 6 field evaluations: fixed field + fixed grid + 6 x (grid + field) + forces/torques/energy."""
+    c = sharding.collectives_per_evaluation(0, 6, pme=True)
+    assert len(c) == 2 + 12 + 3
+    assert sum(1 for w in c if w[0] == "partial induced field") == 6
+    c = sharding.collectives_per_evaluation(2, 3, pme=True)
+    assert sum(1 for w in c if w[0] == "partial induced field gradient") == 3

@@ -91,7 +91,7 @@ def stage_rooflines(stats, n, G, pairs, n_f, pk):
     return out
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, real_stdout):
     """The reference's own CPU implementation (Reference platform, compiled unmodified into oracle/_ref) on a
     bounded sample of the workload: the 996-water box the synthetic boxes are tiled from."""
     if rank != 0:
@@ -119,10 +119,19 @@ def run_reference(args, rank):
                 config=dict(workload=WORKLOADS[wl]["name"], polarization="Mutual eps=1e-5 (DIIS)", sample=sample),
                 cpu_baseline=dict(value=value, unit="ns/day", cores=1, kind="reference", sample=sample, sample_ms_per_eval=ms),
                 e2e=dict(value=value, unit="ns/day", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line, real_stdout)
+
+
+def emit(line, real_stdout):
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    # Libraries loaded below (NCCL's version banner, torch warnings) write to fd 1; the contract is ONE JSON line on
+    # stdout, so fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -136,7 +145,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, real_stdout)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -224,13 +233,22 @@ def main():
         pk = peaks()
         stage_avg = {kk: v/args.steps for kk, v in stage_sum.items()}
         n_f = stats["iterations"] + 1
-        roofs = stage_rooflines(dict(stage_ms=stage_avg), n, G, float(stats["pairs"])*world, n_f, pk)
+        roofs = stage_rooflines(dict(stage_ms=stage_avg), n/world, G, float(stats["pairs"]), n_f, pk)   # rank 0's share of the work over rank 0's stage times
         dominant = max(roofs.items(), key=lambda kv: kv[1]["ms"])[0] if roofs else None
         roof = dict(roofs[dominant]) if dominant else None
         if roof:
             roof["kernel"] = dominant
+            # DRAM traffic of the dominant stage's kernels from the committed `ncu --set full` capture of this workload
+            # (profiles/traffic.json: bytes per evaluation), null when no capture exists for it
             roof["traffic"] = None
-            roof["peak_source"] = pk["source"] if roof["bound"] == "hbm" else "nominal FP32 FMA peak 148 SM x 128 lanes x 2 x %.0f MHz" % pk["sm_max_mhz"]
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tpath) and world == 1:
+                t = json.load(open(tpath)).get(wl, {}).get(dominant)
+                if t:
+                    roof["traffic"] = t["bytes"]
+                    roof["traffic_source"] = t["source"]
+            roof["peak_source"] = pk["source"] if roof["bound"] == "hbm" else "nominal FP32 FMA peak 148 SM x 128 lanes x 2 x %.0f MHz (pair kernels are FMA-pipe bound, not HBM or tensor bound)" % pk["sm_max_mhz"]
+            roof["algorithmic_work"] = "SURVEY.md 8(d): 2240 flop per in-cutoff pair (electrostatics), 430 (fixed field), 150 per field evaluation (induced field)"
         line = dict(metric="ns/day (force-evaluation limited, 2 fs) of one MPIDForce eval, waterbox PME + mutual induced",
                     value=NS_PER_DAY_PER_MS/dev_ms, unit="ns/day", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=dev_ms, higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None,
@@ -253,7 +271,7 @@ def main():
             scale = (n/2988.0)**2
             line["cpu_baseline"] = dict(value=NS_PER_DAY_PER_MS/(ms*scale), unit="ns/day", cores=1, kind="reference", sample_ms_per_eval=ms,
                                         sample="oracle/_ref (reference Reference-platform code, unmodified) on N=2988 (996-water box), %d evaluations at %.0f ms; x(N/2988)^2=%.0f extrapolation to N=%d (O(N^2) pair loops)" % (reps, ms, scale, n))
-        print(json.dumps(line), flush=True)
+        emit(line, real_stdout)
     k.close()
     if world > 1:
         dist.destroy_process_group()

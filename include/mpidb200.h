@@ -123,8 +123,8 @@ enum {
     MPIDB200_STAGE_FIXED_REAL,     /* real-space permanent field (+ mu = alpha.E)            */
     MPIDB200_STAGE_IND_SPREAD,     /* induced dipoles -> grid, all passes                    */
     MPIDB200_STAGE_IND_GATHER,     /* induced potential derivatives, all passes              */
-    MPIDB200_STAGE_IND_REAL,       /* real-space induced field, all passes (+ collectives)   */
-    MPIDB200_STAGE_SOLVER,         /* DIIS / OPT vector work and its host round trips        */
+    MPIDB200_STAGE_IND_REAL,       /* real-space induced field kernels, all passes           */
+    MPIDB200_STAGE_SOLVER,         /* stream joins, field combination, collectives, DIIS/OPT */
     MPIDB200_STAGE_ELECTROSTATICS, /* pair energy / force / torque                           */
     MPIDB200_STAGE_FINISH,         /* reciprocal terms, torque mapping, output               */
     MPIDB200_NUM_STAGES

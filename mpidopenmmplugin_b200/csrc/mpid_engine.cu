@@ -629,6 +629,10 @@ struct Engine : public EngineBase {
                 LAUNCH((k_special_field<0>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
                        dCartD.p, dDampThole.p, dFlagS.p, (const double*) nullptr, dField.p, (double*) nullptr);
         }
+        stageEnd();
+        // join with the reciprocal stream, add its field, exchange, mu0 = alpha.E : accounted to the solver stage so that
+        // the real-space stage times only its own kernels
+        stageBegin(MPIDB200_STAGE_SOLVER);
         if (pme) joinPme();
         if (rows > 0 && pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
         allReduce(dField.p, 3*(size_t) n, NCCL_FLOAT64);
@@ -681,6 +685,8 @@ struct Engine : public EngineBase {
                             dCartD.p, dDampThole.p, dFlagS.p, dMu.p, dIfield.p, (double*) nullptr);
             }
         }
+        stageEnd();
+        stageBegin(MPIDB200_STAGE_SOLVER);
         if (pme) joinPme();
         if (numPol > 0 && pme) {
             if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, grad);

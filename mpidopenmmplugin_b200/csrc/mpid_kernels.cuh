@@ -585,8 +585,12 @@ k_fixed_field(DevParams P, int numPol, const int* __restrict__ polList, const do
         const uint4 cnt = counts[i - P.rowBegin];
         const unsigned nUp = cnt.x, nAll = cnt.x + cnt.y;
         const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        // the list entry of the next trip is fetched one trip ahead so that its latency overlaps the arithmetic
+        unsigned eNext = sub < nAll ? (sub < nUp ? base[sub] : base[P.nbrCap - 1 - (sub - nUp)]) : 0u;
         for (unsigned k = sub; k < nAll; k += MPID_LANES) {
-            const unsigned e = k < nUp ? base[k] : base[P.nbrCap - 1 - (k - nUp)];
+            const unsigned e = eNext;
+            const unsigned kn = k + MPID_LANES;
+            if (kn < nAll) eNext = kn < nUp ? base[kn] : base[P.nbrCap - 1 - (kn - nUp)];
             const unsigned j = e & MPID_JMASK;
             real dx, dy, dz;
             pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
@@ -637,8 +641,10 @@ k_induced_field(DevParams P, int numPol, const int* __restrict__ polList, const 
         const real invDampI = mud[i].w;
         const unsigned nAll = polCount[rp];
         const unsigned* base = polNbr + (size_t) rp*P.nbrCap;
+        unsigned eNext = sub < nAll ? base[sub] : 0u;     // fetched one trip ahead
         for (unsigned k = sub; k < nAll; k += MPID_LANES) {
-            const unsigned e = base[k];
+            const unsigned e = eNext;
+            if (k + MPID_LANES < nAll) eNext = base[k + MPID_LANES];
             const unsigned j = e & MPID_JMASK;
             real dx, dy, dz;
             pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
@@ -766,22 +772,24 @@ k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ p
         atomicAddFixed(&force[3*(size_t) j], (double) f[0]); atomicAddFixed(&force[3*(size_t) j+1], (double) f[1]); atomicAddFixed(&force[3*(size_t) j+2], (double) f[2]);
         if (!SJ) { atomicAddFixed(&torque[3*(size_t) j], (double) tj[0]); atomicAddFixed(&torque[3*(size_t) j+1], (double) tj[1]); atomicAddFixed(&torque[3*(size_t) j+2], (double) tj[2]); }
     }
-    // i side: pairs of one i are contiguous, so a segmented warp reduction leaves one atomic per run
-    double v[6] = {-(double) f[0], -(double) f[1], -(double) f[2], (double) ti[0], (double) ti[1], (double) ti[2]};
+    // i side: pairs of one i are contiguous, so a segmented warp reduction leaves one atomic per run.  The partial
+    // sums (<= 32 terms) are carried in `real`: one shuffle per value and round; the cross-warp sum is fixed point.
+    constexpr int NV = SI ? 3 : 6;      // a simple site feels no torque
+    real v[6] = {-f[0], -f[1], -f[2], ti[0], ti[1], ti[2]};
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const int io = __shfl_down_sync(0xffffffffu, i, off);
         const bool take = (lane + off < 32) && (io == i);
 #pragma unroll
-        for (int q = 0; q < 6; q++) {
-            const double w = __shfl_down_sync(0xffffffffu, v[q], off);
+        for (int q = 0; q < NV; q++) {
+            const real w = __shfl_down_sync(0xffffffffu, v[q], off);
             if (take) v[q] += w;
         }
     }
     const int iprev = __shfl_up_sync(0xffffffffu, i, 1);
     if (active && (lane == 0 || iprev != i)) {
-        atomicAddFixed(&force[3*(size_t) i], v[0]); atomicAddFixed(&force[3*(size_t) i+1], v[1]); atomicAddFixed(&force[3*(size_t) i+2], v[2]);
-        if (!SI) { atomicAddFixed(&torque[3*(size_t) i], v[3]); atomicAddFixed(&torque[3*(size_t) i+1], v[4]); atomicAddFixed(&torque[3*(size_t) i+2], v[5]); }
+        atomicAddFixed(&force[3*(size_t) i], (double) v[0]); atomicAddFixed(&force[3*(size_t) i+1], (double) v[1]); atomicAddFixed(&force[3*(size_t) i+2], (double) v[2]);
+        if (!SI) { atomicAddFixed(&torque[3*(size_t) i], (double) v[3]); atomicAddFixed(&torque[3*(size_t) i+1], (double) v[4]); atomicAddFixed(&torque[3*(size_t) i+2], (double) v[5]); }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
@@ -809,8 +817,11 @@ k_simple_pairs(DevParams P, int numSimple, const int* __restrict__ simpleList, c
         const uint4 cnt = counts[i - P.rowBegin];
         const unsigned nUp = cnt.x, nAll = cnt.x + cnt.y;
         const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        unsigned eNext = sub < nAll ? (sub < nUp ? base[sub] : base[P.nbrCap - 1 - (sub - nUp)]) : 0u;     // fetched one trip ahead
         for (unsigned k = sub; k < nAll; k += MPID_LANES) {
-            const unsigned e = k < nUp ? base[k] : base[P.nbrCap - 1 - (k - nUp)];
+            const unsigned e = eNext;
+            const unsigned kn = k + MPID_LANES;
+            if (kn < nAll) eNext = kn < nUp ? base[kn] : base[P.nbrCap - 1 - (kn - nUp)];
             const unsigned j = e & MPID_JMASK;
             const double4 pj = posS[j];
             if (!(((int) pj.w) & 2)) continue;

@@ -521,6 +521,86 @@ template <typename T> MPID_HD void inducedFieldGradientDirected(T mx, T my, T mz
     g[5] += a*dy*dz - (my*dz + mz*dy)*b;
 }
 
+// Inverse of packPairMoments: the 20 Cartesian components {c, d, Q (6), O (10)} (internal orders) of the traceless
+// tensors the pair-energy code works with.  They equal the lab Cartesian moments with the trace removed -- the
+// reference's energy routine sees the moments through their spherical components, i.e. without any trace the input had.
+template <typename T> MPID_HD void unpackPairMoments(const T* pk, T* m) {
+    m[0] = pk[0]; m[1] = pk[1]; m[2] = pk[2]; m[3] = pk[3];
+    m[4] = pk[4]; m[5] = pk[5]; m[6] = pk[6]; m[7] = pk[7]; m[8] = pk[8]; m[9] = -(pk[4] + pk[7]);
+    m[10] = pk[9]; m[11] = pk[10]; m[12] = pk[11]; m[13] = pk[12]; m[14] = pk[13]; m[15] = -(pk[9] + pk[12]);
+    m[16] = pk[14]; m[17] = pk[15]; m[18] = -(pk[10] + pk[14]); m[19] = -(pk[11] + pk[15]);
+}
+
+// Ordinary pair between a bare-charge site B ("me": charge only, never polarized) and a full site A ("other"),
+// d = r_A - r_B (minimum image).  For this pair class the interaction of calculatePmeDirectElectrostaticPairIxn
+// (:4335-4920; no cutoff :1331-1893) collapses to the potential and the field of A's moments at B, in Cartesian form
+// and without a pair frame:
+//     U     = k qB [ phi_perm(B) + 1/2 phi_mu(B) ]                 (induced dipoles carry the usual 1/2 in the energy)
+//     F_B   = k qB [ E_perm(B) + E_mu(B) ] = -F_A
+//     tau_A = d x k qB E_perm(B)   (+ d x k qB E_mu(B) on anisotropic sites, :4888-4897)
+// with phi = bn0 c - bn1 (p.d) + bn2 (d.Q.d) - bn3 (O:ddd) and E from fixedFieldDirected / inducedFieldDirected.
+// The torque needs no multipole-by-multipole formula: a point charge feels none, so tau_A = -R x F_B with R = -d.
+// Permanent moments are undamped; the induced dipole is Thole-damped with the default width when both sites have a
+// damping factor (invDamp = 1/(damp_A damp_B), 0 otherwise) -- the same factors as the field kernels (:2693-2701),
+// whose radial derivative is what the reference's dthole_c encodes.
+// mA = {c, dx,dy,dz, Qxx..Qzz, Oxxx..Ozzz} from unpackPairMoments (traceless, as the energy routine sees them),
+// u = induced dipole of A.
+// Outputs: fB[3] force on B, tqA[3] torque on A, without the Coulomb constant and without qB (caller scales);
+// returns phi_perm + phi_mu/2.
+template <typename T, bool EWALD>
+MPID_HD T chargeSitePair(const T* mA, T ux, T uy, T uz, T invDamp, bool anisoA, T dx, T dy, T dz, T r2,
+                         T alphaEwald, T defaultThole, T* fB, T* tqA) {
+    const T rinv = t_rsqrt(r2);
+    const T r = r2*rinv, rinv2 = rinv*rinv;
+    T c[4], bn0;
+    T bare3 = rinv*rinv2, bare5 = T(3)*bare3*rinv2;
+    if (EWALD) {
+        const T x = alphaEwald*r;
+        const T ex2 = t_expneg(-(x*x));
+        bn0 = t_erfc_ex(x, ex2)*rinv;
+        const T alsq2 = T(2)*alphaEwald*alphaEwald;
+        T a2n = T(1.0/MPID_SQRT_PI)/alphaEwald;
+        T bn = bn0, fac = T(1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++) {
+            a2n *= alsq2;
+            bn = (fac*bn + a2n*ex2)*rinv2;
+            c[k] = bn;
+            fac += T(2);
+        }
+    } else {
+        bn0 = rinv;
+        c[0] = bare3; c[1] = bare5; c[2] = T(5)*bare5*rinv2; c[3] = T(7)*c[2]*rinv2;
+    }
+    T cu[2] = {c[0], c[1]};
+    if (invDamp != T(0)) {
+        const T au = defaultThole*r*invDamp;
+        if (au < T(50)) {
+            const T ex = t_expneg(-au);
+            const T p3 = T(1) + au + T(0.5)*au*au;
+            cu[0] -= ex*p3*bare3;
+            cu[1] -= ex*(p3 + au*au*au*T(1.0/6.0))*bare5;
+        }
+    }
+    T ex_ = T(0), ey_ = T(0), ez_ = T(0), ix = T(0), iy = T(0), iz = T(0);
+    fixedFieldDirected<T>(mA, dx, dy, dz, c, ex_, ey_, ez_);
+    inducedFieldDirected<T>(ux, uy, uz, dx, dy, dz, cu, ix, iy, iz);
+    // potential: the contractions are recomputed here (cheap) rather than threaded out of fixedFieldDirected
+    const T dd = mA[1]*dx + mA[2]*dy + mA[3]*dz;
+    const T qx = mA[4]*dx + mA[5]*dy + mA[6]*dz, qy = mA[5]*dx + mA[7]*dy + mA[8]*dz, qz = mA[6]*dx + mA[8]*dy + mA[9]*dz;
+    const T qdd = qx*dx + qy*dy + qz*dz;
+    const T oxx = mA[10]*dx + mA[11]*dy + mA[12]*dz, oxy = mA[11]*dx + mA[13]*dy + mA[14]*dz, oxz = mA[12]*dx + mA[14]*dy + mA[15]*dz;
+    const T oyy = mA[13]*dx + mA[16]*dy + mA[17]*dz, oyz = mA[14]*dx + mA[17]*dy + mA[18]*dz, ozz = mA[15]*dx + mA[18]*dy + mA[19]*dz;
+    const T oddd = (oxx*dx + oxy*dy + oxz*dz)*dx + (oxy*dx + oyy*dy + oyz*dz)*dy + (oxz*dx + oyz*dy + ozz*dz)*dz;
+    const T phi = bn0*mA[0] - c[0]*dd + c[1]*qdd - c[2]*oddd - T(0.5)*cu[0]*(ux*dx + uy*dy + uz*dz);
+    fB[0] = ex_ + ix; fB[1] = ey_ + iy; fB[2] = ez_ + iz;
+    const T tx = anisoA ? fB[0] : ex_, ty = anisoA ? fB[1] : ey_, tz = anisoA ? fB[2] : ez_;
+    tqA[0] = dy*tz - dz*ty; tqA[1] = dz*tx - dx*tz; tqA[2] = dx*ty - dy*tx;
+    return phi;
+}
+
 // =====================================================================================================
 // Pair energy / force / torque in the quasi-internal (QI) frame
 // =====================================================================================================

@@ -86,11 +86,11 @@ class FlatSystem:
         return f
 
 
-def make_kernel(system, precision="mixed", device=0, profiling=False):
+def make_kernel(system, precision="mixed", device=0, profiling=False, frameless_alpha_fix=False):
     """Create an engine for a FlatSystem through the raw C ABI (no per-atom python loops)."""
     import ctypes
     from .api import MPIDB200Kernel, _Config, _dp, _ip
-    k = MPIDB200Kernel(precision=precision, device=device)
+    k = MPIDB200Kernel(precision=precision, device=device, frameless_alpha_fix=frameless_alpha_fix)
     lib = k._lib
     cfg = _Config()
     lib.mpidb200_default_config(ctypes.byref(cfg))
@@ -224,3 +224,57 @@ def subset_waters(s, nwaters):
     for k in ("box", "method", "polarization", "cutoff", "alpha", "grid", "ewald_tol", "default_thole", "scale14", "max_iter", "epsilon", "coefs"):
         setattr(t, k, copy.deepcopy(getattr(s, k)))
     return t
+
+
+def ethane_box(polarization=1, cutoff=0.8, default_thole=8.0):
+    """examples/ethane_water_charge_only (BASELINE.json config 2): ethane in 1383 waters, N = 4,157, L = 3.5 nm,
+    charges only, isotropic polarizabilities on OW and CT3, Direct polarization (run_ethane.py:12-13,
+    ethane_water.xml:51-59).  Every <Multipole> entry of that force field lacks kz/kx, so the reference's generator
+    gives every atom NoAxisType with anchors -1 (python/mpidplugin.i:1009-1023) -- and on the Reference platform
+    such atoms end up with a zero lab-frame polarizability.  Covalent12/13/14 maps from the bonds
+    (mpidplugin.i:1042-1044).  Coordinates: tests/golden/ethane_water.npz (made by tests/golden/make_ethane_fixture.py)."""
+    d = np.load(os.path.join(_ROOT, "tests", "golden", "ethane_water.npz"))
+    pos = d["milli_angstrom"].astype(np.float64)*1e-4
+    z = d["atomic_number"]
+    n = len(pos)
+    s = FlatSystem(n)
+    s.pos = pos
+    bonds = [tuple(b) for b in d["ethane_bonds"]]
+    for w in range(8, n, 3):
+        bonds += [(w, w+1), (w, w+2)]
+    nb = [set() for _ in range(n)]
+    for a, b in bonds:
+        nb[a].add(int(b)); nb[b].add(int(a))
+    carbon = {0, 1}
+    for i in range(n):
+        if i < 8:
+            s.charges[i] = -0.27 if i in carbon else 0.09
+            if i in carbon:
+                s.alphas[i] = 0.00068; s.tholes[i] = 8.0
+        elif z[i] == 8:
+            s.charges[i] = -0.834; s.alphas[i] = 0.00088; s.tholes[i] = 8.0
+        else:
+            s.charges[i] = 0.417
+    cov = [[[] for _ in range(8)] for _ in range(n)]
+    for i in range(n):
+        c12 = nb[i]
+        c13 = set()
+        for j in c12:
+            c13 |= nb[j]
+        c13 -= c12 | {i}
+        c14 = set()
+        for j in c13:
+            c14 |= nb[j]
+        c14 -= c12 | c13 | {i}
+        cov[i][0] = sorted(c12); cov[i][1] = sorted(c13); cov[i][2] = sorted(c14)
+    s.covalent = cov
+    L = d["box_angstrom"].astype(np.float64)*0.1
+    s.box = np.diag(L)
+    s.method = 1
+    s.polarization = polarization
+    s.cutoff = cutoff
+    s.alpha = 0.0          # automatic PME parameters, as the example script leaves them (ewaldErrorTolerance 5e-4)
+    s.grid = (0, 0, 0)
+    s.default_thole = default_thole
+    s.scale14 = 1.0
+    return s

@@ -391,7 +391,28 @@ template <typename T> struct Emul {
                 S.lab[i].aniso != 0, S.lab[j].aniso != 0, T(dx), T(dy), T(dz), T(r2), T(S.alpha), T(S.defaultThole), sc, sc, f, ti, tj)
 #define CALL(EW, MU) { if (simple[i] && simple[j]) CALL4(EW, MU, true, true); else if (simple[i]) CALL4(EW, MU, true, false); \
                        else if (simple[j]) CALL4(EW, MU, false, true); else CALL4(EW, MU, false, false); }
-            if (S.method == PME) { if (mutual) CALL(true, true) else CALL(true, false) }
+            if (cls == 0 && (simple[i] != simple[j])) {
+                // ordinary charge-site x full-site pair: the Cartesian specialisation the GPU uses (chargeSitePair)
+                const int b = simple[i] ? i : j, a = simple[i] ? j : i;        // B = bare charge, A = full site
+                const T sgn = simple[i] ? T(1) : T(-1);                        // d = r_A - r_B
+                const T dmp = T(S.damp[a]*S.damp[b]);
+                T fB[3], tA[3], mA[20];
+                unpackPairMoments<T>(&pk[16*a], mA);
+                const T* ua = simple[i] ? uJ : uI;
+                T phi;
+                if (S.method == PME) phi = chargeSitePair<T, true>(mA, ua[0], ua[1], ua[2], dmp != T(0) ? T(1)/dmp : T(0), S.lab[a].aniso != 0,
+                                                                  sgn*T(dx), sgn*T(dy), sgn*T(dz), T(r2), T(S.alpha), T(S.defaultThole), fB, tA);
+                else phi = chargeSitePair<T, false>(mA, ua[0], ua[1], ua[2], dmp != T(0) ? T(1)/dmp : T(0), S.lab[a].aniso != 0,
+                                                    sgn*T(dx), sgn*T(dy), sgn*T(dz), T(r2), T(0), T(S.defaultThole), fB, tA);
+                const T kq = T(MPID_ELECTRIC)*pk[16*b];
+                e = kq*phi;
+                for (int k = 0; k < 3; k++) {
+                    f[k] = (b == j ? T(1) : T(-1))*kq*fB[k];      // f is the force on j
+                    ti[k] = a == i ? kq*tA[k] : T(0);
+                    tj[k] = a == j ? kq*tA[k] : T(0);
+                }
+            }
+            else if (S.method == PME) { if (mutual) CALL(true, true) else CALL(true, false) }
             else { if (mutual) CALL(false, true) else CALL(false, false) }
 #undef CALL
 #undef CALL4

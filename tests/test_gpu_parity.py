@@ -233,3 +233,48 @@ def test_mpidforce_object_path_matches_flat_path():
     e0, _ = Oracle(t).execute()
     assert abs(e1 - e0) < 1e-8*abs(e0)
     k.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_ethane_water_charge_only_example(prec):
+    """BASELINE.json config 2 (examples/ethane_water_charge_only): charges only, Direct polarization, 1-2/1-3/1-4 maps
+    of ethane, automatic PME parameters.  On the Reference platform every induced dipole of this input is exactly
+    zero because its atoms carry no frame; the engine must reproduce that."""
+    from mpidopenmmplugin_b200.workloads import ethane_box
+    s = ethane_box()
+    o = Oracle(s)
+    e0, f0 = o.execute()
+    k, e, f, mu = run(s, prec)
+    assert k.getPMEParameters() == o.pme_parameters()
+    assert rel_err(f, f0) < FTOL[prec]
+    assert abs(e - e0) < FTOL[prec]*abs(e0)
+    assert np.all(mu == 0.0) and np.all(o.dipoles(0) == 0.0)
+    k.close()
+
+
+def test_ethane_water_with_frames_polarizes():
+    """Same input with a frame on every polarizable atom (the frame orientation is irrelevant for isotropic alpha and
+    charge-only sites): the oracle now induces dipoles, and the engine's opt-in `frameless_alpha_fix` on the ORIGINAL
+    frameless input gives the same answer."""
+    from mpidopenmmplugin_b200.workloads import ethane_box
+    s = ethane_box()
+    t = s.copy()
+    for i in range(t.n):
+        if t.alphas[i, 0] != 0.0:
+            nb = t.covalent[i][0]
+            t.axis[i] = MPIDForce.ZThenX; t.atomZ[i] = nb[0]; t.atomX[i] = nb[1]
+    o = Oracle(t)
+    e0, f0 = o.execute()
+    mu0 = o.dipoles(0)
+    assert np.abs(mu0).max() > 1e-4
+    k = make_kernel(t, precision="double")
+    f = np.zeros((t.n, 3))
+    e = k.execute(t.pos, True, True, f)
+    assert rel_err(f, f0) < 1e-8 and rel_err(k.getInducedDipoles(t.pos), mu0) < 1e-8
+    k.close()
+    from mpidopenmmplugin_b200.api import MPIDB200Kernel
+    kf = make_kernel(s, precision="double", frameless_alpha_fix=True)
+    g = np.zeros((s.n, 3))
+    eg = kf.execute(s.pos, True, True, g)
+    assert rel_err(g, f0) < 1e-8 and abs(eg - e0) < 1e-8*abs(e0)
+    kf.close()

@@ -130,6 +130,10 @@ enum {
     MPIDB200_NUM_STAGES
 };
 int mpidb200_get_stats(mpidb200_handle h, int* iterations, double* epsilon, double* stage_ms, long long* num_pairs);
+/* Ordinary in-cutoff pairs (i<j) of the last execute by site class: out3[0] full-full (quasi-internal-frame kernel),
+ * out3[1] full x bare-charge (Cartesian gather kernel), out3[2] charge-charge.  "bare charge" = a site with no
+ * permanent dipole/quadrupole/octopole and no polarizability. */
+int mpidb200_get_pair_class_counts(mpidb200_handle h, long long* out3);
 /* per-stage CUDA-event timing: events are recorded on the engine's stream around each stage and read
  * after the call's final synchronisation (no extra synchronisation is added); off by default */
 int mpidb200_set_profiling(mpidb200_handle h, int enabled);

@@ -39,7 +39,7 @@ EXPORTS = ["mpidb200_last_error", "mpidb200_default_config", "mpidb200_create", 
            "mpidb200_set_covalent_maps", "mpidb200_set_box", "mpidb200_execute", "mpidb200_execute_device",
            "mpidb200_get_dipoles", "mpidb200_get_system_multipole_moments", "mpidb200_get_electrostatic_potential",
            "mpidb200_get_pme_parameters", "mpidb200_get_stats", "mpidb200_set_profiling", "mpidb200_last_launch_count",
-           "mpidb200_get_pair_list", "mpidb200_nccl_unique_id", "mpidb200_comm_init", "mpidb200_set_stream"]
+           "mpidb200_get_pair_list", "mpidb200_get_pair_class_counts", "mpidb200_nccl_unique_id", "mpidb200_comm_init", "mpidb200_set_stream"]
 
 
 def load_library():
@@ -415,7 +415,10 @@ class MPIDB200Kernel:
         it = ctypes.c_int(); eps = ctypes.c_double(); ms = (ctypes.c_double*16)(); pairs = ctypes.c_longlong()
         self._check(self._lib.mpidb200_get_stats(self._h, ctypes.byref(it), ctypes.byref(eps), ms, ctypes.byref(pairs)))
         names = STAGE_NAMES
+        cls = (ctypes.c_longlong*3)()
+        self._check(self._lib.mpidb200_get_pair_class_counts(self._h, cls))
         return dict(iterations=it.value, epsilon=eps.value, pairs=pairs.value,
+                    pair_classes=dict(full_full=cls[0], full_charge=cls[1], charge_charge=cls[2]),
                     stage_ms={k: ms[i] for i, k in enumerate(names)},
                     launches=int(self._lib.mpidb200_last_launch_count(self._h)))
 

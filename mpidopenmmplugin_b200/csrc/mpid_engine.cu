@@ -89,6 +89,7 @@ struct EngineBase {
     virtual void getDipoles(const double* pos, int which, double* out) = 0;
     virtual void getPme(double& alpha, int& nx, int& ny, int& nz) = 0;
     virtual void getStats(int* it, double* eps, double* ms, long long* pairs) = 0;
+    virtual void getPairClassCounts(long long* out3) = 0;
     virtual long long getPairList(long long cap, int* pi, int* pj, int* pc) = 0;
     virtual void commInit(int rank, int nranks, const unsigned char* id) = 0;
     virtual void setStream(void* st) = 0;
@@ -122,6 +123,8 @@ struct Engine : public EngineBase {
     int n;
     cudaStream_t stream = nullptr, ownStream = nullptr;
     cudaStream_t stream2 = nullptr;     // reciprocal-space work runs here, concurrently with the real-space kernels
+    cudaStream_t stream3 = nullptr;     // pair work that does not depend on the induced dipoles (fills the SMs the solver leaves idle)
+    cudaEvent_t evFork3 = nullptr, evJoin3 = nullptr;
     cudaStream_t cur = nullptr;         // stream the LAUNCH macro / stage timers currently target
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool haveParticles = false, haveBox = false, pmeReady = false;
@@ -149,8 +152,10 @@ struct Engine : public EngineBase {
     DevBuf<real4> dMud;
     DevBuf<uint4> dCounts;
     DevBuf<unsigned> dTypeCount, dTypeStart, dMaxCount, dNbr, dPairI, dPairJ, dPolNbr, dPolCount;
-    DevBuf<int> dFlagS, dPolFlag, dPolRank, dPolList, dSimpleRank, dSimpleList;
+    DevBuf<int> dFlagS, dPolFlag, dPolRank, dPolList, dSimpleRank, dSimpleList, dFullRank, dFullList;
     int numSimpleTotal = 0, numSimple = 0, simpleBegin = 0;
+    int numFull = 0, fullBegin = 0;       // sites that are not bare charges, among this rank's rows
+    bool classCountsValid = false;
     int nbrCap = 0;
     int numPolTotal = 0;            // polarizable sites (static: follows from the parameters)
     int numPol = 0, polBegin = 0;   // polarizable sites among this rank's rows
@@ -179,6 +184,9 @@ struct Engine : public EngineBase {
         stream = ownStream;
         cur = stream;
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream3, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evFork3, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evJoin3, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
         CUDA_CHECK(cudaMallocHost((void**) &hPinned, 256*sizeof(double)));
@@ -200,6 +208,9 @@ struct Engine : public EngineBase {
         if (evFork) cudaEventDestroy(evFork);
         if (evJoin) cudaEventDestroy(evJoin);
         if (stream2) cudaStreamDestroy(stream2);
+        if (evFork3) cudaEventDestroy(evFork3);
+        if (evJoin3) cudaEventDestroy(evJoin3);
+        if (stream3) cudaStreamDestroy(stream3);
         if (ownStream) cudaStreamDestroy(ownStream);
     }
     // Reciprocal space is independent of the real-space pair kernels until their results are combined, and
@@ -273,6 +284,7 @@ struct Engine : public EngineBase {
         dThole.upload(hThole, stream); dAlpha.upload(hAlpha, stream); dDamp.upload(hDamp, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         haveParticles = true;
+        classCountsValid = false;
         if (hSpStart.empty()) {   // no covalent maps yet: empty special lists
             std::vector<int> off(8*(size_t) (n+1), 0), idx(1, 0);
             setCovalent(off.data(), idx.data());
@@ -477,7 +489,8 @@ struct Engine : public EngineBase {
         return pp;
     }
 
-    void buildNeighbors(const double* dPosIn) {
+    // wrap, cell sort, lab-frame moments, site-class lists (everything the reciprocal-space pass needs)
+    void sortAndFrames(const double* dPosIn) {
         const int B = 256;
         int numCells = P.ncell[0]*P.ncell[1]*P.ncell[2];
         dPosW.ensure(3*(size_t) n); dCellKey.ensure(n); dAtomIdx.ensure(n); dSortedKey.ensure(n); dOrder.ensure(n); dInv.ensure(n);
@@ -505,24 +518,26 @@ struct Engine : public EngineBase {
         dAlphaLab.ensure(6*(size_t) n); dAniso.ensure(n); dDampThole.ensure(n); dMud.ensure(n); dSpSorted.ensure(n);
         dFlagS.ensure(n); dPolFlag.ensure((size_t) n + 1); dPolRank.ensure((size_t) n + 1); dPolList.ensure((size_t) n + 1);
         dSimpleRank.ensure((size_t) n + 1); dSimpleList.ensure((size_t) n + 1);
+        dFullRank.ensure((size_t) n + 1); dFullList.ensure((size_t) n + 1);
         real* cartR; real* pkR;
         if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
         LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
                dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p,
                dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p, dFlagS.p);
-        // polarizable rows and simple rows: rank (exclusive scan of the class flag) and compact list
-        for (int cls = 0; cls < 2; cls++) {
-            int bit = cls == 0 ? 1 : 2;
-            int* rank = cls == 0 ? dPolRank.p : dSimpleRank.p;
-            int* list = cls == 0 ? dPolList.p : dSimpleList.p;
-            LAUNCH(k_pol_flags, blocksFor(n + 1, B), B, n, bit, dFlagS.p, dPolFlag.p);
+        // polarizable rows, bare-charge ("simple") rows and their complement ("full"): rank (exclusive scan of the
+        // class flag) and compact list
+        for (int cls = 0; cls < 3; cls++) {
+            const int bit = cls == 0 ? 1 : 2, want = cls == 2 ? 0 : 1;
+            int* rank = cls == 0 ? dPolRank.p : (cls == 1 ? dSimpleRank.p : dFullRank.p);
+            int* list = cls == 0 ? dPolList.p : (cls == 1 ? dSimpleList.p : dFullList.p);
+            LAUNCH(k_pol_flags, blocksFor(n + 1, B), B, n, bit, want, dFlagS.p, dPolFlag.p);
             size_t tb = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb, dPolFlag.p, rank, n + 1, stream);
             dScanTemp.ensure(tb + 16);
             CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tb, dPolFlag.p, rank, n + 1, stream));
             launches += 1;
-            LAUNCH(k_pol_list, blocksFor(n, B), B, n, bit, dFlagS.p, rank, list);
+            LAUNCH(k_pol_list, blocksFor(n, B), B, n, bit, want, dFlagS.p, rank, list);
         }
         if (numRanks > 1) {
             int* pr = (int*) hPinned;
@@ -533,9 +548,28 @@ struct Engine : public EngineBase {
             CUDA_CHECK(cudaStreamSynchronize(stream));
             polBegin = pr[0]; numPol = pr[1] - pr[0];
             simpleBegin = pr[2]; numSimple = pr[3] - pr[2];
-        } else { polBegin = 0; numPol = numPolTotal; simpleBegin = 0; numSimple = numSimpleTotal; }
+        } else {
+            if (!classCountsValid) {
+                // site classes follow from the parameters: count them on the device once per parameter set, with the
+                // same tests the kernels apply (lab-frame tensors), instead of trusting a host-side restatement
+                int* pr = (int*) hPinned;
+                CUDA_CHECK(cudaMemcpyAsync(&pr[0], dPolRank.p + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CUDA_CHECK(cudaMemcpyAsync(&pr[1], dSimpleRank.p + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+                numPolTotal = pr[0]; numSimpleTotal = pr[1];
+                classCountsValid = true;
+            }
+            polBegin = 0; numPol = numPolTotal; simpleBegin = 0; numSimple = numSimpleTotal;
+        }
+        // full = complement of simple within the same row range
+        fullBegin = P.rowBegin - simpleBegin; numFull = (P.rowEnd - P.rowBegin) - numSimple;
         stageEnd();
-        // neighbour list: single pass into per-atom runs, then the flat half list for the energy kernel
+    }
+
+    // neighbour list: single pass into per-atom runs, then the flat half list for the energy kernel
+    void buildNeighborList(const double* dPosIn) {
+        const int B = 256;
+        const int numCells = P.ncell[0]*P.ncell[1]*P.ncell[2];
         stageBegin(MPIDB200_STAGE_NLIST);
         int rows = P.rowEnd - P.rowBegin;
         const size_t tlen = 5*((size_t) rows + 1);
@@ -578,10 +612,38 @@ struct Engine : public EngineBase {
         }
         for (int t = 0; t < 5; t++) typeBegin[t] = totals[1 + t];
         lastPairs = totals[6];                       // every ordinary pair (i<j) of this rank's rows
-        const long long flatPairs = typeBegin[4];    // pairs in the flat class lists (simple-simple pairs are gathered instead)
+        const long long flatPairs = typeBegin[1];    // the flat list holds the full-full class only (it comes first)
         dPairI.ensure((size_t) flatPairs + 1); dPairJ.ensure((size_t) flatPairs + 1);
-        if (rows > 0 && flatPairs > 0)
+        stageEnd();
+    }
+
+    // Pair work that needs the neighbour list but not the induced dipoles -- the flat full-full list for the energy
+    // kernel and the charge-charge pairs -- goes to a third stream right after the neighbour search and is joined
+    // before the energy stage: it runs on the SMs the (latency-bound) solver iterations leave idle.
+    bool forked3 = false;
+    void startDipoleIndependentPairs() {
+        const int B = 256;
+        const int rows = P.rowEnd - P.rowBegin;
+        const bool pme = P.method == PME;
+        CUDA_CHECK(cudaEventRecord(evFork3, stream));
+        CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
+        cudaStream_t keep = cur;
+        cur = stream3;
+        if (rows > 0 && typeBegin[1] > 0)
             LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, dPairI.p, dPairJ.p);
+        if (numSimple > 0) {
+            const int nbS = blocksFor((long long) numSimple*MPID_LANES, 256);
+            if (pme) LAUNCH((k_simple_pairs<real, true>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
+            else LAUNCH((k_simple_pairs<real, false>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
+        }
+        cur = keep;
+        forked3 = true;
+    }
+    void joinDipoleIndependentPairs() {
+        if (!forked3) return;
+        CUDA_CHECK(cudaEventRecord(evJoin3, stream3));
+        CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin3, 0));
+        forked3 = false;
     }
 
     void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
@@ -598,26 +660,32 @@ struct Engine : public EngineBase {
     real* cartR() { return sizeof(real) == sizeof(double) ? (real*) dCartD.p : dCartR.p; }
     real* pkR() { return sizeof(real) == sizeof(double) ? (real*) dPkD.p : dPkR.p; }
 
+    // Reciprocal-space part of the permanent field on the second stream: it needs the sorted atoms and their lab-frame
+    // moments only, so it is started BEFORE the neighbour list is built and runs beside it.
+    void fixedReciprocalStart() {
+        if (P.method != PME) return;
+        const int rows = P.rowEnd - P.rowBegin;
+        size_t G = (size_t) grid[0]*grid[1]*grid[2];
+        dPhi.ensure(35*(size_t) n); dPhidp.ensure(35*(size_t) n);
+        forkPme();
+        stageBegin(MPIDB200_STAGE_FIXED_SPREAD);
+        dFrac.ensure(20*(size_t) n);
+        LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
+        CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
+        if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, rows, (const int*) nullptr, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
+        stageEnd();
+        reciprocalPass();
+        stageBegin(MPIDB200_STAGE_FIXED_GATHER);
+        if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhi.p);
+        stageEnd();
+        backToMain();
+    }
+
     void fixedFieldStage(const double* dPosIn) {
         const bool pme = P.method == PME;
         const int rows = P.rowEnd - P.rowBegin;
-        size_t G = (size_t) grid[0]*grid[1]*grid[2];
         dField.ensure(3*(size_t) n); dEfix.ensure(3*(size_t) n); dMu.ensure(3*(size_t) n);
         dPhi.ensure(35*(size_t) n); dPhidp.ensure(35*(size_t) n);
-        if (pme) {
-            forkPme();
-            stageBegin(MPIDB200_STAGE_FIXED_SPREAD);
-            dFrac.ensure(20*(size_t) n);
-            LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
-            CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
-            if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, rows, (const int*) nullptr, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
-            stageEnd();
-            reciprocalPass();
-            stageBegin(MPIDB200_STAGE_FIXED_GATHER);
-            if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhi.p);
-            stageEnd();
-            backToMain();
-        }
         stageBegin(MPIDB200_STAGE_FIXED_REAL);
         // the field is consumed at polarizable sites only; everything else stays zero
         CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
@@ -827,19 +895,22 @@ struct Engine : public EngineBase {
         if (!haveParticles) throw std::runtime_error("mpidb200: particles have not been set");
         if (!haveBox) throw std::runtime_error("mpidb200: periodic box vectors have not been set");
         CUDA_CHECK(cudaSetDevice(cfg.device));
+        if (forked3) { CUDA_CHECK(cudaStreamSynchronize(stream3)); forked3 = false; }     // a previous call ended early (exception)
         launches = 0;
         lastPosDevice = dPosIn;
         memset(stageMs, 0, sizeof(stageMs));
         const bool pme = P.method == PME;
         P.numRanks = numRanks; P.rank = rank;
         stageBegin(MPIDB200_STAGE_SORT);
-        buildNeighbors(dPosIn);
+        sortAndFrames(dPosIn);
+        fixedReciprocalStart();                    // stream 2, beside the neighbour search
+        buildNeighborList(dPosIn);
         dForce.ensure(3*(size_t) n); dTorque.ensure(3*(size_t) n); dEnergy.ensure(2);
         CUDA_CHECK(cudaMemsetAsync(dForce.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
         CUDA_CHECK(cudaMemsetAsync(dTorque.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
         CUDA_CHECK(cudaMemsetAsync(dEnergy.p, 0, 2*sizeof(unsigned long long), stream));
-        stageEnd();
         const int rows = P.rowEnd - P.rowBegin;
+        if (!dipolesOnly) startDipoleIndependentPairs();      // stream 3, beside the field and solver stages
 
         fixedFieldStage(dPosIn);
         lastIterations = 0; lastEps = 0;
@@ -861,38 +932,42 @@ struct Engine : public EngineBase {
 
         const bool mutual = P.polarization == Mutual;
         bool forked = false;
-        if (!hSpLo.empty()) {
-            // FP64 covalent pairs run on the second stream beside the FP32 pair kernel; both accumulate with
-            // order-independent fixed-point atomics
+        if (!hSpLo.empty() || (pme && rows > 0)) {
+            // FP64 work runs on the second stream beside the FP32 pair kernels -- the covalent pairs and the per-atom
+            // reciprocal-space / self terms; everything accumulates with order-independent fixed-point atomics
             const int ns = (int) hSpLo.size();
             forkPme(); forked = true;
-            if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                               dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
-            else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                        dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+            if (ns > 0) {
+                if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                                   dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+                else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                            dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+            }
+            if (pme && rows > 0)
+                LAUNCH((k_reciprocal_terms<real>), blocksFor(rows, 128), 128, P, dPhi.p, dPhidp.p, dCartD.p, dSphD.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
             backToMain();
         }
         stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
-        if (numSimple > 0) {
-            const int nbS = blocksFor((long long) numSimple*MPID_LANES, 256);
-            if (pme) LAUNCH((k_simple_pairs<real, true>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
-            else LAUNCH((k_simple_pairs<real, false>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
+        joinDipoleIndependentPairs();      // flat full-full list + charge-charge pairs (stream 3)
+        // full x bare-charge pairs: gathered from the full site (Cartesian form)
+        if (numFull > 0 && numSimpleTotal > 0) {
+            const int nbF = blocksFor((long long) numFull*MPID_LANES, 256);
+            if (pme) LAUNCH((k_charge_site_pairs<real, true>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
+            else LAUNCH((k_charge_site_pairs<real, false>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
         }
-        // the remaining pair classes (full/simple site on either side), each with its own specialised instantiation
-#define ES_LAUNCH(EW, MU, A, B, T) { const long long cnt = typeBegin[T+1] - typeBegin[T]; \
-            if (cnt > 0) LAUNCH((k_electrostatics<real, EW, MU, A, B>), blocksFor(cnt, 128), 128, P, cnt, dPairI.p + typeBegin[T], dPairJ.p + typeBegin[T], \
+        // full x full pairs: quasi-internal frame kernel over the flat half list
+        {
+            const long long cnt = typeBegin[1] - typeBegin[0];
+#define ES_LAUNCH(EW, MU) { if (cnt > 0) LAUNCH((k_electrostatics<real, EW, MU, false, false>), blocksFor(cnt, 128), 128, P, cnt, dPairI.p + typeBegin[0], dPairJ.p + typeBegin[0], \
                                 dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p); }
-#define ES_ALL(EW, MU) { ES_LAUNCH(EW, MU, false, false, 0) ES_LAUNCH(EW, MU, false, true, 1) ES_LAUNCH(EW, MU, true, false, 2) }
-        if (pme) { if (mutual) ES_ALL(true, true) else ES_ALL(true, false) }
-        else { if (mutual) ES_ALL(false, true) else ES_ALL(false, false) }
-#undef ES_ALL
+            if (pme) { if (mutual) ES_LAUNCH(true, true) else ES_LAUNCH(true, false) }
+            else { if (mutual) ES_LAUNCH(false, true) else ES_LAUNCH(false, false) }
 #undef ES_LAUNCH
+        }
         stageEnd();
         if (forked) joinPme();
 
         stageBegin(MPIDB200_STAGE_FINISH);
-        if (pme && rows > 0)
-            LAUNCH((k_reciprocal_terms<real>), blocksFor(rows, 128), 128, P, dPhi.p, dPhidp.p, dCartD.p, dSphD.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
         if (P.polarization == Extrapolated && rows > 0) {
             OptLists L;
             L.K = cfg.num_extrapolation_coefficients;
@@ -1040,6 +1115,13 @@ struct Engine : public EngineBase {
         if (pairs) *pairs = lastPairs;
     }
 
+    void getPairClassCounts(long long* out3) override {
+        // typeBegin holds the exclusive scan of the five class counts (0 F-F, 1 F-S, 2 S-F, 3 unused, 4 S-S)
+        out3[0] = typeBegin[1] - typeBegin[0];
+        out3[1] = typeBegin[3] - typeBegin[1];
+        out3[2] = lastPairs - typeBegin[4];
+    }
+
     long long getPairList(long long cap, int* pi, int* pj, int* pc) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
         const int rows = P.rowEnd - P.rowBegin;
@@ -1173,6 +1255,9 @@ int mpidb200_get_pme_parameters(mpidb200_handle h, double* alpha, int* nx, int* 
 }
 int mpidb200_get_stats(mpidb200_handle h, int* iterations, double* epsilon, double* stage_ms, long long* num_pairs) {
     return guarded([&] { asEngine(h)->getStats(iterations, epsilon, stage_ms, num_pairs); });
+}
+int mpidb200_get_pair_class_counts(mpidb200_handle h, long long* out3) {
+    return guarded([&] { asEngine(h)->getPairClassCounts(out3); });
 }
 int mpidb200_set_profiling(mpidb200_handle h, int enabled) {
     return guarded([&] { asEngine(h)->profiling = enabled != 0; });

@@ -110,79 +110,103 @@ struct ParticleParams {       // original order, as handed to mpidb200_set_parti
     const double* thole; const double* alpha; const double* damp;
 };
 
+// Per-atom records are written through a per-warp shared-memory tile so that the 32 consecutive sorted atoms of a
+// warp store each output array as one contiguous, coalesced block (a thread-per-record store touches 32 lines per
+// instruction and throttles the LSU).
+template <typename TD, int W>
+__device__ __forceinline__ void storeWarpRows(double (*tile)[21], int lane, int nValid, const double* vals, TD* dst) {
+#pragma unroll
+    for (int k = 0; k < W; k++) tile[lane][k] = vals[k];
+    __syncwarp();
+    for (int idx = lane; idx < nValid*W; idx += 32) dst[idx] = (TD) tile[idx/W][idx % W];
+    __syncwarp();
+}
+
 template <typename real>
-__global__ void k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restrict__ order,
-                            const double* __restrict__ posOrig, const double* __restrict__ poswOrig,
-                            double4* __restrict__ posS, float4* __restrict__ posF,
-                            double* __restrict__ cartD, double* __restrict__ pkD, real* __restrict__ cartR, real* __restrict__ pkR,
-                            double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso,
-                            double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud,
-                            const int* __restrict__ inv, const int* __restrict__ spStart, const int* __restrict__ spPartner,
-                            int4* __restrict__ spSorted, int* __restrict__ flagS) {
-    int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= P.n) return;
-    int o = order[s];
-    {   // sorted indices of up to four covalently scaled partners (x = -2 flags "more than four: use the list")
-        const int k0 = spStart[o], k1 = spStart[o+1];
-        int4 q = make_int4(-1, -1, -1, -1);
-        if (k1 - k0 > 4) q.x = -2;
-        else {
-            if (k1 - k0 > 0) q.x = inv[spPartner[k0]];
-            if (k1 - k0 > 1) q.y = inv[spPartner[k0+1]];
-            if (k1 - k0 > 2) q.z = inv[spPartner[k0+2]];
-            if (k1 - k0 > 3) q.w = inv[spPartner[k0+3]];
+__global__ void __launch_bounds__(128)
+k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restrict__ order,
+            const double* __restrict__ posOrig, const double* __restrict__ poswOrig,
+            double4* __restrict__ posS, float4* __restrict__ posF,
+            double* __restrict__ cartD, double* __restrict__ pkD, real* __restrict__ cartR, real* __restrict__ pkR,
+            double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso,
+            double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud,
+            const int* __restrict__ inv, const int* __restrict__ spStart, const int* __restrict__ spPartner,
+            int4* __restrict__ spSorted, int* __restrict__ flagS) {
+    __shared__ double tiles[4][32][21];
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = s - lane;                                  // first atom of this warp
+    if (s0 >= P.n) return;
+    const int nValid = min(32, P.n - s0);
+    const bool valid = s < P.n;
+    double c[20], pk[16], sph[16], alpha[6];
+    if (valid) {
+        const int o = order[s];
+        {   // sorted indices of up to four covalently scaled partners (x = -2 flags "more than four: use the list")
+            const int k0 = spStart[o], k1 = spStart[o+1];
+            int4 q = make_int4(-1, -1, -1, -1);
+            if (k1 - k0 > 4) q.x = -2;
+            else {
+                if (k1 - k0 > 0) q.x = inv[spPartner[k0]];
+                if (k1 - k0 > 1) q.y = inv[spPartner[k0+1]];
+                if (k1 - k0 > 2) q.z = inv[spPartner[k0+2]];
+                if (k1 - k0 > 3) q.w = inv[spPartner[k0+3]];
+            }
+            spSorted[s] = q;
         }
-        spSorted[s] = q;
+        const int az = pp.atomZ[o], ax = pp.atomX[o], ay = pp.atomY[o];
+        const double* pi = posOrig + 3*o;
+        const double* pz = az >= 0 ? posOrig + 3*az : pi;
+        const double* px = ax >= 0 ? posOrig + 3*ax : pi;
+        const double* py = ay >= 0 ? posOrig + 3*ay : pi;
+        LabAtom a;
+        labFrameAtom(pi, pz, px, py, pp.axis[o], az, ax, ay, pp.charge[o], pp.dipole + 3*o, pp.quadrupole + 6*o,
+                     pp.octopole + 10*o, pp.alpha + 3*o, a);
+        if (framelessFix && az < 0) {
+            a.alpha[0] = pp.alpha[3*o]; a.alpha[3] = pp.alpha[3*o+1]; a.alpha[5] = pp.alpha[3*o+2];
+        }
+        c[0] = a.charge;
+        for (int k = 0; k < 3; k++) c[1+k] = a.dip[k];
+        for (int k = 0; k < 6; k++) c[4+k] = a.quad[k];
+        for (int k = 0; k < 10; k++) c[10+k] = a.oct[k];
+        packPairMoments(a, pk);
+        for (int k = 0; k < 16; k++) sph[k] = a.sph[k];
+        for (int k = 0; k < 6; k++) alpha[k] = a.alpha[k];
+        aniso[s] = a.aniso;
+        const double x = poswOrig[3*o], y = poswOrig[3*o+1], z = poswOrig[3*o+2];
+        // site class: bit 0 = polarizable (non-zero lab polarizability), bit 1 = "simple" (charge only, never polarized)
+        bool pol = false, perm = false;
+        for (int k = 0; k < 6; k++) pol = pol || (a.alpha[k] != 0.0);
+        for (int k = 1; k < 16; k++) perm = perm || (pk[k] != 0.0);
+        const int flag = (pol ? 1 : 0) | ((!pol && !perm) ? 2 : 0);
+        flagS[s] = flag;
+        posS[s] = make_double4(x, y, z, (double) flag);
+        posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
+        dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
+        typename Real4<real>::type m;
+        m.x = 0; m.y = 0; m.z = 0; m.w = pp.damp[o] != 0.0 ? (real) (1.0/pp.damp[o]) : real(0);   // inverse damping factor
+        mud[s] = m;
     }
-    int az = pp.atomZ[o], ax = pp.atomX[o], ay = pp.atomY[o];
-    const double* pi = posOrig + 3*o;
-    const double* pz = az >= 0 ? posOrig + 3*az : pi;
-    const double* px = ax >= 0 ? posOrig + 3*ax : pi;
-    const double* py = ay >= 0 ? posOrig + 3*ay : pi;
-    LabAtom a;
-    labFrameAtom(pi, pz, px, py, pp.axis[o], az, ax, ay, pp.charge[o], pp.dipole + 3*o, pp.quadrupole + 6*o,
-                 pp.octopole + 10*o, pp.alpha + 3*o, a);
-    if (framelessFix && az < 0) {
-        a.alpha[0] = pp.alpha[3*o]; a.alpha[3] = pp.alpha[3*o+1]; a.alpha[5] = pp.alpha[3*o+2];
-    }
-    double c[20], pk[16];
-    c[0] = a.charge;
-    for (int k = 0; k < 3; k++) c[1+k] = a.dip[k];
-    for (int k = 0; k < 6; k++) c[4+k] = a.quad[k];
-    for (int k = 0; k < 10; k++) c[10+k] = a.oct[k];
-    packPairMoments(a, pk);
-    for (int k = 0; k < 20; k++) cartD[20*(size_t) s + k] = c[k];
-    for (int k = 0; k < 16; k++) pkD[16*(size_t) s + k] = pk[k];
+    double (*tile)[21] = tiles[warp];
+    storeWarpRows<double, 20>(tile, lane, nValid, c, cartD + 20*(size_t) s0);
+    storeWarpRows<double, 16>(tile, lane, nValid, pk, pkD + 16*(size_t) s0);
     if ((void*) cartR != (void*) cartD) {
-        for (int k = 0; k < 20; k++) cartR[20*(size_t) s + k] = (real) c[k];
-        for (int k = 0; k < 16; k++) pkR[16*(size_t) s + k] = (real) pk[k];
+        storeWarpRows<real, 20>(tile, lane, nValid, c, cartR + 20*(size_t) s0);
+        storeWarpRows<real, 16>(tile, lane, nValid, pk, pkR + 16*(size_t) s0);
     }
-    for (int k = 0; k < 16; k++) sphD[16*(size_t) s + k] = a.sph[k];
-    for (int k = 0; k < 6; k++) alphaLab[6*(size_t) s + k] = a.alpha[k];
-    aniso[s] = a.aniso;
-    double x = poswOrig[3*o], y = poswOrig[3*o+1], z = poswOrig[3*o+2];
-    // site class: bit 0 = polarizable (non-zero lab polarizability), bit 1 = "simple" (charge only, never polarized)
-    bool pol = false, perm = false;
-    for (int k = 0; k < 6; k++) pol = pol || (a.alpha[k] != 0.0);
-    for (int k = 1; k < 16; k++) perm = perm || (pk[k] != 0.0);
-    const int flag = (pol ? 1 : 0) | ((!pol && !perm) ? 2 : 0);
-    flagS[s] = flag;
-    posS[s] = make_double4(x, y, z, (double) flag);
-    posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
-    dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
-    typename Real4<real>::type m;
-    m.x = 0; m.y = 0; m.z = 0; m.w = pp.damp[o] != 0.0 ? (real) (1.0/pp.damp[o]) : real(0);   // inverse damping factor
-    mud[s] = m;
+    storeWarpRows<double, 16>(tile, lane, nValid, sph, sphD + 16*(size_t) s0);
+    storeWarpRows<double, 6>(tile, lane, nValid, alpha, alphaLab + 6*(size_t) s0);
 }
 
 // site-class bookkeeping: classFlag[s] = (flag & bit) != 0 (scanned into a rank), classList[rank[s]] = s
-__global__ void k_pol_flags(int n, int bit, const int* __restrict__ flagS, int* __restrict__ classFlag) {
+// (want = 1: sites with the bit set, want = 0: sites without it)
+__global__ void k_pol_flags(int n, int bit, int want, const int* __restrict__ flagS, int* __restrict__ classFlag) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s <= n) classFlag[s] = (s < n && (flagS[s] & bit)) ? 1 : 0;
+    if (s <= n) classFlag[s] = (s < n && (((flagS[s] & bit) != 0) == (want != 0))) ? 1 : 0;
 }
-__global__ void k_pol_list(int n, int bit, const int* __restrict__ flagS, const int* __restrict__ rank, int* __restrict__ classList) {
+__global__ void k_pol_list(int n, int bit, int want, const int* __restrict__ flagS, const int* __restrict__ rank, int* __restrict__ classList) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s < n && (flagS[s] & bit)) classList[rank[s]] = s;
+    if (s < n && (((flagS[s] & bit) != 0) == (want != 0))) classList[rank[s]] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -422,6 +446,9 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
                 cand[c] = make_float4(p.x + rShift[r][0], p.y + rShift[r][1], p.z + rShift[r][2], __uint_as_float((unsigned) j | (rCode[r] << MPID_CODE_SHIFT)));
                 cflag[c] = (unsigned char) (int) p.w;
             }
+            // pad to a multiple of 64 slots with far-away sentinels so that the pre-test loop needs no bounds check
+            const int cntPad = (cnt + 63) & ~63;
+            for (int c = cnt + tid; c < cntPad; c += 256) cand[c] = make_float4(1.0e18f, 0.f, 0.f, 0.f);
             __syncthreads();
             for (int i = ib0 + warp; i < ib1; i += 8) {
                 const int row = i - P.rowBegin;
@@ -438,17 +465,19 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
                 // phase 1: bare distance pre-test of every candidate; survivors (about a quarter) are queued in order
                 unsigned short* const myq = hitq[warp];
                 int qn = 0;
-                for (int c0 = 0; c0 < cnt; c0 += 32) {
-                    const int c = c0 + lane;
-                    bool hit = false;
-                    if (c < cnt) {
-                        const float4 q = cand[c];
-                        const float ddx = q.x - pi.x, ddy = q.y - pi.y, ddz = q.z - pi.z;
-                        hit = ddx*ddx + ddy*ddy + ddz*ddz <= rcHi2;
-                    }
-                    const unsigned m = __ballot_sync(FULL, hit);
-                    if (hit) myq[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short) c;
-                    qn += __popc(m);
+                const unsigned ltMask = (1u << lane) - 1u;
+                for (int c0 = 0; c0 < cntPad; c0 += 64) {          // two candidates per lane and trip, branch free
+                    const int ca = c0 + lane, cb = ca + 32;
+                    const float4 qa = cand[ca], qb = cand[cb];
+                    const float ax_ = qa.x - pi.x, ay_ = qa.y - pi.y, az_ = qa.z - pi.z;
+                    const float bx_ = qb.x - pi.x, by_ = qb.y - pi.y, bz_ = qb.z - pi.z;
+                    const bool hitA = ax_*ax_ + ay_*ay_ + az_*az_ <= rcHi2;
+                    const bool hitB = bx_*bx_ + by_*by_ + bz_*bz_ <= rcHi2;
+                    const unsigned ma = __ballot_sync(FULL, hitA), mb = __ballot_sync(FULL, hitB);
+                    const int na = __popc(ma);
+                    if (hitA) myq[qn + __popc(ma & ltMask)] = (unsigned short) ca;
+                    if (hitB) myq[qn + na + __popc(mb & ltMask)] = (unsigned short) cb;
+                    qn += na + __popc(mb);
                 }
                 __syncwarp();
                 // phase 2: classify the survivors (self, covalent partners, borderline distances, list membership)
@@ -516,7 +545,8 @@ __global__ void k_half_counts(DevParams P, int rows, const uint4* __restrict__ c
         const uint4 q = counts[r];
         const int si = (flagS[P.rowBegin + r] >> 1) & 1;
         c[2*si] = q.x - q.z;
-        // simple-simple pairs go to k_simple_pairs (gather, no atomics); class 4 only counts them
+        // only class 0 (full-full) is compacted into the flat list: simple-simple pairs go to k_simple_pairs and
+        // simple-full pairs to k_charge_site_pairs (both gather over the per-atom lists); classes 1, 2, 4 only count
         if (si) c[4] = q.z; else c[1] = q.z;
     }
     for (int t = 0; t < 5; t++) typeCount[(size_t) t*(rows + 1) + r] = c[t];
@@ -544,8 +574,8 @@ __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, co
         if (valid) { e = base[k]; sj = (((int) posF[e & MPID_JMASK].w >> 1) & 1) != 0; }
         const unsigned mF = __ballot_sync(FULL, valid && !sj), mS = __ballot_sync(FULL, valid && sj);
         const unsigned lt = (1u << lane) - 1u;
-        if (valid && !(si && sj)) {
-            const unsigned d = sj ? dstS + __popc(mS & lt) : dstF + __popc(mF & lt);
+        if (valid && !si && !sj) {
+            const unsigned d = dstF + __popc(mF & lt);
             pairI[d] = (unsigned) i;
             pairJ[d] = e;
         }
@@ -851,6 +881,78 @@ k_simple_pairs(DevParams P, int numSimple, const int* __restrict__ simpleList, c
     }
     if (act && sub == 0) {
         atomicAddFixed(&force[3*(size_t) i], dfx); atomicAddFixed(&force[3*(size_t) i+1], dfy); atomicAddFixed(&force[3*(size_t) i+2], dfz);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) de += __shfl_xor_sync(0xffffffffu, de, off);
+    if ((threadIdx.x & 31) == 0 && de != 0.0) atomicAddFixed(energy, de);
+}
+
+// Full site x bare-charge site pairs (e.g. O-H between waters: 44 % of all pairs).  Every full site A gathers over
+// its own full neighbour list (8 lanes per site) and handles the partners that are bare charges with the Cartesian
+// form chargeSitePair: A's moments stay in registers, a partner costs one position and one charge, A's force and
+// torque need no atomics until the end, the partner's force is three fixed-point atomics.  Each such pair is seen
+// exactly once (from its full site), whichever index is larger.
+//   reference stage: :4932-4946 + :4335-4920 (PME), :2140-2158 + :1331-1893 (no cutoff)
+template <typename real, bool EWALD>
+__global__ void __launch_bounds__(256)
+k_charge_site_pairs(DevParams P, int numFull, const int* __restrict__ fullList, const double4* __restrict__ posS,
+                    const real* __restrict__ pk, const typename Real4<real>::type* __restrict__ mud, const int* __restrict__ aniso,
+                    const uint4* __restrict__ counts, const unsigned* __restrict__ nbr,
+                    unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque, unsigned long long* __restrict__ energy) {
+    typedef typename Real4<real>::type R4;
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int rf = t/MPID_LANES;
+    const int sub = t % MPID_LANES;
+    const bool act = rf < numFull;
+    const int i = act ? fullList[rf] : 0;
+    real fx = 0, fy = 0, fz = 0, tx = 0, ty = 0, tz = 0, en = 0;
+    if (act) {
+        const double4 pi = posS[i];
+        real mA[20];
+        {
+            real q[16];
+            const R4* src = reinterpret_cast<const R4*>(pk + 16*(size_t) i);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const R4 v = src[k]; q[4*k] = v.x; q[4*k+1] = v.y; q[4*k+2] = v.z; q[4*k+3] = v.w; }
+            unpackPairMoments<real>(q, mA);
+        }
+        const R4 mi = mud[i];
+        const bool anisoA = aniso[i] != 0;
+        const uint4 cnt = counts[i - P.rowBegin];
+        const unsigned nUp = cnt.x, nAll = cnt.x + cnt.y;
+        const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        unsigned eNext = sub < nAll ? (sub < nUp ? base[sub] : base[P.nbrCap - 1 - (sub - nUp)]) : 0u;     // fetched one trip ahead
+        for (unsigned k = sub; k < nAll; k += MPID_LANES) {
+            const unsigned e = eNext;
+            const unsigned kn = k + MPID_LANES;
+            if (kn < nAll) eNext = kn < nUp ? base[kn] : base[P.nbrCap - 1 - (kn - nUp)];
+            const unsigned j = e & MPID_JMASK;
+            const double4 pj = posS[j];
+            if (!(((int) pj.w) & 2)) continue;          // partner is not a bare charge
+            real rx, ry, rz;
+            pairDelta<real>(P, pi, pj, e >> MPID_CODE_SHIFT, rx, ry, rz);     // r_j - r_i ; chargeSitePair wants d = r_A - r_B
+            const real r2 = rx*rx + ry*ry + rz*rz;
+            const real kq = real(MPID_ELECTRIC)*pk[16*(size_t) j];
+            real fB[3], tA[3];
+            const real phi = chargeSitePair<real, EWALD>(mA, mi.x, mi.y, mi.z, mi.w*mud[j].w, anisoA, -rx, -ry, -rz, r2,
+                                                         (real) P.alpha, (real) P.defaultThole, fB, tA);
+            en += kq*phi;
+            const real bx = kq*fB[0], by = kq*fB[1], bz = kq*fB[2];
+            fx -= bx; fy -= by; fz -= bz;
+            tx += kq*tA[0]; ty += kq*tA[1]; tz += kq*tA[2];
+            atomicAddFixed(&force[3*(size_t) j], (double) bx); atomicAddFixed(&force[3*(size_t) j+1], (double) by); atomicAddFixed(&force[3*(size_t) j+2], (double) bz);
+        }
+    }
+    double v[6] = {fx, fy, fz, tx, ty, tz};
+    double de = en;
+#pragma unroll
+    for (int off = MPID_LANES/2; off > 0; off >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+    }
+    if (act && sub == 0) {
+        atomicAddFixed(&force[3*(size_t) i], v[0]); atomicAddFixed(&force[3*(size_t) i+1], v[1]); atomicAddFixed(&force[3*(size_t) i+2], v[2]);
+        atomicAddFixed(&torque[3*(size_t) i], v[3]); atomicAddFixed(&torque[3*(size_t) i+1], v[4]); atomicAddFixed(&torque[3*(size_t) i+2], v[5]);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) de += __shfl_xor_sync(0xffffffffu, de, off);

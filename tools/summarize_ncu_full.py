@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Summarise an `ncu --set full` report: one row per captured launch with duration, registers, achieved occupancy,
+issue utilisation, FMA / FP64 pipe utilisation, DRAM bytes, L1/L2 hit rates and the three largest stall reasons.
+Usage: summarize_ncu_full.py report.ncu-rep   (needs ncu on PATH; no GPU required)"""
+import csv
+import io
+import re
+import subprocess
+import sys
+
+
+def main():
+    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, data = rows[0], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    stall = [h for h in hdr if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
+
+    def g(d, key, scale=1.0, fmt="%.1f"):
+        try:
+            return fmt % (float(d[idx[key]])*scale)
+        except Exception:
+            return "-"
+
+    print("| kernel | us | regs | warps active % | issue active % | FMA pipe % | FP64 pipe % | warp instr (M) | DRAM rd MB | DRAM wr MB | L1 hit % | L2 hit % | top stalls (warps per issue) |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|")
+    seen = {}
+    for d in data:
+        name = re.sub(r"\(.*", "", d[idx["Kernel Name"]]).replace("void ", "").replace("mpid::", "")
+        seen[name] = seen.get(name, 0) + 1
+        if seen[name] > 1:
+            continue                      # first launch of each kernel only
+        st = sorted(((float(d[idx[h]] or 0), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")) for h in stall), reverse=True)[:3]
+        print("| `%s` | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s |" % (
+            name[:60], g(d, "gpu__time_duration.sum"), g(d, "launch__registers_per_thread", fmt="%.0f"),
+            g(d, "sm__warps_active.avg.pct_of_peak_sustained_active"), g(d, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            g(d, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"), g(d, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            g(d, "smsp__inst_executed.sum", 1e-6, "%.2f"), g(d, "dram__bytes_read.sum", 1.0, "%.2f"), g(d, "dram__bytes_write.sum", 1.0, "%.2f"),
+            g(d, "l1tex__t_sector_hit_rate.pct"), g(d, "lts__t_sector_hit_rate.pct"),
+            ", ".join("%s %.1f" % (n, v) for v, n in st)))
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpidb200.so")
 SOURCES = ["mpid_engine.cu"]
-HEADERS = ["mpid_math.h", "mpid_kernels.cuh", os.path.join("..", "..", "include", "mpidb200.h")]
+HEADERS = ["mpid_math.h", "mpid_kernels.cuh", "mpid_fft.cuh", os.path.join("..", "..", "include", "mpidb200.h")]
 
 
 def _nvcc():

@@ -6,6 +6,7 @@
 // 179-239, SimTKReference/MPIDReferenceForce.cpp:2193-2269); the stage order is our own.
 #include "../../include/mpidb200.h"
 #include "mpid_kernels.cuh"
+#include "mpid_fft.cuh"
 
 #include <cub/cub.cuh>
 #include <cufft.h>
@@ -153,6 +154,7 @@ struct Engine : public EngineBase {
     DevBuf<uint4> dCounts;
     DevBuf<unsigned> dTypeCount, dTypeStart, dMaxCount, dNbr, dPairI, dPairJ, dPolNbr, dPolCount;
     DevBuf<int> dFlagS, dPolFlag, dPolRank, dPolList, dSimpleRank, dSimpleList, dFullRank, dFullList;
+    DevBuf<unsigned long long> dClassPacked, dClassScan;
     int numSimpleTotal = 0, numSimple = 0, simpleBegin = 0;
     int numFull = 0, fullBegin = 0;       // sites that are not bare charges, among this rank's rows
     bool classCountsValid = false;
@@ -168,6 +170,9 @@ struct Engine : public EngineBase {
     DevBuf<double> dHistDip, dHistErr, dDotPartial, dDots;
     DevBuf<double> dPtDip, dPtField, dPtGrad;
     cufftHandle planF = 0, planB = 0;
+    bool customFft = false;             // fused shared-memory reciprocal pass (mpid_fft.cuh) instead of cuFFT
+    DevBuf<float2> dTwiddle;
+    size_t fftSmemPlane = 0, fftSmemX = 0;
     bool plansMade = false;
     double* hPinned = nullptr;      // small pinned scratch (dot products, energy, totals)
     double* hPinnedPos = nullptr; size_t hPinnedPosCap = 0;
@@ -180,11 +185,16 @@ struct Engine : public EngineBase {
 
     explicit Engine(const mpidb200_config& c) : cfg(c), n(c.num_particles) {
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
+        // Stream priorities follow the critical path: the reciprocal-space chain (many short dependent kernels) paces
+        // the solver, so its blocks are scheduled first; the side stream only fills SMs the others leave idle.
+        int prLeast = 0, prGreatest = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+        const int prMid = (prLeast + prGreatest)/2;
+        CUDA_CHECK(cudaStreamCreateWithPriority(&ownStream, cudaStreamNonBlocking, prMid));
         stream = ownStream;
         cur = stream;
-        CUDA_CHECK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&stream3, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prGreatest));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&stream3, cudaStreamNonBlocking, prLeast));
         CUDA_CHECK(cudaEventCreateWithFlags(&evFork3, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evJoin3, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
@@ -204,6 +214,8 @@ struct Engine : public EngineBase {
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
         if (hDiis) cudaFreeHost(hDiis);
+        if (hNlTotals) cudaFreeHost(hNlTotals);
+        if (evNlTotals) cudaEventDestroy(evNlTotals);
         for (cudaEvent_t e : evPool) cudaEventDestroy(e);
         if (evFork) cudaEventDestroy(evFork);
         if (evJoin) cudaEventDestroy(evJoin);
@@ -241,8 +253,45 @@ struct Engine : public EngineBase {
         setPlanStreams();
     }
 
-#define LAUNCH(kernel, gridDim, blockDim, ...) do { kernel<<<(gridDim), (blockDim), 0, cur>>>(__VA_ARGS__); launches++; \
+#define LAUNCH(kernel, gridDim, blockDim, ...) do { traceBegin(#kernel); kernel<<<(gridDim), (blockDim), 0, cur>>>(__VA_ARGS__); launches++; traceEnd(); \
         cudaError_t le__ = cudaGetLastError(); if (le__ != cudaSuccess) throw CudaError(std::string("launch of " #kernel " failed: ") + cudaGetErrorString(le__)); } while (0)
+
+#define LAUNCH_SMEM(kernel, gridDim, blockDim, smemBytes, ...) do { traceBegin(#kernel); kernel<<<(gridDim), (blockDim), (smemBytes), cur>>>(__VA_ARGS__); launches++; traceEnd(); \
+        cudaError_t le__ = cudaGetLastError(); if (le__ != cudaSuccess) throw CudaError(std::string("launch of " #kernel " failed: ") + cudaGetErrorString(le__)); } while (0)
+
+    // ---- launch trace (developer aid, MPIDB200_TRACE=<file>): an event pair around every kernel of one evaluation,
+    // written as "stream,name,start_us,end_us" relative to the first launch.  Shows gaps and cross-stream overlap.
+    struct TraceRec { const char* name; int streamId; cudaEvent_t a, b; };
+    std::vector<TraceRec> trace;
+    const char* tracePath = getenv("MPIDB200_TRACE");
+    bool tracing = false;
+    long long evalCounter = 0;
+    int streamId(cudaStream_t st) const { return st == stream ? 1 : (st == stream2 ? 2 : 3); }
+    void traceBegin(const char* name) {
+        if (!tracing) return;
+        TraceRec r; r.name = name; r.streamId = streamId(cur);
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, cur);
+        trace.push_back(r);
+    }
+    void traceEnd() { if (tracing) cudaEventRecord(trace.back().b, cur); }
+    void traceDump() {
+        if (!tracing || trace.empty()) return;
+        cudaDeviceSynchronize();
+        FILE* f = fopen(tracePath, "w");
+        if (f) {
+            fprintf(f, "stream,name,start_us,end_us\n");
+            for (const TraceRec& r : trace) {
+                float t0 = 0, t1 = 0;
+                cudaEventElapsedTime(&t0, trace.front().a, r.a);
+                cudaEventElapsedTime(&t1, trace.front().a, r.b);
+                fprintf(f, "%d,%s,%.2f,%.2f\n", r.streamId, r.name, t0*1e3, t1*1e3);
+            }
+            fclose(f);
+        }
+        for (TraceRec& r : trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        trace.clear();
+    }
 
     // ---- parameters --------------------------------------------------------------------------------
     void setParticles(const double* charges, const double* dipoles, const double* quadrupoles, const double* octopoles,
@@ -284,7 +333,7 @@ struct Engine : public EngineBase {
         dThole.upload(hThole, stream); dAlpha.upload(hAlpha, stream); dDamp.upload(hDamp, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         haveParticles = true;
-        classCountsValid = false;
+        classCountsValid = false; nlCapsKnown = false;
         if (hSpStart.empty()) {   // no covalent maps yet: empty special lists
             std::vector<int> off(8*(size_t) (n+1), 0), idx(1, 0);
             setCovalent(off.data(), idx.data());
@@ -423,7 +472,7 @@ struct Engine : public EngineBase {
             else if (n1 >= 3) { P.ncell[d] = n1; P.reach[d] = 1; }
             else { P.ncell[d] = 1; P.reach[d] = 0; }
         }
-        nbrCap = 0;
+        nbrCap = 0; nlCapsKnown = false;
         // FFT plans + convolution table
         size_t G = (size_t) g[0]*g[1]*g[2], GC = (size_t) g[0]*g[1]*(g[2]/2 + 1);
         if (gridChanged || !plansMade) {
@@ -437,9 +486,37 @@ struct Engine : public EngineBase {
             dModX.upload(mx, stream); dModY.upload(my, stream); dModZ.upload(mz, stream);
         }
         dGrid.ensure(G); dGridC.ensure(GC); dEterm.ensure(GC);
+        setupCustomFft(g);
         LAUNCH((k_eterm_table<real>), blocksFor((long long) GC, 256), 256, P, dModX.p, dModY.p, dModZ.p, dEterm.p);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         haveBox = true;
+    }
+
+    // Fused reciprocal pass (mpid_fft.cuh): single precision, power-of-two grid whose y-z and x-z slabs fit in shared
+    // memory.  Opt-in with MPIDB200_FFT=fused: measured on B200 at 128x128x64 it only ties the library path (three
+    // 16-20 us single-wave kernels against seven ~6 us ones, profiles/r01_fft_experiment.md), so cuFFT stays the default.
+    void setupCustomFft(const int* g) {
+        customFft = false;
+        if (sizeof(real) != sizeof(float)) return;
+        const char* env = getenv("MPIDB200_FFT");
+        if (!env || std::string(env) != "fused") return;
+        for (int d = 0; d < 3; d++) if (g[d] < 8 || g[d] > MPID_FFT_MAXLEN || (g[d] & (g[d] - 1)) != 0) return;
+        const size_t nzc = (size_t) g[2]/2 + 1;
+        fftSmemPlane = 2*(size_t) g[1]*nzc*sizeof(float2);
+        fftSmemX = 2*(size_t) g[0]*nzc*sizeof(float2);
+        if (fftSmemPlane > 200*1024 || fftSmemX > 200*1024) return;
+        if (!dTwiddle.p) {
+            std::vector<float2> tw(MPID_FFT_MAXLEN);
+            for (int t = 0; t < MPID_FFT_MAXLEN; t++) {
+                const double a = -2.0*MPID_PI*t/MPID_FFT_MAXLEN;
+                tw[t] = make_float2((float) cos(a), (float) sin(a));
+            }
+            dTwiddle.upload(tw, stream);
+        }
+        CUDA_CHECK(cudaFuncSetAttribute(k_fft_planes_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fftSmemPlane));
+        CUDA_CHECK(cudaFuncSetAttribute(k_fft_planes_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fftSmemPlane));
+        CUDA_CHECK(cudaFuncSetAttribute(k_fft_x_convolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fftSmemX));
+        customFft = true;
     }
 
     // ---- timing helpers: event pairs recorded on the stream, read back after the final sync ----------
@@ -502,7 +579,9 @@ struct Engine : public EngineBase {
             size_t tempBytes = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, dCellKey.p, dSortedKey.p, dAtomIdx.p, dOrder.p, n, 0, bits, stream);
             dSortTemp.ensure(tempBytes + 16);
+            traceBegin("cub_radix_sort");
             CUDA_CHECK(cub::DeviceRadixSort::SortPairs(dSortTemp.p, tempBytes, dCellKey.p, dSortedKey.p, dAtomIdx.p, dOrder.p, n, 0, bits, stream));
+            traceEnd();
             launches += 4;
         } else {
             CUDA_CHECK(cudaMemcpyAsync(dSortedKey.p, dCellKey.p, n*sizeof(int), cudaMemcpyDeviceToDevice, stream));
@@ -519,25 +598,25 @@ struct Engine : public EngineBase {
         dFlagS.ensure(n); dPolFlag.ensure((size_t) n + 1); dPolRank.ensure((size_t) n + 1); dPolList.ensure((size_t) n + 1);
         dSimpleRank.ensure((size_t) n + 1); dSimpleList.ensure((size_t) n + 1);
         dFullRank.ensure((size_t) n + 1); dFullList.ensure((size_t) n + 1);
+        dClassPacked.ensure((size_t) n + 1); dClassScan.ensure((size_t) n + 1);
         real* cartR; real* pkR;
         if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
         LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
                dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p,
-               dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p, dFlagS.p);
-        // polarizable rows, bare-charge ("simple") rows and their complement ("full"): rank (exclusive scan of the
-        // class flag) and compact list
-        for (int cls = 0; cls < 3; cls++) {
-            const int bit = cls == 0 ? 1 : 2, want = cls == 2 ? 0 : 1;
-            int* rank = cls == 0 ? dPolRank.p : (cls == 1 ? dSimpleRank.p : dFullRank.p);
-            int* list = cls == 0 ? dPolList.p : (cls == 1 ? dSimpleList.p : dFullList.p);
-            LAUNCH(k_pol_flags, blocksFor(n + 1, B), B, n, bit, want, dFlagS.p, dPolFlag.p);
+               dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p, dFlagS.p, dClassPacked.p);
+        // polarizable rows, bare-charge ("simple") rows and their complement ("full"): one scan of the packed class
+        // flags k_lab_frame wrote, then ranks and compact lists
+        {
             size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, dPolFlag.p, rank, n + 1, stream);
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, dClassPacked.p, dClassScan.p, n + 1, stream);
             dScanTemp.ensure(tb + 16);
-            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tb, dPolFlag.p, rank, n + 1, stream));
+            traceBegin("cub_scan_classes");
+            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tb, dClassPacked.p, dClassScan.p, n + 1, stream));
+            traceEnd();
             launches += 1;
-            LAUNCH(k_pol_list, blocksFor(n, B), B, n, bit, want, dFlagS.p, rank, list);
+            LAUNCH(k_class_lists, blocksFor(n + 1, B), B, n, dFlagS.p, dClassScan.p, dPolRank.p, dSimpleRank.p, dFullRank.p,
+                   dPolList.p, dSimpleList.p, dFullList.p);
         }
         if (numRanks > 1) {
             int* pr = (int*) hPinned;
@@ -582,7 +661,13 @@ struct Engine : public EngineBase {
             nbrCap = std::min(std::max(nbrCap, 32), std::max(n, 32));
         }
         const bool roundMode = P.method != PME || P.reach[0] == 0 || P.reach[1] == 0 || P.reach[2] == 0;
-        unsigned* totals = (unsigned*) hPinned;
+        if (!hNlTotals) CUDA_CHECK(cudaMallocHost((void**) &hNlTotals, 8*sizeof(unsigned)));
+        if (!evNlTotals) CUDA_CHECK(cudaEventCreateWithFlags(&evNlTotals, cudaEventDisableTiming));
+        unsigned* totals = hNlTotals;
+        // Speculative mode: capacities (per-row neighbours, flat full-full pairs) are taken from the previous
+        // evaluation, the counts are read back asynchronously and checked just before the forces are written
+        // (nlistTotalsOk); nothing waits for the host here.  Kernels are memory-safe when a capacity is exceeded.
+        nlSpeculative = nlCapsKnown && numRanks == 1;
         for (int attempt = 0; ; attempt++) {
             P.nbrCap = nbrCap;
             dNbr.ensure((size_t) std::max(rows, 1)*nbrCap);
@@ -594,27 +679,64 @@ struct Engine : public EngineBase {
                 else LAUNCH(k_neighbor_list_cell, numCells, 256, P, dPosF.p, dPosIn, dOrder.p, dCellStart.p,
                             dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
             }
-            // one scan over the four concatenated per-class count arrays gives absolute offsets into pairI/pairJ
+            // one scan over the concatenated per-class count arrays gives absolute offsets into pairI/pairJ
             LAUNCH(k_half_counts, blocksFor(rows + 1, B), B, P, rows, dCounts.p, dFlagS.p, dTypeCount.p);
             size_t tempBytes = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, stream);
             dScanTemp.ensure(tempBytes + 16);
+            traceBegin("cub_scan_pair_classes");
             CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, stream));
+            traceEnd();
             launches += 1;
-            CUDA_CHECK(cudaMemcpyAsync(&totals[0], dMaxCount.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-            for (int t = 0; t < 5; t++)
-                CUDA_CHECK(cudaMemcpyAsync(&totals[1 + t], dTypeStart.p + (size_t) t*(rows + 1), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaMemcpyAsync(&totals[6], dTypeStart.p + tlen - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            // one small kernel + one copy; in speculative mode on the side stream so that the main stream moves on
+            dTotals.ensure(8);
+            if (nlSpeculative) {
+                CUDA_CHECK(cudaEventRecord(evFork3, stream));
+                CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
+                cudaStream_t keep = cur; cur = stream3;
+                LAUNCH(k_collect_totals, 1, 32, rows, dMaxCount.p, dTypeStart.p, dTotals.p);
+                cur = keep;
+                CUDA_CHECK(cudaMemcpyAsync(totals, dTotals.p, 7*sizeof(unsigned), cudaMemcpyDeviceToHost, stream3));
+                CUDA_CHECK(cudaEventRecord(evNlTotals, stream3));
+                break;
+            }
+            LAUNCH(k_collect_totals, 1, 32, rows, dMaxCount.p, dTypeStart.p, dTotals.p);
+            CUDA_CHECK(cudaMemcpyAsync(totals, dTotals.p, 7*sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaEventRecord(evNlTotals, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             if ((int) totals[0] <= nbrCap) break;
             if (attempt > 3) throw std::runtime_error("mpidb200: neighbour list capacity could not be established");
             nbrCap = (int) (totals[0]*1.2) + 16;       // rare: density fluctuation beyond the guess
         }
-        for (int t = 0; t < 5; t++) typeBegin[t] = totals[1 + t];
-        lastPairs = totals[6];                       // every ordinary pair (i<j) of this rank's rows
-        const long long flatPairs = typeBegin[1];    // the flat list holds the full-full class only (it comes first)
-        dPairI.ensure((size_t) flatPairs + 1); dPairJ.ensure((size_t) flatPairs + 1);
+        if (!nlSpeculative) {
+            adoptNlistTotals();
+            // flat full-full list: 10 % head room so that the next evaluations can run speculatively
+            pairCap = (size_t) (typeBegin[1] + typeBegin[1]/10 + 1024);
+            dPairI.ensure(pairCap); dPairJ.ensure(pairCap);
+            nlCapsKnown = true;
+        }
         stageEnd();
+    }
+    unsigned* hNlTotals = nullptr;
+    DevBuf<unsigned> dTotals;
+    cudaEvent_t evNlTotals = nullptr;
+    bool nlSpeculative = false, nlCapsKnown = false;
+    size_t pairCap = 0;
+    void adoptNlistTotals() {
+        for (int t = 0; t < 5; t++) typeBegin[t] = hNlTotals[1 + t];
+        lastPairs = hNlTotals[6];                    // every ordinary pair (i<j) of this rank's rows
+    }
+    // Speculative evaluations: wait for the (long finished) read-back and verify the capacities that were assumed.
+    bool nlistTotalsOk() {
+        if (!nlSpeculative) return true;
+        CUDA_CHECK(cudaEventSynchronize(evNlTotals));
+        const bool ok = (int) hNlTotals[0] <= nbrCap && (size_t) hNlTotals[2] <= pairCap;
+        if (ok) adoptNlistTotals();
+        else {
+            nlCapsKnown = false;                     // the repeat runs synchronously and re-establishes the capacities
+            nbrCap = std::max(nbrCap, (int) (hNlTotals[0]*1.2) + 16);
+        }
+        return ok;
     }
 
     // Pair work that needs the neighbour list but not the induced dipoles -- the flat full-full list for the energy
@@ -629,8 +751,8 @@ struct Engine : public EngineBase {
         CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
         cudaStream_t keep = cur;
         cur = stream3;
-        if (rows > 0 && typeBegin[1] > 0)
-            LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, dPairI.p, dPairJ.p);
+        if (rows > 0 && pairCap > 0)
+            LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, (unsigned) pairCap, dPairI.p, dPairJ.p);
         if (numSimple > 0) {
             const int nbS = blocksFor((long long) numSimple*MPID_LANES, 256);
             if (pme) LAUNCH((k_simple_pairs<real, true>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
@@ -650,10 +772,21 @@ struct Engine : public EngineBase {
         size_t GC = (size_t) grid[0]*grid[1]*(grid[2]/2 + 1);
         stageBegin(MPIDB200_STAGE_FFT);
         if (numRanks > 1) allReduce(dGrid.p, (size_t) grid[0]*grid[1]*grid[2], sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64);
-        CUFFT_CHECK(FftTraits<real>::fwd(planF, dGrid.p, dGridC.p));
-        LAUNCH((k_convolution<cplx, real>), blocksFor((long long) GC, 256), 256, GC, dEterm.p, dGridC.p);
-        CUFFT_CHECK(FftTraits<real>::bwd(planB, dGridC.p, dGrid.p));
-        launches += 2;
+        if (customFft) {
+            // (only instantiated for real = float; the casts keep the double engine compiling)
+            LAUNCH_SMEM(k_fft_planes_forward, grid[0], MPID_FFT_THREADS, fftSmemPlane, grid[1], grid[2], (const float*) (const void*) dGrid.p, (float2*) (void*) dGridC.p, dTwiddle.p);
+            LAUNCH_SMEM(k_fft_x_convolve, grid[1], MPID_FFT_THREADS, fftSmemX, grid[0], grid[1], grid[2]/2 + 1, (const float*) (const void*) dEterm.p, (float2*) (void*) dGridC.p, dTwiddle.p);
+            LAUNCH_SMEM(k_fft_planes_backward, grid[0], MPID_FFT_THREADS, fftSmemPlane, grid[1], grid[2], (const float2*) (const void*) dGridC.p, (float*) (void*) dGrid.p, dTwiddle.p);
+        } else {
+            traceBegin("cufft_forward");
+            CUFFT_CHECK(FftTraits<real>::fwd(planF, dGrid.p, dGridC.p));
+            traceEnd();
+            LAUNCH((k_convolution<cplx, real>), blocksFor((long long) GC, 256), 256, GC, dEterm.p, dGridC.p);
+            traceBegin("cufft_backward");
+            CUFFT_CHECK(FftTraits<real>::bwd(planB, dGridC.p, dGrid.p));
+            traceEnd();
+            launches += 2;
+        }
         stageEnd();
     }
 
@@ -710,7 +843,7 @@ struct Engine : public EngineBase {
 
     // Field of the current induced dipoles into dIfield (and gradient into `grad`, which the caller zeroed).
     // level: highest derivative order gathered from the reciprocal grid (1 field, 2 +gradient, 4 everything)
-    void inducedFieldPass(const double* dPosIn, int level, double* grad, bool realSpace) {
+    void inducedFieldPass(const double* dPosIn, int level, double* grad, bool realSpace, bool callerFinishes = false) {
         const bool pme = P.method == PME;
         const int rows = P.rowEnd - P.rowBegin;
         size_t G = (size_t) grid[0]*grid[1]*grid[2];
@@ -756,7 +889,7 @@ struct Engine : public EngineBase {
         stageEnd();
         stageBegin(MPIDB200_STAGE_SOLVER);
         if (pme) joinPme();
-        if (numPol > 0 && pme) {
+        if (numPol > 0 && pme && !callerFinishes) {
             if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, grad);
             else LAUNCH((k_induced_finish<real, false>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
         }
@@ -826,7 +959,8 @@ struct Engine : public EngineBase {
         for (int k = H-1; k >= 0; k--) freeSlots.push_back(k);
         lastIterations = 0; lastEps = 0;
         for (int it = 0; ; it++) {
-            inducedFieldPass(dPosIn, 1, nullptr, true);
+            const bool fused = numRanks == 1;       // with several ranks the field is all-reduced between "finish" and "record"
+            inducedFieldPass(dPosIn, 1, nullptr, true, fused);
             stageBegin(MPIDB200_STAGE_SOLVER);
             if ((int) slots.size() == H) {     // drop the oldest (:1232-1236)
                 freeSlots.push_back(slots.front());
@@ -843,12 +977,17 @@ struct Engine : public EngineBase {
                 dl.v[k] = dHistDip.p + (size_t) slots[k]*3*n;
                 sl.s[k] = slots[k];
             }
-            LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p);
-            LAUNCH(k_diis_solve, 1, 512, nb, m, sl, it, n, cfg.target_epsilon, dDotPartial.p, dDiis.p);
+            if (fused) {
+                LAUNCH((k_diis_step<real>), 148, 512, P, dFlagS.p, dPhidp.p, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, sl, it,
+                       cfg.target_epsilon, dDiis.p, dDotPartial.p);
+            } else {
+                LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p);
+                LAUNCH(k_diis_solve, 1, 512, nb, m, sl, it, n, cfg.target_epsilon, dDotPartial.p, dDiis.p);
+            }
             const bool last = it == cfg.max_iterations;
             if (!last) LAUNCH((k_diis_combine<real>), blocksFor(n, 256), 256, n, m, dl, dDiis.p, dMu.p, dMud.p);
             if (it + 1 >= predictedEvals || last || syncEveryIteration) {
-                CUDA_CHECK(cudaMemcpyAsync(hDiis, dDiis.p, 3*sizeof(double), cudaMemcpyDeviceToHost, stream));   // done, iterations, eps
+                CUDA_CHECK(cudaMemcpyAsync(hDiis, dDiis.p, 4*sizeof(double), cudaMemcpyDeviceToHost, stream));   // done, ticket, iterations, eps
                 CUDA_CHECK(cudaStreamSynchronize(stream));
                 lastIterations = hDiis->iterations; lastEps = hDiis->eps;
                 if (hDiis->done || last) {
@@ -897,6 +1036,8 @@ struct Engine : public EngineBase {
         CUDA_CHECK(cudaSetDevice(cfg.device));
         if (forked3) { CUDA_CHECK(cudaStreamSynchronize(stream3)); forked3 = false; }     // a previous call ended early (exception)
         launches = 0;
+        evalCounter++;
+        tracing = tracePath != nullptr && evalCounter == 4 && !dipolesOnly;     // one warmed-up evaluation
         lastPosDevice = dPosIn;
         memset(stageMs, 0, sizeof(stageMs));
         const bool pme = P.method == PME;
@@ -928,15 +1069,26 @@ struct Engine : public EngineBase {
         } else {
             solveExtrapolated(dPosIn);
         }
-        if (dipolesOnly) { collectTimings(); return; }
+        if (dipolesOnly) {
+            if (!nlistTotalsOk()) {
+                CUDA_CHECK(cudaStreamSynchronize(stream)); CUDA_CHECK(cudaStreamSynchronize(stream2)); CUDA_CHECK(cudaStreamSynchronize(stream3));
+                evUsed = 0; curStage = -1;
+                evaluate(dPosIn, includeForces, includeEnergy, energy, dForcesOut, dipolesOnly);
+                return;
+            }
+            collectTimings(); return;
+        }
 
         const bool mutual = P.polarization == Mutual;
         bool forked = false;
+        joinDipoleIndependentPairs();      // flat full-full list + charge-charge pairs (side stream), before more is queued there
         if (!hSpLo.empty() || (pme && rows > 0)) {
-            // FP64 work runs on the second stream beside the FP32 pair kernels -- the covalent pairs and the per-atom
+            // FP64 work runs on the side stream beside the FP32 pair kernels -- the covalent pairs and the per-atom
             // reciprocal-space / self terms; everything accumulates with order-independent fixed-point atomics
             const int ns = (int) hSpLo.size();
-            forkPme(); forked = true;
+            CUDA_CHECK(cudaEventRecord(evFork3, stream));
+            CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
+            cur = stream3; forked = true;
             if (ns > 0) {
                 if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
                                    dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
@@ -948,7 +1100,6 @@ struct Engine : public EngineBase {
             backToMain();
         }
         stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
-        joinDipoleIndependentPairs();      // flat full-full list + charge-charge pairs (stream 3)
         // full x bare-charge pairs: gathered from the full site (Cartesian form)
         if (numFull > 0 && numSimpleTotal > 0) {
             const int nbF = blocksFor((long long) numFull*MPID_LANES, 256);
@@ -957,16 +1108,29 @@ struct Engine : public EngineBase {
         }
         // full x full pairs: quasi-internal frame kernel over the flat half list
         {
-            const long long cnt = typeBegin[1] - typeBegin[0];
-#define ES_LAUNCH(EW, MU) { if (cnt > 0) LAUNCH((k_electrostatics<real, EW, MU, false, false>), blocksFor(cnt, 128), 128, P, cnt, dPairI.p + typeBegin[0], dPairJ.p + typeBegin[0], \
+            // launch sized for the capacity of the flat list when the count is still on its way from the device
+            const long long cnt = nlSpeculative ? (long long) pairCap : typeBegin[1];
+            const unsigned* dyn = dTypeStart.p + (size_t) (P.rowEnd - P.rowBegin) + 1;      // start of class 1 = number of full-full pairs
+#define ES_LAUNCH(EW, MU) { if (cnt > 0) LAUNCH((k_electrostatics<real, EW, MU, false, false>), blocksFor(cnt, 128), 128, P, cnt, dyn, dPairI.p, dPairJ.p, \
                                 dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p); }
             if (pme) { if (mutual) ES_LAUNCH(true, true) else ES_LAUNCH(true, false) }
             else { if (mutual) ES_LAUNCH(false, true) else ES_LAUNCH(false, false) }
 #undef ES_LAUNCH
         }
         stageEnd();
-        if (forked) joinPme();
+        if (forked) {
+            CUDA_CHECK(cudaEventRecord(evJoin3, stream3));
+            CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin3, 0));
+        }
 
+        if (!nlistTotalsOk()) {
+            // a capacity assumed from the previous evaluation was exceeded (rare): nothing has been written to the
+            // caller's force buffer yet, so drain the streams and evaluate again with measured capacities
+            CUDA_CHECK(cudaStreamSynchronize(stream)); CUDA_CHECK(cudaStreamSynchronize(stream2)); CUDA_CHECK(cudaStreamSynchronize(stream3));
+            evUsed = 0; curStage = -1;
+            evaluate(dPosIn, includeForces, includeEnergy, energy, dForcesOut, dipolesOnly);
+            return;
+        }
         stageBegin(MPIDB200_STAGE_FINISH);
         if (P.polarization == Extrapolated && rows > 0) {
             OptLists L;
@@ -992,6 +1156,7 @@ struct Engine : public EngineBase {
         stageEnd();
         CUDA_CHECK(cudaStreamSynchronize(stream));
         collectTimings();
+        if (tracing) { traceDump(); tracing = false; }
         if (energy) *energy = includeEnergy ? (double) ((long long) he[0])*(1.0/MPID_FIXED_SCALE) : 0.0;
     }
 

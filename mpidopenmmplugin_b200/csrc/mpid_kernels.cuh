@@ -131,7 +131,7 @@ k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restr
             double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso,
             double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud,
             const int* __restrict__ inv, const int* __restrict__ spStart, const int* __restrict__ spPartner,
-            int4* __restrict__ spSorted, int* __restrict__ flagS) {
+            int4* __restrict__ spSorted, int* __restrict__ flagS, unsigned long long* __restrict__ classPacked) {
     __shared__ double tiles[4][32][21];
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -180,6 +180,9 @@ k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restr
         for (int k = 1; k < 16; k++) perm = perm || (pk[k] != 0.0);
         const int flag = (pol ? 1 : 0) | ((!pol && !perm) ? 2 : 0);
         flagS[s] = flag;
+        // low word counts polarizable sites, high word bare-charge sites: one 64-bit scan ranks both classes
+        classPacked[s] = (unsigned long long) (flag & 1) | ((unsigned long long) ((flag >> 1) & 1) << 32);
+        if (s == P.n - 1) classPacked[P.n] = 0ull;
         posS[s] = make_double4(x, y, z, (double) flag);
         posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
         dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
@@ -198,15 +201,20 @@ k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restr
     storeWarpRows<double, 6>(tile, lane, nValid, alpha, alphaLab + 6*(size_t) s0);
 }
 
-// site-class bookkeeping: classFlag[s] = (flag & bit) != 0 (scanned into a rank), classList[rank[s]] = s
-// (want = 1: sites with the bit set, want = 0: sites without it)
-__global__ void k_pol_flags(int n, int bit, int want, const int* __restrict__ flagS, int* __restrict__ classFlag) {
+// site-class bookkeeping from the exclusive scan of the packed flags: rank of every sorted atom within the
+// polarizable / bare-charge ("simple") / full (= not simple) classes, and the three compact lists
+__global__ void k_class_lists(int n, const int* __restrict__ flagS, const unsigned long long* __restrict__ scanned,
+                              int* __restrict__ polRank, int* __restrict__ simpleRank, int* __restrict__ fullRank,
+                              int* __restrict__ polList, int* __restrict__ simpleList, int* __restrict__ fullList) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s <= n) classFlag[s] = (s < n && (((flagS[s] & bit) != 0) == (want != 0))) ? 1 : 0;
-}
-__global__ void k_pol_list(int n, int bit, int want, const int* __restrict__ flagS, const int* __restrict__ rank, int* __restrict__ classList) {
-    const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s < n && (((flagS[s] & bit) != 0) == (want != 0))) classList[rank[s]] = s;
+    if (s > n) return;
+    const unsigned long long v = scanned[s];
+    const int rp = (int) (v & 0xffffffffull), rs = (int) (v >> 32), rf = s - rs;
+    polRank[s] = rp; simpleRank[s] = rs; fullRank[s] = rf;
+    if (s == n) return;
+    const int flag = flagS[s];
+    if (flag & 1) polList[rp] = s;
+    if (flag & 2) simpleList[rs] = s; else fullList[rf] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -355,8 +363,11 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
         }
     }
     if (lane == 0) {
-        counts[row] = make_uint4(nUp, nLow, nUpSimple, nPol);
-        if (iPol) polCount[polRank[i] - polBegin] = nPol;
+        // a row that did not fit is published as empty (the evaluation is repeated with a larger capacity; maxCount
+        // carries the true size), so that no consumer ever walks past the entries that were stored
+        const bool fits = nUp + nLow <= cap;
+        counts[row] = fits ? make_uint4(nUp, nLow, nUpSimple, nPol) : make_uint4(0u, 0u, 0u, 0u);
+        if (iPol) polCount[polRank[i] - polBegin] = fits ? nPol : 0u;
         atomicMax(maxCount, nUp + nLow);
     }
 }
@@ -523,8 +534,9 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
                 if (lane == 0) {
                     ctr[i - ib0][0] = nUp; ctr[i - ib0][1] = nLow; ctr[i - ib0][2] = nUpSimple; ctr[i - ib0][3] = nPol;
                     if (chunk0 + MPID_NL_MAXC >= total) {
-                        counts[row] = make_uint4(nUp, nLow, nUpSimple, nPol);
-                        if (iPol) polCount[polRank[i] - polBegin] = nPol;
+                        const bool fits = nUp + nLow <= cap;       // see k_neighbor_list
+                        counts[row] = fits ? make_uint4(nUp, nLow, nUpSimple, nPol) : make_uint4(0u, 0u, 0u, 0u);
+                        if (iPol) polCount[polRank[i] - polBegin] = fits ? nPol : 0u;
                         atomicMax(maxCount, nUp + nLow);
                     }
                 }
@@ -551,10 +563,18 @@ __global__ void k_half_counts(DevParams P, int rows, const uint4* __restrict__ c
     }
     for (int t = 0; t < 5; t++) typeCount[(size_t) t*(rows + 1) + r] = c[t];
 }
+// the eight numbers the host wants from a neighbour search, gathered for a single device-to-host copy:
+// out[0] = largest row, out[1..5] = start of each pair class, out[6] = total number of ordinary pairs
+__global__ void k_collect_totals(int rows, const unsigned* __restrict__ maxCount, const unsigned* __restrict__ typeStart, unsigned* __restrict__ out) {
+    const int t = threadIdx.x;
+    if (t == 0) out[0] = maxCount[0];
+    else if (t <= 5) out[t] = typeStart[(size_t) (t - 1)*(rows + 1)];
+    else if (t == 6) out[6] = typeStart[(size_t) 5*(rows + 1) - 1];
+}
 // four flat i-major half lists (one warp per atom distributes its upper run by the class of j)
 __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, const uint4* __restrict__ counts,
                                const float4* __restrict__ posF, const unsigned* __restrict__ typeStart, int rows,
-                               unsigned listBase1, unsigned listBase2, unsigned listBase3,
+                               unsigned listBase1, unsigned listBase2, unsigned listBase3, unsigned pairCap,
                                unsigned* __restrict__ pairI, unsigned* __restrict__ pairJ) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -576,8 +596,7 @@ __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, co
         const unsigned lt = (1u << lane) - 1u;
         if (valid && !si && !sj) {
             const unsigned d = dstF + __popc(mF & lt);
-            pairI[d] = (unsigned) i;
-            pairJ[d] = e;
+            if (d < pairCap) { pairI[d] = (unsigned) i; pairJ[d] = e; }
         }
         dstF += __popc(mF); dstS += __popc(mS);
     }
@@ -622,13 +641,23 @@ k_fixed_field(DevParams P, int numPol, const int* __restrict__ polList, const do
             const unsigned kn = k + MPID_LANES;
             if (kn < nAll) eNext = kn < nUp ? base[kn] : base[P.nbrCap - 1 - (kn - nUp)];
             const unsigned j = e & MPID_JMASK;
+            const double4 pj = posS[j];
             real dx, dy, dz;
-            pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
+            pairDelta<real>(P, pi, pj, e >> MPID_CODE_SHIFT, dx, dy, dz);
             const real r2 = dx*dx + dy*dy + dz*dz;
+            const typename Real4<real>::type* src = reinterpret_cast<const typename Real4<real>::type*>(cart + 20*(size_t) j);
+            if (((int) pj.w) & 2) {
+                // bare-charge partner (two thirds of the neighbours in water): only the charge term of the field exists
+                // and only its first coefficient is needed -- no moment loads, no higher radial functions
+                real c[1];
+                fieldCoefficientsOrdinary<real, EWALD, 1>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mud[j].w, c);
+                const real s0 = -c[0]*src[0].x;
+                ex += s0*dx; ey += s0*dy; ez += s0*dz;
+                continue;
+            }
             real c[4];
             fieldCoefficientsOrdinary<real, EWALD, 4>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mud[j].w, c);
             real m[20];
-            const typename Real4<real>::type* src = reinterpret_cast<const typename Real4<real>::type*>(cart + 20*(size_t) j);
 #pragma unroll
             for (int q = 0; q < 5; q++) {
                 typename Real4<real>::type v = src[q];
@@ -729,13 +758,16 @@ __global__ void k_special_field(DevParams P, const int* __restrict__ order, cons
     for (int k = k0; k < k1; k++) {
         const int oj = spPartner[k];
         const int cls = spClass[k];
+        const int sj = inv[oj];
+        // induced dipoles exist on polarizable sites only: a partner without one (e.g. the hydrogens of a water
+        // oxygen) contributes exactly zero to the induced field
+        if (MODE != 0 && !(flagS[sj] & 1)) continue;
         const int lo = min(o, oj), hi = max(o, oj);
         double dx = posOrig[3*hi] - posOrig[3*lo], dy = posOrig[3*hi+1] - posOrig[3*lo+1], dz = posOrig[3*hi+2] - posOrig[3*lo+2];
         if (P.method == PME) periodicDelta(P.box, dx, dy, dz);
         const double r2 = dist2Exact(dx, dy, dz);
         if (P.method == PME && r2 > P.cutoff2) continue;
         if (o == hi) { dx = -dx; dy = -dy; dz = -dz; }      // d = r_other - r_me
-        const int sj = inv[oj];
         const double2 dtJ = dampTholeD[sj];
         const double scale = cls == 1 ? 0.0 : P.scale14;
         const double r = sqrt(r2);
@@ -763,7 +795,7 @@ __global__ void k_special_field(DevParams P, const int* __restrict__ order, cons
 //   reference stage: :4932-4946 + :4335-4920 (PME), :2140-2158 + :1331-1893 (no cutoff)
 template <typename real, bool EWALD, bool MUTUAL, bool SI, bool SJ>
 __global__ void __launch_bounds__(128)
-k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ pairI, const unsigned* __restrict__ pairJ,
+k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ dynCount, const unsigned* __restrict__ pairI, const unsigned* __restrict__ pairJ,
                  const double4* __restrict__ posS, const real* __restrict__ pk, const typename Real4<real>::type* __restrict__ mud,
                  const int* __restrict__ aniso,
                  unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque, unsigned long long* __restrict__ energy) {
@@ -773,6 +805,8 @@ k_electrostatics(DevParams P, long long numPairs, const unsigned* __restrict__ p
     unsigned j = 0;
     double e = 0;
     real f[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, tj[3] = {0, 0, 0};
+    // dynCount: number of pairs as counted on the device (the launch is sized from the previous evaluation's count)
+    if (dynCount) numPairs = min((long long) *dynCount, numPairs);
     const bool active = p < numPairs;
     if (active) {
         i = (int) pairI[p];
@@ -1321,6 +1355,8 @@ k_dots_final(int numBlocks, int m, const double* __restrict__ partial, double* _
 // then read the status back.  Extra iterations are no-ops on mu, hence idempotent.
 struct DiisStatus {
     int done;                     // eps < target reached
+    unsigned ticket;              // CTAs of the fused step kernel that have finished (last one solves)
+    int pad_;
     int iterations;               // index of the iteration that converged / last one run (:1219-1231)
     double eps;
     double coef[MPID_MAX_HISTORY + 1];
@@ -1370,10 +1406,9 @@ k_diis_record_dots(DevParams P, const double* __restrict__ alphaLab, const doubl
 // One CTA: finish the dot products, update B, test convergence (eps = 48.033324 sqrt(<e,e>/N), :1219) and, if not
 // converged, solve the (m+1)x(m+1) DIIS system (:1254-1291 does it through an SVD) by Gauss-Jordan elimination
 // with partial pivoting, one thread per matrix element.
-__global__ void __launch_bounds__(512)
-k_diis_solve(int numBlocks, int m, SlotList slots, int iteration, int numAtoms, double targetEps,
-             const double* __restrict__ partial, DiisStatus* __restrict__ status) {
-    if (status->done) return;
+__device__ __forceinline__ void diisSolveBlock(int numBlocks, int m, const SlotList& slots, int iteration, int numAtoms, double targetEps,
+                                               const double* __restrict__ partial, DiisStatus* __restrict__ status) {
+    // requires blockDim.x == 512
     constexpr int H = MPID_MAX_HISTORY, R = MPID_MAX_HISTORY + 1, W = MPID_MAX_HISTORY + 2;
     __shared__ double red[512];
     __shared__ double dotv[R];
@@ -1450,6 +1485,76 @@ k_diis_solve(int numBlocks, int m, SlotList slots, int iteration, int numAtoms, 
         const double d = a[tid+1][tid+1];
         status->coef[tid] = d != 0.0 ? a[tid+1][rank]/d : 0.0;
     }
+}
+
+__global__ void __launch_bounds__(512)
+k_diis_solve(int numBlocks, int m, SlotList slots, int iteration, int numAtoms, double targetEps,
+             const double* __restrict__ partial, DiisStatus* __restrict__ status) {
+    if (status->done) return;
+    diisSolveBlock(numBlocks, m, slots, iteration, numAtoms, targetEps, partial, status);
+}
+
+// Single-GPU fusion of one solver step: (1) finish the induced field at polarizable sites (reciprocal part from
+// phidp + self term, what k_induced_finish does), (2) newDip / err / history and the partial error overlaps (what
+// k_diis_record_dots does), (3) the CTA that finishes last reduces the partials and runs the convergence test and
+// the DIIS solve (k_diis_solve).  One launch instead of three on the solver's critical path.
+template <typename real>
+__global__ void __launch_bounds__(512)
+k_diis_step(DevParams P, const int* __restrict__ flagS, const real* __restrict__ phidp,
+            const double* __restrict__ alphaLab, const double* __restrict__ efix,
+            const double* __restrict__ ifield, const double* __restrict__ mu,
+            double* __restrict__ histDip, double* __restrict__ histErr, int m, VecList errs, SlotList slots,
+            int iteration, double targetEps, DiisStatus* __restrict__ status, double* __restrict__ partial) {
+    if (status->done) return;
+    __shared__ double sh[512/32][MPID_MAX_HISTORY + 1];
+    __shared__ int isLast;
+    double acc[MPID_MAX_HISTORY + 1];
+    for (int k = 0; k < m; k++) acc[k] = 0;
+    const bool pme = P.method == PME;
+    for (int s = blockIdx.x*blockDim.x + threadIdx.x; s < P.n; s += gridDim.x*blockDim.x) {
+        double fx = ifield[3*(size_t) s], fy = ifield[3*(size_t) s+1], fz = ifield[3*(size_t) s+2];
+        const double ux = mu[3*(size_t) s], uy = mu[3*(size_t) s+1], uz = mu[3*(size_t) s+2];
+        if (pme && (flagS[s] & 1)) {
+            double rx, ry, rz;
+            reciprocalFieldOf<real>(P, phidp, s, rx, ry, rz);
+            fx += rx + P.selfFieldTerm*ux; fy += ry + P.selfFieldTerm*uy; fz += rz + P.selfFieldTerm*uz;
+        }
+        double ox, oy, oz;
+        applyAlphaLab(alphaLab + 6*(size_t) s, fx, fy, fz, ox, oy, oz);
+        const double nx = efix[3*(size_t) s] + ox, ny = efix[3*(size_t) s+1] + oy, nz = efix[3*(size_t) s+2] + oz;
+        histDip[3*(size_t) s] = nx; histDip[3*(size_t) s+1] = ny; histDip[3*(size_t) s+2] = nz;
+        const double e0 = nx - ux, e1 = ny - uy, e2 = nz - uz;
+        histErr[3*(size_t) s] = e0; histErr[3*(size_t) s+1] = e1; histErr[3*(size_t) s+2] = e2;
+        for (int k = 0; k < m - 1; k++) {
+            const double* h = errs.v[k] + 3*(size_t) s;
+            acc[k] += e0*h[0] + e1*h[1] + e2*h[2];
+        }
+        acc[m-1] += e0*e0 + e1*e1 + e2*e2;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = 0; k < m; k++) {
+        double v = acc[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sh[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < m) {
+        double v = 0;
+        for (int w = 0; w < 512/32; w++) v += sh[w][threadIdx.x];
+        partial[(size_t) blockIdx.x*(MPID_MAX_HISTORY + 1) + threadIdx.x] = v;
+    }
+    // last CTA done: every CTA publishes its partials, then takes a ticket
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&status->ticket, 1u);
+        isLast = t == gridDim.x - 1;
+        if (isLast) status->ticket = 0u;
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    diisSolveBlock((int) gridDim.x, m, slots, iteration, P.n, targetEps, partial, status);
 }
 
 // mu = sum_k coef[k] * histDip_k with the coefficients k_diis_solve left in the status block (:1240-1249)

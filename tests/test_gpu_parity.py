@@ -278,3 +278,54 @@ def test_ethane_water_with_frames_polarizes():
     eg = kf.execute(s.pos, True, True, g)
     assert rel_err(g, f0) < 1e-8 and abs(eg - e0) < 1e-8*abs(e0)
     kf.close()
+
+
+def test_speculative_neighbour_list_recovers_from_capacity_overflow():
+    """From the second evaluation on the engine sizes its neighbour rows and flat pair list from the previous call and
+    checks the device-side counts only before the forces are written.  Squeezing all atoms into 70 % of the box
+    (density x2.9 locally) overflows those capacities: the call must notice, re-measure and still return exactly what a
+    fresh engine computes for the same coordinates."""
+    s = water_box((1, 1, 1), polarization=1)
+    k = make_kernel(s, precision="double")
+    f0 = np.zeros((s.n, 3))
+    k.execute(s.pos, True, True, f0)
+    k.execute(s.pos, True, True, np.zeros((s.n, 3)))          # speculative path, capacities hold
+    pairs_normal = k.getStats()["pairs"]
+    squeezed = s.pos*0.7
+    f1 = np.zeros((s.n, 3))
+    e1 = k.execute(squeezed, True, True, f1)                   # speculative path, capacities exceeded -> repeat
+    assert k.getStats()["pairs"] > 1.5*pairs_normal
+    t = s.copy(); t.pos = squeezed
+    k2 = make_kernel(t, precision="double")
+    f2 = np.zeros((s.n, 3))
+    e2 = k2.execute(squeezed, True, True, f2)
+    assert abs(e1 - e2) <= 1e-12*abs(e2)
+    assert rel_err(f1, f2) < 1e-12
+    pi1, pj1, pc1 = k.getPairList(); pi2, pj2, pc2 = k2.getPairList()
+    assert set(zip(pi1.tolist(), pj1.tolist(), pc1.tolist())) == set(zip(pi2.tolist(), pj2.tolist(), pc2.tolist()))
+    # and back to the normal density: same answer as the very first call
+    f3 = np.zeros((s.n, 3))
+    k.execute(s.pos, True, True, f3)
+    assert rel_err(f3, f0) < 1e-12
+    k.close(); k2.close()
+
+
+@pytest.mark.parametrize("tiles,pol", [((1, 1, 1), 0), ((1, 1, 1), 2), ((2, 1, 1), 1)])
+def test_fused_reciprocal_pass_matches_cufft(tiles, pol, monkeypatch):
+    """MPIDB200_FFT=fused selects the shared-memory reciprocal pass of mpid_fft.cuh (3 launches per pass, power-of-two
+    grids, mixed precision) instead of cuFFT R2C/C2R + convolution (7 launches).  Both are single-precision
+    unnormalised transforms of the same data, so forces, energy and dipoles agree to FP32 round-off of the grid."""
+    s = water_box(tiles, polarization=pol, epsilon=1e-6)
+    monkeypatch.delenv("MPIDB200_FFT", raising=False)
+    ka = make_kernel(s, precision="mixed")
+    monkeypatch.setenv("MPIDB200_FFT", "fused")
+    kb = make_kernel(s, precision="mixed")
+    monkeypatch.delenv("MPIDB200_FFT")
+    fa = np.zeros((s.n, 3)); fb = np.zeros((s.n, 3))
+    ea = ka.execute(s.pos, True, True, fa)
+    eb = kb.execute(s.pos, True, True, fb)
+    assert not np.array_equal(fa, fb)          # two different transform implementations ran
+    assert rel_err(fb, fa) < 2e-6
+    assert abs(eb - ea) < 1e-7*abs(ea)
+    assert rel_err(kb.getInducedDipoles(s.pos), ka.getInducedDipoles(s.pos)) < 2e-6
+    ka.close(); kb.close()

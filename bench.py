@@ -173,11 +173,16 @@ def main():
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
         k.commInit(rank, world, bytes(uid.cpu().tolist()))
-    stream = torch.cuda.current_stream()
+    # One explicit (non-default) stream for everything: the engine runs its main work on it (mpidb200_set_stream), so
+    # the L2 flush, the zeroing of the force buffer, the timing events and the evaluation are ordered on the device.
+    # (Handle 0, torch's legacy default stream, would make the engine fall back to its private stream.)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     k.setStream(stream.cuda_stream)
     pos_d = torch.tensor(s.pos, dtype=torch.float64, device="cuda").contiguous()
     f_d = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
     flush = torch.empty(256*1024*1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -272,7 +277,11 @@ def main():
                     dtype="f32 pair/grid math, f64 accumulation" if args.precision == "mixed" else "f64", data="synthetic",
                     config=dict(workload=WORKLOADS[wl]["name"], polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % n_f,
                                 cutoff_nm=s.cutoff, ewald_alpha=s.alpha, l2="256 MB buffer written between timed iterations",
-                                parallelism="atom-block rows x%d, NCCL all-reduce of partial fields" % world if world > 1 else "1 GPU"),
+                                parallelism=("atom-block rows x%d: NCCL all-reduce of the partial induced field every solver iteration, of the charge grid "
+                                             "every reciprocal pass (second communicator, reciprocal stream), of forces/torques once; FFT replicated" % world) if world > 1 else "1 GPU",
+                                note=("N>1 runs the 1,024,884-atom box of BASELINE.json config 5 (strong scaling of ONE system); the N=1 default runs the "
+                                      "95,616-atom box of config 4, so values at N=1 and N>1 are different workloads -- run `--gpus 1 --workload 1m` for the "
+                                      "single-GPU point of the same system") if world > 1 else "N=1 default = BASELINE.json config 4 (96k atoms, 1 B200)"),
                     e2e=dict(value=NS_PER_DAY_PER_MS/e2e_ms, unit="ns/day", ms_per_step=e2e_ms, h2d_bytes_per_step=24*n, d2h_bytes_per_step=24*n + 8),
                     gpu_launches=int(launches), energy_kj_mol=energy, wall_ms_per_step=t_wall/args.steps, ms_per_step_with_stage_timers=prof_ms,
                     clocks=sampler.summary(), roofline=roof, roofline_stages=roofs, stage_ms=stage_avg)

@@ -34,12 +34,15 @@ struct CudaError : public std::runtime_error {
 #define CUFFT_CHECK(expr) do { cufftResult r__ = (expr); if (r__ != CUFFT_SUCCESS) { \
     throw CudaError(std::string(#expr) + " failed with cufftResult " + std::to_string((int) r__)); } } while (0)
 
+long long g_allocEpoch = 0;     // bumped whenever a device buffer is (re)allocated: captured graphs hold raw pointers
+
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
     ~DevBuf() { if (p) cudaFree(p); }
     void ensure(size_t count) {
         if (count <= cap) return;
+        g_allocEpoch++;
         if (p) { cudaFree(p); p = nullptr; }
         size_t want = count + count/8 + 64;
         CUDA_CHECK(cudaMalloc((void**) &p, want*sizeof(T)));
@@ -58,6 +61,7 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -73,6 +77,7 @@ bool loadNccl() {
     g_nccl.GetUniqueId = (int (*)(void*)) dlsym(g_nccl.lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, Id128, int)) dlsym(g_nccl.lib, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclBroadcast");
     g_nccl.CommDestroy = (int (*)(void*)) dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int)) dlsym(g_nccl.lib, "ncclGetErrorString");
     return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
@@ -180,6 +185,7 @@ struct Engine : public EngineBase {
     int lastIterations = 0; double lastEps = 0; double stageMs[MPIDB200_NUM_STAGES]; long long lastPairs = 0, lastFull = 0;
     // multi-GPU
     void* comm = nullptr; int rank = 0, numRanks = 1;
+    void* commPme = nullptr;            // second communicator: the charge-grid all-reduce runs on the reciprocal stream
     const double* lastPosDevice = nullptr;
     std::vector<double> hLastMu;
 
@@ -209,11 +215,13 @@ struct Engine : public EngineBase {
     }
     ~Engine() {
         cudaSetDevice(cfg.device);
+        if (commPme && g_nccl.CommDestroy) g_nccl.CommDestroy(commPme);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); }
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
         if (hDiis) cudaFreeHost(hDiis);
+        if (iterGraph) cudaGraphExecDestroy(iterGraph);
         if (hNlTotals) cudaFreeHost(hNlTotals);
         if (evNlTotals) cudaEventDestroy(evNlTotals);
         for (cudaEvent_t e : evPool) cudaEventDestroy(e);
@@ -226,9 +234,10 @@ struct Engine : public EngineBase {
         if (ownStream) cudaStreamDestroy(ownStream);
     }
     // Reciprocal space is independent of the real-space pair kernels until their results are combined, and
-    // neither fills the GPU on its own at these sizes: fork it onto stream2 (single rank only -- with NCCL the
-    // grid all-reduce must stay ordered with the field all-reduce on one stream).
-    bool overlapPme() const { return numRanks == 1; }
+    // neither fills the GPU on its own at these sizes: fork it onto stream2.  With several ranks the charge-grid
+    // all-reduce travels with it on a communicator of its own (commPme), so the two streams never share one; the
+    // fork/join events keep the grid and field collectives from ever being in flight together.
+    bool overlapPme() const { return numRanks == 1 || commPme != nullptr; }
     cudaStream_t pmeStream() const { return overlapPme() ? stream2 : stream; }
     void forkPme() {
         if (!overlapPme()) return;
@@ -553,7 +562,8 @@ struct Engine : public EngineBase {
 
     void allReduce(void* buf, size_t count, int dtype) {
         if (numRanks <= 1) return;
-        int rc = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, comm, cur);
+        void* c = (cur == stream2 && commPme) ? commPme : comm;
+        int rc = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, c, cur);
         if (rc != 0) throw CudaError(std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     }
 
@@ -946,59 +956,99 @@ struct Engine : public EngineBase {
     DiisStatus* hDiis = nullptr;
     int predictedEvals = 0;
     const bool syncEveryIteration = getenv("MPIDB200_DIIS_SYNC") != nullptr;   // debugging aid: host check after every iteration
+    // ---- one solver iteration as a CUDA graph -----------------------------------------------------------------
+    // An iteration is ~20 short launches on two streams with identical arguments every time (the DIIS kernels take
+    // the iteration index from the status block), so it is captured once and replayed: graph edges replace the
+    // event fork/join and the per-launch gaps of the dependent chain shrink.  The graph holds raw pointers and the
+    // by-value kernel parameters, so it is re-captured when any of them changes.
+    struct GraphKey { DevParams P; const double* pos; int numPol, polBegin; long long epoch; cudaStream_t st; bool special; };
+    cudaGraphExec_t iterGraph = nullptr;
+    GraphKey iterKey;
+    bool iterKeyValid = false;
+    int iterGraphKernels = 0;
+    const bool graphsEnabled = getenv("MPIDB200_NO_GRAPH") == nullptr;
+    void launchSolverStep(const double* dPosIn, int itHost, bool withCombine) {
+        inducedFieldPass(dPosIn, 1, nullptr, true, true);
+        stageBegin(MPIDB200_STAGE_SOLVER);
+        LAUNCH((k_diis_step<real>), 148, 512, P, dFlagS.p, dPhidp.p, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, dHistDip.p, dHistErr.p, itHost,
+               cfg.target_epsilon, dDiis.p, dDotPartial.p);
+        if (withCombine) LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, itHost, dHistDip.p, dDiis.p, dMu.p, dMud.p);
+        stageEnd();
+    }
+    bool ensureIterationGraph(const double* dPosIn) {
+        GraphKey key;
+        memset(&key, 0, sizeof(key));
+        key.P = P; key.pos = dPosIn; key.numPol = numPol; key.polBegin = polBegin; key.epoch = g_allocEpoch; key.st = stream;
+        key.special = !hSpPartner.empty();
+        if (iterGraph && iterKeyValid && memcmp(&key, &iterKey, sizeof(key)) == 0) return true;
+        if (iterGraph) { cudaGraphExecDestroy(iterGraph); iterGraph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+        bool ok = true;
+        const long long launchesBefore = launches;
+        try { launchSolverStep(dPosIn, -1, true); }
+        catch (...) { ok = false; }
+        iterGraphKernels = (int) (launches - launchesBefore);      // capture records, it does not execute
+        launches = launchesBefore;
+        cudaError_t ec = cudaStreamEndCapture(stream, &graph);
+        if (ec != cudaSuccess || !graph) { cudaGetLastError(); ok = false; }
+        if (ok && cudaGraphInstantiate(&iterGraph, graph, 0) != cudaSuccess) { cudaGetLastError(); iterGraph = nullptr; ok = false; }
+        if (graph) cudaGraphDestroy(graph);
+        if (g_allocEpoch != key.epoch) ok = false;        // something was allocated during capture: pointers are stale
+        iterKey = key; iterKeyValid = ok;
+        if (!ok && iterGraph) { cudaGraphExecDestroy(iterGraph); iterGraph = nullptr; }
+        return ok;
+    }
+
     void solveMutualDiis(const double* dPosIn) {
         const int H = MPID_MAX_HISTORY;
         const int nb = 296;   // 2 x 148 SMs
         dHistDip.ensure((size_t) H*3*n); dHistErr.ensure((size_t) H*3*n);
         dDotPartial.ensure((size_t) nb*(MPID_MAX_HISTORY + 1));
         dDiis.ensure(1);
+        dIfield.ensure(3*(size_t) n);
         if (!hDiis) CUDA_CHECK(cudaMallocHost((void**) &hDiis, sizeof(DiisStatus)));
         CUDA_CHECK(cudaMemsetAsync(dDiis.p, 0, sizeof(DiisStatus), stream));
-        std::vector<int> slots;                 // history slots in age order
-        std::vector<int> freeSlots;
-        for (int k = H-1; k >= 0; k--) freeSlots.push_back(k);
         lastIterations = 0; lastEps = 0;
+        const bool fused = numRanks == 1;       // with several ranks the field is all-reduced between "finish" and "record"
+        // graph replay needs a quiet host side: no stage timers, no launch trace, a prediction to run ahead with
+        bool useGraph = fused && graphsEnabled && !profiling && !tracing && !syncEveryIteration && predictedEvals > 0;
+        if (useGraph) useGraph = ensureIterationGraph(dPosIn);
+        std::vector<int> slots;                 // history slots in age order (multi-rank path; ring order, see diisHistory)
         for (int it = 0; ; it++) {
-            const bool fused = numRanks == 1;       // with several ranks the field is all-reduced between "finish" and "record"
-            inducedFieldPass(dPosIn, 1, nullptr, true, fused);
-            stageBegin(MPIDB200_STAGE_SOLVER);
-            if ((int) slots.size() == H) {     // drop the oldest (:1232-1236)
-                freeSlots.push_back(slots.front());
-                slots.erase(slots.begin());
-            }
-            int slot = freeSlots.back(); freeSlots.pop_back();
-            slots.push_back(slot);
-            const int m = (int) slots.size();
-            double* hd = dHistDip.p + (size_t) slot*3*n;
-            double* he = dHistErr.p + (size_t) slot*3*n;
-            VecList el, dl; SlotList sl;
-            for (int k = 0; k < m; k++) {
-                el.v[k] = dHistErr.p + (size_t) slots[k]*3*n;
-                dl.v[k] = dHistDip.p + (size_t) slots[k]*3*n;
-                sl.s[k] = slots[k];
-            }
-            if (fused) {
-                LAUNCH((k_diis_step<real>), 148, 512, P, dFlagS.p, dPhidp.p, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, sl, it,
-                       cfg.target_epsilon, dDiis.p, dDotPartial.p);
+            const bool last = it == cfg.max_iterations;
+            if (useGraph) {
+                CUDA_CHECK(cudaGraphLaunch(iterGraph, stream));
+                launches += iterGraphKernels;
+            } else if (fused) {
+                launchSolverStep(dPosIn, it, !last);
             } else {
+                inducedFieldPass(dPosIn, 1, nullptr, true, false);
+                stageBegin(MPIDB200_STAGE_SOLVER);
+                const int m = std::min(it + 1, H);
+                VecList el; SlotList sl;
+                for (int k = 0; k < m; k++) {
+                    sl.s[k] = (it - (m - 1) + k) % H;
+                    el.v[k] = dHistErr.p + (size_t) sl.s[k]*3*n;
+                }
+                double* hd = dHistDip.p + (size_t) sl.s[m-1]*3*n;
+                double* he = dHistErr.p + (size_t) sl.s[m-1]*3*n;
                 LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p);
                 LAUNCH(k_diis_solve, 1, 512, nb, m, sl, it, n, cfg.target_epsilon, dDotPartial.p, dDiis.p);
+                if (!last) LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p);
+                stageEnd();
             }
-            const bool last = it == cfg.max_iterations;
-            if (!last) LAUNCH((k_diis_combine<real>), blocksFor(n, 256), 256, n, m, dl, dDiis.p, dMu.p, dMud.p);
             if (it + 1 >= predictedEvals || last || syncEveryIteration) {
-                CUDA_CHECK(cudaMemcpyAsync(hDiis, dDiis.p, 4*sizeof(double), cudaMemcpyDeviceToHost, stream));   // done, ticket, iterations, eps
+                CUDA_CHECK(cudaMemcpyAsync(hDiis, dDiis.p, 4*sizeof(double), cudaMemcpyDeviceToHost, stream));   // done, ticket, iter, iterations, eps
                 CUDA_CHECK(cudaStreamSynchronize(stream));
                 lastIterations = hDiis->iterations; lastEps = hDiis->eps;
                 if (hDiis->done || last) {
-                    stageEnd();
                     if (!hDiis->done)
                         throw std::runtime_error("Induced dipoles did not converge:  iterations=" + std::to_string(it) + " eps=" + std::to_string(lastEps));
                     predictedEvals = lastIterations + 1;
                     return;
                 }
             }
-            stageEnd();
         }
     }
 
@@ -1332,6 +1382,21 @@ struct Engine : public EngineBase {
         Id128 uid;
         memcpy(uid.bytes, id, 128);
         int rc = g_nccl.CommInitRank(&comm, nr, uid, rk);
+        if (rc == 0 && nr > 1 && g_nccl.Broadcast && !getenv("MPIDB200_SINGLE_COMM")) {
+            // second communicator for the reciprocal stream: rank 0 makes another id and broadcasts it over the first
+            Id128 uid2;
+            memset(uid2.bytes, 0, 128);
+            if (rk == 0 && g_nccl.GetUniqueId(uid2.bytes) != 0) throw std::runtime_error("ncclGetUniqueId failed");
+            DevBuf<unsigned char> dId;
+            dId.ensure(128);
+            CUDA_CHECK(cudaMemcpyAsync(dId.p, uid2.bytes, 128, cudaMemcpyHostToDevice, stream));
+            int rb = g_nccl.Broadcast(dId.p, dId.p, 128, /*ncclUint8*/ 1, 0, comm, stream);
+            if (rb != 0) throw std::runtime_error("ncclBroadcast of the second communicator id failed");
+            CUDA_CHECK(cudaMemcpyAsync(uid2.bytes, dId.p, 128, cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            int r2 = g_nccl.CommInitRank(&commPme, nr, uid2, rk);
+            if (r2 != 0) throw std::runtime_error(std::string("ncclCommInitRank (reciprocal communicator) failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r2) : "?"));
+        }
         if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
         rank = rk; numRanks = nr;
         P.rank = rk; P.numRanks = nr;

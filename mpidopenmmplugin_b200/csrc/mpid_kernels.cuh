@@ -645,16 +645,9 @@ k_fixed_field(DevParams P, int numPol, const int* __restrict__ polList, const do
             real dx, dy, dz;
             pairDelta<real>(P, pi, pj, e >> MPID_CODE_SHIFT, dx, dy, dz);
             const real r2 = dx*dx + dy*dy + dz*dz;
+            // (a one-coefficient shortcut for bare-charge partners was tried and measured slower: the 8-lane groups of a
+            // warp then diverge between the two partner kinds and pay for both paths, profiles/r01r_ncu_full_96k.md)
             const typename Real4<real>::type* src = reinterpret_cast<const typename Real4<real>::type*>(cart + 20*(size_t) j);
-            if (((int) pj.w) & 2) {
-                // bare-charge partner (two thirds of the neighbours in water): only the charge term of the field exists
-                // and only its first coefficient is needed -- no moment loads, no higher radial functions
-                real c[1];
-                fieldCoefficientsOrdinary<real, EWALD, 1>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mud[j].w, c);
-                const real s0 = -c[0]*src[0].x;
-                ex += s0*dx; ey += s0*dy; ez += s0*dz;
-                continue;
-            }
             real c[4];
             fieldCoefficientsOrdinary<real, EWALD, 4>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mud[j].w, c);
             real m[20];
@@ -700,14 +693,22 @@ k_induced_field(DevParams P, int numPol, const int* __restrict__ polList, const 
         const real invDampI = mud[i].w;
         const unsigned nAll = polCount[rp];
         const unsigned* base = polNbr + (size_t) rp*P.nbrCap;
-        unsigned eNext = sub < nAll ? base[sub] : 0u;     // fetched one trip ahead
+        // software pipeline, two trips deep: the list entry is fetched two trips ahead and the partner's position and
+        // dipole one trip ahead, so both dependent global-memory latencies overlap the arithmetic of earlier pairs
+        typedef typename Real4<real>::type R4;
+        unsigned e1 = sub < nAll ? base[sub] : 0u;
+        unsigned e2 = sub + MPID_LANES < nAll ? base[sub + MPID_LANES] : 0u;
+        double4 pjN = posS[e1 & MPID_JMASK];
+        R4 mjN = mud[e1 & MPID_JMASK];
         for (unsigned k = sub; k < nAll; k += MPID_LANES) {
-            const unsigned e = eNext;
-            if (k + MPID_LANES < nAll) eNext = base[k + MPID_LANES];
-            const unsigned j = e & MPID_JMASK;
+            const unsigned e = e1;
+            const double4 pj = pjN;
+            const R4 mj = mjN;
+            e1 = e2;
+            if (k + 2*MPID_LANES < nAll) e2 = base[k + 2*MPID_LANES];
+            if (k + MPID_LANES < nAll) { pjN = posS[e1 & MPID_JMASK]; mjN = mud[e1 & MPID_JMASK]; }
             real dx, dy, dz;
-            pairDelta<real>(P, pi, posS[j], e >> MPID_CODE_SHIFT, dx, dy, dz);
-            const typename Real4<real>::type mj = mud[j];
+            pairDelta<real>(P, pi, pj, e >> MPID_CODE_SHIFT, dx, dy, dz);
             const real r2 = dx*dx + dy*dy + dz*dz;
             real c[4];
             fieldCoefficientsOrdinary<real, EWALD, (GRAD ? 3 : 2)>(r2, (real) P.alpha, (real) P.defaultThole, invDampI*mj.w, c);
@@ -1356,7 +1357,7 @@ k_dots_final(int numBlocks, int m, const double* __restrict__ partial, double* _
 struct DiisStatus {
     int done;                     // eps < target reached
     unsigned ticket;              // CTAs of the fused step kernel that have finished (last one solves)
-    int pad_;
+    int iter;                     // device-side iteration counter (graph-replayed solver steps read it instead of a launch argument)
     int iterations;               // index of the iteration that converged / last one run (:1219-1231)
     double eps;
     double coef[MPID_MAX_HISTORY + 1];
@@ -1498,16 +1499,33 @@ k_diis_solve(int numBlocks, int m, SlotList slots, int iteration, int numAtoms, 
 // phidp + self term, what k_induced_finish does), (2) newDip / err / history and the partial error overlaps (what
 // k_diis_record_dots does), (3) the CTA that finishes last reduces the partials and runs the convergence test and
 // the DIIS solve (k_diis_solve).  One launch instead of three on the solver's critical path.
+// History bookkeeping as a function of the iteration index (what the host loop of the reference does with its
+// vectors, :1232-1236): iteration `it` writes ring slot it % H; the m = min(it+1, H) live vectors in age order are
+// the slots (it-m+1 .. it) % H.
+__device__ __forceinline__ int diisHistory(int it, SlotList& sl) {
+    const int H = MPID_MAX_HISTORY;
+    const int m = min(it + 1, H);
+    for (int a = 0; a < m; a++) sl.s[a] = (it - (m - 1) + a) % H;
+    return m;
+}
+
 template <typename real>
 __global__ void __launch_bounds__(512)
 k_diis_step(DevParams P, const int* __restrict__ flagS, const real* __restrict__ phidp,
             const double* __restrict__ alphaLab, const double* __restrict__ efix,
             const double* __restrict__ ifield, const double* __restrict__ mu,
-            double* __restrict__ histDip, double* __restrict__ histErr, int m, VecList errs, SlotList slots,
-            int iteration, double targetEps, DiisStatus* __restrict__ status, double* __restrict__ partial) {
+            double* __restrict__ histDipBase, double* __restrict__ histErrBase,
+            int itHost, double targetEps, DiisStatus* __restrict__ status, double* __restrict__ partial) {
     if (status->done) return;
     __shared__ double sh[512/32][MPID_MAX_HISTORY + 1];
     __shared__ int isLast;
+    // itHost < 0: the launch is a replayed graph node and the iteration index lives in the status block
+    const int it = itHost >= 0 ? itHost : status->iter;
+    SlotList slots;
+    const int m = diisHistory(it, slots);
+    const size_t vlen = 3*(size_t) P.n;
+    double* histDip = histDipBase + (size_t) slots.s[m-1]*vlen;
+    double* histErr = histErrBase + (size_t) slots.s[m-1]*vlen;
     double acc[MPID_MAX_HISTORY + 1];
     for (int k = 0; k < m; k++) acc[k] = 0;
     const bool pme = P.method == PME;
@@ -1526,7 +1544,7 @@ k_diis_step(DevParams P, const int* __restrict__ flagS, const real* __restrict__
         const double e0 = nx - ux, e1 = ny - uy, e2 = nz - uz;
         histErr[3*(size_t) s] = e0; histErr[3*(size_t) s+1] = e1; histErr[3*(size_t) s+2] = e2;
         for (int k = 0; k < m - 1; k++) {
-            const double* h = errs.v[k] + 3*(size_t) s;
+            const double* h = histErrBase + (size_t) slots.s[k]*vlen + 3*(size_t) s;
             acc[k] += e0*h[0] + e1*h[1] + e2*h[2];
         }
         acc[m-1] += e0*e0 + e1*e1 + e2*e2;
@@ -1554,20 +1572,28 @@ k_diis_step(DevParams P, const int* __restrict__ flagS, const real* __restrict__
     __syncthreads();
     if (!isLast) return;
     __threadfence();
-    diisSolveBlock((int) gridDim.x, m, slots, iteration, P.n, targetEps, partial, status);
+    diisSolveBlock((int) gridDim.x, m, slots, it, P.n, targetEps, partial, status);
+    __syncthreads();
+    if (threadIdx.x == 0) status->iter = it + 1;
 }
 
-// mu = sum_k coef[k] * histDip_k with the coefficients k_diis_solve left in the status block (:1240-1249)
+// mu = sum_k coef[k] * histDip_k with the coefficients the solve left in the status block (:1240-1249).
+// itHost < 0: replayed graph node, the iteration just solved is status->iter - 1.
 template <typename real>
-__global__ void k_diis_combine(int n, int m, VecList vecs, const DiisStatus* __restrict__ status, double* __restrict__ mu,
-                               typename Real4<real>::type* __restrict__ mud) {
+__global__ void k_diis_combine_ring(int n, int itHost, const double* __restrict__ histDipBase, const DiisStatus* __restrict__ status,
+                                    double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud) {
     if (status->done) return;
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= n) return;
+    const int it = itHost >= 0 ? itHost : status->iter - 1;
+    SlotList slots;
+    const int m = diisHistory(it, slots);
+    const size_t vlen = 3*(size_t) n;
     double x = 0, y = 0, z = 0;
     for (int k = 0; k < m; k++) {
         const double c = status->coef[k];
-        x += c*vecs.v[k][3*(size_t) s]; y += c*vecs.v[k][3*(size_t) s+1]; z += c*vecs.v[k][3*(size_t) s+2];
+        const double* v = histDipBase + (size_t) slots.s[k]*vlen + 3*(size_t) s;
+        x += c*v[0]; y += c*v[1]; z += c*v[2];
     }
     mu[3*(size_t) s] = x; mu[3*(size_t) s+1] = y; mu[3*(size_t) s+2] = z;
     typename Real4<real>::type v = mud[s];

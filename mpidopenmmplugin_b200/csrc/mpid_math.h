@@ -555,9 +555,11 @@ MPID_HD T chargeSitePair(const T* mA, T ux, T uy, T uz, T invDamp, bool anisoA, 
     T c[4], bn0;
     T bare3 = rinv*rinv2, bare5 = T(3)*bare3*rinv2;
     if (EWALD) {
+        // full-accuracy erfc / exp here (not the fast field-kernel primitives): these terms enter the ENERGY, a sum
+        // of large cancelling pair terms in which a systematic 3e-7 relative error of erfc shows up at the 1e-6 level
         const T x = alphaEwald*r;
-        const T ex2 = t_expneg(-(x*x));
-        bn0 = t_erfc_ex(x, ex2)*rinv;
+        const T ex2 = t_exp(-(x*x));
+        bn0 = t_erfc(x)*rinv;
         const T alsq2 = T(2)*alphaEwald*alphaEwald;
         T a2n = T(1.0/MPID_SQRT_PI)/alphaEwald;
         T bn = bn0, fac = T(1);

@@ -221,6 +221,7 @@ struct Engine : public EngineBase {
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
         if (hDiis) cudaFreeHost(hDiis);
+        if (hCg) cudaFreeHost(hCg);
         if (iterGraph) cudaGraphExecDestroy(iterGraph);
         if (hNlTotals) cudaFreeHost(hNlTotals);
         if (evNlTotals) cudaEventDestroy(evNlTotals);
@@ -1052,6 +1053,56 @@ struct Engine : public EngineBase {
         }
     }
 
+    // Preconditioned conjugate gradient for the mutual dipoles (MPIDB200_SOLVER_CG): same first guess, same
+    // convergence measure and tolerance as the DIIS loop of the reference (:1182-1252), one field pass per iteration,
+    // device-resident scalars, speculative enqueue like the DIIS path.  See the kernels' header comment for the algebra.
+    DevBuf<CgStatus> dCg;
+    CgStatus* hCg = nullptr;
+    DevBuf<double> dCgR, dCgW, dCgAp, dCgZ, dCgMu, dCgPartial;
+    int predictedCgEvals = 0;
+    void solveMutualCg(const double* dPosIn) {
+        const int nb = 148;
+        const size_t len = 3*(size_t) n;
+        dCgR.ensure(len); dCgW.ensure(len); dCgAp.ensure(len); dCgZ.ensure(len); dCgMu.ensure(len);
+        dCgPartial.ensure(2*(size_t) nb);
+        dCg.ensure(1);
+        if (!hCg) CUDA_CHECK(cudaMallocHost((void**) &hCg, sizeof(CgStatus)));
+        CUDA_CHECK(cudaMemsetAsync(dCg.p, 0, sizeof(CgStatus), stream));
+        lastIterations = 0; lastEps = 0;
+        const bool single = numRanks == 1;
+        auto readStatus = [&]() {
+            CUDA_CHECK(cudaMemcpyAsync(hCg, dCg.p, sizeof(CgStatus), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            lastIterations = hCg->iterations; lastEps = hCg->eps;
+            return hCg->done != 0;
+        };
+        // field of the first guess mu0 = alpha E
+        inducedFieldPass(dPosIn, 1, nullptr, true, single);
+        stageBegin(MPIDB200_STAGE_SOLVER);
+        if (single) LAUNCH((k_cg_init<real, true>), nb, 512, P, dFlagS.p, dPhidp.p, dAlphaLab.p, dIfield.p, dMu.p, dMud.p, dCgR.p, dCgW.p, dCgMu.p, cfg.target_epsilon, dCg.p, dCgPartial.p);
+        else LAUNCH((k_cg_init<real, false>), nb, 512, P, dFlagS.p, dPhidp.p, dAlphaLab.p, dIfield.p, dMu.p, dMud.p, dCgR.p, dCgW.p, dCgMu.p, cfg.target_epsilon, dCg.p, dCgPartial.p);
+        LAUNCH((k_cg_direction<real>), blocksFor(n, 256), 256, n, dCgZ.p, dCgR.p, dCgMu.p, dMu.p, dMud.p, dCgW.p, dCg.p, 1);
+        stageEnd();
+        for (int it = 1; ; it++) {            // `it` field evaluations done so far
+            const bool last = it > cfg.max_iterations;
+            if (it >= predictedCgEvals || last || syncEveryIteration) {
+                if (readStatus() || last) {
+                    if (!hCg->done)
+                        throw std::runtime_error("Induced dipoles did not converge:  iterations=" + std::to_string(lastIterations) + " eps=" + std::to_string(lastEps));
+                    predictedCgEvals = lastIterations + 1;
+                    return;
+                }
+            }
+            inducedFieldPass(dPosIn, 1, nullptr, true, single);
+            stageBegin(MPIDB200_STAGE_SOLVER);
+            if (single) LAUNCH((k_cg_ap<real, true>), nb, 512, P, dFlagS.p, dPhidp.p, dIfield.p, dMu.p, dCgW.p, dCgAp.p, dCg.p, dCgPartial.p);
+            else LAUNCH((k_cg_ap<real, false>), nb, 512, P, dFlagS.p, dPhidp.p, dIfield.p, dMu.p, dCgW.p, dCgAp.p, dCg.p, dCgPartial.p);
+            LAUNCH(k_cg_update, nb, 512, P, dAlphaLab.p, dMu.p, dCgAp.p, dCgMu.p, dCgR.p, dCgZ.p, cfg.target_epsilon, dCg.p, dCgPartial.p);
+            LAUNCH((k_cg_direction<real>), blocksFor(n, 256), 256, n, dCgZ.p, dCgR.p, dCgMu.p, dMu.p, dMud.p, dCgW.p, dCg.p, 0);
+            stageEnd();
+        }
+    }
+
     // convergeInduceDipolesByExtrapolation (:1125-1180)
     std::vector<double> optPart;
     void solveExtrapolated(const double* dPosIn) {
@@ -1107,8 +1158,11 @@ struct Engine : public EngineBase {
         lastIterations = 0; lastEps = 0;
         if (P.polarization == Direct) {
             if (pme && !dipolesOnly) inducedFieldPass(dPosIn, 4, nullptr, false);
+        } else if (P.polarization == Mutual && cfg.solver == MPIDB200_SOLVER_CG) {
+            solveMutualCg(dPosIn);
+            // the last field pass belonged to a search direction: one reciprocal pass of the converged dipoles for phidp
+            if (pme && !dipolesOnly) inducedFieldPass(dPosIn, 4, nullptr, false);
         } else if (P.polarization == Mutual) {
-            if (cfg.solver != MPIDB200_SOLVER_DIIS) throw std::runtime_error("mpidb200: only the DIIS solver is available in this build");
             solveMutualDiis(dPosIn);
             if (pme && !dipolesOnly && rows > 0) {
                 // the converged dipoles' reciprocal potential is still on the grid: fetch all 35 derivatives

@@ -1619,6 +1619,174 @@ __global__ void k_combine(int n, int m, VecList vecs, CoefList coef, double* __r
     mud[s] = v;
 }
 
+// ---- preconditioned conjugate gradient (the alternative mutual solver, MPIDB200_SOLVER_CG) -----------------
+// Solves A mu = E with A = alpha^-1 - T (symmetric positive definite on the polarizable sites) and the diagonal-block
+// preconditioner M^-1 = alpha_lab, starting from the reference's own first guess mu0 = alpha E (:936-946).  One field
+// pass per iteration gives T p.  alpha^-1 p never needs an inverse: p = z + beta p with z = alpha r, so
+// w := alpha^-1 p obeys w = r + beta w.  Convergence is tested on the same quantity as the reference's DIIS loop,
+// eps = 48.033324 sqrt(sum |mu_new - mu|^2 / N) (:1219): for a Jacobi update mu_new - mu = alpha (E - A mu) = z.
+// The scalars (gamma, beta, r.z) live in the status block; all kernels return at once when `done` is set.
+struct CgStatus {
+    int done;
+    unsigned ticket;
+    int iter;                     // field evaluations used so far - 1
+    int iterations;
+    double eps;
+    double rz;                    // r.z of the current residual
+    double gamma, beta;
+};
+
+// block-level sum of two doubles per thread, then last-CTA-done reduction over the grid; returns true in the last CTA
+// with the totals in out[0..1] (block size 512)
+__device__ __forceinline__ bool cgGridReduce2(double a, double b, double* __restrict__ partial, unsigned* ticket, double* out) {
+    __shared__ double sh2[512/32][2];
+    __shared__ int last2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int off = 16; off > 0; off >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+    if (lane == 0) { sh2[wid][0] = a; sh2[wid][1] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0, tb = 0;
+        for (int w = 0; w < 512/32; w++) { ta += sh2[w][0]; tb += sh2[w][1]; }
+        partial[2*blockIdx.x] = ta; partial[2*blockIdx.x + 1] = tb;
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        last2 = t == gridDim.x - 1;
+        if (last2) *ticket = 0u;
+    }
+    __syncthreads();
+    if (!last2) return false;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        double ta = 0, tb = 0;
+        for (unsigned b2 = 0; b2 < gridDim.x; b2++) { ta += partial[2*b2]; tb += partial[2*b2 + 1]; }     // fixed order: deterministic
+        out[0] = ta; out[1] = tb;
+    }
+    __syncthreads();
+    return true;
+}
+
+// Start: r0 = T mu0 (the induced field of the first guess, reciprocal + self part added here on a single GPU),
+// z0 = alpha r0, p0 = z0 (into mu / mud, the input of the next field pass), w0 = r0, muAcc = mu0; eps0, r.z.
+template <typename real, bool FINISH>
+__global__ void __launch_bounds__(512)
+k_cg_init(DevParams P, const int* __restrict__ flagS, const real* __restrict__ phidp, const double* __restrict__ alphaLab,
+          const double* __restrict__ ifield, double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud,
+          double* __restrict__ r, double* __restrict__ w, double* __restrict__ muAcc, double targetEps,
+          CgStatus* __restrict__ status, double* __restrict__ partial) {
+    double rz = 0, zz = 0;
+    for (int s = blockIdx.x*blockDim.x + threadIdx.x; s < P.n; s += gridDim.x*blockDim.x) {
+        double fx = ifield[3*(size_t) s], fy = ifield[3*(size_t) s+1], fz = ifield[3*(size_t) s+2];
+        const double ux = mu[3*(size_t) s], uy = mu[3*(size_t) s+1], uz = mu[3*(size_t) s+2];
+        const bool pol = (flagS[s] & 1) != 0;
+        if (FINISH && P.method == PME && pol) {
+            double rx, ry, rzc;
+            reciprocalFieldOf<real>(P, phidp, s, rx, ry, rzc);
+            fx += rx + P.selfFieldTerm*ux; fy += ry + P.selfFieldTerm*uy; fz += rzc + P.selfFieldTerm*uz;
+        }
+        if (!pol) { fx = fy = fz = 0; }
+        double zx, zy, zzc;
+        applyAlphaLab(alphaLab + 6*(size_t) s, fx, fy, fz, zx, zy, zzc);
+        muAcc[3*(size_t) s] = ux; muAcc[3*(size_t) s+1] = uy; muAcc[3*(size_t) s+2] = uz;
+        r[3*(size_t) s] = fx; r[3*(size_t) s+1] = fy; r[3*(size_t) s+2] = fz;
+        w[3*(size_t) s] = fx; w[3*(size_t) s+1] = fy; w[3*(size_t) s+2] = fz;
+        mu[3*(size_t) s] = zx; mu[3*(size_t) s+1] = zy; mu[3*(size_t) s+2] = zzc;
+        typename Real4<real>::type v = mud[s];
+        v.x = (real) zx; v.y = (real) zy; v.z = (real) zzc;
+        mud[s] = v;
+        rz += fx*zx + fy*zy + fz*zzc;
+        zz += zx*zx + zy*zy + zzc*zzc;
+    }
+    double tot[2];
+    if (!cgGridReduce2(rz, zz, partial, &status->ticket, tot)) return;
+    if (threadIdx.x == 0) {
+        status->rz = tot[0];
+        status->eps = MPID_DEBYE*sqrt(tot[1]/P.n);
+        status->iterations = 0; status->iter = 0;
+        if (status->eps < targetEps) status->done = 1;
+    }
+}
+
+// Ap = w - T p ; p.Ap ; gamma = r.z / p.Ap
+template <typename real, bool FINISH>
+__global__ void __launch_bounds__(512)
+k_cg_ap(DevParams P, const int* __restrict__ flagS, const real* __restrict__ phidp, const double* __restrict__ ifield,
+        const double* __restrict__ p, const double* __restrict__ w, double* __restrict__ ap,
+        CgStatus* __restrict__ status, double* __restrict__ partial) {
+    if (status->done) return;
+    double pap = 0;
+    for (int s = blockIdx.x*blockDim.x + threadIdx.x; s < P.n; s += gridDim.x*blockDim.x) {
+        double fx = ifield[3*(size_t) s], fy = ifield[3*(size_t) s+1], fz = ifield[3*(size_t) s+2];
+        const double px = p[3*(size_t) s], py = p[3*(size_t) s+1], pz = p[3*(size_t) s+2];
+        const bool pol = (flagS[s] & 1) != 0;
+        if (FINISH && P.method == PME && pol) {
+            double rx, ry, rzc;
+            reciprocalFieldOf<real>(P, phidp, s, rx, ry, rzc);
+            fx += rx + P.selfFieldTerm*px; fy += ry + P.selfFieldTerm*py; fz += rzc + P.selfFieldTerm*pz;
+        }
+        double ax = 0, ay = 0, az = 0;
+        if (pol) { ax = w[3*(size_t) s] - fx; ay = w[3*(size_t) s+1] - fy; az = w[3*(size_t) s+2] - fz; }
+        ap[3*(size_t) s] = ax; ap[3*(size_t) s+1] = ay; ap[3*(size_t) s+2] = az;
+        pap += px*ax + py*ay + pz*az;
+    }
+    double tot[2];
+    if (!cgGridReduce2(pap, 0.0, partial, &status->ticket, tot)) return;
+    if (threadIdx.x == 0) status->gamma = tot[0] != 0.0 ? status->rz/tot[0] : 0.0;
+}
+
+// muAcc += gamma p ; r -= gamma Ap ; z = alpha r (kept in `z`) ; new r.z and eps ; beta
+__global__ void __launch_bounds__(512)
+k_cg_update(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ p, const double* __restrict__ ap,
+            double* __restrict__ muAcc, double* __restrict__ r, double* __restrict__ z, double targetEps,
+            CgStatus* __restrict__ status, double* __restrict__ partial) {
+    if (status->done) return;
+    const double gamma = status->gamma;
+    double rz = 0, zz = 0;
+    for (int s = blockIdx.x*blockDim.x + threadIdx.x; s < P.n; s += gridDim.x*blockDim.x) {
+        double rx = r[3*(size_t) s], ry = r[3*(size_t) s+1], rzc = r[3*(size_t) s+2];
+        for (int k = 0; k < 3; k++) muAcc[3*(size_t) s + k] += gamma*p[3*(size_t) s + k];
+        rx -= gamma*ap[3*(size_t) s]; ry -= gamma*ap[3*(size_t) s+1]; rzc -= gamma*ap[3*(size_t) s+2];
+        r[3*(size_t) s] = rx; r[3*(size_t) s+1] = ry; r[3*(size_t) s+2] = rzc;
+        double zx, zy, zzc;
+        applyAlphaLab(alphaLab + 6*(size_t) s, rx, ry, rzc, zx, zy, zzc);
+        z[3*(size_t) s] = zx; z[3*(size_t) s+1] = zy; z[3*(size_t) s+2] = zzc;
+        rz += rx*zx + ry*zy + rzc*zzc;
+        zz += zx*zx + zy*zy + zzc*zzc;
+    }
+    double tot[2];
+    if (!cgGridReduce2(rz, zz, partial, &status->ticket, tot)) return;
+    if (threadIdx.x == 0) {
+        status->beta = status->rz != 0.0 ? tot[0]/status->rz : 0.0;
+        status->rz = tot[0];
+        status->eps = MPID_DEBYE*sqrt(tot[1]/P.n);
+        status->iter += 1;
+        status->iterations = status->iter;
+        if (status->eps < targetEps) status->done = 1;
+    }
+}
+
+// p = z + beta p (into mu / mud for the next field pass) ; w = r + beta w.   When converged: mu = muAcc instead.
+template <typename real>
+__global__ void k_cg_direction(int n, const double* __restrict__ z, const double* __restrict__ r, const double* __restrict__ muAcc,
+                               double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud, double* __restrict__ w,
+                               const CgStatus* __restrict__ status, int finalOnly) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double x, y, zc;
+    if (status->done) {
+        x = muAcc[3*(size_t) s]; y = muAcc[3*(size_t) s+1]; zc = muAcc[3*(size_t) s+2];
+    } else {
+        if (finalOnly) return;
+        const double beta = status->beta;
+        x = z[3*(size_t) s] + beta*mu[3*(size_t) s]; y = z[3*(size_t) s+1] + beta*mu[3*(size_t) s+1]; zc = z[3*(size_t) s+2] + beta*mu[3*(size_t) s+2];
+        for (int k = 0; k < 3; k++) w[3*(size_t) s + k] = r[3*(size_t) s + k] + beta*w[3*(size_t) s + k];
+    }
+    mu[3*(size_t) s] = x; mu[3*(size_t) s+1] = y; mu[3*(size_t) s+2] = zc;
+    typename Real4<real>::type v = mud[s];
+    v.x = (real) x; v.y = (real) y; v.z = (real) zc;
+    mud[s] = v;
+}
+
 // OPT recursion step (:1149-1167): mu = alpha.E_ind ; store mu, field (gradient is stored by the caller's buffer)
 template <typename real>
 __global__ void k_opt_step(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ ifield,

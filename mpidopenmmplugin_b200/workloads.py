@@ -86,11 +86,11 @@ class FlatSystem:
         return f
 
 
-def make_kernel(system, precision="mixed", device=0, profiling=False, frameless_alpha_fix=False):
+def make_kernel(system, precision="mixed", device=0, profiling=False, frameless_alpha_fix=False, solver="diis"):
     """Create an engine for a FlatSystem through the raw C ABI (no per-atom python loops)."""
     import ctypes
     from .api import MPIDB200Kernel, _Config, _dp, _ip
-    k = MPIDB200Kernel(precision=precision, device=device, frameless_alpha_fix=frameless_alpha_fix)
+    k = MPIDB200Kernel(precision=precision, device=device, frameless_alpha_fix=frameless_alpha_fix, solver=solver)
     lib = k._lib
     cfg = _Config()
     lib.mpidb200_default_config(ctypes.byref(cfg))

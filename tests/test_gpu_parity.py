@@ -329,3 +329,50 @@ def test_fused_reciprocal_pass_matches_cufft(tiles, pol, monkeypatch):
     assert abs(eb - ea) < 1e-7*abs(ea)
     assert rel_err(kb.getInducedDipoles(s.pos), ka.getInducedDipoles(s.pos)) < 2e-6
     ka.close(); kb.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+@pytest.mark.parametrize("case", ["waterbox", "waterbox-aniso", "dimer-nocutoff", "methanol-pme"])
+def test_conjugate_gradient_solver_matches_oracle(case, prec):
+    """MPIDB200_SOLVER_CG (preconditioned conjugate gradient, the north star's alternative to DIIS) converges to the
+    same self-consistent dipoles: with eps = 1e-8 on both sides forces, energy and dipoles match the oracle's DIIS
+    result as tightly as the DIIS path does."""
+    if case == "waterbox":
+        s = water_box((1, 1, 1), polarization=0, epsilon=1e-8)
+    elif case == "waterbox-aniso":
+        s = water_box((1, 1, 1), polarization=0, epsilon=1e-8, anisotropic=True)
+    elif case == "dimer-nocutoff":
+        s = water_dimer(0, 0); s.epsilon = 1e-8
+    else:
+        s = methanol_dimer(1, 0); s.epsilon = 1e-8
+    if prec == "mixed":
+        s.epsilon = 1e-7          # the FP32 field noise floor sits near 1e-8
+    o = Oracle(s)
+    e0, f0 = o.execute()
+    mu0 = o.dipoles(0)
+    k = make_kernel(s, precision=prec, solver="cg")
+    f = np.zeros((s.n, 3))
+    e = k.execute(s.pos, True, True, f)
+    mu = k.getInducedDipoles(s.pos)
+    st = k.getStats()
+    assert 1 <= st["iterations"] <= 30 and st["epsilon"] < s.epsilon
+    tol = 1e-8 if prec == "double" else 1e-5
+    assert rel_err(f, f0) < max(tol, 20*s.epsilon*1e-2)
+    assert abs(e - e0) < max(tol, 1e-7)*abs(e0)
+    # both solvers stop when 48.03 sqrt(sum |Jacobi update|^2 / N) < eps, which bounds the distance to the fixed point by a
+    # small multiple of eps sqrt(N) / 48: the two answers may differ by that much, not by round-off
+    assert np.linalg.norm(mu - mu0) < 0.5*s.epsilon*np.sqrt(s.n) + (2e-7 if prec == "mixed" else 0.0)*np.linalg.norm(mu0)
+    # the second evaluation runs with the predicted iteration count (no host check per iteration): same answer
+    g = np.zeros((s.n, 3))
+    e2 = k.execute(s.pos, True, True, g)
+    assert rel_err(g, f) < (1e-10 if prec == "double" else 1e-6)
+    k.close()
+
+
+def test_conjugate_gradient_reports_non_convergence():
+    s = water_box((1, 1, 1), polarization=0, epsilon=1e-30)
+    s.max_iter = 3
+    k = make_kernel(s, precision="double", solver="cg")
+    with pytest.raises(MPIDB200Error, match="Induced dipoles did not converge"):
+        k.execute(s.pos, True, True, np.zeros((s.n, 3)))
+    k.close()

@@ -7,23 +7,26 @@ from _common import Oracle, make_kernel, rel_err, water_box
 pytestmark = pytest.mark.gpu
 
 
-def test_96k_box_equals_32_copies_of_the_oracle_box():
-    """Without jitter the 4x4x2 tiling is an exact periodic replication of the 996-water box on a grid that is
-    also replicated (128x128x64 = 4x4x2 x 32^3), so E = 32 E_996 and every image atom feels the same force.  The
-    oracle value for the 996-water box therefore pins the full-size run."""
-    base = water_box((1, 1, 1), polarization=0, epsilon=1e-7)
+@pytest.mark.parametrize("tiles,pol", [((4, 4, 2), 0), ((4, 4, 2), 1), ((4, 4, 2), 2), ((7, 7, 7), 0)])
+def test_tiled_boxes_equal_copies_of_the_oracle_box(tiles, pol):
+    """Without jitter a tiling is an exact periodic replication of the 996-water box on a grid that is also
+    replicated (128x128x64 = 4x4x2 x 32^3, 224^3 = 7^3 x 32^3), so E = copies x E_996 and every image atom feels the
+    same force.  The oracle value for the 996-water box therefore pins the full-size runs of BASELINE.json: config 4
+    (95,616 atoms; Mutual, Direct and Extrapolated) and config 5 (1,024,884 atoms)."""
+    copies = tiles[0]*tiles[1]*tiles[2]
+    base = water_box((1, 1, 1), polarization=pol, epsilon=1e-7)
     e0, f0 = Oracle(base).execute()
-    s = water_box((4, 4, 2), jitter=0.0, polarization=0, epsilon=1e-7)
-    assert s.n == 95616
+    s = water_box(tiles, jitter=0.0, polarization=pol, epsilon=1e-7)
+    assert s.n == copies*2988
     k = make_kernel(s, precision="mixed")
     f = np.zeros((s.n, 3))
     e = k.execute(s.pos, True, True, f)
-    assert abs(e - 32*e0) < 1e-5*abs(32*e0)
-    fr = f.reshape(32, 2988, 3)
+    assert abs(e - copies*e0) < 1e-5*abs(copies*e0)
+    fr = f.reshape(copies, 2988, 3)
     assert rel_err(fr.mean(axis=0), f0) < 1e-5
     assert np.abs(fr - fr[0]).max() < 2e-3*np.sqrt(np.mean(f0*f0))*10
     st = k.getStats()
-    assert st["pairs"] + 32*2988 == 32*312265           # ordinary pairs + covalently scaled pairs
+    assert st["pairs"] + copies*2988 == copies*312265           # ordinary pairs + covalently scaled pairs
     k.close()
 
 

@@ -6,6 +6,9 @@
 // 179-239, SimTKReference/MPIDReferenceForce.cpp:2193-2269); the stage order is our own.
 #include "../../include/mpidb200.h"
 #include "mpid_kernels.cuh"
+#ifndef MPIDB200_FFT2_DEFAULT
+#define MPIDB200_FFT2_DEFAULT 0      // flipped to 1 once measured faster than the library path
+#endif
 #include "mpid_fft.cuh"
 
 #include <cub/cub.cuh>
@@ -120,6 +123,8 @@ template <> struct FftTraits<double> {
 };
 
 inline int blocksFor(long long count, int block) { return (int) std::max<long long>(1, (count + block - 1)/block); }
+// k_gather: five atoms per warp (six lanes each), four warps per block
+inline int gatherBlocks(long long atoms) { return blocksFor((atoms + MPID_GATHER_ATOMS_PER_WARP - 1)/MPID_GATHER_ATOMS_PER_WARP*32, 128); }
 
 template <typename real>
 struct Engine : public EngineBase {
@@ -132,18 +137,18 @@ struct Engine : public EngineBase {
     cudaStream_t stream3 = nullptr;     // pair work that does not depend on the induced dipoles (fills the SMs the solver leaves idle)
     cudaEvent_t evFork3 = nullptr, evJoin3 = nullptr;
     cudaStream_t cur = nullptr;         // stream the LAUNCH macro / stage timers currently target
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evFrames = nullptr;
     bool haveParticles = false, haveBox = false, pmeReady = false;
     // host copies
     std::vector<double> hCharge, hDipole, hQuad, hOct, hThole, hAlpha, hDamp;
-    std::vector<int> hAxis, hZ, hX, hY;
+    std::vector<int> hAxis, hZ, hX, hY, hFlag;
     std::vector<int> hSpStart, hSpPartner, hSpClass, hSpLo, hSpHi, hSpPairClass;
     double boxA[3], boxB[3], boxC[3];
     DevParams P;
     double alphaEwald = 0; int grid[3] = {0, 0, 0};
     // static device data
     DevBuf<double> dCharge, dDipole, dQuad, dOct, dThole, dAlpha, dDamp;
-    DevBuf<int> dAxis, dZ, dX, dY;
+    DevBuf<int> dAxis, dZ, dX, dY, dFlagOrig;
     DevBuf<int> dSpStart, dSpPartner, dSpClass, dSpLo, dSpHi, dSpPairClass;
     // per-evaluation device data
     DevBuf<double> dPos, dPosW, dForcesOut;
@@ -162,20 +167,21 @@ struct Engine : public EngineBase {
     DevBuf<unsigned long long> dClassPacked, dClassScan;
     int numSimpleTotal = 0, numSimple = 0, simpleBegin = 0;
     int numFull = 0, fullBegin = 0;       // sites that are not bare charges, among this rank's rows
-    bool classCountsValid = false;
     int nbrCap = 0;
     int numPolTotal = 0;            // polarizable sites (static: follows from the parameters)
     int numPol = 0, polBegin = 0;   // polarizable sites among this rank's rows
     long long typeBegin[6] = {0, 0, 0, 0, 0, 0};   // boundaries of the four pair-class lists inside pairI/pairJ
     DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
     DevBuf<unsigned long long> dForce, dTorque, dEnergy;
-    DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp;
+    DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp, dThetaAll, dThetaPol;
+    DevBuf<int4> dIgridAll, dIgridPol;
     DevBuf<cplx> dGridC;
     DevBuf<double> dModX, dModY, dModZ;
     DevBuf<double> dHistDip, dHistErr, dDotPartial, dDots;
     DevBuf<double> dPtDip, dPtField, dPtGrad;
     cufftHandle planF = 0, planB = 0;
-    bool customFft = false;             // fused shared-memory reciprocal pass (mpid_fft.cuh) instead of cuFFT
+    bool customFft = false;             // fused shared-memory reciprocal pass (mpid_fft.cuh, Stockham version) instead of cuFFT
+    Fft2Plan fft2;                      // register-radix version of the same three kernels (preferred when the grid qualifies)
     DevBuf<float2> dTwiddle;
     size_t fftSmemPlane = 0, fftSmemX = 0;
     bool plansMade = false;
@@ -205,6 +211,7 @@ struct Engine : public EngineBase {
         CUDA_CHECK(cudaEventCreateWithFlags(&evJoin3, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evFrames, cudaEventDisableTiming));
         CUDA_CHECK(cudaMallocHost((void**) &hPinned, 256*sizeof(double)));
         memset(&P, 0, sizeof(P));
         memset(stageMs, 0, sizeof(stageMs));
@@ -228,6 +235,7 @@ struct Engine : public EngineBase {
         for (cudaEvent_t e : evPool) cudaEventDestroy(e);
         if (evFork) cudaEventDestroy(evFork);
         if (evJoin) cudaEventDestroy(evJoin);
+        if (evFrames) cudaEventDestroy(evFrames);
         if (stream2) cudaStreamDestroy(stream2);
         if (evFork3) cudaEventDestroy(evFork3);
         if (evJoin3) cudaEventDestroy(evJoin3);
@@ -326,7 +334,11 @@ struct Engine : public EngineBase {
             // dampingFactor (MPIDReferenceKernels.cpp:123)
             hDamp[i] = pow((hAlpha[3*i] + hAlpha[3*i+1] + hAlpha[3*i+2])/3.0, 1.0/6.0);
         }
+        // Site classes are static: a rotation cannot turn a non-zero tensor into zero or the reverse, so whether the
+        // lab-frame polarizability / higher moments of a site vanish follows from the parameters alone.
+        //   bit 0 = polarizable, bit 1 = "simple" (bare charge, never polarized)
         numPolTotal = 0; numSimpleTotal = 0;
+        hFlag.resize(n);
         for (int i = 0; i < n; i++) {
             bool anyAlpha = hAlpha[3*i] != 0.0 || hAlpha[3*i+1] != 0.0 || hAlpha[3*i+2] != 0.0;
             // a site without a z anchor keeps a zero lab-frame tensor unless the opt-in fix is on
@@ -337,13 +349,15 @@ struct Engine : public EngineBase {
             for (int k = 0; k < 6; k++) perm = perm || hQuad[6*(size_t) i + k] != 0.0;
             for (int k = 0; k < 10; k++) perm = perm || hOct[10*(size_t) i + k] != 0.0;
             if (!pol && !perm) numSimpleTotal++;
+            hFlag[i] = (pol ? 1 : 0) | ((!pol && !perm) ? 2 : 0);
         }
+        dFlagOrig.upload(hFlag, stream);
         dCharge.upload(hCharge, stream); dDipole.upload(hDipole, stream); dQuad.upload(hQuad, stream); dOct.upload(hOct, stream);
         dAxis.upload(hAxis, stream); dZ.upload(hZ, stream); dX.upload(hX, stream); dY.upload(hY, stream);
         dThole.upload(hThole, stream); dAlpha.upload(hAlpha, stream); dDamp.upload(hDamp, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         haveParticles = true;
-        classCountsValid = false; nlCapsKnown = false;
+        nlCapsKnown = false;
         if (hSpStart.empty()) {   // no covalent maps yet: empty special lists
             std::vector<int> off(8*(size_t) (n+1), 0), idx(1, 0);
             setCovalent(off.data(), idx.data());
@@ -506,23 +520,35 @@ struct Engine : public EngineBase {
     // memory.  Opt-in with MPIDB200_FFT=fused: measured on B200 at 128x128x64 it only ties the library path (three
     // 16-20 us single-wave kernels against seven ~6 us ones, profiles/r01_fft_experiment.md), so cuFFT stays the default.
     void setupCustomFft(const int* g) {
-        customFft = false;
+        customFft = false; fft2 = Fft2Plan();
         if (sizeof(real) != sizeof(float)) return;
         const char* env = getenv("MPIDB200_FFT");
-        if (!env || std::string(env) != "fused") return;
+        const std::string mode = env ? env : "";
+        if (mode == "cufft") return;
         for (int d = 0; d < 3; d++) if (g[d] < 8 || g[d] > MPID_FFT_MAXLEN || (g[d] & (g[d] - 1)) != 0) return;
-        const size_t nzc = (size_t) g[2]/2 + 1;
-        fftSmemPlane = 2*(size_t) g[1]*nzc*sizeof(float2);
-        fftSmemX = 2*(size_t) g[0]*nzc*sizeof(float2);
-        if (fftSmemPlane > 200*1024 || fftSmemX > 200*1024) return;
-        if (!dTwiddle.p) {
+        auto uploadTwiddles = [&]() {
+            if (dTwiddle.p) return;
             std::vector<float2> tw(MPID_FFT_MAXLEN);
             for (int t = 0; t < MPID_FFT_MAXLEN; t++) {
                 const double a = -2.0*MPID_PI*t/MPID_FFT_MAXLEN;
                 tw[t] = make_float2((float) cos(a), (float) sin(a));
             }
             dTwiddle.upload(tw, stream);
+        };
+        if (mode != "fused") {
+            // register-radix kernels (x, y in {32,64,128,256}, z in {32,64,128}): MPIDB200_FFT=fused2, or the default when
+            // the grid qualifies
+            if (mode == "fused2" || (mode.empty() && MPIDB200_FFT2_DEFAULT)) {
+                fft2 = fft2MakePlan(g[0], g[1], g[2]);
+                if (fft2.ok) uploadTwiddles();
+            }
+            return;
         }
+        const size_t nzc = (size_t) g[2]/2 + 1;
+        fftSmemPlane = 2*(size_t) g[1]*nzc*sizeof(float2);
+        fftSmemX = 2*(size_t) g[0]*nzc*sizeof(float2);
+        if (fftSmemPlane > 200*1024 || fftSmemX > 200*1024) return;
+        uploadTwiddles();
         CUDA_CHECK(cudaFuncSetAttribute(k_fft_planes_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fftSmemPlane));
         CUDA_CHECK(cudaFuncSetAttribute(k_fft_planes_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fftSmemPlane));
         CUDA_CHECK(cudaFuncSetAttribute(k_fft_x_convolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fftSmemX));
@@ -598,12 +624,9 @@ struct Engine : public EngineBase {
             CUDA_CHECK(cudaMemcpyAsync(dSortedKey.p, dCellKey.p, n*sizeof(int), cudaMemcpyDeviceToDevice, stream));
             CUDA_CHECK(cudaMemcpyAsync(dOrder.p, dAtomIdx.p, n*sizeof(int), cudaMemcpyDeviceToDevice, stream));
         }
-        LAUNCH(k_cell_starts, blocksFor(numCells + 1, B), B, n, numCells, dSortedKey.p, dCellStart.p);
-        LAUNCH(k_inverse_order, blocksFor(n, B), B, n, dOrder.p, dInv.p);
         // row partition of the sorted atoms across ranks
         P.rowBegin = (int) ((long long) n*rank/numRanks);
         P.rowEnd = (int) ((long long) n*(rank+1)/numRanks);
-        // lab frames
         dPosS.ensure(n); dPosF.ensure(n); dCartD.ensure(20*(size_t) n); dPkD.ensure(16*(size_t) n); dSphD.ensure(16*(size_t) n);
         dAlphaLab.ensure(6*(size_t) n); dAniso.ensure(n); dDampThole.ensure(n); dMud.ensure(n); dSpSorted.ensure(n);
         dFlagS.ensure(n); dPolFlag.ensure((size_t) n + 1); dPolRank.ensure((size_t) n + 1); dPolList.ensure((size_t) n + 1);
@@ -613,11 +636,26 @@ struct Engine : public EngineBase {
         real* cartR; real* pkR;
         if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
-        LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn, dPosW.p,
-               dPosS.p, dPosF.p, dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, dDampThole.p, dMud.p,
-               dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p, dFlagS.p, dClassPacked.p);
+        // what the neighbour search needs from the sort (positions, site classes, cell starts, inverse order) ...
+        LAUNCH((k_sorted_sites<real>), blocksFor(n, B), B, n, numCells, dOrder.p, dSortedKey.p, dPosW.p, dFlagOrig.p, dDamp.p, dThole.p,
+               dInv.p, dPosS.p, dPosF.p, dFlagS.p, dClassPacked.p, dDampThole.p, dMud.p, dCellStart.p);
+        // ... while the lab-frame moments (needed by the reciprocal pass first, by the pair kernels after the neighbour
+        // search) are built on the second stream; evaluate() makes the main stream wait for evFrames
+        {
+            CUDA_CHECK(cudaEventRecord(evFork, stream));
+            CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
+            stageEnd();
+            cur = stream2;
+            stageBegin(MPIDB200_STAGE_SORT);
+            LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn,
+                   dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p);
+            stageEnd();
+            CUDA_CHECK(cudaEventRecord(evFrames, stream2));
+            cur = stream;
+            stageBegin(MPIDB200_STAGE_SORT);
+        }
         // polarizable rows, bare-charge ("simple") rows and their complement ("full"): one scan of the packed class
-        // flags k_lab_frame wrote, then ranks and compact lists
+        // flags, then ranks, compact lists and the sorted indices of each site's covalent partners
         {
             size_t tb = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb, dClassPacked.p, dClassScan.p, n + 1, stream);
@@ -627,7 +665,7 @@ struct Engine : public EngineBase {
             traceEnd();
             launches += 1;
             LAUNCH(k_class_lists, blocksFor(n + 1, B), B, n, dFlagS.p, dClassScan.p, dPolRank.p, dSimpleRank.p, dFullRank.p,
-                   dPolList.p, dSimpleList.p, dFullList.p);
+                   dPolList.p, dSimpleList.p, dFullList.p, dOrder.p, dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p);
         }
         if (numRanks > 1) {
             int* pr = (int*) hPinned;
@@ -639,16 +677,6 @@ struct Engine : public EngineBase {
             polBegin = pr[0]; numPol = pr[1] - pr[0];
             simpleBegin = pr[2]; numSimple = pr[3] - pr[2];
         } else {
-            if (!classCountsValid) {
-                // site classes follow from the parameters: count them on the device once per parameter set, with the
-                // same tests the kernels apply (lab-frame tensors), instead of trusting a host-side restatement
-                int* pr = (int*) hPinned;
-                CUDA_CHECK(cudaMemcpyAsync(&pr[0], dPolRank.p + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                CUDA_CHECK(cudaMemcpyAsync(&pr[1], dSimpleRank.p + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                CUDA_CHECK(cudaStreamSynchronize(stream));
-                numPolTotal = pr[0]; numSimpleTotal = pr[1];
-                classCountsValid = true;
-            }
             polBegin = 0; numPol = numPolTotal; simpleBegin = 0; numSimple = numSimpleTotal;
         }
         // full = complement of simple within the same row range
@@ -783,7 +811,22 @@ struct Engine : public EngineBase {
         size_t GC = (size_t) grid[0]*grid[1]*(grid[2]/2 + 1);
         stageBegin(MPIDB200_STAGE_FFT);
         if (numRanks > 1) allReduce(dGrid.p, (size_t) grid[0]*grid[1]*grid[2], sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64);
-        if (customFft) {
+        if (fft2.ok) {
+            const float* g = (const float*) (const void*) dGrid.p;
+            float2* c = (float2*) (void*) dGridC.p;
+            traceBegin("k_fft2_planes_forward");
+            fft2.fwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(g, c, dTwiddle.p);
+            traceEnd();
+            traceBegin("k_fft2_x_convolve");
+            fft2.xcv<<<dim3(grid[1], fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(grid[1], grid[2]/2 + 1, fft2.chunk, (const float*) (const void*) dEterm.p, c, dTwiddle.p);
+            traceEnd();
+            traceBegin("k_fft2_planes_backward");
+            fft2.bwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(c, (float*) (void*) dGrid.p, dTwiddle.p);
+            traceEnd();
+            launches += 3;
+            cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) throw CudaError(std::string("launch of the fused reciprocal pass failed: ") + cudaGetErrorString(le));
+        } else if (customFft) {
             // (only instantiated for real = float; the casts keep the double engine compiling)
             LAUNCH_SMEM(k_fft_planes_forward, grid[0], MPID_FFT_THREADS, fftSmemPlane, grid[1], grid[2], (const float*) (const void*) dGrid.p, (float2*) (void*) dGridC.p, dTwiddle.p);
             LAUNCH_SMEM(k_fft_x_convolve, grid[1], MPID_FFT_THREADS, fftSmemX, grid[0], grid[1], grid[2]/2 + 1, (const float*) (const void*) dEterm.p, (float2*) (void*) dGridC.p, dTwiddle.p);
@@ -801,6 +844,11 @@ struct Engine : public EngineBase {
         stageEnd();
     }
 
+    // potential derivatives from the grid: six lanes per atom, or (MPIDB200_GATHER=thread) one thread per atom
+    const bool gatherPerThread = getenv("MPIDB200_GATHER") != nullptr && std::string(getenv("MPIDB200_GATHER")) == "thread";
+#define GATHER(LEVEL, POLREC, count, list, base, th, ig, out) do { \
+        if (gatherPerThread) LAUNCH((k_gather_thread<real, LEVEL, POLREC>), blocksFor(count, 128), 128, P, count, list, base, th, ig, dGrid.p, out); \
+        else LAUNCH((k_gather<real, LEVEL, POLREC>), gatherBlocks(count), 128, P, count, list, base, th, ig, dGrid.p, out); } while (0)
     real* cartR() { return sizeof(real) == sizeof(double) ? (real*) dCartD.p : dCartR.p; }
     real* pkR() { return sizeof(real) == sizeof(double) ? (real*) dPkD.p : dPkR.p; }
 
@@ -812,15 +860,20 @@ struct Engine : public EngineBase {
         size_t G = (size_t) grid[0]*grid[1]*grid[2];
         dPhi.ensure(35*(size_t) n); dPhidp.ensure(35*(size_t) n);
         forkPme();
+        if (!overlapPme()) CUDA_CHECK(cudaStreamWaitEvent(stream, evFrames, 0));   // single-stream mode: moments come from stream2
         stageBegin(MPIDB200_STAGE_FIXED_SPREAD);
         dFrac.ensure(20*(size_t) n);
         LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
+        // B-spline weights of this rank's rows, once per evaluation: every spread and gather below reads them
+        dThetaAll.ensure((size_t) n*MPID_THETA_ALL); dIgridAll.ensure(n);
+        dThetaPol.ensure((size_t) std::max(numPolTotal, 1)*MPID_THETA_POL); dIgridPol.ensure(std::max(numPolTotal, 1));
+        if (rows > 0) LAUNCH((k_spline_weights<real>), blocksFor(rows, 128), 128, P, dPosS.p, dPolRank.p, dThetaAll.p, dIgridAll.p, dThetaPol.p, dIgridPol.p);
         CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
-        if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, rows, (const int*) nullptr, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
+        if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dFrac.p, (const double*) nullptr, dGrid.p);
         stageEnd();
         reciprocalPass();
         stageBegin(MPIDB200_STAGE_FIXED_GATHER);
-        if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhi.p);
+        if (rows > 0) GATHER(4, false, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dPhi.p);
         stageEnd();
         backToMain();
     }
@@ -864,16 +917,16 @@ struct Engine : public EngineBase {
             forkPme();
             stageBegin(MPIDB200_STAGE_IND_SPREAD);
             CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
-            if (numPol > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) numPol*6, 192), 192, P, numPol, polRows, dPosS.p, (const real*) nullptr, dMu.p, dGrid.p);
+            if (numPol > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) numPol*6, 192), 192, P, numPol, polRows, polBegin, dThetaPol.p, dIgridPol.p, (const real*) nullptr, dMu.p, dGrid.p);
             stageEnd();
             reciprocalPass();
             stageBegin(MPIDB200_STAGE_IND_GATHER);
             if (level == 4) {
-                if (rows > 0) LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhidp.p);
+                if (rows > 0) GATHER(4, false, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dPhidp.p);
             } else if (numPol > 0) {
                 // solver iterations need the reciprocal field (and its gradient for OPT) at polarizable sites only
-                if (level == 1) LAUNCH((k_gather<real, 1>), blocksFor(numPol, 128), 128, P, numPol, polRows, dPosS.p, dGrid.p, dPhidp.p);
-                else LAUNCH((k_gather<real, 2>), blocksFor(numPol, 128), 128, P, numPol, polRows, dPosS.p, dGrid.p, dPhidp.p);
+                if (level == 1) GATHER(1, true, numPol, polRows, polBegin, dThetaPol.p, dIgridPol.p, dPhidp.p);
+                else GATHER(2, true, numPol, polRows, polBegin, dThetaPol.p, dIgridPol.p, dPhidp.p);
             }
             stageEnd();
             backToMain();
@@ -1147,6 +1200,7 @@ struct Engine : public EngineBase {
         sortAndFrames(dPosIn);
         fixedReciprocalStart();                    // stream 2, beside the neighbour search
         buildNeighborList(dPosIn);
+        CUDA_CHECK(cudaStreamWaitEvent(stream, evFrames, 0));      // lab-frame moments (second stream) before any pair kernel
         dForce.ensure(3*(size_t) n); dTorque.ensure(3*(size_t) n); dEnergy.ensure(2);
         CUDA_CHECK(cudaMemsetAsync(dForce.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
         CUDA_CHECK(cudaMemsetAsync(dTorque.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
@@ -1167,7 +1221,7 @@ struct Engine : public EngineBase {
             if (pme && !dipolesOnly && rows > 0) {
                 // the converged dipoles' reciprocal potential is still on the grid: fetch all 35 derivatives
                 stageBegin(MPIDB200_STAGE_IND_GATHER);
-                LAUNCH((k_gather<real, 4>), blocksFor(rows, 128), 128, P, rows, (const int*) nullptr, dPosS.p, dGrid.p, dPhidp.p);
+                GATHER(4, false, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dPhidp.p);
                 stageEnd();
             }
         } else {
@@ -1184,34 +1238,30 @@ struct Engine : public EngineBase {
         }
 
         const bool mutual = P.polarization == Mutual;
-        bool forked = false;
         joinDipoleIndependentPairs();      // flat full-full list + charge-charge pairs (side stream), before more is queued there
-        if (!hSpLo.empty() || (pme && rows > 0)) {
-            // FP64 work runs on the side stream beside the FP32 pair kernels -- the covalent pairs and the per-atom
-            // reciprocal-space / self terms; everything accumulates with order-independent fixed-point atomics
+        // The energy/force stage is four independent kernels that accumulate with order-independent fixed-point atomics.
+        // None of them fills the GPU (57-61 % issue utilisation for the FP32 pair kernels, latency-bound FP64 for the
+        // rest), so they run side by side on three streams:
+        //   main    : full x bare-charge pairs (Cartesian gather kernel)
+        //   stream2 : per-atom reciprocal-space / self terms, then full x full pairs (quasi-internal frame kernel)
+        //   stream3 : covalent (1-2/1-3/1-4) pairs in FP64
+        stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
+        CUDA_CHECK(cudaEventRecord(evFork3, stream));
+        CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
+        CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork3, 0));
+        {
             const int ns = (int) hSpLo.size();
-            CUDA_CHECK(cudaEventRecord(evFork3, stream));
-            CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
-            cur = stream3; forked = true;
+            cur = stream3;
             if (ns > 0) {
                 if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
                                    dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
                 else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
                             dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
             }
+            cur = stream2;
             if (pme && rows > 0)
                 LAUNCH((k_reciprocal_terms<real>), blocksFor(rows, 128), 128, P, dPhi.p, dPhidp.p, dCartD.p, dSphD.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
-            backToMain();
-        }
-        stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
-        // full x bare-charge pairs: gathered from the full site (Cartesian form)
-        if (numFull > 0 && numSimpleTotal > 0) {
-            const int nbF = blocksFor((long long) numFull*MPID_LANES, 256);
-            if (pme) LAUNCH((k_charge_site_pairs<real, true>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
-            else LAUNCH((k_charge_site_pairs<real, false>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
-        }
-        // full x full pairs: quasi-internal frame kernel over the flat half list
-        {
+            // full x full pairs: quasi-internal frame kernel over the flat half list
             // launch sized for the capacity of the flat list when the count is still on its way from the device
             const long long cnt = nlSpeculative ? (long long) pairCap : typeBegin[1];
             const unsigned* dyn = dTypeStart.p + (size_t) (P.rowEnd - P.rowBegin) + 1;      // start of class 1 = number of full-full pairs
@@ -1220,12 +1270,19 @@ struct Engine : public EngineBase {
             if (pme) { if (mutual) ES_LAUNCH(true, true) else ES_LAUNCH(true, false) }
             else { if (mutual) ES_LAUNCH(false, true) else ES_LAUNCH(false, false) }
 #undef ES_LAUNCH
+            backToMain();
         }
+        // full x bare-charge pairs: gathered from the full site (Cartesian form)
+        if (numFull > 0 && numSimpleTotal > 0) {
+            const int nbF = blocksFor((long long) numFull*MPID_LANES, 256);
+            if (pme) LAUNCH((k_charge_site_pairs<real, true>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
+            else LAUNCH((k_charge_site_pairs<real, false>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
+        }
+        CUDA_CHECK(cudaEventRecord(evJoin3, stream3));
+        CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin3, 0));
+        CUDA_CHECK(cudaEventRecord(evJoin, stream2));
+        CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin, 0));
         stageEnd();
-        if (forked) {
-            CUDA_CHECK(cudaEventRecord(evJoin3, stream3));
-            CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin3, 0));
-        }
 
         if (!nlistTotalsOk()) {
             // a capacity assumed from the previous evaluation was exceeded (rare): nothing has been written to the

@@ -15,6 +15,7 @@
 #define MPIDB200_FFT_CUH_
 
 #include <cuda_runtime.h>
+#include <algorithm>
 
 namespace mpid {
 
@@ -216,6 +217,260 @@ k_fft_planes_backward(int ny, int nz, const float2* __restrict__ in, float* __re
         const int y = t / m, j = t - y*m;
         plane[t] = z[y*mc + j];
     }
+}
+
+// =====================================================================================================
+// Second generation ("fused2"): the same three kernels with register-resident radix-4/8/16 butterflies.
+//
+// The Stockham version above spends its time on index arithmetic and barriers: a radix-4 pass moves two butterflies
+// per thread between barriers, ten barriers per plane (ncu: 28 % issue utilisation, profiles/r01_fft_experiment.md).
+// Here every 1-D transform of length L = R1*R2 is exactly two passes (Cooley-Tukey, n = R2 r + j, k = q + R1 p):
+//   pass 1, task (j):  A[q] = DFT_R1 over r of x[R2 r + j];  B[j][q] = A[q] w_L^(j q)   -- in place (slots R2 q + j)
+//   pass 2, task (q):  X[q + R1 p] = DFT_R2 over j of B[j][q]                          -- to the next stage
+// with the R-point DFTs unrolled in registers (constant twiddles), so a plane costs five barriers and the x
+// direction three.  Lanes always walk the transform index, and rows are MC = nz/2+1 (odd) complex numbers apart, so
+// shared-memory accesses are conflict free in both directions.
+// =====================================================================================================
+#define MPID_FFT2_MAX_THREADS 576
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// R-point DFT in registers (R = 2, 4, 8, 16), natural order in and out, decimation in time; INV conjugates.
+template <int R, bool INV>
+__device__ __forceinline__ void dftReg(float2* v) {
+    if constexpr (R == 2) {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    } else {
+        constexpr int H = R/2;
+        float2 e[H], o[H];
+#pragma unroll
+        for (int k = 0; k < H; k++) { e[k] = v[2*k]; o[k] = v[2*k+1]; }
+        dftReg<H, INV>(e);
+        dftReg<H, INV>(o);
+        // exp(-2 pi i k/16), k = 0..7
+        const float c16[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                              0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+        const float s16[8] = {0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                              -1.f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+#pragma unroll
+        for (int k = 0; k < H; k++) {
+            float2 t;
+            if (k == 0) t = o[0];
+            else if (4*k == R) t = INV ? make_float2(-o[k].y, o[k].x) : make_float2(o[k].y, -o[k].x);     // -+ i
+            else {
+                const float wr = c16[k*(16/R)], wi = INV ? -s16[k*(16/R)] : s16[k*(16/R)];
+                t = make_float2(o[k].x*wr - o[k].y*wi, o[k].x*wi + o[k].y*wr);
+            }
+            v[k] = cadd(e[k], t);
+            v[k + H] = csub(e[k], t);
+        }
+    }
+}
+
+// element e of transform b sits at buf[e*sE + b*sB]; twL[t] = exp(-2 pi i t/L), t < L
+template <int R1, int R2, bool INV>
+__device__ __forceinline__ void fft2Pass1(float2* buf, int count, int sE, int sB, const float2* twL) {
+    const int tasks = count*R2;
+    for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+        const int j = t / count, b = t - j*count;
+        float2* base = buf + b*sB + j*sE;
+        float2 v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; r++) v[r] = base[r*R2*sE];
+        dftReg<R1, INV>(v);
+#pragma unroll
+        for (int q = 1; q < R1; q++) {
+            float2 w = twL[j*q];
+            if (INV) w.y = -w.y;
+            v[q] = cmul(v[q], w);
+        }
+#pragma unroll
+        for (int q = 0; q < R1; q++) base[q*R2*sE] = v[q];
+    }
+}
+template <int R1, int R2, bool INV, typename Store>
+__device__ __forceinline__ void fft2Pass2(const float2* buf, int count, int sE, int sB, Store store) {
+    const int tasks = count*R1;
+    for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+        const int q = t / count, b = t - q*count;
+        const float2* base = buf + b*sB + q*R2*sE;
+        float2 v[R2];
+#pragma unroll
+        for (int j = 0; j < R2; j++) v[j] = base[j*sE];
+        dftReg<R2, INV>(v);
+#pragma unroll
+        for (int p = 0; p < R2; p++) store(b, q + R1*p, v[p]);
+    }
+}
+__device__ __forceinline__ void fft2LoadTable(float2* dst, int len, const float2* __restrict__ tw) {
+    const int step = MPID_FFT_MAXLEN/len;
+    for (int t = threadIdx.x; t < len; t += blockDim.x) dst[t] = tw[t*step];
+}
+
+// real grid plane x -> half-complex plane x.  Dynamic shared memory: (2 NY MC + NY + 2 M) float2, M = NZ/2, MC = M+1.
+template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
+__global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
+k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw) {
+    constexpr int M = NZ/2, MC = M + 1;
+    static_assert(R1Y*R2Y == NY && R1Z*R2Z == M, "radix split");
+    extern __shared__ float2 fftsm[];
+    float2* buf0 = fftsm;
+    float2* buf1 = buf0 + NY*MC;
+    float2* twY = buf1 + NY*MC;
+    float2* twZ = twY + NY;
+    float2* twU = twZ + M;
+    fft2LoadTable(twY, NY, tw);
+    fft2LoadTable(twZ, M, tw);
+    for (int t = threadIdx.x; t < M; t += blockDim.x) twU[t] = tw[t*(MPID_FFT_MAXLEN/NZ)];
+    // rows of NZ reals read as M complex numbers z_j = x_{2j} + i x_{2j+1}
+    const float2* plane = reinterpret_cast<const float2*>(grid + (size_t) blockIdx.x*NY*NZ);
+    for (int t = threadIdx.x; t < NY*M; t += blockDim.x) buf0[(t / M)*MC + (t % M)] = plane[t];
+    __syncthreads();
+    fft2Pass1<R1Z, R2Z, false>(buf0, NY, 1, MC, twZ);
+    __syncthreads();
+    fft2Pass2<R1Z, R2Z, false>(buf0, NY, 1, MC, [&](int y, int k, float2 v) { buf1[y*MC + k] = v; });
+    __syncthreads();
+    // untangle: X[k] = E[k] + w^k O[k], E = (Z[k] + conj Z[M-k])/2, O = -i (Z[k] - conj Z[M-k])/2, k = 0..M (Z[M] = Z[0])
+    for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) {
+        const int k = t / NY, y = t - k*NY;
+        const float2 zk = buf1[y*MC + (k == M ? 0 : k)];
+        const float2 zr = cconj(buf1[y*MC + (k == 0 ? 0 : M - k)]);
+        const float2 e = make_float2(0.5f*(zk.x + zr.x), 0.5f*(zk.y + zr.y));
+        const float2 d = make_float2(0.5f*(zk.x - zr.x), 0.5f*(zk.y - zr.y));
+        const float2 o = make_float2(d.y, -d.x);                                  // -i d
+        const float2 w = k == M ? make_float2(-1.f, 0.f) : twU[k];
+        buf0[y*MC + k] = cadd(e, cmul(w, o));
+    }
+    __syncthreads();
+    fft2Pass1<R1Y, R2Y, false>(buf0, MC, MC, 1, twY);
+    __syncthreads();
+    float2* dstp = out + (size_t) blockIdx.x*NY*MC;
+    fft2Pass2<R1Y, R2Y, false>(buf0, MC, MC, 1, [&](int kz, int ky, float2 v) { dstp[ky*MC + kz] = v; });
+}
+
+// half-complex plane x -> real grid plane x (unnormalised, like cufftExecC2R).  Same shared memory as the forward kernel.
+template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
+__global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
+k_fft2_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, const float2* __restrict__ tw) {
+    constexpr int M = NZ/2, MC = M + 1;
+    extern __shared__ float2 fftsm[];
+    float2* buf0 = fftsm;
+    float2* buf1 = buf0 + NY*MC;
+    float2* twY = buf1 + NY*MC;
+    float2* twZ = twY + NY;
+    float2* twU = twZ + M;
+    fft2LoadTable(twY, NY, tw);
+    fft2LoadTable(twZ, M, tw);
+    for (int t = threadIdx.x; t < M; t += blockDim.x) twU[t] = tw[t*(MPID_FFT_MAXLEN/NZ)];
+    const float2* src = in + (size_t) blockIdx.x*NY*MC;
+    for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) buf0[t] = src[t];
+    __syncthreads();
+    fft2Pass1<R1Y, R2Y, true>(buf0, MC, MC, 1, twY);
+    __syncthreads();
+    fft2Pass2<R1Y, R2Y, true>(buf0, MC, MC, 1, [&](int kz, int y, float2 v) { buf1[y*MC + kz] = v; });
+    __syncthreads();
+    // Z[k] = (X[k] + conj X[M-k]) + i w^-k (X[k] - conj X[M-k]), k = 0..M-1; a length-M backward transform then gives
+    // x_{2j} + i x_{2j+1} scaled by NZ, the unnormalised C2R result
+    for (int t = threadIdx.x; t < NY*M; t += blockDim.x) {
+        const int k = t / NY, y = t - k*NY;
+        const float2 a = buf1[y*MC + k];
+        const float2 b = cconj(buf1[y*MC + (M - k)]);
+        const float2 s = cadd(a, b), d = csub(a, b);
+        const float2 wd = cmul(cconj(twU[k]), d);
+        buf0[y*MC + k] = make_float2(s.x - wd.y, s.y + wd.x);                   // s + i wd
+    }
+    __syncthreads();
+    fft2Pass1<R1Z, R2Z, true>(buf0, NY, 1, MC, twZ);
+    __syncthreads();
+    fft2Pass2<R1Z, R2Z, true>(buf0, NY, 1, MC, [&](int y, int j, float2 v) { buf1[y*MC + j] = v; });
+    __syncthreads();
+    float2* plane = reinterpret_cast<float2*>(grid + (size_t) blockIdx.x*NY*NZ);
+    for (int t = threadIdx.x; t < NY*M; t += blockDim.x) plane[t] = buf1[(t / M)*MC + (t % M)];
+}
+
+// For one ky and a chunk of kz: forward transform along x, multiply by the influence function, backward transform
+// along x, in place.  grid = (ny, ceil(nzc/chunk)).  Dynamic shared memory: (2 NX S + NX) float2, S = chunk | 1.
+template <int NX, int R1, int R2>
+__global__ void __launch_bounds__(256)
+k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, float2* __restrict__ data, const float2* __restrict__ tw) {
+    static_assert(R1*R2 == NX, "radix split");
+    extern __shared__ float2 fftsm[];
+    const int S = chunk | 1;
+    float2* buf0 = fftsm;
+    float2* buf1 = buf0 + NX*S;
+    float2* twX = buf1 + NX*S;
+    fft2LoadTable(twX, NX, tw);
+    const int ky = blockIdx.x, kz0 = blockIdx.y*chunk;
+    const int count = min(chunk, nzc - kz0);
+    const size_t line = (size_t) ky*nzc + kz0, xStride = (size_t) ny*nzc;
+    for (int t = threadIdx.x; t < NX*count; t += blockDim.x) {
+        const int x = t / count, c = t - x*count;
+        buf0[x*S + c] = data[x*xStride + line + c];
+    }
+    __syncthreads();
+    fft2Pass1<R1, R2, false>(buf0, count, S, 1, twX);
+    __syncthreads();
+    fft2Pass2<R1, R2, false>(buf0, count, S, 1, [&](int c, int kx, float2 v) {
+        const float e = eterm[kx*xStride + line + c];
+        buf1[kx*S + c] = make_float2(v.x*e, v.y*e);
+    });
+    __syncthreads();
+    fft2Pass1<R1, R2, true>(buf1, count, S, 1, twX);
+    __syncthreads();
+    fft2Pass2<R1, R2, true>(buf1, count, S, 1, [&](int c, int x, float2 v) { data[x*xStride + line + c] = v; });
+}
+
+// ---- host-side dispatch over the supported sizes: x, y in {32, 64, 128, 256}, z in {32, 64, 128} -------------------------------
+struct Fft2Plan {
+    bool ok = false;
+    int nx = 0, ny = 0, nz = 0, chunk = 0, chunks = 0;
+    int planeThreads = 0, xThreads = 0;
+    size_t planeSmem = 0, xSmem = 0;
+    void (*fwd)(const float*, float2*, const float2*) = nullptr;
+    void (*bwd)(const float2*, float*, const float2*) = nullptr;
+    void (*xcv)(int, int, int, const float*, float2*, const float2*) = nullptr;
+};
+template <int NY, int R1Y, int R2Y> inline bool fft2PickPlanes(Fft2Plan& p, int nz) {
+    if (nz == 32)  { p.fwd = k_fft2_planes_forward<NY, R1Y, R2Y, 32, 4, 4>;  p.bwd = k_fft2_planes_backward<NY, R1Y, R2Y, 32, 4, 4>;  return true; }
+    if (nz == 64)  { p.fwd = k_fft2_planes_forward<NY, R1Y, R2Y, 64, 8, 4>;  p.bwd = k_fft2_planes_backward<NY, R1Y, R2Y, 64, 8, 4>;  return true; }
+    if (nz == 128) { p.fwd = k_fft2_planes_forward<NY, R1Y, R2Y, 128, 8, 8>; p.bwd = k_fft2_planes_backward<NY, R1Y, R2Y, 128, 8, 8>; return true; }
+    return false;
+}
+inline Fft2Plan fft2MakePlan(int nx, int ny, int nz) {
+    Fft2Plan p;
+    p.nx = nx; p.ny = ny; p.nz = nz;
+    int r2y = 0, r1x = 0;
+    bool okP = false;
+    if (ny == 32)  { okP = fft2PickPlanes<32, 8, 4>(p, nz);    r2y = 4; }
+    if (ny == 64)  { okP = fft2PickPlanes<64, 8, 8>(p, nz);    r2y = 8; }
+    if (ny == 128) { okP = fft2PickPlanes<128, 16, 8>(p, nz);  r2y = 8; }
+    if (ny == 256) { okP = fft2PickPlanes<256, 16, 16>(p, nz); r2y = 16; }
+    if (nx == 32)  { p.xcv = k_fft2_x_convolve<32, 8, 4>;    r1x = 8; }
+    if (nx == 64)  { p.xcv = k_fft2_x_convolve<64, 8, 8>;    r1x = 8; }
+    if (nx == 128) { p.xcv = k_fft2_x_convolve<128, 16, 8>;  r1x = 16; }
+    if (nx == 256) { p.xcv = k_fft2_x_convolve<256, 16, 16>; r1x = 16; }
+    if (!okP || !p.xcv) return p;
+    const int m = nz/2, mc = m + 1;
+    p.planeSmem = ((size_t) 2*ny*mc + ny + 2*m)*sizeof(float2);
+    if (p.planeSmem > 200*1024) return p;
+    // one round of the widest y pass per block when it fits, else two
+    int tasks = mc*r2y;
+    if (tasks > MPID_FFT2_MAX_THREADS) tasks = (tasks + 1)/2;
+    p.planeThreads = std::min(MPID_FFT2_MAX_THREADS, (tasks + 31)/32*32);
+    p.chunks = (mc + 11)/12;
+    p.chunk = (mc + p.chunks - 1)/p.chunks;
+    p.chunks = (mc + p.chunk - 1)/p.chunk;
+    const int S = p.chunk | 1;
+    p.xSmem = ((size_t) 2*nx*S + nx)*sizeof(float2);
+    p.xThreads = std::min(256, (p.chunk*r1x + 31)/32*32);
+    if (cudaFuncSetAttribute((const void*) p.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p.planeSmem) != cudaSuccess) return p;
+    if (cudaFuncSetAttribute((const void*) p.bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p.planeSmem) != cudaSuccess) return p;
+    if (cudaFuncSetAttribute((const void*) p.xcv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p.xSmem) != cudaSuccess) return p;
+    p.ok = true;
+    return p;
 }
 
 } // namespace mpid

@@ -84,21 +84,43 @@ __global__ void k_wrap_cells(DevParams P, const double* __restrict__ posOrig, do
     atomIdx[o] = o;
 }
 
-// cellStart[c] = first sorted atom whose cell key is >= c   (c = 0..numCells)
-__global__ void k_cell_starts(int n, int numCells, const int* __restrict__ sortedKey, int* __restrict__ cellStart) {
-    int c = blockIdx.x*blockDim.x + threadIdx.x;
-    if (c > numCells) return;
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (sortedKey[mid] < c) lo = mid + 1; else hi = mid;
+// Everything the neighbour search needs from the sort, in one pass over the sorted atoms: the inverse permutation,
+// wrapped positions with the site class (double and float), the packed class counters for the scan, damping
+// parameters, and cellStart[c] = first sorted atom whose cell key is >= c (c = 0..numCells) from the key boundaries.
+// The site class is static (it follows from the parameters, flagOrig is filled by set_particles), so the
+// lab-frame moments are NOT on this path: k_lab_frame runs beside the neighbour search on the second stream.
+template <typename real>
+__global__ void k_sorted_sites(int n, int numCells, const int* __restrict__ order, const int* __restrict__ sortedKey,
+                               const double* __restrict__ poswOrig, const int* __restrict__ flagOrig,
+                               const double* __restrict__ damp, const double* __restrict__ thole,
+                               int* __restrict__ inv, double4* __restrict__ posS, float4* __restrict__ posF,
+                               int* __restrict__ flagS, unsigned long long* __restrict__ classPacked,
+                               double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud,
+                               int* __restrict__ cellStart) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int o = order[s];
+    inv[o] = s;
+    const int key = sortedKey[s];
+    const int prev = s > 0 ? sortedKey[s-1] : -1;
+    for (int c = prev + 1; c <= key; c++) cellStart[c] = s;
+    if (s == n - 1) {
+        for (int c = key + 1; c <= numCells; c++) cellStart[c] = n;
+        classPacked[n] = 0ull;
     }
-    cellStart[c] = lo;
-}
-
-__global__ void k_inverse_order(int n, const int* __restrict__ order, int* __restrict__ inv) {
-    int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s < n) inv[order[s]] = s;
+    const double x = poswOrig[3*o], y = poswOrig[3*o+1], z = poswOrig[3*o+2];
+    // site class: bit 0 = polarizable (non-zero lab polarizability), bit 1 = "simple" (charge only, never polarized)
+    const int flag = flagOrig[o];
+    flagS[s] = flag;
+    // low word counts polarizable sites, high word bare-charge sites: one 64-bit scan ranks both classes
+    classPacked[s] = (unsigned long long) (flag & 1) | ((unsigned long long) ((flag >> 1) & 1) << 32);
+    posS[s] = make_double4(x, y, z, (double) flag);
+    posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
+    const double dmp = damp[o];
+    dampTholeD[s] = make_double2(dmp, thole[o]);
+    typename Real4<real>::type m;
+    m.x = 0; m.y = 0; m.z = 0; m.w = dmp != 0.0 ? (real) (1.0/dmp) : real(0);   // inverse damping factor
+    mud[s] = m;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -125,13 +147,9 @@ __device__ __forceinline__ void storeWarpRows(double (*tile)[21], int lane, int 
 template <typename real>
 __global__ void __launch_bounds__(128)
 k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restrict__ order,
-            const double* __restrict__ posOrig, const double* __restrict__ poswOrig,
-            double4* __restrict__ posS, float4* __restrict__ posF,
+            const double* __restrict__ posOrig,
             double* __restrict__ cartD, double* __restrict__ pkD, real* __restrict__ cartR, real* __restrict__ pkR,
-            double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso,
-            double2* __restrict__ dampTholeD, typename Real4<real>::type* __restrict__ mud,
-            const int* __restrict__ inv, const int* __restrict__ spStart, const int* __restrict__ spPartner,
-            int4* __restrict__ spSorted, int* __restrict__ flagS, unsigned long long* __restrict__ classPacked) {
+            double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso) {
     __shared__ double tiles[4][32][21];
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,18 +160,6 @@ k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restr
     double c[20], pk[16], sph[16], alpha[6];
     if (valid) {
         const int o = order[s];
-        {   // sorted indices of up to four covalently scaled partners (x = -2 flags "more than four: use the list")
-            const int k0 = spStart[o], k1 = spStart[o+1];
-            int4 q = make_int4(-1, -1, -1, -1);
-            if (k1 - k0 > 4) q.x = -2;
-            else {
-                if (k1 - k0 > 0) q.x = inv[spPartner[k0]];
-                if (k1 - k0 > 1) q.y = inv[spPartner[k0+1]];
-                if (k1 - k0 > 2) q.z = inv[spPartner[k0+2]];
-                if (k1 - k0 > 3) q.w = inv[spPartner[k0+3]];
-            }
-            spSorted[s] = q;
-        }
         const int az = pp.atomZ[o], ax = pp.atomX[o], ay = pp.atomY[o];
         const double* pi = posOrig + 3*o;
         const double* pz = az >= 0 ? posOrig + 3*az : pi;
@@ -173,22 +179,6 @@ k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restr
         for (int k = 0; k < 16; k++) sph[k] = a.sph[k];
         for (int k = 0; k < 6; k++) alpha[k] = a.alpha[k];
         aniso[s] = a.aniso;
-        const double x = poswOrig[3*o], y = poswOrig[3*o+1], z = poswOrig[3*o+2];
-        // site class: bit 0 = polarizable (non-zero lab polarizability), bit 1 = "simple" (charge only, never polarized)
-        bool pol = false, perm = false;
-        for (int k = 0; k < 6; k++) pol = pol || (a.alpha[k] != 0.0);
-        for (int k = 1; k < 16; k++) perm = perm || (pk[k] != 0.0);
-        const int flag = (pol ? 1 : 0) | ((!pol && !perm) ? 2 : 0);
-        flagS[s] = flag;
-        // low word counts polarizable sites, high word bare-charge sites: one 64-bit scan ranks both classes
-        classPacked[s] = (unsigned long long) (flag & 1) | ((unsigned long long) ((flag >> 1) & 1) << 32);
-        if (s == P.n - 1) classPacked[P.n] = 0ull;
-        posS[s] = make_double4(x, y, z, (double) flag);
-        posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
-        dampTholeD[s] = make_double2(pp.damp[o], pp.thole[o]);
-        typename Real4<real>::type m;
-        m.x = 0; m.y = 0; m.z = 0; m.w = pp.damp[o] != 0.0 ? (real) (1.0/pp.damp[o]) : real(0);   // inverse damping factor
-        mud[s] = m;
     }
     double (*tile)[21] = tiles[warp];
     storeWarpRows<double, 20>(tile, lane, nValid, c, cartD + 20*(size_t) s0);
@@ -205,13 +195,28 @@ k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restr
 // polarizable / bare-charge ("simple") / full (= not simple) classes, and the three compact lists
 __global__ void k_class_lists(int n, const int* __restrict__ flagS, const unsigned long long* __restrict__ scanned,
                               int* __restrict__ polRank, int* __restrict__ simpleRank, int* __restrict__ fullRank,
-                              int* __restrict__ polList, int* __restrict__ simpleList, int* __restrict__ fullList) {
+                              int* __restrict__ polList, int* __restrict__ simpleList, int* __restrict__ fullList,
+                              const int* __restrict__ order, const int* __restrict__ inv, const int* __restrict__ spStart,
+                              const int* __restrict__ spPartner, int4* __restrict__ spSorted) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s > n) return;
     const unsigned long long v = scanned[s];
     const int rp = (int) (v & 0xffffffffull), rs = (int) (v >> 32), rf = s - rs;
     polRank[s] = rp; simpleRank[s] = rs; fullRank[s] = rf;
     if (s == n) return;
+    {   // sorted indices of up to four covalently scaled partners (x = -2 flags "more than four: use the list")
+        const int o = order[s];
+        const int k0 = spStart[o], k1 = spStart[o+1];
+        int4 q = make_int4(-1, -1, -1, -1);
+        if (k1 - k0 > 4) q.x = -2;
+        else {
+            if (k1 - k0 > 0) q.x = inv[spPartner[k0]];
+            if (k1 - k0 > 1) q.y = inv[spPartner[k0+1]];
+            if (k1 - k0 > 2) q.z = inv[spPartner[k0+2]];
+            if (k1 - k0 > 3) q.w = inv[spPartner[k0+3]];
+        }
+        spSorted[s] = q;
+    }
     const int flag = flagS[s];
     if (flag & 1) polList[rp] = s;
     if (flag & 2) simpleList[rs] = s; else fullList[rf] = s;
@@ -1069,24 +1074,82 @@ __device__ __forceinline__ void redLine6(double* p, const double* v) {
     for (int k = 0; k < 6; k++) atomicAdd(p + k, v[k]);
 }
 
-// B-spline spreading: 6 threads per atom (one per x plane), 36 grid points each.
+// B-spline weights of every atom, once per evaluation (positions do not change between the reciprocal passes of
+// the solver iterations, and each pass used to rebuild them in every thread of every spread and gather launch).
+//   thetaAll[s][axis][k][8] : k-th derivative (k = 0..4) of the six weights of atom s along `axis` (two pad floats:
+//                             every (axis, k) row is one 32-byte sector), igridAll[s] = first grid point per axis
+//   thetaPol[r][axis][k][8] : the same for polarizable sites only (r = rank among them), k = 0..2 -- what the
+//                             induced-dipole passes read (6 MB instead of 46 MB at 95,616 atoms)
+//   reference: computeMPIDBsplines (:3049-3075), computeBSplinePoint (:2956-3044)
+#define MPID_THETA_ALL (3*5*8)
+#define MPID_THETA_POL (3*3*8)
+template <typename real>
+__global__ void __launch_bounds__(128)
+k_spline_weights(DevParams P, const double4* __restrict__ posS, const int* __restrict__ polRank,
+                 real* __restrict__ thetaAll, int4* __restrict__ igridAll, real* __restrict__ thetaPol, int4* __restrict__ igridPol) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;      // the rows this rank spreads and gathers
+    if (s >= P.rowEnd) return;
+    const double4 p = posS[s];
+    int ig[3]; double w[3];
+    pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
+    const bool pol = ((int) p.w & 1) != 0;
+    const int r = pol ? polRank[s] : 0;
+    const int4 g = make_int4(ig[0], ig[1], ig[2], 0);
+    igridAll[s] = g;
+    if (pol) igridPol[r] = g;
+    typedef typename Real4<real>::type real4;
+#pragma unroll
+    for (int axis = 0; axis < 3; axis++) {
+        real th[6][5];
+        bsplineWeights<real>((real) w[axis], th);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            real4 lo, hi;
+            lo.x = th[0][k]; lo.y = th[1][k]; lo.z = th[2][k]; lo.w = th[3][k];
+            hi.x = th[4][k]; hi.y = th[5][k]; hi.z = 0; hi.w = 0;
+            real4* dst = reinterpret_cast<real4*>(thetaAll + (size_t) s*MPID_THETA_ALL + (axis*5 + k)*8);
+            dst[0] = lo; dst[1] = hi;
+            if (pol && k < 3) {
+                real4* dp = reinterpret_cast<real4*>(thetaPol + (size_t) r*MPID_THETA_POL + (axis*3 + k)*8);
+                dp[0] = lo; dp[1] = hi;
+            }
+        }
+    }
+}
+// rows (axis, k = 0..NK-1) of one atom's weight record -> t[point][k]; KSTRIDE = derivatives stored per axis
+template <typename real, int NK, int KSTRIDE>
+__device__ __forceinline__ void loadTheta(const real* __restrict__ rec, int axis, real (*t)[5]) {
+    typedef typename Real4<real>::type real4;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const real4* src = reinterpret_cast<const real4*>(rec + (axis*KSTRIDE + k)*8);
+        const real4 lo = src[0], hi = src[1];
+        t[0][k] = lo.x; t[1][k] = lo.y; t[2][k] = lo.z; t[3][k] = lo.w; t[4][k] = hi.x; t[5][k] = hi.y;
+    }
+}
+
+// B-spline spreading: 6 threads per atom (one per x plane), 36 grid points each; weights from k_spline_weights
+// (FIXED: the all-atom record, row s; induced dipoles: the polarizable-site record, row polBase + t/6).
 //   reference: spreadFixedMultipolesOntoGrid (:3269-3327), spreadInducedDipolesOnGrid (:3532-3573)
 template <typename real, bool FIXED>
 __global__ void __launch_bounds__(192)
-k_spread(DevParams P, int numRows, const int* __restrict__ rowList, const double4* __restrict__ posS, const real* __restrict__ frac,
-         const double* __restrict__ mu, real* __restrict__ grid) {
+k_spread(DevParams P, int numRows, const int* __restrict__ rowList, int recBase, const real* __restrict__ theta,
+         const int4* __restrict__ igrid, const real* __restrict__ frac, const double* __restrict__ mu, real* __restrict__ grid) {
     // rowList == nullptr: rows rowBegin .. rowBegin+numRows-1; otherwise the listed (polarizable) rows
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int ix = t % 6;
     if (t/6 >= numRows) return;
     const int s = rowList ? rowList[t/6] : P.rowBegin + t/6;
-    const double4 p = posS[s];
-    int ig[3]; double w[3];
-    pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
-    real tx[6][5], ty[6][5], tz[6][5];
-    bsplineWeights<real>((real) w[0], tx);
-    bsplineWeights<real>((real) w[1], ty);
-    bsplineWeights<real>((real) w[2], tz);
+    const int rec = FIXED ? s : recBase + t/6;
+    constexpr int NK = FIXED ? 4 : 2, KS = FIXED ? 5 : 3, RS = FIXED ? MPID_THETA_ALL : MPID_THETA_POL;
+    const real* th = theta + (size_t) rec*RS;
+    const int4 ig = igrid[rec];
+    real ty[6][5], tz[6][5];
+    loadTheta<real, NK, KS>(th, 1, ty);
+    loadTheta<real, NK, KS>(th, 2, tz);
+    real txr[5];
+#pragma unroll
+    for (int k = 0; k < NK; k++) txr[k] = th[k*8 + ix];
     real f[20];
     if (FIXED) {
         for (int k = 0; k < 20; k++) f[k] = frac[20*(size_t) s + k];
@@ -1096,22 +1159,19 @@ k_spread(DevParams P, int numRows, const int* __restrict__ rowList, const double
         for (int k = 0; k < 3; k++) f[1+k] = (real) (P.geom.A[k][0]*mx + P.geom.A[k][1]*my + P.geom.A[k][2]*mz);
     }
     const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2];
-    int x = ig[0] + ix; x -= (x >= nx) ? nx : 0;
-    real txr[5];
-    for (int k = 0; k < 5; k++) txr[k] = tx[0][k];
-    for (int a = 1; a < 6; a++) if (a == ix) for (int k = 0; k < 5; k++) txr[k] = tx[a][k];
+    int x = ig.x + ix; x -= (x >= nx) ? nx : 0;
 #pragma unroll
     for (int iy = 0; iy < 6; iy++) {
-        int y = ig[1] + iy; y -= (y >= ny) ? ny : 0;
+        int y = ig.y + iy; y -= (y >= ny) ? ny : 0;
         real* row = grid + ((size_t) x*ny + y)*nz;
         real v[6];
 #pragma unroll
         for (int iz = 0; iz < 6; iz++) v[iz] = spreadTerm<real, FIXED>(f, txr, ty[iy], tz[iz]);
-        if (ig[2] + 5 < nz) redLine6(row + ig[2], v);
+        if (ig.z + 5 < nz) redLine6(row + ig.z, v);
         else {
 #pragma unroll
             for (int iz = 0; iz < 6; iz++) {
-                int z = ig[2] + iz; z -= (z >= nz) ? nz : 0;
+                int z = ig.z + iz; z -= (z >= nz) ? nz : 0;
                 atomicAdd(row + z, v[iz]);
             }
         }
@@ -1153,34 +1213,111 @@ __global__ void k_eterm_table(DevParams P, const double* __restrict__ modX, cons
 }
 
 // Potential derivatives at the atoms up to total order LEVEL (4 -> all 35), SoA output phi[idx*n + s].
+// Six lanes per atom, one x plane of the 6x6x6 support each (five atoms per warp): the 216 grid reads of an atom
+// are in flight at once instead of queueing behind one thread.  Each lane contracts its plane z -> y, scales by its
+// x weights, and the six partial results meet in the first lane of the group through three shuffles per derivative.
+// Weights come from k_spline_weights: POL = the polarizable-site record (row recBase + t), else the all-atom one.
 //   reference: computeFixedPotentialFromGrid (:3368-3530), computeInducedPotentialFromGrid (:3575-3737)
-template <typename real, int LEVEL>
+#define MPID_GATHER_ATOMS_PER_WARP 5
+template <typename real, int LEVEL, bool POL>
 __global__ void __launch_bounds__(128)
-k_gather(DevParams P, int numRows, const int* __restrict__ rowList, const double4* __restrict__ posS, const real* __restrict__ grid,
-         real* __restrict__ phi) {
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    if (t >= numRows) return;
-    const int s = rowList ? rowList[t] : P.rowBegin + t;
-    const double4 p = posS[s];
-    int ig[3]; double w[3];
-    pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
-    real tx[6][5], ty[6][5], tz[6][5];
-    bsplineWeights<real>((real) w[0], tx);
-    bsplineWeights<real>((real) w[1], ty);
-    bsplineWeights<real>((real) w[2], tz);
+k_gather(DevParams P, int numRows, const int* __restrict__ rowList, int recBase, const real* __restrict__ theta,
+         const int4* __restrict__ igrid, const real* __restrict__ grid, real* __restrict__ phi) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int grp = lane/6, ix = lane - 6*grp;
+    const int t0 = warp*MPID_GATHER_ATOMS_PER_WARP + grp;
+    const bool active = grp < MPID_GATHER_ATOMS_PER_WARP && t0 < numRows;
+    if (numRows <= 0) return;
+    // idle lanes follow the warp with a valid atom so that the shuffles below stay convergent
+    const int tt = active ? t0 : 0;
+    const int s = rowList ? rowList[tt] : P.rowBegin + tt;
+    const int rec = POL ? recBase + tt : s;
+    constexpr int NV = LEVEL + 1, KS = POL ? 3 : 5, RS = POL ? MPID_THETA_POL : MPID_THETA_ALL;
+    static_assert(!POL || LEVEL <= 2, "the polarizable-site record holds derivatives 0..2");
+    const real* th = theta + (size_t) rec*RS;
+    const int4 ig = igrid[rec];
+    real ty[6][5], tz[6][5];
+    loadTheta<real, NV, KS>(th, 1, ty);
+    loadTheta<real, NV, KS>(th, 2, tz);
+    real txr[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) txr[k] = th[k*8 + ix];
     const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2];
-    constexpr int NV = LEVEL + 1;
-    // acc[t][u][v] with t+u+v <= LEVEL; built by successive contraction z -> y -> x
-    real acc[NV][NV][NV];
+    int x = ig.x + ix; x -= (x >= nx) ? nx : 0;
+    // yz[u][v] with u+v <= LEVEL: this lane's plane contracted z -> y
+    real yz[NV][NV];
+#pragma unroll
+    for (int u = 0; u < NV; u++)
+#pragma unroll
+        for (int v = 0; v < NV; v++) yz[u][v] = 0;
+    const bool zWrap = ig.z + 5 >= nz;
+#pragma unroll
+    for (int iy = 0; iy < 6; iy++) {
+        int y = ig.y + iy; y -= (y >= ny) ? ny : 0;
+        const real* row = grid + ((size_t) x*ny + y)*nz;
+        real q[6];
+#pragma unroll
+        for (int iz = 0; iz < 6; iz++) {
+            int z = ig.z + iz; z -= (zWrap && z >= nz) ? nz : 0;
+            q[iz] = row[z];
+        }
+        real zs[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            zs[v] = 0;
+#pragma unroll
+            for (int iz = 0; iz < 6; iz++) zs[v] += q[iz]*tz[iz][v];
+        }
+#pragma unroll
+        for (int u = 0; u < NV; u++)
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                if (u + v <= LEVEL) yz[u][v] += zs[v]*ty[iy][u];
+    }
 #pragma unroll
     for (int t = 0; t < NV; t++)
 #pragma unroll
         for (int u = 0; u < NV; u++)
 #pragma unroll
-            for (int v = 0; v < NV; v++) acc[t][u][v] = 0;
+            for (int v = 0; v < NV; v++)
+                if (t + u + v <= LEVEL) {
+                    real a = yz[u][v]*txr[t];
+                    a += __shfl_down_sync(FULL, a, 3);
+                    const real b = __shfl_down_sync(FULL, a, 1), c = __shfl_down_sync(FULL, a, 2);
+                    if (active && ix == 0) phi[(size_t) phiIndex(t, u, v)*P.n + s] = a + b + c;
+                }
+}
+
+// One thread per atom (the whole 6x6x6 support), same inputs and outputs as k_gather.
+template <typename real, int LEVEL, bool POL>
+__global__ void __launch_bounds__(128)
+k_gather_thread(DevParams P, int numRows, const int* __restrict__ rowList, int recBase, const real* __restrict__ theta,
+                const int4* __restrict__ igrid, const real* __restrict__ grid, real* __restrict__ phi) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= numRows) return;
+    const int s = rowList ? rowList[t] : P.rowBegin + t;
+    const int rec = POL ? recBase + t : s;
+    constexpr int NV = LEVEL + 1, KS = POL ? 3 : 5, RS = POL ? MPID_THETA_POL : MPID_THETA_ALL;
+    const real* th = theta + (size_t) rec*RS;
+    const int4 ig = igrid[rec];
+    real tx[6][5], ty[6][5], tz[6][5];
+    loadTheta<real, NV, KS>(th, 0, tx);
+    loadTheta<real, NV, KS>(th, 1, ty);
+    loadTheta<real, NV, KS>(th, 2, tz);
+    const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2];
+    real acc[NV][NV][NV];
+#pragma unroll
+    for (int a = 0; a < NV; a++)
+#pragma unroll
+        for (int u = 0; u < NV; u++)
+#pragma unroll
+            for (int v = 0; v < NV; v++) acc[a][u][v] = 0;
+    const bool zWrap = ig.z + 5 >= nz;
 #pragma unroll
     for (int ix = 0; ix < 6; ix++) {
-        int x = ig[0] + ix; x -= (x >= nx) ? nx : 0;
+        int x = ig.x + ix; x -= (x >= nx) ? nx : 0;
         real yz[NV][NV];
 #pragma unroll
         for (int u = 0; u < NV; u++)
@@ -1188,14 +1325,14 @@ k_gather(DevParams P, int numRows, const int* __restrict__ rowList, const double
             for (int v = 0; v < NV; v++) yz[u][v] = 0;
 #pragma unroll
         for (int iy = 0; iy < 6; iy++) {
-            int y = ig[1] + iy; y -= (y >= ny) ? ny : 0;
+            int y = ig.y + iy; y -= (y >= ny) ? ny : 0;
             const real* row = grid + ((size_t) x*ny + y)*nz;
             real zs[NV];
 #pragma unroll
             for (int v = 0; v < NV; v++) zs[v] = 0;
 #pragma unroll
             for (int iz = 0; iz < 6; iz++) {
-                int z = ig[2] + iz; z -= (z >= nz) ? nz : 0;
+                int z = ig.z + iz; z -= (zWrap && z >= nz) ? nz : 0;
                 const real q = row[z];
 #pragma unroll
                 for (int v = 0; v < NV; v++) zs[v] += q*tz[iz][v];
@@ -1207,20 +1344,20 @@ k_gather(DevParams P, int numRows, const int* __restrict__ rowList, const double
                     if (u + v <= LEVEL) yz[u][v] += zs[v]*ty[iy][u];
         }
 #pragma unroll
-        for (int t = 0; t < NV; t++)
+        for (int a = 0; a < NV; a++)
 #pragma unroll
             for (int u = 0; u < NV; u++)
 #pragma unroll
                 for (int v = 0; v < NV; v++)
-                    if (t + u + v <= LEVEL) acc[t][u][v] += yz[u][v]*tx[ix][t];
+                    if (a + u + v <= LEVEL) acc[a][u][v] += yz[u][v]*tx[ix][a];
     }
 #pragma unroll
-    for (int t = 0; t < NV; t++)
+    for (int a = 0; a < NV; a++)
 #pragma unroll
         for (int u = 0; u < NV; u++)
 #pragma unroll
             for (int v = 0; v < NV; v++)
-                if (t + u + v <= LEVEL) phi[(size_t) phiIndex(t, u, v)*P.n + s] = acc[t][u][v];
+                if (a + u + v <= LEVEL) phi[(size_t) phiIndex(a, u, v)*P.n + s] = acc[a][u][v];
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -310,15 +310,17 @@ def test_speculative_neighbour_list_recovers_from_capacity_overflow():
     k.close(); k2.close()
 
 
-@pytest.mark.parametrize("tiles,pol", [((1, 1, 1), 0), ((1, 1, 1), 2), ((2, 1, 1), 1)])
-def test_fused_reciprocal_pass_matches_cufft(tiles, pol, monkeypatch):
-    """MPIDB200_FFT=fused selects the shared-memory reciprocal pass of mpid_fft.cuh (3 launches per pass, power-of-two
-    grids, mixed precision) instead of cuFFT R2C/C2R + convolution (7 launches).  Both are single-precision
-    unnormalised transforms of the same data, so forces, energy and dipoles agree to FP32 round-off of the grid."""
+@pytest.mark.parametrize("mode", ["fused", "fused2"])
+@pytest.mark.parametrize("tiles,pol", [((1, 1, 1), 0), ((1, 1, 1), 2), ((2, 1, 1), 1), ((2, 4, 2), 0), ((8, 1, 4), 1), ((1, 8, 1), 1)])
+def test_fused_reciprocal_pass_matches_cufft(tiles, pol, mode, monkeypatch):
+    """MPIDB200_FFT=fused / fused2 select the shared-memory reciprocal passes of mpid_fft.cuh (3 launches per pass,
+    power-of-two grids, mixed precision; fused2 = register-resident radix-4/8/16 butterflies) instead of cuFFT R2C/C2R
+    + convolution (7 launches, MPIDB200_FFT=cufft).  All are single-precision unnormalised transforms of the same
+    data, so forces, energy and dipoles agree to FP32 round-off of the grid.  Grids: 32^3, 64x32x32, 64x128x64, 256x32x128, 32x256x32 (every radix split of fused2)."""
     s = water_box(tiles, polarization=pol, epsilon=1e-6)
-    monkeypatch.delenv("MPIDB200_FFT", raising=False)
+    monkeypatch.setenv("MPIDB200_FFT", "cufft")
     ka = make_kernel(s, precision="mixed")
-    monkeypatch.setenv("MPIDB200_FFT", "fused")
+    monkeypatch.setenv("MPIDB200_FFT", mode)
     kb = make_kernel(s, precision="mixed")
     monkeypatch.delenv("MPIDB200_FFT")
     fa = np.zeros((s.n, 3)); fb = np.zeros((s.n, 3))

@@ -7,7 +7,7 @@
 #include "../../include/mpidb200.h"
 #include "mpid_kernels.cuh"
 #ifndef MPIDB200_FFT2_DEFAULT
-#define MPIDB200_FFT2_DEFAULT 0      // flipped to 1 once measured faster than the library path
+#define MPIDB200_FFT2_DEFAULT 1      // measured faster than the library path on B200 (profiles/r01x_*)
 #endif
 #include "mpid_fft.cuh"
 
@@ -123,8 +123,6 @@ template <> struct FftTraits<double> {
 };
 
 inline int blocksFor(long long count, int block) { return (int) std::max<long long>(1, (count + block - 1)/block); }
-// k_gather: five atoms per warp (six lanes each), four warps per block
-inline int gatherBlocks(long long atoms) { return blocksFor((atoms + MPID_GATHER_ATOMS_PER_WARP - 1)/MPID_GATHER_ATOMS_PER_WARP*32, 128); }
 
 template <typename real>
 struct Engine : public EngineBase {
@@ -844,11 +842,8 @@ struct Engine : public EngineBase {
         stageEnd();
     }
 
-    // potential derivatives from the grid: six lanes per atom, or (MPIDB200_GATHER=thread) one thread per atom
-    const bool gatherPerThread = getenv("MPIDB200_GATHER") != nullptr && std::string(getenv("MPIDB200_GATHER")) == "thread";
-#define GATHER(LEVEL, POLREC, count, list, base, th, ig, out) do { \
-        if (gatherPerThread) LAUNCH((k_gather_thread<real, LEVEL, POLREC>), blocksFor(count, 128), 128, P, count, list, base, th, ig, dGrid.p, out); \
-        else LAUNCH((k_gather<real, LEVEL, POLREC>), gatherBlocks(count), 128, P, count, list, base, th, ig, dGrid.p, out); } while (0)
+#define GATHER(LEVEL, POLREC, count, list, base, th, ig, out) \
+        LAUNCH((k_gather<real, LEVEL, POLREC>), blocksFor(count, 128), 128, P, count, list, base, th, ig, dGrid.p, out)
     real* cartR() { return sizeof(real) == sizeof(double) ? (real*) dCartD.p : dCartR.p; }
     real* pkR() { return sizeof(real) == sizeof(double) ? (real*) dPkD.p : dPkR.p; }
 
@@ -1024,9 +1019,11 @@ struct Engine : public EngineBase {
     void launchSolverStep(const double* dPosIn, int itHost, bool withCombine) {
         inducedFieldPass(dPosIn, 1, nullptr, true, true);
         stageBegin(MPIDB200_STAGE_SOLVER);
+        // single rank: numPol = every polarizable site; the other entries of mu / the history are zero and stay zero
         LAUNCH((k_diis_step<real>), 148, 512, P, dFlagS.p, dPhidp.p, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, dHistDip.p, dHistErr.p, itHost,
-               cfg.target_epsilon, dDiis.p, dDotPartial.p);
-        if (withCombine) LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, itHost, dHistDip.p, dDiis.p, dMu.p, dMud.p);
+               cfg.target_epsilon, dDiis.p, dDotPartial.p, numPol, (const int*) dPolList.p);
+        if (withCombine && numPol > 0) LAUNCH((k_diis_combine_ring<real>), blocksFor(numPol, 256), 256, n, itHost, dHistDip.p, dDiis.p, dMu.p, dMud.p,
+                                              numPol, (const int*) dPolList.p);
         stageEnd();
     }
     bool ensureIterationGraph(const double* dPosIn) {
@@ -1089,7 +1086,7 @@ struct Engine : public EngineBase {
                 double* he = dHistErr.p + (size_t) sl.s[m-1]*3*n;
                 LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p);
                 LAUNCH(k_diis_solve, 1, 512, nb, m, sl, it, n, cfg.target_epsilon, dDotPartial.p, dDiis.p);
-                if (!last) LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p);
+                if (!last) LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, n, (const int*) nullptr);
                 stageEnd();
             }
             if (it + 1 >= predictedEvals || last || syncEveryIteration) {

@@ -1212,89 +1212,17 @@ __global__ void k_eterm_table(DevParams P, const double* __restrict__ modX, cons
     eterm[k] = (real) (scaleFactor*exp(-expFactor*m2)/(m2*modX[kx]*modY[ky]*modZ[kz]));
 }
 
-// Potential derivatives at the atoms up to total order LEVEL (4 -> all 35), SoA output phi[idx*n + s].
-// Six lanes per atom, one x plane of the 6x6x6 support each (five atoms per warp): the 216 grid reads of an atom
-// are in flight at once instead of queueing behind one thread.  Each lane contracts its plane z -> y, scales by its
-// x weights, and the six partial results meet in the first lane of the group through three shuffles per derivative.
-// Weights come from k_spline_weights: POL = the polarizable-site record (row recBase + t), else the all-atom one.
+// Potential derivatives at the atoms up to total order LEVEL (4 -> all 35), SoA output phi[idx*n + s]; one thread
+// per atom contracts its 6x6x6 support z -> y -> x.  Weights come from k_spline_weights: POL = the polarizable-site
+// record (row recBase + t), else the all-atom one.  (A six-lanes-per-atom variant, one x plane per lane with a
+// shuffle reduction, was measured slower on B200 -- 22 us against 16 us for the field-only gather, 79 us against
+// 40 us for all 35 derivatives -- although it exposes six times the loads: the kernel is bound by L1 sector
+// traffic, 36 sectors per atom whichever way they are issued; profiles/r01x_ncu_full_96k.md.)
 //   reference: computeFixedPotentialFromGrid (:3368-3530), computeInducedPotentialFromGrid (:3575-3737)
-#define MPID_GATHER_ATOMS_PER_WARP 5
 template <typename real, int LEVEL, bool POL>
 __global__ void __launch_bounds__(128)
 k_gather(DevParams P, int numRows, const int* __restrict__ rowList, int recBase, const real* __restrict__ theta,
          const int4* __restrict__ igrid, const real* __restrict__ grid, real* __restrict__ phi) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    const int grp = lane/6, ix = lane - 6*grp;
-    const int t0 = warp*MPID_GATHER_ATOMS_PER_WARP + grp;
-    const bool active = grp < MPID_GATHER_ATOMS_PER_WARP && t0 < numRows;
-    if (numRows <= 0) return;
-    // idle lanes follow the warp with a valid atom so that the shuffles below stay convergent
-    const int tt = active ? t0 : 0;
-    const int s = rowList ? rowList[tt] : P.rowBegin + tt;
-    const int rec = POL ? recBase + tt : s;
-    constexpr int NV = LEVEL + 1, KS = POL ? 3 : 5, RS = POL ? MPID_THETA_POL : MPID_THETA_ALL;
-    static_assert(!POL || LEVEL <= 2, "the polarizable-site record holds derivatives 0..2");
-    const real* th = theta + (size_t) rec*RS;
-    const int4 ig = igrid[rec];
-    real ty[6][5], tz[6][5];
-    loadTheta<real, NV, KS>(th, 1, ty);
-    loadTheta<real, NV, KS>(th, 2, tz);
-    real txr[NV];
-#pragma unroll
-    for (int k = 0; k < NV; k++) txr[k] = th[k*8 + ix];
-    const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2];
-    int x = ig.x + ix; x -= (x >= nx) ? nx : 0;
-    // yz[u][v] with u+v <= LEVEL: this lane's plane contracted z -> y
-    real yz[NV][NV];
-#pragma unroll
-    for (int u = 0; u < NV; u++)
-#pragma unroll
-        for (int v = 0; v < NV; v++) yz[u][v] = 0;
-    const bool zWrap = ig.z + 5 >= nz;
-#pragma unroll
-    for (int iy = 0; iy < 6; iy++) {
-        int y = ig.y + iy; y -= (y >= ny) ? ny : 0;
-        const real* row = grid + ((size_t) x*ny + y)*nz;
-        real q[6];
-#pragma unroll
-        for (int iz = 0; iz < 6; iz++) {
-            int z = ig.z + iz; z -= (zWrap && z >= nz) ? nz : 0;
-            q[iz] = row[z];
-        }
-        real zs[NV];
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-            zs[v] = 0;
-#pragma unroll
-            for (int iz = 0; iz < 6; iz++) zs[v] += q[iz]*tz[iz][v];
-        }
-#pragma unroll
-        for (int u = 0; u < NV; u++)
-#pragma unroll
-            for (int v = 0; v < NV; v++)
-                if (u + v <= LEVEL) yz[u][v] += zs[v]*ty[iy][u];
-    }
-#pragma unroll
-    for (int t = 0; t < NV; t++)
-#pragma unroll
-        for (int u = 0; u < NV; u++)
-#pragma unroll
-            for (int v = 0; v < NV; v++)
-                if (t + u + v <= LEVEL) {
-                    real a = yz[u][v]*txr[t];
-                    a += __shfl_down_sync(FULL, a, 3);
-                    const real b = __shfl_down_sync(FULL, a, 1), c = __shfl_down_sync(FULL, a, 2);
-                    if (active && ix == 0) phi[(size_t) phiIndex(t, u, v)*P.n + s] = a + b + c;
-                }
-}
-
-// One thread per atom (the whole 6x6x6 support), same inputs and outputs as k_gather.
-template <typename real, int LEVEL, bool POL>
-__global__ void __launch_bounds__(128)
-k_gather_thread(DevParams P, int numRows, const int* __restrict__ rowList, int recBase, const real* __restrict__ theta,
-                const int4* __restrict__ igrid, const real* __restrict__ grid, real* __restrict__ phi) {
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     if (t >= numRows) return;
     const int s = rowList ? rowList[t] : P.rowBegin + t;
@@ -1652,7 +1580,9 @@ k_diis_step(DevParams P, const int* __restrict__ flagS, const real* __restrict__
             const double* __restrict__ alphaLab, const double* __restrict__ efix,
             const double* __restrict__ ifield, const double* __restrict__ mu,
             double* __restrict__ histDipBase, double* __restrict__ histErrBase,
-            int itHost, double targetEps, DiisStatus* __restrict__ status, double* __restrict__ partial) {
+            int itHost, double targetEps, DiisStatus* __restrict__ status, double* __restrict__ partial,
+            int numSites, const int* __restrict__ siteList) {
+    // siteList: the polarizable sites (every other entry of the solver vectors is and stays zero); nullptr = all atoms
     if (status->done) return;
     __shared__ double sh[512/32][MPID_MAX_HISTORY + 1];
     __shared__ int isLast;
@@ -1666,7 +1596,8 @@ k_diis_step(DevParams P, const int* __restrict__ flagS, const real* __restrict__
     double acc[MPID_MAX_HISTORY + 1];
     for (int k = 0; k < m; k++) acc[k] = 0;
     const bool pme = P.method == PME;
-    for (int s = blockIdx.x*blockDim.x + threadIdx.x; s < P.n; s += gridDim.x*blockDim.x) {
+    for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < numSites; idx += gridDim.x*blockDim.x) {
+        const int s = siteList ? siteList[idx] : idx;
         double fx = ifield[3*(size_t) s], fy = ifield[3*(size_t) s+1], fz = ifield[3*(size_t) s+2];
         const double ux = mu[3*(size_t) s], uy = mu[3*(size_t) s+1], uz = mu[3*(size_t) s+2];
         if (pme && (flagS[s] & 1)) {
@@ -1718,10 +1649,12 @@ k_diis_step(DevParams P, const int* __restrict__ flagS, const real* __restrict__
 // itHost < 0: replayed graph node, the iteration just solved is status->iter - 1.
 template <typename real>
 __global__ void k_diis_combine_ring(int n, int itHost, const double* __restrict__ histDipBase, const DiisStatus* __restrict__ status,
-                                    double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud) {
+                                    double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud,
+                                    int numSites, const int* __restrict__ siteList) {
     if (status->done) return;
-    const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    const int idx = blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= numSites) return;
+    const int s = siteList ? siteList[idx] : idx;
     const int it = itHost >= 0 ? itHost : status->iter - 1;
     SlotList slots;
     const int m = diisHistory(it, slots);

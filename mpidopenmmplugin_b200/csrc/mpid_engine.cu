@@ -634,24 +634,9 @@ struct Engine : public EngineBase {
         real* cartR; real* pkR;
         if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
         else { dCartR.ensure(20*(size_t) n); dPkR.ensure(16*(size_t) n); cartR = dCartR.p; pkR = dPkR.p; }
-        // what the neighbour search needs from the sort (positions, site classes, cell starts, inverse order) ...
+        // what the neighbour search needs from the sort (positions, site classes, cell starts, inverse order)
         LAUNCH((k_sorted_sites<real>), blocksFor(n, B), B, n, numCells, dOrder.p, dSortedKey.p, dPosW.p, dFlagOrig.p, dDamp.p, dThole.p,
                dInv.p, dPosS.p, dPosF.p, dFlagS.p, dClassPacked.p, dDampThole.p, dMud.p, dCellStart.p);
-        // ... while the lab-frame moments (needed by the reciprocal pass first, by the pair kernels after the neighbour
-        // search) are built on the second stream; evaluate() makes the main stream wait for evFrames
-        {
-            CUDA_CHECK(cudaEventRecord(evFork, stream));
-            CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
-            stageEnd();
-            cur = stream2;
-            stageBegin(MPIDB200_STAGE_SORT);
-            LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn,
-                   dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p);
-            stageEnd();
-            CUDA_CHECK(cudaEventRecord(evFrames, stream2));
-            cur = stream;
-            stageBegin(MPIDB200_STAGE_SORT);
-        }
         // polarizable rows, bare-charge ("simple") rows and their complement ("full"): one scan of the packed class
         // flags, then ranks, compact lists and the sorted indices of each site's covalent partners
         {
@@ -664,6 +649,23 @@ struct Engine : public EngineBase {
             launches += 1;
             LAUNCH(k_class_lists, blocksFor(n + 1, B), B, n, dFlagS.p, dClassScan.p, dPolRank.p, dSimpleRank.p, dFullRank.p,
                    dPolList.p, dSimpleList.p, dFullList.p, dOrder.p, dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p);
+        }
+        // ... while the lab-frame moments (needed by the reciprocal pass first, by the pair kernels after the neighbour
+        // search) are built on the second stream; evaluate() makes the main stream wait for evFrames.  Forked after
+        // the class lists so that its blocks (higher-priority stream) do not delay the short kernels the neighbour
+        // search is waiting for.
+        {
+            CUDA_CHECK(cudaEventRecord(evFork, stream));
+            CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
+            stageEnd();
+            cur = stream2;
+            stageBegin(MPIDB200_STAGE_SORT);
+            LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn,
+                   dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p);
+            stageEnd();
+            CUDA_CHECK(cudaEventRecord(evFrames, stream2));
+            cur = stream;
+            stageBegin(MPIDB200_STAGE_SORT);
         }
         if (numRanks > 1) {
             int* pr = (int*) hPinned;
@@ -894,9 +896,13 @@ struct Engine : public EngineBase {
         // the real-space stage times only its own kernels
         stageBegin(MPIDB200_STAGE_SOLVER);
         if (pme) joinPme();
-        if (rows > 0 && pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
-        allReduce(dField.p, 3*(size_t) n, NCCL_FLOAT64);
-        LAUNCH((k_fixed_mu<real>), blocksFor(n, 256), 256, P, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
+        if (numRanks == 1) {
+            LAUNCH((k_fixed_recip_mu<real>), blocksFor(n, 256), 256, P, dPhi.p, dCartD.p, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
+        } else {
+            if (rows > 0 && pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
+            allReduce(dField.p, 3*(size_t) n, NCCL_FLOAT64);
+            LAUNCH((k_fixed_mu<real>), blocksFor(n, 256), 256, P, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
+        }
         stageEnd();
     }
 

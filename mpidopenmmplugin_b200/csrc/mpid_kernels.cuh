@@ -1008,30 +1008,39 @@ __global__ void k_special_electrostatics(DevParams P, int numSpecial, const int*
                                          unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque,
                                          unsigned long long* __restrict__ energy) {
     const int k = blockIdx.x*blockDim.x + threadIdx.x;
-    if (k >= numSpecial) return;
-    if ((k % P.numRanks) != P.rank) return;
-    const int lo = spPairLo[k], hi = spPairHi[k];
-    double dx = posOrig[3*hi] - posOrig[3*lo], dy = posOrig[3*hi+1] - posOrig[3*lo+1], dz = posOrig[3*hi+2] - posOrig[3*lo+2];
-    if (P.method == PME) periodicDelta(P.box, dx, dy, dz);
-    const double r2 = dist2Exact(dx, dy, dz);
-    if (P.method == PME && r2 > P.cutoff2) return;
-    const int si = inv[lo], sj = inv[hi];
-    const double scale = spPairClass[k] == 1 ? 0.0 : P.scale14;
-    const double2 dtI = dampTholeD[si], dtJ = dampTholeD[sj];
-    double f[3], ti[3], tj[3], e;
-    if (P.method == PME)
-        e = pairElectrostatics<double, true, MUTUAL>(pkD + 16*(size_t) si, pkD + 16*(size_t) sj, mu + 3*(size_t) si, mu + 3*(size_t) sj,
-                dtI.x, dtJ.x, dtI.y, dtJ.y, aniso[si] != 0, aniso[sj] != 0, dx, dy, dz, r2, P.alpha, P.defaultThole, scale, scale, f, ti, tj);
-    else
-        e = pairElectrostatics<double, false, MUTUAL>(pkD + 16*(size_t) si, pkD + 16*(size_t) sj, mu + 3*(size_t) si, mu + 3*(size_t) sj,
-                dtI.x, dtJ.x, dtI.y, dtJ.y, aniso[si] != 0, aniso[sj] != 0, dx, dy, dz, r2, 0.0, P.defaultThole, scale, scale, f, ti, tj);
-    for (int q = 0; q < 3; q++) {
-        atomicAddFixed(&force[3*(size_t) si + q], -f[q]);
-        atomicAddFixed(&force[3*(size_t) sj + q], f[q]);
-        atomicAddFixed(&torque[3*(size_t) si + q], ti[q]);
-        atomicAddFixed(&torque[3*(size_t) sj + q], tj[q]);
+    // no early return: the pair energies of a warp are summed with shuffles and leave through ONE atomic per warp
+    // (one atomic per pair on the single energy word serialises at the L2: 95,616 of them at 95,616 atoms)
+    bool active = k < numSpecial && (k % P.numRanks) == P.rank;
+    double e = 0.0;
+    if (active) {
+        const int lo = spPairLo[k], hi = spPairHi[k];
+        double dx = posOrig[3*hi] - posOrig[3*lo], dy = posOrig[3*hi+1] - posOrig[3*lo+1], dz = posOrig[3*hi+2] - posOrig[3*lo+2];
+        if (P.method == PME) periodicDelta(P.box, dx, dy, dz);
+        const double r2 = dist2Exact(dx, dy, dz);
+        if (!(P.method == PME && r2 > P.cutoff2)) {
+            const int si = inv[lo], sj = inv[hi];
+            const double scale = spPairClass[k] == 1 ? 0.0 : P.scale14;
+            const double2 dtI = dampTholeD[si], dtJ = dampTholeD[sj];
+            double f[3], ti[3], tj[3];
+            if (P.method == PME)
+                e = pairElectrostatics<double, true, MUTUAL>(pkD + 16*(size_t) si, pkD + 16*(size_t) sj, mu + 3*(size_t) si, mu + 3*(size_t) sj,
+                        dtI.x, dtJ.x, dtI.y, dtJ.y, aniso[si] != 0, aniso[sj] != 0, dx, dy, dz, r2, P.alpha, P.defaultThole, scale, scale, f, ti, tj);
+            else
+                e = pairElectrostatics<double, false, MUTUAL>(pkD + 16*(size_t) si, pkD + 16*(size_t) sj, mu + 3*(size_t) si, mu + 3*(size_t) sj,
+                        dtI.x, dtJ.x, dtI.y, dtJ.y, aniso[si] != 0, aniso[sj] != 0, dx, dy, dz, r2, 0.0, P.defaultThole, scale, scale, f, ti, tj);
+            for (int q = 0; q < 3; q++) {
+                atomicAddFixed(&force[3*(size_t) si + q], -f[q]);
+                atomicAddFixed(&force[3*(size_t) sj + q], f[q]);
+                atomicAddFixed(&torque[3*(size_t) si + q], ti[q]);
+                atomicAddFixed(&torque[3*(size_t) sj + q], tj[q]);
+            }
+        }
     }
-    atomicAddFixed(energy, e);
+    // fixed point before the reduction, so that the sum does not depend on which pairs share a warp
+    long long ef = __double2ll_rn(e*MPID_FIXED_SCALE);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ef += __shfl_xor_sync(0xffffffffu, ef, off);
+    if ((threadIdx.x & 31) == 0 && ef != 0) atomicAdd(energy, (unsigned long long) ef);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1325,6 +1334,30 @@ __global__ void k_fixed_mu(DevParams P, const double* __restrict__ alphaLab, con
     if (s >= P.n) return;
     double ox, oy, oz;
     applyAlphaLab(alphaLab + 6*(size_t) s, field[3*(size_t) s], field[3*(size_t) s+1], field[3*(size_t) s+2], ox, oy, oz);
+    efix[3*(size_t) s] = ox; efix[3*(size_t) s+1] = oy; efix[3*(size_t) s+2] = oz;
+    mu[3*(size_t) s] = ox; mu[3*(size_t) s+1] = oy; mu[3*(size_t) s+2] = oz;
+    typename Real4<real>::type m = mud[s];
+    m.x = (real) ox; m.y = (real) oy; m.z = (real) oz;
+    mud[s] = m;
+}
+
+// Single-rank fusion of k_fixed_recip and k_fixed_mu (no collective between them): one pass over the atoms.
+template <typename real>
+__global__ void k_fixed_recip_mu(DevParams P, const real* __restrict__ phi, const double* __restrict__ cartD,
+                                 const double* __restrict__ alphaLab, const double* __restrict__ field,
+                                 double* __restrict__ efix, double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    double fx = field[3*(size_t) s], fy = field[3*(size_t) s+1], fz = field[3*(size_t) s+2];
+    if (P.method == PME) {
+        double rx, ry, rz;
+        reciprocalFieldOf<real>(P, phi, s, rx, ry, rz);
+        fx += rx + P.selfFieldTerm*cartD[20*(size_t) s+1];
+        fy += ry + P.selfFieldTerm*cartD[20*(size_t) s+2];
+        fz += rz + P.selfFieldTerm*cartD[20*(size_t) s+3];
+    }
+    double ox, oy, oz;
+    applyAlphaLab(alphaLab + 6*(size_t) s, fx, fy, fz, ox, oy, oz);
     efix[3*(size_t) s] = ox; efix[3*(size_t) s+1] = oy; efix[3*(size_t) s+2] = oz;
     mu[3*(size_t) s] = ox; mu[3*(size_t) s+1] = oy; mu[3*(size_t) s+2] = oz;
     typename Real4<real>::type m = mud[s];

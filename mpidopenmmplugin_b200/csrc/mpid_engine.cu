@@ -65,6 +65,12 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -81,6 +87,12 @@ bool loadNccl() {
     g_nccl.CommInitRank = (int (*)(void**, int, Id128, int)) dlsym(g_nccl.lib, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclAllReduce");
     g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclBroadcast");
+    g_nccl.ReduceScatter = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclReduceScatter");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t)) dlsym(g_nccl.lib, "ncclRecv");
+    g_nccl.GroupStart = (int (*)()) dlsym(g_nccl.lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)()) dlsym(g_nccl.lib, "ncclGroupEnd");
     g_nccl.CommDestroy = (int (*)(void*)) dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int)) dlsym(g_nccl.lib, "ncclGetErrorString");
     return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
@@ -114,12 +126,16 @@ template <> struct FftTraits<float> {
     static const cufftType fwdType = CUFFT_R2C, bwdType = CUFFT_C2R;
     static cufftResult fwd(cufftHandle p, float* in, cplx* out) { return cufftExecR2C(p, in, out); }
     static cufftResult bwd(cufftHandle p, cplx* in, float* out) { return cufftExecC2R(p, in, out); }
+    static const cufftType c2cType = CUFFT_C2C;
+    static cufftResult c2c(cufftHandle p, cplx* data, int dir) { return cufftExecC2C(p, data, data, dir); }
 };
 template <> struct FftTraits<double> {
     typedef cufftDoubleComplex cplx;
     static const cufftType fwdType = CUFFT_D2Z, bwdType = CUFFT_Z2D;
     static cufftResult fwd(cufftHandle p, double* in, cplx* out) { return cufftExecD2Z(p, in, out); }
     static cufftResult bwd(cufftHandle p, cplx* in, double* out) { return cufftExecZ2D(p, in, out); }
+    static const cufftType c2cType = CUFFT_Z2Z;
+    static cufftResult c2c(cufftHandle p, cplx* data, int dir) { return cufftExecZ2Z(p, data, data, dir); }
 };
 
 inline int blocksFor(long long count, int block) { return (int) std::max<long long>(1, (count + block - 1)/block); }
@@ -171,13 +187,17 @@ struct Engine : public EngineBase {
     long long typeBegin[6] = {0, 0, 0, 0, 0, 0};   // boundaries of the four pair-class lists inside pairI/pairJ
     DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
     DevBuf<unsigned long long> dForce, dTorque, dEnergy;
-    DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp, dThetaAll, dThetaPol;
-    DevBuf<int4> dIgridAll, dIgridPol;
+    DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp, dThetaPol;
+    DevBuf<int4> dIgridPol;
     DevBuf<cplx> dGridC;
     DevBuf<double> dModX, dModY, dModZ;
     DevBuf<double> dHistDip, dHistErr, dDotPartial, dDots;
     DevBuf<double> dPtDip, dPtField, dPtGrad;
     cufftHandle planF = 0, planB = 0;
+    // slab-decomposed reciprocal pass (several ranks): 2-D plans over this rank's x planes, strided 1-D plan along x
+    cufftHandle planSlabF = 0, planSlabB = 0, planSlabX = 0;
+    bool slabPlansMade = false; int slabRanks = 0;
+    DevBuf<real> dSlabR; DevBuf<cplx> dSlabC, dSlabPack, dSlabT;
     bool customFft = false;             // fused shared-memory reciprocal pass (mpid_fft.cuh, Stockham version) instead of cuFFT
     Fft2Plan fft2;                      // register-radix version of the same three kernels (preferred when the grid qualifies)
     DevBuf<float2> dTwiddle;
@@ -199,6 +219,7 @@ struct Engine : public EngineBase {
         // the solver, so its blocks are scheduled first; the side stream only fills SMs the others leave idle.
         int prLeast = 0, prGreatest = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+        CUDA_CHECK(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, cfg.device));
         const int prMid = (prLeast + prGreatest)/2;
         CUDA_CHECK(cudaStreamCreateWithPriority(&ownStream, cudaStreamNonBlocking, prMid));
         stream = ownStream;
@@ -223,6 +244,7 @@ struct Engine : public EngineBase {
         if (commPme && g_nccl.CommDestroy) g_nccl.CommDestroy(commPme);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); }
+        destroySlabPlans();
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
         if (hDiis) cudaFreeHost(hDiis);
@@ -260,6 +282,9 @@ struct Engine : public EngineBase {
     }
     void setPlanStreams() {
         if (plansMade) { CUFFT_CHECK(cufftSetStream(planF, pmeStream())); CUFFT_CHECK(cufftSetStream(planB, pmeStream())); }
+        if (slabPlansMade) {
+            CUFFT_CHECK(cufftSetStream(planSlabF, pmeStream())); CUFFT_CHECK(cufftSetStream(planSlabB, pmeStream())); CUFFT_CHECK(cufftSetStream(planSlabX, pmeStream()));
+        }
     }
     void setStream(void* st) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
@@ -499,6 +524,7 @@ struct Engine : public EngineBase {
         size_t G = (size_t) g[0]*g[1]*g[2], GC = (size_t) g[0]*g[1]*(g[2]/2 + 1);
         if (gridChanged || !plansMade) {
             if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); plansMade = false; }
+            destroySlabPlans();
             CUFFT_CHECK(cufftPlan3d(&planF, g[0], g[1], g[2], FftTraits<real>::fwdType));
             CUFFT_CHECK(cufftPlan3d(&planB, g[0], g[1], g[2], FftTraits<real>::bwdType));
             plansMade = true;
@@ -782,6 +808,8 @@ struct Engine : public EngineBase {
     // kernel and the charge-charge pairs -- goes to a third stream right after the neighbour search and is joined
     // before the energy stage: it runs on the SMs the (latency-bound) solver iterations leave idle.
     bool forked3 = false;
+    const int sideCtasPerSm = getenv("MPIDB200_SIDE_CTAS") ? atoi(getenv("MPIDB200_SIDE_CTAS")) : 0;     // CTAs per SM, 0 = no cap
+    int numSms = 148;
     void startDipoleIndependentPairs() {
         const int B = 256;
         const int rows = P.rowEnd - P.rowBegin;
@@ -790,10 +818,16 @@ struct Engine : public EngineBase {
         CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
         cudaStream_t keep = cur;
         cur = stream3;
+        // Optional residency cap (MPIDB200_SIDE_CTAS = CTAs per SM; both kernels walk virtual blocks).  Blocks are not
+        // preempted, so while these kernels fill the SMs a short kernel of the main streams queues behind them whatever
+        // the priorities say: a 5 us per-atom kernel took 58 us beside k_simple_pairs, 9 us with a cap of 4.  The cap
+        // does not pay, though: capped, the side work reaches into the solver iterations and slows those by as much
+        // (1.62 / 1.68 / 1.79 ms per evaluation at 95,616 atoms with no cap / 2 / 1 CTAs per SM), so it is off.
+        const int sideCtas = sideCtasPerSm > 0 ? sideCtasPerSm*numSms : (1 << 30);
         if (rows > 0 && pairCap > 0)
-            LAUNCH(k_half_compact, blocksFor((long long) rows*32, B), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, (unsigned) pairCap, dPairI.p, dPairJ.p);
+            LAUNCH(k_half_compact, std::min(sideCtas, blocksFor((long long) rows*32, B)), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, (unsigned) pairCap, dPairI.p, dPairJ.p);
         if (numSimple > 0) {
-            const int nbS = blocksFor((long long) numSimple*MPID_LANES, 256);
+            const int nbS = std::min(sideCtas, blocksFor((long long) numSimple*MPID_LANES, 256));
             if (pme) LAUNCH((k_simple_pairs<real, true>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
             else LAUNCH((k_simple_pairs<real, false>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
         }
@@ -807,9 +841,76 @@ struct Engine : public EngineBase {
         forked3 = false;
     }
 
+    // ---- slab-decomposed reciprocal pass for several ranks -------------------------------------------------------
+    // Every rank spreads its rows into a full-size grid.  Instead of all-reducing that grid and transforming it on
+    // every rank (replicated: the part of the evaluation that did not scale), the ranks split the transform by x planes:
+    //   reduce-scatter   : rank r receives the summed planes x in [r nx/R, (r+1) nx/R)
+    //   2-D R2C (y, z)   : on the nx/R own planes
+    //   all-to-all       : [x own][ky][kz] -> [x all][ky own][kz]    (pack kernel + grouped ncclSend/ncclRecv)
+    //   1-D C2C along x, influence function, 1-D C2C back : on the ny/R own ky rows
+    //   all-to-all back, 2-D C2R (y, z) on the own planes
+    //   all-gather       : every rank gets the full real grid back for its gather kernels
+    // The spread and gather kernels are unchanged (no halo logic), and a pass moves half the bytes of the all-reduce
+    // version over NVLink while the transform itself is divided by R.  Needs nx and ny divisible by R.
+    void destroySlabPlans() {
+        if (slabPlansMade) { cufftDestroy(planSlabF); cufftDestroy(planSlabB); cufftDestroy(planSlabX); slabPlansMade = false; }
+    }
+    const bool slabFftEnabled = !(getenv("MPIDB200_SLAB_FFT") && atoi(getenv("MPIDB200_SLAB_FFT")) == 0);
+    bool useSlabFft() const {
+        return numRanks > 1 && slabFftEnabled && grid[0] % numRanks == 0 && grid[1] % numRanks == 0 &&
+               g_nccl.ReduceScatter && g_nccl.AllGather && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
+    }
+    void ncclCheck(int rc, const char* what) {
+        if (rc != 0) throw CudaError(std::string(what) + " failed: " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    }
+    void slabReciprocalPass() {
+        const int R = numRanks, nx = grid[0], ny = grid[1], nz = grid[2], nzc = nz/2 + 1;
+        const int nxl = nx/R, nyl = ny/R;
+        const size_t slabReal = (size_t) nxl*ny*nz, slabCplx = (size_t) nxl*ny*nzc, blk = (size_t) nxl*nyl*nzc;
+        if (!slabPlansMade || slabRanks != R) {
+            destroySlabPlans();
+            int n2[2] = {ny, nz};
+            CUFFT_CHECK(cufftPlanMany(&planSlabF, 2, n2, nullptr, 1, 0, nullptr, 1, 0, FftTraits<real>::fwdType, nxl));
+            CUFFT_CHECK(cufftPlanMany(&planSlabB, 2, n2, nullptr, 1, 0, nullptr, 1, 0, FftTraits<real>::bwdType, nxl));
+            int n1[1] = {nx}, embed[1] = {nx};
+            CUFFT_CHECK(cufftPlanMany(&planSlabX, 1, n1, embed, nyl*nzc, 1, embed, nyl*nzc, 1, FftTraits<real>::c2cType, nyl*nzc));
+            slabPlansMade = true; slabRanks = R;
+            setPlanStreams();
+        }
+        dSlabR.ensure(slabReal); dSlabC.ensure(slabCplx); dSlabPack.ensure(slabCplx); dSlabT.ensure(slabCplx);
+        void* c = (cur == stream2 && commPme) ? commPme : comm;
+        const int dt = sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
+        ncclCheck(g_nccl.ReduceScatter(dGrid.p, dSlabR.p, slabReal, dt, NCCL_SUM, c, cur), "ncclReduceScatter");
+        CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, dSlabR.p, dSlabC.p));
+        launches += 1;
+        LAUNCH((k_slab_transpose<cplx, true>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabC.p, dSlabPack.p);
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < R; r++) {
+            ncclCheck(g_nccl.Send(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
+            ncclCheck(g_nccl.Recv(dSlabT.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
+        }
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        // dSlabT = [x = 0..nx-1][ky own][kz]
+        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_FORWARD));
+        LAUNCH((k_slab_convolution<cplx, real>), blocksFor((long long) slabCplx, 256), 256, nx, ny, nyl, rank*nyl, nzc, dEterm.p, dSlabT.p);
+        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_INVERSE));
+        launches += 2;
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < R; r++) {
+            ncclCheck(g_nccl.Send(dSlabT.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
+            ncclCheck(g_nccl.Recv(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
+        }
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
+        CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, dSlabC.p, dSlabR.p));
+        launches += 1;
+        ncclCheck(g_nccl.AllGather(dSlabR.p, dGrid.p, slabReal, dt, c, cur), "ncclAllGather");
+    }
+
     void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
         size_t GC = (size_t) grid[0]*grid[1]*(grid[2]/2 + 1);
         stageBegin(MPIDB200_STAGE_FFT);
+        if (useSlabFft()) { slabReciprocalPass(); stageEnd(); return; }
         if (numRanks > 1) allReduce(dGrid.p, (size_t) grid[0]*grid[1]*grid[2], sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64);
         if (fft2.ok) {
             const float* g = (const float*) (const void*) dGrid.p;
@@ -845,7 +946,7 @@ struct Engine : public EngineBase {
     }
 
 #define GATHER(LEVEL, POLREC, count, list, base, th, ig, out) \
-        LAUNCH((k_gather<real, LEVEL, POLREC>), blocksFor(count, 128), 128, P, count, list, base, th, ig, dGrid.p, out)
+        LAUNCH((k_gather<real, LEVEL, POLREC>), blocksFor(count, 128), 128, P, count, list, base, th, ig, dPosS.p, dGrid.p, out)
     real* cartR() { return sizeof(real) == sizeof(double) ? (real*) dCartD.p : dCartR.p; }
     real* pkR() { return sizeof(real) == sizeof(double) ? (real*) dPkD.p : dPkR.p; }
 
@@ -861,16 +962,16 @@ struct Engine : public EngineBase {
         stageBegin(MPIDB200_STAGE_FIXED_SPREAD);
         dFrac.ensure(20*(size_t) n);
         LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
-        // B-spline weights of this rank's rows, once per evaluation: every spread and gather below reads them
-        dThetaAll.ensure((size_t) n*MPID_THETA_ALL); dIgridAll.ensure(n);
+        // B-spline weights of this rank's polarizable rows, once per evaluation: every induced-dipole pass reads them
         dThetaPol.ensure((size_t) std::max(numPolTotal, 1)*MPID_THETA_POL); dIgridPol.ensure(std::max(numPolTotal, 1));
-        if (rows > 0) LAUNCH((k_spline_weights<real>), blocksFor(rows, 128), 128, P, dPosS.p, dPolRank.p, dThetaAll.p, dIgridAll.p, dThetaPol.p, dIgridPol.p);
+        if (numPol > 0)
+            LAUNCH((k_spline_weights<real>), blocksFor(numPol, 128), 128, P, numPol, (const int*) dPolList.p + polBegin, polBegin, dPosS.p, dThetaPol.p, dIgridPol.p);
         CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
-        if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dFrac.p, (const double*) nullptr, dGrid.p);
+        if (rows > 0) LAUNCH((k_spread<real, true>), blocksFor((long long) rows*6, 192), 192, P, rows, (const int*) nullptr, 0, (const real*) nullptr, (const int4*) nullptr, dPosS.p, dFrac.p, (const double*) nullptr, dGrid.p);
         stageEnd();
         reciprocalPass();
         stageBegin(MPIDB200_STAGE_FIXED_GATHER);
-        if (rows > 0) GATHER(4, false, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dPhi.p);
+        if (rows > 0) GATHER(4, false, rows, (const int*) nullptr, 0, (const real*) nullptr, (const int4*) nullptr, dPhi.p);
         stageEnd();
         backToMain();
     }
@@ -918,12 +1019,12 @@ struct Engine : public EngineBase {
             forkPme();
             stageBegin(MPIDB200_STAGE_IND_SPREAD);
             CUDA_CHECK(cudaMemsetAsync(dGrid.p, 0, G*sizeof(real), cur));
-            if (numPol > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) numPol*6, 192), 192, P, numPol, polRows, polBegin, dThetaPol.p, dIgridPol.p, (const real*) nullptr, dMu.p, dGrid.p);
+            if (numPol > 0) LAUNCH((k_spread<real, false>), blocksFor((long long) numPol*6, 192), 192, P, numPol, polRows, polBegin, dThetaPol.p, dIgridPol.p, dPosS.p, (const real*) nullptr, dMu.p, dGrid.p);
             stageEnd();
             reciprocalPass();
             stageBegin(MPIDB200_STAGE_IND_GATHER);
             if (level == 4) {
-                if (rows > 0) GATHER(4, false, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dPhidp.p);
+                if (rows > 0) GATHER(4, false, rows, (const int*) nullptr, 0, (const real*) nullptr, (const int4*) nullptr, dPhidp.p);
             } else if (numPol > 0) {
                 // solver iterations need the reciprocal field (and its gradient for OPT) at polarizable sites only
                 if (level == 1) GATHER(1, true, numPol, polRows, polBegin, dThetaPol.p, dIgridPol.p, dPhidp.p);
@@ -1224,7 +1325,7 @@ struct Engine : public EngineBase {
             if (pme && !dipolesOnly && rows > 0) {
                 // the converged dipoles' reciprocal potential is still on the grid: fetch all 35 derivatives
                 stageBegin(MPIDB200_STAGE_IND_GATHER);
-                GATHER(4, false, rows, (const int*) nullptr, 0, dThetaAll.p, dIgridAll.p, dPhidp.p);
+                GATHER(4, false, rows, (const int*) nullptr, 0, (const real*) nullptr, (const int4*) nullptr, dPhidp.p);
                 stageEnd();
             }
         } else {

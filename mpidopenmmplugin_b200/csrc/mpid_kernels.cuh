@@ -583,8 +583,11 @@ __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, co
                                unsigned* __restrict__ pairI, unsigned* __restrict__ pairJ) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x*blockDim.x + threadIdx.x)/32;
-    if (row >= rows) return;
+    // virtual blocks, see k_simple_pairs
+    const int warpsPerBlock = blockDim.x >> 5, numBlocks = (rows + warpsPerBlock - 1)/warpsPerBlock;
+    for (int vb = blockIdx.x; vb < numBlocks; vb += gridDim.x) {
+    const int row = vb*warpsPerBlock + (threadIdx.x >> 5);
+    if (row >= rows) continue;
     const int i = P.rowBegin + row;
     const unsigned nUp = counts[row].x;
     const int si = ((int) posF[i].w >> 1) & 1;
@@ -604,6 +607,7 @@ __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, co
             if (d < pairCap) { pairI[d] = (unsigned) i; pairJ[d] = e; }
         }
         dstF += __popc(mF); dstS += __popc(mS);
+    }
     }
 }
 
@@ -875,7 +879,10 @@ __global__ void __launch_bounds__(256)
 k_simple_pairs(DevParams P, int numSimple, const int* __restrict__ simpleList, const double4* __restrict__ posS,
                const real* __restrict__ pk, const uint4* __restrict__ counts, const unsigned* __restrict__ nbr,
                unsigned long long* __restrict__ force, unsigned long long* __restrict__ energy) {
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    // virtual blocks: the launch may hold fewer CTAs than the work has blocks (residency cap of the side stream)
+    const int numBlocks = (numSimple*MPID_LANES + blockDim.x - 1)/blockDim.x;
+    for (int vb = blockIdx.x; vb < numBlocks; vb += gridDim.x) {
+    const int t = vb*blockDim.x + threadIdx.x;
     const int rs = t/MPID_LANES;
     const int sub = t % MPID_LANES;
     const bool act = rs < numSimple;
@@ -924,7 +931,7 @@ k_simple_pairs(DevParams P, int numSimple, const int* __restrict__ simpleList, c
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) de += __shfl_xor_sync(0xffffffffu, de, off);
-    if ((threadIdx.x & 31) == 0 && de != 0.0) atomicAddFixed(energy, de);
+    if ((threadIdx.x & 31) == 0 && de != 0.0) atomicAddFixed(energy, de);    }
 }
 
 // Full site x bare-charge site pairs (e.g. O-H between waters: 44 % of all pairs).  Every full site A gathers over
@@ -1083,82 +1090,93 @@ __device__ __forceinline__ void redLine6(double* p, const double* v) {
     for (int k = 0; k < 6; k++) atomicAdd(p + k, v[k]);
 }
 
-// B-spline weights of every atom, once per evaluation (positions do not change between the reciprocal passes of
-// the solver iterations, and each pass used to rebuild them in every thread of every spread and gather launch).
-//   thetaAll[s][axis][k][8] : k-th derivative (k = 0..4) of the six weights of atom s along `axis` (two pad floats:
-//                             every (axis, k) row is one 32-byte sector), igridAll[s] = first grid point per axis
-//   thetaPol[r][axis][k][8] : the same for polarizable sites only (r = rank among them), k = 0..2 -- what the
-//                             induced-dipole passes read (6 MB instead of 46 MB at 95,616 atoms)
+// B-spline weights of the polarizable sites, once per evaluation: their positions do not change between the
+// reciprocal passes of the solver iterations, and each pass used to rebuild the weights in every thread of its spread
+// and gather launch.   thetaPol[r][axis][k][8] : k-th derivative (k = 0..2) of the six weights of polarizable site r
+// (rank among the polarizable sites) along `axis`, two pad floats so that every (axis, k) row is one 32-byte sector;
+// igridPol[r] = first grid point per axis.  The permanent-moment pass (all atoms, once per evaluation) builds its
+// weights in the kernel: a record for every atom costs more HBM traffic than the arithmetic it saves (measured at
+// 1,024,884 atoms: 0.39 ms to write it, gathers 0.1 ms slower each, spread 0.13 ms faster).
 //   reference: computeMPIDBsplines (:3049-3075), computeBSplinePoint (:2956-3044)
-#define MPID_THETA_ALL (3*5*8)
 #define MPID_THETA_POL (3*3*8)
 template <typename real>
 __global__ void __launch_bounds__(128)
-k_spline_weights(DevParams P, const double4* __restrict__ posS, const int* __restrict__ polRank,
-                 real* __restrict__ thetaAll, int4* __restrict__ igridAll, real* __restrict__ thetaPol, int4* __restrict__ igridPol) {
-    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;      // the rows this rank spreads and gathers
-    if (s >= P.rowEnd) return;
-    const double4 p = posS[s];
+k_spline_weights(DevParams P, int numPol, const int* __restrict__ polList, int recBase, const double4* __restrict__ posS,
+                 real* __restrict__ thetaPol, int4* __restrict__ igridPol) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= numPol) return;
+    const int r = recBase + t;
+    const double4 p = posS[polList[t]];
     int ig[3]; double w[3];
     pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, ig, w);
-    const bool pol = ((int) p.w & 1) != 0;
-    const int r = pol ? polRank[s] : 0;
-    const int4 g = make_int4(ig[0], ig[1], ig[2], 0);
-    igridAll[s] = g;
-    if (pol) igridPol[r] = g;
+    igridPol[r] = make_int4(ig[0], ig[1], ig[2], 0);
     typedef typename Real4<real>::type real4;
 #pragma unroll
     for (int axis = 0; axis < 3; axis++) {
         real th[6][5];
         bsplineWeights<real>((real) w[axis], th);
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < 3; k++) {
             real4 lo, hi;
             lo.x = th[0][k]; lo.y = th[1][k]; lo.z = th[2][k]; lo.w = th[3][k];
             hi.x = th[4][k]; hi.y = th[5][k]; hi.z = 0; hi.w = 0;
-            real4* dst = reinterpret_cast<real4*>(thetaAll + (size_t) s*MPID_THETA_ALL + (axis*5 + k)*8);
-            dst[0] = lo; dst[1] = hi;
-            if (pol && k < 3) {
-                real4* dp = reinterpret_cast<real4*>(thetaPol + (size_t) r*MPID_THETA_POL + (axis*3 + k)*8);
-                dp[0] = lo; dp[1] = hi;
-            }
+            real4* dp = reinterpret_cast<real4*>(thetaPol + (size_t) r*MPID_THETA_POL + (axis*3 + k)*8);
+            dp[0] = lo; dp[1] = hi;
         }
     }
 }
-// rows (axis, k = 0..NK-1) of one atom's weight record -> t[point][k]; KSTRIDE = derivatives stored per axis
-template <typename real, int NK, int KSTRIDE>
+// rows (axis, k = 0..NK-1) of one site's weight record -> t[point][k]
+template <typename real, int NK>
 __device__ __forceinline__ void loadTheta(const real* __restrict__ rec, int axis, real (*t)[5]) {
     typedef typename Real4<real>::type real4;
 #pragma unroll
     for (int k = 0; k < NK; k++) {
-        const real4* src = reinterpret_cast<const real4*>(rec + (axis*KSTRIDE + k)*8);
+        const real4* src = reinterpret_cast<const real4*>(rec + (axis*3 + k)*8);
         const real4 lo = src[0], hi = src[1];
         t[0][k] = lo.x; t[1][k] = lo.y; t[2][k] = lo.z; t[3][k] = lo.w; t[4][k] = hi.x; t[5][k] = hi.y;
     }
 }
 
-// B-spline spreading: 6 threads per atom (one per x plane), 36 grid points each; weights from k_spline_weights
-// (FIXED: the all-atom record, row s; induced dipoles: the polarizable-site record, row polBase + t/6).
+// B-spline spreading: 6 threads per atom (one per x plane), 36 grid points each.  FIXED: permanent moments of rows
+// rowBegin.., weights built here from the positions; otherwise induced dipoles of the listed polarizable rows with
+// the weights of k_spline_weights (record recBase + t/6).
 //   reference: spreadFixedMultipolesOntoGrid (:3269-3327), spreadInducedDipolesOnGrid (:3532-3573)
 template <typename real, bool FIXED>
 __global__ void __launch_bounds__(192)
 k_spread(DevParams P, int numRows, const int* __restrict__ rowList, int recBase, const real* __restrict__ theta,
-         const int4* __restrict__ igrid, const real* __restrict__ frac, const double* __restrict__ mu, real* __restrict__ grid) {
-    // rowList == nullptr: rows rowBegin .. rowBegin+numRows-1; otherwise the listed (polarizable) rows
+         const int4* __restrict__ igrid, const double4* __restrict__ posS, const real* __restrict__ frac,
+         const double* __restrict__ mu, real* __restrict__ grid) {
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int ix = t % 6;
     if (t/6 >= numRows) return;
     const int s = rowList ? rowList[t/6] : P.rowBegin + t/6;
-    const int rec = FIXED ? s : recBase + t/6;
-    constexpr int NK = FIXED ? 4 : 2, KS = FIXED ? 5 : 3, RS = FIXED ? MPID_THETA_ALL : MPID_THETA_POL;
-    const real* th = theta + (size_t) rec*RS;
-    const int4 ig = igrid[rec];
-    real ty[6][5], tz[6][5];
-    loadTheta<real, NK, KS>(th, 1, ty);
-    loadTheta<real, NK, KS>(th, 2, tz);
-    real txr[5];
+    int4 ig;
+    real ty[6][5], tz[6][5], txr[5];
+    if (FIXED) {
+        const double4 p = posS[s];
+        int g[3]; double w[3];
+        pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, g, w);
+        ig = make_int4(g[0], g[1], g[2], 0);
+        real tx[6][5];
+        bsplineWeights<real>((real) w[0], tx);
+        bsplineWeights<real>((real) w[1], ty);
+        bsplineWeights<real>((real) w[2], tz);
 #pragma unroll
-    for (int k = 0; k < NK; k++) txr[k] = th[k*8 + ix];
+        for (int k = 0; k < 5; k++) txr[k] = tx[0][k];
+#pragma unroll
+        for (int a = 1; a < 6; a++)
+            if (a == ix)
+#pragma unroll
+                for (int k = 0; k < 5; k++) txr[k] = tx[a][k];
+    } else {
+        const int rec = recBase + t/6;
+        const real* th = theta + (size_t) rec*MPID_THETA_POL;
+        ig = igrid[rec];
+        loadTheta<real, 2>(th, 1, ty);
+        loadTheta<real, 2>(th, 2, tz);
+#pragma unroll
+        for (int k = 0; k < 2; k++) txr[k] = th[k*8 + ix];
+    }
     real f[20];
     if (FIXED) {
         for (int k = 0; k < 20; k++) f[k] = frac[20*(size_t) s + k];
@@ -1198,6 +1216,34 @@ __global__ void k_convolution(size_t count, const real* __restrict__ eterm, cplx
     g[k] = v;
 }
 
+// Slab-decomposed reciprocal pass (several ranks), see Engine::slabReciprocalPass.
+// PACK: [xl][r][e] -> [r][xl][e] (e = one rank's ky rows x kz of a plane, contiguous) so that the block for rank r is
+// one contiguous send buffer; !PACK: the inverse, after the transpose back.
+template <typename cplx, bool PACK>
+__global__ void k_slab_transpose(int nxl, int R, int rowLen, const cplx* __restrict__ src, cplx* __restrict__ dst) {
+    const size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    const size_t total = (size_t) nxl*R*rowLen;
+    if (idx >= total) return;
+    const int e = (int) (idx % rowLen);
+    const size_t q = idx / rowLen;
+    const int r = (int) (q % R), xl = (int) (q / R);          // idx enumerates [xl][r][e]
+    const size_t packed = ((size_t) r*nxl + xl)*rowLen + e;   // [r][xl][e]
+    if (PACK) dst[packed] = src[idx]; else dst[idx] = src[packed];
+}
+// influence function on this rank's ky rows: data[x][kyl][kz] *= eterm[x][ky0 + kyl][kz]
+template <typename cplx, typename real>
+__global__ void k_slab_convolution(int nx, int ny, int nyl, int ky0, int nzc, const real* __restrict__ eterm, cplx* __restrict__ data) {
+    const size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= (size_t) nx*nyl*nzc) return;
+    const int kz = (int) (idx % nzc);
+    const size_t q = idx / nzc;
+    const int kyl = (int) (q % nyl), x = (int) (q / nyl);
+    const real e = eterm[((size_t) x*ny + ky0 + kyl)*nzc + kz];
+    cplx v = data[idx];
+    v.x *= e; v.y *= e;
+    data[idx] = v;
+}
+
 // eterm[kx][ky][kz<=nz/2] = exp(-pi^2 m^2/alpha^2) / (pi V m^2 Bx By Bz), zero at the origin
 template <typename real>
 __global__ void k_eterm_table(DevParams P, const double* __restrict__ modX, const double* __restrict__ modY,
@@ -1222,27 +1268,39 @@ __global__ void k_eterm_table(DevParams P, const double* __restrict__ modX, cons
 }
 
 // Potential derivatives at the atoms up to total order LEVEL (4 -> all 35), SoA output phi[idx*n + s]; one thread
-// per atom contracts its 6x6x6 support z -> y -> x.  Weights come from k_spline_weights: POL = the polarizable-site
-// record (row recBase + t), else the all-atom one.  (A six-lanes-per-atom variant, one x plane per lane with a
-// shuffle reduction, was measured slower on B200 -- 22 us against 16 us for the field-only gather, 79 us against
-// 40 us for all 35 derivatives -- although it exposes six times the loads: the kernel is bound by L1 sector
-// traffic, 36 sectors per atom whichever way they are issued; profiles/r01x_ncu_full_96k.md.)
+// per atom contracts its 6x6x6 support z -> y -> x.  POL: the listed polarizable rows with the weights of
+// k_spline_weights (record recBase + t, LEVEL <= 2); otherwise weights are built here from the positions.
+// (A six-lanes-per-atom variant, one x plane per lane with a shuffle reduction, was measured slower on B200 -- 22 us
+// against 16 us for the field-only gather, 79 us against 40 us for all 35 derivatives -- although it exposes six
+// times the loads: the kernel is bound by L1 sector traffic, 36 sectors per atom whichever way they are issued.)
 //   reference: computeFixedPotentialFromGrid (:3368-3530), computeInducedPotentialFromGrid (:3575-3737)
 template <typename real, int LEVEL, bool POL>
 __global__ void __launch_bounds__(128)
 k_gather(DevParams P, int numRows, const int* __restrict__ rowList, int recBase, const real* __restrict__ theta,
-         const int4* __restrict__ igrid, const real* __restrict__ grid, real* __restrict__ phi) {
+         const int4* __restrict__ igrid, const double4* __restrict__ posS, const real* __restrict__ grid, real* __restrict__ phi) {
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     if (t >= numRows) return;
     const int s = rowList ? rowList[t] : P.rowBegin + t;
-    const int rec = POL ? recBase + t : s;
-    constexpr int NV = LEVEL + 1, KS = POL ? 3 : 5, RS = POL ? MPID_THETA_POL : MPID_THETA_ALL;
-    const real* th = theta + (size_t) rec*RS;
-    const int4 ig = igrid[rec];
+    constexpr int NV = LEVEL + 1;
+    static_assert(!POL || LEVEL <= 2, "the polarizable-site record holds derivatives 0..2");
+    int4 ig;
     real tx[6][5], ty[6][5], tz[6][5];
-    loadTheta<real, NV, KS>(th, 0, tx);
-    loadTheta<real, NV, KS>(th, 1, ty);
-    loadTheta<real, NV, KS>(th, 2, tz);
+    if (POL) {
+        const int rec = recBase + t;
+        const real* th = theta + (size_t) rec*MPID_THETA_POL;
+        ig = igrid[rec];
+        loadTheta<real, NV>(th, 0, tx);
+        loadTheta<real, NV>(th, 1, ty);
+        loadTheta<real, NV>(th, 2, tz);
+    } else {
+        const double4 p = posS[s];
+        int g[3]; double w[3];
+        pmeAtomCell(P.box, P.geom, p.x, p.y, p.z, g, w);
+        ig = make_int4(g[0], g[1], g[2], 0);
+        bsplineWeights<real>((real) w[0], tx);
+        bsplineWeights<real>((real) w[1], ty);
+        bsplineWeights<real>((real) w[2], tz);
+    }
     const int nx = P.grid[0], ny = P.grid[1], nz = P.grid[2];
     real acc[NV][NV][NV];
 #pragma unroll

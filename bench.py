@@ -155,6 +155,7 @@ def main():
     import torch.distributed as dist
     from mpidopenmmplugin_b200 import MPIDB200Kernel
     from mpidopenmmplugin_b200.workloads import water_box, make_kernel
+    from mpidopenmmplugin_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the MPIDB200 engine has no CPU fallback")
@@ -277,8 +278,11 @@ def main():
                     dtype="f32 pair/grid math, f64 accumulation" if args.precision == "mixed" else "f64", data="synthetic",
                     config=dict(workload=WORKLOADS[wl]["name"], polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % n_f,
                                 cutoff_nm=s.cutoff, ewald_alpha=s.alpha, l2="256 MB buffer written between timed iterations",
-                                parallelism=("atom-block rows x%d: NCCL all-reduce of the partial induced field every solver iteration, of the charge grid "
-                                             "every reciprocal pass (second communicator, reciprocal stream), of forces/torques once; FFT replicated" % world) if world > 1 else "1 GPU",
+                                parallelism=("atom-block rows x%d: NCCL all-reduce of the partial induced field every solver iteration and of forces/torques once; "
+                                             "reciprocal pass on a second communicator / stream: %s" % (world, (
+                                                 "slab decomposition (reduce-scatter, 2-D FFT on own x planes, all-to-all, x FFT + influence function on own ky rows, "
+                                                 "all-to-all back, all-gather)" if sharding.uses_slab_fft(world, s.grid) else
+                                                 "all-reduce of the charge grid, FFT replicated"))) if world > 1 else "1 GPU",
                                 note=("N>1 runs the 1,024,884-atom box of BASELINE.json config 5 (strong scaling of ONE system); the N=1 default runs the "
                                       "95,616-atom box of config 4, so values at N=1 and N>1 are different workloads -- run `--gpus 1 --workload 1m` for the "
                                       "single-GPU point of the same system") if world > 1 else "N=1 default = BASELINE.json config 4 (96k atoms, 1 B200)"),

@@ -855,9 +855,11 @@ struct Engine : public EngineBase {
     void destroySlabPlans() {
         if (slabPlansMade) { cufftDestroy(planSlabF); cufftDestroy(planSlabB); cufftDestroy(planSlabX); slabPlansMade = false; }
     }
-    const bool slabFftEnabled = !(getenv("MPIDB200_SLAB_FFT") && atoi(getenv("MPIDB200_SLAB_FFT")) == 0);
+    // MPIDB200_SLAB_FFT = smallest rank count that uses it (0 = never).  Measured on the 1,024,884-atom box, 224^3 grid,
+    // ms per evaluation all-reduce / slab: 10.04 / 10.26 at 2 ranks, 8.22 / 7.73 at 4, 7.62 / 6.50 at 8 -- so from 4 on.
+    const int slabFftMinRanks = getenv("MPIDB200_SLAB_FFT") ? atoi(getenv("MPIDB200_SLAB_FFT")) : 4;
     bool useSlabFft() const {
-        return numRanks > 1 && slabFftEnabled && grid[0] % numRanks == 0 && grid[1] % numRanks == 0 &&
+        return slabFftMinRanks > 0 && numRanks > 1 && numRanks >= slabFftMinRanks && grid[0] % numRanks == 0 && grid[1] % numRanks == 0 &&
                g_nccl.ReduceScatter && g_nccl.AllGather && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
     }
     void ncclCheck(int rc, const char* what) {

@@ -74,9 +74,29 @@ def test_two_rank_partition_and_plumbing(n):
 
 
 def test_collective_inventory_matches_the_engine():
-    """Mutual, PME, 6 field evaluations: fixed field + fixed grid + 6 x (grid + field) + forces/torques/energy."""
-    c = sharding.collectives_per_evaluation(0, 6, pme=True)
+    """Mutual, PME, 6 field evaluations: fixed field + fixed grid + 6 x (grid + field) + forces/torques/energy; from
+    4 ranks on every grid all-reduce becomes reduce-scatter + two all-to-all transposes + all-gather."""
+    c = sharding.collectives_per_evaluation(0, 6, pme=True, world=2)
     assert len(c) == 2 + 12 + 3
     assert sum(1 for w in c if w[0] == "partial induced field") == 6
-    c = sharding.collectives_per_evaluation(2, 3, pme=True)
+    c = sharding.collectives_per_evaluation(2, 3, pme=True, world=2)
     assert sum(1 for w in c if w[0] == "partial induced field gradient") == 3
+    c = sharding.collectives_per_evaluation(0, 6, pme=True, world=8, grid=(224, 224, 224))
+    assert len(c) == 1 + 4 + 6*(4 + 1) + 3
+    assert sum(1 for w in c if w[0].endswith("all-to-all")) == 7
+    assert not sharding.uses_slab_fft(8, (225, 224, 224)) and not sharding.uses_slab_fft(2, (224, 224, 224))
+
+
+@pytest.mark.parametrize("world,shape", [(2, (8, 6, 10)), (4, (8, 12, 6)), (8, (16, 8, 9))])
+def test_slab_reciprocal_pass_equals_the_full_transform(world, shape):
+    """The slab-decomposed reciprocal pass (reduce-scatter, 2-D transforms on own planes, all-to-all, x transforms and
+    influence function on own ky rows, all-to-all back, all-gather) restated in numpy with the engine's index
+    arithmetic reproduces forward FFT -> influence function -> backward FFT of the summed grid."""
+    rng = np.random.default_rng(7)
+    nx, ny, nz = shape
+    parts = [rng.normal(size=shape) for _ in range(world)]
+    eterm = rng.uniform(0.1, 1.0, size=(nx, ny, nz//2 + 1))
+    ref = np.fft.irfftn(eterm*np.fft.rfftn(np.sum(parts, axis=0)), s=shape, axes=(0, 1, 2))*(nx*ny*nz)
+    # irfftn drops the imaginary parts a C2R transform drops, so both sides treat a non-Hermitian product alike
+    got = sharding.slab_reciprocal_pass(parts, eterm)
+    assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)

@@ -1011,7 +1011,10 @@ struct Engine : public EngineBase {
 
     // Field of the current induced dipoles into dIfield (and gradient into `grad`, which the caller zeroed).
     // level: highest derivative order gathered from the reciprocal grid (1 field, 2 +gradient, 4 everything)
-    void inducedFieldPass(const double* dPosIn, int level, double* grad, bool realSpace, bool callerFinishes = false) {
+    // compactReduce (several ranks, DIIS): only the polarizable entries of the partial field are all-reduced, into
+    // dFieldCompact (indexed like dPolList); otherwise the whole per-atom vector is reduced in place.
+    DevBuf<double> dFieldCompact;
+    void inducedFieldPass(const double* dPosIn, int level, double* grad, bool realSpace, bool callerFinishes = false, bool compactReduce = false) {
         const bool pme = P.method == PME;
         const int rows = P.rowEnd - P.rowBegin;
         size_t G = (size_t) grid[0]*grid[1]*grid[2];
@@ -1062,7 +1065,11 @@ struct Engine : public EngineBase {
             else LAUNCH((k_induced_finish<real, false>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
         }
         // the per-iteration collective of the partitioned solver: partial induced fields -> full field
-        allReduce(dIfield.p, 3*(size_t) n, NCCL_FLOAT64);
+        if (compactReduce && numRanks > 1 && numPolTotal > 0) {
+            dFieldCompact.ensure(3*(size_t) numPolTotal);
+            LAUNCH(k_pack_sites, blocksFor(3*(long long) numPolTotal, 256), 256, numPolTotal, (const int*) dPolList.p, dIfield.p, dFieldCompact.p);
+            allReduce(dFieldCompact.p, 3*(size_t) numPolTotal, NCCL_FLOAT64);
+        } else allReduce(dIfield.p, 3*(size_t) n, NCCL_FLOAT64);
         if (grad) allReduce(grad, 6*(size_t) n, NCCL_FLOAT64);
         stageEnd();
     }
@@ -1183,7 +1190,8 @@ struct Engine : public EngineBase {
             } else if (fused) {
                 launchSolverStep(dPosIn, it, !last);
             } else {
-                inducedFieldPass(dPosIn, 1, nullptr, true, false);
+                const bool compact = numPolTotal > 0;
+                inducedFieldPass(dPosIn, 1, nullptr, true, false, compact);
                 stageBegin(MPIDB200_STAGE_SOLVER);
                 const int m = std::min(it + 1, H);
                 VecList el; SlotList sl;
@@ -1193,9 +1201,15 @@ struct Engine : public EngineBase {
                 }
                 double* hd = dHistDip.p + (size_t) sl.s[m-1]*3*n;
                 double* he = dHistErr.p + (size_t) sl.s[m-1]*3*n;
-                LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p);
+                // the solver vectors are replicated, but only their polarizable entries are ever non-zero: walk those
+                if (compact) LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dFieldCompact.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p,
+                                    numPolTotal, (const int*) dPolList.p, 1);
+                else LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p, n, (const int*) nullptr, 0);
                 LAUNCH(k_diis_solve, 1, 512, nb, m, sl, it, n, cfg.target_epsilon, dDotPartial.p, dDiis.p);
-                if (!last) LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, n, (const int*) nullptr);
+                if (!last) {
+                    if (compact) LAUNCH((k_diis_combine_ring<real>), blocksFor(numPolTotal, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, numPolTotal, (const int*) dPolList.p);
+                    else LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, n, (const int*) nullptr);
+                }
                 stageEnd();
             }
             if (it + 1 >= predictedEvals || last || syncEveryIteration) {

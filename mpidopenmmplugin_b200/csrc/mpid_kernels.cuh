@@ -1523,19 +1523,33 @@ struct SlotList { int s[MPID_MAX_HISTORY + 1]; };
 
 // newDip = efix + alpha.E_ind, err = newDip - mu into history slot (:1195-1218), fused with the partial dot
 // products <err_new, err_k> over the m vectors of the history (the last one being err_new itself).
+// dst[3 idx + c] = src[3 siteList[idx] + c]: the polarizable entries of a per-atom vector, contiguous -- what the
+// per-iteration all-reduce of the partial induced field moves (a third of the atoms in water).
+__global__ void k_pack_sites(int numSites, const int* __restrict__ siteList, const double* __restrict__ src, double* __restrict__ dst) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= 3*numSites) return;
+    const int idx = t/3, c = t - 3*idx;
+    dst[t] = src[3*(size_t) siteList[idx] + c];
+}
+
 // Fixed block partition + ordered second pass => deterministic.
 __global__ void __launch_bounds__(256)
 k_diis_record_dots(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ efix,
                    const double* __restrict__ ifield, const double* __restrict__ mu,
                    double* __restrict__ histDip, double* __restrict__ histErr, int m, VecList errs,
-                   const DiisStatus* __restrict__ status, double* __restrict__ partial) {
+                   const DiisStatus* __restrict__ status, double* __restrict__ partial,
+                   int numSites, const int* __restrict__ siteList, int fieldIsCompact) {
+    // siteList: the polarizable sites (every other entry of the solver vectors is and stays zero), nullptr = all atoms;
+    // fieldIsCompact: ifield is indexed by the position in siteList (k_pack_sites) instead of by atom
     if (status->done) return;
     __shared__ double sh[256/32][MPID_MAX_HISTORY + 1];
     double acc[MPID_MAX_HISTORY + 1];
     for (int k = 0; k < m; k++) acc[k] = 0;
-    for (int s = blockIdx.x*blockDim.x + threadIdx.x; s < P.n; s += gridDim.x*blockDim.x) {
+    for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < numSites; idx += gridDim.x*blockDim.x) {
+        const int s = siteList ? siteList[idx] : idx;
+        const size_t fi = fieldIsCompact ? (size_t) idx : (size_t) s;
         double ox, oy, oz;
-        applyAlphaLab(alphaLab + 6*(size_t) s, ifield[3*(size_t) s], ifield[3*(size_t) s+1], ifield[3*(size_t) s+2], ox, oy, oz);
+        applyAlphaLab(alphaLab + 6*(size_t) s, ifield[3*fi], ifield[3*fi+1], ifield[3*fi+2], ox, oy, oz);
         const double nx = efix[3*(size_t) s] + ox, ny = efix[3*(size_t) s+1] + oy, nz = efix[3*(size_t) s+2] + oz;
         histDip[3*(size_t) s] = nx; histDip[3*(size_t) s+1] = ny; histDip[3*(size_t) s+2] = nz;
         const double e0 = nx - mu[3*(size_t) s], e1 = ny - mu[3*(size_t) s+1], e2 = nz - mu[3*(size_t) s+2];

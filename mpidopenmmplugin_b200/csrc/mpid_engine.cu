@@ -987,10 +987,11 @@ struct Engine : public EngineBase {
         // the field is consumed at polarizable sites only; everything else stays zero
         CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
         const int* polRows = dPolList.p + polBegin;
+        const bool fuseFinish = numRanks == 1 && !hSpPartner.empty();
         if (numPol > 0) {
             if (pme) LAUNCH((k_fixed_field<real, true>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
             else LAUNCH((k_fixed_field<real, false>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
-            if (!hSpPartner.empty())
+            if (!hSpPartner.empty() && !fuseFinish)
                 LAUNCH((k_special_field<0>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
                        dCartD.p, dDampThole.p, dFlagS.p, (const double*) nullptr, dField.p, (double*) nullptr);
         }
@@ -999,7 +1000,11 @@ struct Engine : public EngineBase {
         // the real-space stage times only its own kernels
         stageBegin(MPIDB200_STAGE_SOLVER);
         if (pme) joinPme();
-        if (numRanks == 1) {
+        if (fuseFinish) {
+            // single rank: covalent-partner field + reciprocal field + self term + mu0 in one per-atom pass
+            LAUNCH((k_special_field_finish<real>), blocksFor(n, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
+                   dCartD.p, dDampThole.p, dFlagS.p, dPhi.p, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
+        } else if (numRanks == 1) {
             LAUNCH((k_fixed_recip_mu<real>), blocksFor(n, 256), 256, P, dPhi.p, dCartD.p, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
         } else {
             if (rows > 0 && pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
@@ -1009,8 +1014,6 @@ struct Engine : public EngineBase {
         stageEnd();
     }
 
-    // Field of the current induced dipoles into dIfield (and gradient into `grad`, which the caller zeroed).
-    // level: highest derivative order gathered from the reciprocal grid (1 field, 2 +gradient, 4 everything)
     // compactReduce (several ranks, DIIS): only the polarizable entries of the partial field are all-reduced, into
     // dFieldCompact (indexed like dPolList); otherwise the whole per-atom vector is reduced in place.
     DevBuf<double> dFieldCompact;

@@ -10,7 +10,7 @@
 //   field/... double   accumulators written by exactly one thread per atom (no atomics)
 //   force/torque/energy  64-bit fixed point (2^32), atomics, order independent => deterministic
 // Neighbour list: full CSR list for the gather-style field kernels, flat i-major half list for the
-// energy kernel.  Entries pack the sorted index of j (27 bits) and the periodic image code (5 bits).
+// energy kernel.  Entries pack the sorted index of j (26 bits), a bare-charge flag and the periodic image code (5 bits).
 #ifndef MPIDB200_KERNELS_CUH_
 #define MPIDB200_KERNELS_CUH_
 
@@ -19,8 +19,9 @@
 
 namespace mpid {
 
-#define MPID_JMASK 0x07FFFFFFu
-#define MPID_CODE_SHIFT 27
+#define MPID_JMASK 0x03FFFFFFu        // sorted index of j: 26 bits (67 M atoms)
+#define MPID_SIMPLE_BIT 0x04000000u   // bit 26: j is a bare charge ("simple" site), so list consumers need not look it up
+#define MPID_CODE_SHIFT 27            // bits 27-31: periodic image code (0..26)
 #define MPID_FIXED_SCALE 4294967296.0
 #define MPID_MAX_HISTORY 20
 
@@ -359,7 +360,7 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
             const unsigned cu = __popc(maskU), cl = __popc(maskL);
             if (nUp + nLow + cu + cl <= cap) {
                 const unsigned lt = (1u << lane) - 1u;
-                const unsigned entry = (unsigned) j | (code << MPID_CODE_SHIFT);
+                const unsigned entry = (unsigned) j | (code << MPID_CODE_SHIFT) | ((jflag & 2) ? MPID_SIMPLE_BIT : 0u);
                 if (upper) base[nUp + __popc(maskU & lt)] = entry;
                 else if (in) base[cap - 1 - (nLow + __popc(maskL & lt))] = entry;
                 if (in && iPol && (jflag & 1)) polBase[nPol + __popc(maskP & lt)] = entry;
@@ -459,7 +460,7 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
                 for (int step = 32; step > 0; step >>= 1) if (r + step < 64 && rBegin[r + step] <= g) r += step;
                 const int j = rJb[r] + (g - rBegin[r]);
                 const float4 p = posF[j];
-                cand[c] = make_float4(p.x + rShift[r][0], p.y + rShift[r][1], p.z + rShift[r][2], __uint_as_float((unsigned) j | (rCode[r] << MPID_CODE_SHIFT)));
+                cand[c] = make_float4(p.x + rShift[r][0], p.y + rShift[r][1], p.z + rShift[r][2], __uint_as_float((unsigned) j | (rCode[r] << MPID_CODE_SHIFT) | (((int) p.w & 2) ? MPID_SIMPLE_BIT : 0u)));
                 cflag[c] = (unsigned char) (int) p.w;
             }
             // pad to a multiple of 64 slots with far-away sentinels so that the pre-test loop needs no bounds check
@@ -599,7 +600,7 @@ __global__ void k_half_compact(DevParams P, const unsigned* __restrict__ nbr, co
         const unsigned k = k0 + lane;
         const bool valid = k < nUp;
         unsigned e = 0; bool sj = false;
-        if (valid) { e = base[k]; sj = (((int) posF[e & MPID_JMASK].w >> 1) & 1) != 0; }
+        if (valid) { e = base[k]; sj = (e & MPID_SIMPLE_BIT) != 0; }
         const unsigned mF = __ballot_sync(FULL, valid && !sj), mS = __ballot_sync(FULL, valid && sj);
         const unsigned lt = (1u << lane) - 1u;
         if (valid && !si && !sj) {
@@ -751,19 +752,33 @@ k_induced_field(DevParams P, int numPol, const int* __restrict__ polList, const 
 // Covalently scaled pairs (1-2, 1-3, 1-4): always FP64, exact reference cutoff test, one thread per
 // atom over its (static) partner list, added on top of what the gather kernels wrote.
 //   MODE 0: permanent field   MODE 1: induced field   MODE 2: induced field + gradient
+// per-atom solver helpers (used from here on)
+__device__ __forceinline__ void applyAlphaLab(const double* a, double fx, double fy, double fz, double& ox, double& oy, double& oz) {
+    ox = a[0]*fx + a[1]*fy + a[2]*fz;
+    oy = a[1]*fx + a[3]*fy + a[4]*fz;
+    oz = a[2]*fx + a[4]*fy + a[5]*fz;
+}
+
+template <typename real>
+__device__ __forceinline__ void reciprocalFieldOf(const DevParams& P, const real* __restrict__ phi, int s, double& fx, double& fy, double& fz) {
+    const double p1 = phi[(size_t) 1*P.n + s], p2 = phi[(size_t) 2*P.n + s], p3 = phi[(size_t) 3*P.n + s];
+    fx = -(p1*P.geom.A[0][0] + p2*P.geom.A[1][0] + p3*P.geom.A[2][0]);
+    fy = -(p1*P.geom.A[0][1] + p2*P.geom.A[1][1] + p3*P.geom.A[2][1]);
+    fz = -(p1*P.geom.A[0][2] + p2*P.geom.A[1][2] + p3*P.geom.A[2][2]);
+}
+
+// Field (MODE 0: of the permanent moments, 1: of the induced dipoles, 2: + its gradient) that the covalently scaled
+// partners of sorted atom s produce at s, in FP64; returns false when s has no such partner.
 template <int MODE>
-__global__ void k_special_field(DevParams P, const int* __restrict__ order, const int* __restrict__ inv,
-                                const double* __restrict__ posOrig, const int* __restrict__ spStart,
-                                const int* __restrict__ spPartner, const int* __restrict__ spClass,
-                                const double* __restrict__ cartD, const double2* __restrict__ dampTholeD, const int* __restrict__ flagS,
-                                const double* __restrict__ mu, double* __restrict__ field, double* __restrict__ grad) {
-    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= P.rowEnd) return;
-    if (!(flagS[s] & 1)) return;            // fields are only consumed at polarizable sites
+__device__ __forceinline__ bool specialFieldAt(const DevParams& P, int s, const int* __restrict__ order, const int* __restrict__ inv,
+                                               const double* __restrict__ posOrig, const int* __restrict__ spStart,
+                                               const int* __restrict__ spPartner, const int* __restrict__ spClass,
+                                               const double* __restrict__ cartD, const double2* __restrict__ dampTholeD,
+                                               const int* __restrict__ flagS, const double* __restrict__ mu,
+                                               double& ex, double& ey, double& ez, double* g) {
     const int o = order[s];
     const int k0 = spStart[o], k1 = spStart[o+1];
-    if (k1 == k0) return;
-    double ex = 0, ey = 0, ez = 0, g[6] = {0, 0, 0, 0, 0, 0};
+    if (k1 == k0) return false;
     const double2 dtI = dampTholeD[s];
     for (int k = k0; k < k1; k++) {
         const int oj = spPartner[k];
@@ -795,8 +810,55 @@ __global__ void k_special_field(DevParams P, const int* __restrict__ order, cons
             if (MODE == 2) inducedFieldGradientDirected<double>(mx, my, mz, dx, dy, dz, c, g);
         }
     }
+    return true;
+}
+
+template <int MODE>
+__global__ void k_special_field(DevParams P, const int* __restrict__ order, const int* __restrict__ inv,
+                                const double* __restrict__ posOrig, const int* __restrict__ spStart,
+                                const int* __restrict__ spPartner, const int* __restrict__ spClass,
+                                const double* __restrict__ cartD, const double2* __restrict__ dampTholeD, const int* __restrict__ flagS,
+                                const double* __restrict__ mu, double* __restrict__ field, double* __restrict__ grad) {
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.rowEnd) return;
+    if (!(flagS[s] & 1)) return;            // fields are only consumed at polarizable sites
+    double ex = 0, ey = 0, ez = 0, g[6] = {0, 0, 0, 0, 0, 0};
+    if (!specialFieldAt<MODE>(P, s, order, inv, posOrig, spStart, spPartner, spClass, cartD, dampTholeD, flagS, mu, ex, ey, ez, g)) return;
     field[3*(size_t) s] += ex; field[3*(size_t) s+1] += ey; field[3*(size_t) s+2] += ez;
     if (MODE == 2) for (int q = 0; q < 6; q++) grad[6*(size_t) s + q] += g[q];
+}
+
+// Single rank: the covalent-partner part of the permanent field and everything that follows it per atom in one pass
+// -- + reciprocal field + self term, efix = alpha.E, mu0 = efix (k_special_field<0> + k_fixed_recip_mu).  The short
+// per-atom kernel otherwise sits on the critical path behind the resident CTAs of the side-stream pair kernels.
+template <typename real>
+__global__ void k_special_field_finish(DevParams P, const int* __restrict__ order, const int* __restrict__ inv,
+                                       const double* __restrict__ posOrig, const int* __restrict__ spStart,
+                                       const int* __restrict__ spPartner, const int* __restrict__ spClass,
+                                       const double* __restrict__ cartD, const double2* __restrict__ dampTholeD, const int* __restrict__ flagS,
+                                       const real* __restrict__ phi, const double* __restrict__ alphaLab, const double* __restrict__ field,
+                                       double* __restrict__ efix, double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= P.n) return;
+    double ox = 0, oy = 0, oz = 0;
+    if (flagS[s] & 1) {
+        double ex = 0, ey = 0, ez = 0;
+        specialFieldAt<0>(P, s, order, inv, posOrig, spStart, spPartner, spClass, cartD, dampTholeD, flagS, (const double*) nullptr, ex, ey, ez, (double*) nullptr);
+        double fx = field[3*(size_t) s] + ex, fy = field[3*(size_t) s+1] + ey, fz = field[3*(size_t) s+2] + ez;
+        if (P.method == PME) {
+            double rx, ry, rz;
+            reciprocalFieldOf<real>(P, phi, s, rx, ry, rz);
+            fx += rx + P.selfFieldTerm*cartD[20*(size_t) s+1];
+            fy += ry + P.selfFieldTerm*cartD[20*(size_t) s+2];
+            fz += rz + P.selfFieldTerm*cartD[20*(size_t) s+3];
+        }
+        applyAlphaLab(alphaLab + 6*(size_t) s, fx, fy, fz, ox, oy, oz);
+    }
+    efix[3*(size_t) s] = ox; efix[3*(size_t) s+1] = oy; efix[3*(size_t) s+2] = oz;
+    mu[3*(size_t) s] = ox; mu[3*(size_t) s+1] = oy; mu[3*(size_t) s+2] = oz;
+    typename Real4<real>::type m = mud[s];
+    m.x = (real) ox; m.y = (real) oy; m.z = (real) oz;
+    mud[s] = m;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1358,20 +1420,6 @@ k_gather(DevParams P, int numRows, const int* __restrict__ rowList, int recBase,
 // ---------------------------------------------------------------------------------------------------
 // Stage 6: per-atom solver arithmetic
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void applyAlphaLab(const double* a, double fx, double fy, double fz, double& ox, double& oy, double& oz) {
-    ox = a[0]*fx + a[1]*fy + a[2]*fz;
-    oy = a[1]*fx + a[3]*fy + a[4]*fz;
-    oz = a[2]*fx + a[4]*fy + a[5]*fz;
-}
-
-template <typename real>
-__device__ __forceinline__ void reciprocalFieldOf(const DevParams& P, const real* __restrict__ phi, int s, double& fx, double& fy, double& fz) {
-    const double p1 = phi[(size_t) 1*P.n + s], p2 = phi[(size_t) 2*P.n + s], p3 = phi[(size_t) 3*P.n + s];
-    fx = -(p1*P.geom.A[0][0] + p2*P.geom.A[1][0] + p3*P.geom.A[2][0]);
-    fy = -(p1*P.geom.A[0][1] + p2*P.geom.A[1][1] + p3*P.geom.A[2][1]);
-    fz = -(p1*P.geom.A[0][2] + p2*P.geom.A[1][2] + p3*P.geom.A[2][2]);
-}
-
 // E_fixed += reciprocal + self for the rows this rank owns   (:2922-2949)
 template <typename real>
 __global__ void k_fixed_recip(DevParams P, const real* __restrict__ phi, const double* __restrict__ cartD, double* __restrict__ field) {

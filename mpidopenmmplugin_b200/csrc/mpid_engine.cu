@@ -186,7 +186,11 @@ struct Engine : public EngineBase {
     int numPol = 0, polBegin = 0;   // polarizable sites among this rank's rows
     long long typeBegin[6] = {0, 0, 0, 0, 0, 0};   // boundaries of the four pair-class lists inside pairI/pairJ
     DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
-    DevBuf<unsigned long long> dForce, dTorque, dEnergy;
+    // force[3n], torque[3n], energy[2] in ONE allocation: one memset per evaluation, one all-reduce with several ranks
+    DevBuf<unsigned long long> dAccum;
+    unsigned long long* forceP() { return dAccum.p; }
+    unsigned long long* torqueP() { return dAccum.p + 3*(size_t) n; }
+    unsigned long long* energyP() { return dAccum.p + 6*(size_t) n; }
     DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp, dThetaPol;
     DevBuf<int4> dIgridPol;
     DevBuf<cplx> dGridC;
@@ -828,8 +832,8 @@ struct Engine : public EngineBase {
             LAUNCH(k_half_compact, std::min(sideCtas, blocksFor((long long) rows*32, B)), B, P, dNbr.p, dCounts.p, dPosF.p, dTypeStart.p, rows, 0u, 0u, 0u, (unsigned) pairCap, dPairI.p, dPairJ.p);
         if (numSimple > 0) {
             const int nbS = std::min(sideCtas, blocksFor((long long) numSimple*MPID_LANES, 256));
-            if (pme) LAUNCH((k_simple_pairs<real, true>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
-            else LAUNCH((k_simple_pairs<real, false>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, dForce.p, dEnergy.p);
+            if (pme) LAUNCH((k_simple_pairs<real, true>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, forceP(), energyP());
+            else LAUNCH((k_simple_pairs<real, false>), nbS, 256, P, numSimple, dSimpleList.p + simpleBegin, dPosS.p, pkR(), dCounts.p, dNbr.p, forceP(), energyP());
         }
         cur = keep;
         forked3 = true;
@@ -1324,10 +1328,8 @@ struct Engine : public EngineBase {
         fixedReciprocalStart();                    // stream 2, beside the neighbour search
         buildNeighborList(dPosIn);
         CUDA_CHECK(cudaStreamWaitEvent(stream, evFrames, 0));      // lab-frame moments (second stream) before any pair kernel
-        dForce.ensure(3*(size_t) n); dTorque.ensure(3*(size_t) n); dEnergy.ensure(2);
-        CUDA_CHECK(cudaMemsetAsync(dForce.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
-        CUDA_CHECK(cudaMemsetAsync(dTorque.p, 0, 3*(size_t) n*sizeof(unsigned long long), stream));
-        CUDA_CHECK(cudaMemsetAsync(dEnergy.p, 0, 2*sizeof(unsigned long long), stream));
+        dAccum.ensure(6*(size_t) n + 2);
+        CUDA_CHECK(cudaMemsetAsync(dAccum.p, 0, (6*(size_t) n + 2)*sizeof(unsigned long long), stream));
         const int rows = P.rowEnd - P.rowBegin;
         if (!dipolesOnly) startDipoleIndependentPairs();      // stream 3, beside the field and solver stages
 
@@ -1377,19 +1379,19 @@ struct Engine : public EngineBase {
             cur = stream3;
             if (ns > 0) {
                 if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                                   dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+                                   dPkD.p, dDampThole.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP());
                 else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                            dPkD.p, dDampThole.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+                            dPkD.p, dDampThole.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP());
             }
             cur = stream2;
             if (pme && rows > 0)
-                LAUNCH((k_reciprocal_terms<real>), blocksFor(rows, 128), 128, P, dPhi.p, dPhidp.p, dCartD.p, dSphD.p, dMu.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p);
+                LAUNCH((k_reciprocal_terms<real>), blocksFor(rows, 128), 128, P, dPhi.p, dPhidp.p, dCartD.p, dSphD.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP());
             // full x full pairs: quasi-internal frame kernel over the flat half list
             // launch sized for the capacity of the flat list when the count is still on its way from the device
             const long long cnt = nlSpeculative ? (long long) pairCap : typeBegin[1];
             const unsigned* dyn = dTypeStart.p + (size_t) (P.rowEnd - P.rowBegin) + 1;      // start of class 1 = number of full-full pairs
 #define ES_LAUNCH(EW, MU) { if (cnt > 0) LAUNCH((k_electrostatics<real, EW, MU, false, false>), blocksFor(cnt, 128), 128, P, cnt, dyn, dPairI.p, dPairJ.p, \
-                                dPosS.p, pkR(), dMud.p, dAniso.p, dForce.p, dTorque.p, dEnergy.p); }
+                                dPosS.p, pkR(), dMud.p, dAniso.p, forceP(), torqueP(), energyP()); }
             if (pme) { if (mutual) ES_LAUNCH(true, true) else ES_LAUNCH(true, false) }
             else { if (mutual) ES_LAUNCH(false, true) else ES_LAUNCH(false, false) }
 #undef ES_LAUNCH
@@ -1398,8 +1400,8 @@ struct Engine : public EngineBase {
         // full x bare-charge pairs: gathered from the full site (Cartesian form)
         if (numFull > 0 && numSimpleTotal > 0) {
             const int nbF = blocksFor((long long) numFull*MPID_LANES, 256);
-            if (pme) LAUNCH((k_charge_site_pairs<real, true>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
-            else LAUNCH((k_charge_site_pairs<real, false>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, dForce.p, dTorque.p, dEnergy.p);
+            if (pme) LAUNCH((k_charge_site_pairs<real, true>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, forceP(), torqueP(), energyP());
+            else LAUNCH((k_charge_site_pairs<real, false>), nbF, 256, P, numFull, dFullList.p + fullBegin, dPosS.p, pkR(), dMud.p, dAniso.p, dCounts.p, dNbr.p, forceP(), torqueP(), energyP());
         }
         CUDA_CHECK(cudaEventRecord(evJoin3, stream3));
         CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin3, 0));
@@ -1424,19 +1426,17 @@ struct Engine : public EngineBase {
                 L.dip[k] = dPtDip.p + (size_t) k*3*n; L.part[k] = optPart[k];
                 L.field[k] = dPtField.p + (size_t) k*3*n; L.grad[k] = dPtGrad.p + (size_t) k*6*n;
             }
-            LAUNCH(k_opt_force, blocksFor(rows, 128), 128, P, L, dAniso.p, dForce.p, dTorque.p);
+            LAUNCH(k_opt_force, blocksFor(rows, 128), 128, P, L, dAniso.p, forceP(), torqueP());
         }
         if (numRanks > 1) {
-            allReduce(dForce.p, 3*(size_t) n, NCCL_UINT64);
-            allReduce(dTorque.p, 3*(size_t) n, NCCL_UINT64);
-            allReduce(dEnergy.p, 1, NCCL_UINT64);
+            allReduce(dAccum.p, 6*(size_t) n + 1, NCCL_UINT64);      // forces, torques, energy: 64-bit integers, order independent
         }
         if (includeForces) {
-            LAUNCH(k_torque_to_force, blocksFor(n, 128), 128, P, particleParams(), dOrder.p, dInv.p, dPosIn, dTorque.p, dForce.p);
-            LAUNCH(k_output_forces, blocksFor(n, 256), 256, n, dOrder.p, dForce.p, dForcesOut);
+            LAUNCH(k_torque_to_force, blocksFor(n, 128), 128, P, particleParams(), dOrder.p, dInv.p, dPosIn, torqueP(), forceP());
+            LAUNCH(k_output_forces, blocksFor(n, 256), 256, n, dOrder.p, forceP(), dForcesOut);
         }
         unsigned long long* he = (unsigned long long*) hPinned;
-        CUDA_CHECK(cudaMemcpyAsync(he, dEnergy.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaMemcpyAsync(he, energyP(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         stageEnd();
         CUDA_CHECK(cudaStreamSynchronize(stream));
         collectTimings();

@@ -46,7 +46,7 @@ def collectives_per_evaluation(polarization, field_evaluations, pme=True, world=
         out.append(("partial induced field", 3, 8))
         if polarization == 2:
             out.append(("partial induced field gradient", 6, 8))
-    out += [("forces", 3, 8), ("torques", 3, 8), ("energy", 0, 8)]
+    out.append(("forces + torques + energy (one buffer of 64-bit integers)", 6, 8))
     return out
 
 

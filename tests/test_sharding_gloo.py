@@ -74,15 +74,15 @@ def test_two_rank_partition_and_plumbing(n):
 
 
 def test_collective_inventory_matches_the_engine():
-    """Mutual, PME, 6 field evaluations: fixed field + fixed grid + 6 x (grid + field) + forces/torques/energy; from
+    """Mutual, PME, 6 field evaluations: fixed field + fixed grid + 6 x (grid + field) + one force/torque/energy buffer; from
     4 ranks on every grid all-reduce becomes reduce-scatter + two all-to-all transposes + all-gather."""
     c = sharding.collectives_per_evaluation(0, 6, pme=True, world=2)
-    assert len(c) == 2 + 12 + 3
+    assert len(c) == 2 + 12 + 1
     assert sum(1 for w in c if w[0] == "partial induced field") == 6
     c = sharding.collectives_per_evaluation(2, 3, pme=True, world=2)
     assert sum(1 for w in c if w[0] == "partial induced field gradient") == 3
     c = sharding.collectives_per_evaluation(0, 6, pme=True, world=8, grid=(224, 224, 224))
-    assert len(c) == 1 + 4 + 6*(4 + 1) + 3
+    assert len(c) == 1 + 4 + 6*(4 + 1) + 1
     assert sum(1 for w in c if w[0].endswith("all-to-all")) == 7
     assert not sharding.uses_slab_fft(8, (225, 224, 224)) and not sharding.uses_slab_fft(2, (224, 224, 224))
 

@@ -14,6 +14,10 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, data = rows[0], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
+    for i, h in enumerate(hdr):          # newer ncu prefixes some columns with their section ("X.Y.metric"): index by bare metric name too
+        m = re.search(r"([a-z0-9_]+__[A-Za-z0-9_.]+)$", h)
+        if m and m.group(1) not in idx:
+            idx[m.group(1)] = i
     stall = [h for h in hdr if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
 
     def g(d, key, scale=1.0, fmt="%.1f"):

@@ -251,6 +251,7 @@ struct Engine : public EngineBase {
         destroySlabPlans();
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
+        if (evEnergyDone) { cudaEventDestroy(evEnergyDone); for (int c = 0; c < kHostChunks; c++) cudaEventDestroy(evChunk[c]); }
         if (hDiis) cudaFreeHost(hDiis);
         if (hCg) cudaFreeHost(hCg);
         if (iterGraph) cudaGraphExecDestroy(iterGraph);
@@ -1438,45 +1439,89 @@ struct Engine : public EngineBase {
         unsigned long long* he = (unsigned long long*) hPinned;
         CUDA_CHECK(cudaMemcpyAsync(he, energyP(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         stageEnd();
-        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (readbackPending && includeForces) {
+            // host-buffer call: the forces follow the energy in chunks; the caller adds chunk k into its array while
+            // chunk k+1 is still on the bus, so only the energy is waited for here
+            CUDA_CHECK(cudaEventRecord(evEnergyDone, stream));
+            enqueueForceReadback(dForcesOut);
+            CUDA_CHECK(cudaEventSynchronize(evEnergyDone));
+        } else CUDA_CHECK(cudaStreamSynchronize(stream));
         collectTimings();
         if (tracing) { traceDump(); tracing = false; }
         if (energy) *energy = includeEnergy ? (double) ((long long) he[0])*(1.0/MPID_FIXED_SCALE) : 0.0;
     }
 
-    const double* stagePositions(const double* pos, bool onDevice) {
-        if (onDevice) return pos;
-        size_t bytes = 3*(size_t) n*sizeof(double);
+    // ---- host-buffer entry (mpidb200_execute): positions in, forces accumulated out, both pipelined in chunks ----
+    static const int kHostChunks = 4;
+    cudaEvent_t evEnergyDone = nullptr, evChunk[kHostChunks] = {nullptr, nullptr, nullptr, nullptr};
+    bool readbackPending = false;
+    static void chunkRange(size_t count, int c, size_t& begin, size_t& end) {
+        const int chunks = count >= 65536 ? kHostChunks : 1;
+        begin = c < chunks ? count*c/chunks : count;
+        end = c < chunks ? count*(c + 1)/chunks : count;
+    }
+    void ensureHostStage(size_t bytes) {
         if (hPinnedPosCap < bytes) {
             if (hPinnedPos) cudaFreeHost(hPinnedPos);
             CUDA_CHECK(cudaMallocHost((void**) &hPinnedPos, 2*bytes));
             hPinnedPosCap = bytes;
         }
-        memcpy(hPinnedPos, pos, bytes);
-        dPos.ensure(3*(size_t) n);
-        CUDA_CHECK(cudaMemcpyAsync(dPos.p, hPinnedPos, bytes, cudaMemcpyHostToDevice, stream));
+        if (!evEnergyDone) {
+            CUDA_CHECK(cudaEventCreateWithFlags(&evEnergyDone, cudaEventDisableTiming));
+            for (int c = 0; c < kHostChunks; c++) CUDA_CHECK(cudaEventCreateWithFlags(&evChunk[c], cudaEventDisableTiming));
+        }
+    }
+    const double* stagePositions(const double* pos, bool onDevice) {
+        if (onDevice) return pos;
+        const size_t count = 3*(size_t) n;
+        ensureHostStage(count*sizeof(double));
+        dPos.ensure(count);
+        // the copy of chunk k into pinned memory overlaps the transfer of chunk k-1
+        for (int c = 0; c < kHostChunks; c++) {
+            size_t b, e;
+            chunkRange(count, c, b, e);
+            if (e == b) continue;
+            memcpy(hPinnedPos + b, pos + b, (e - b)*sizeof(double));
+            CUDA_CHECK(cudaMemcpyAsync(dPos.p + b, hPinnedPos + b, (e - b)*sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
         return dPos.p;
+    }
+    void enqueueForceReadback(const double* dSrc) {
+        const size_t count = 3*(size_t) n;
+        double* stage = hPinnedPos + count;
+        for (int c = 0; c < kHostChunks; c++) {
+            size_t b, e;
+            chunkRange(count, c, b, e);
+            if (e > b) CUDA_CHECK(cudaMemcpyAsync(stage + b, dSrc + b, (e - b)*sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaEventRecord(evChunk[c], stream));
+        }
     }
 
     void execute(const double* pos, bool onDevice, bool includeForces, bool includeEnergy, double* energy, double* forces) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
         const double* dp = stagePositions(pos, onDevice);
-        size_t bytes = 3*(size_t) n*sizeof(double);
+        const size_t count = 3*(size_t) n;
         double* df = nullptr;
         if (includeForces) {
             if (onDevice) df = forces;
             else {
-                dForcesOut.ensure(3*(size_t) n);
-                CUDA_CHECK(cudaMemsetAsync(dForcesOut.p, 0, bytes, stream));
+                dForcesOut.ensure(count);
+                CUDA_CHECK(cudaMemsetAsync(dForcesOut.p, 0, count*sizeof(double), stream));
                 df = dForcesOut.p;
             }
         }
-        evaluate(dp, includeForces, includeEnergy, energy, df, false);
-        if (includeForces && !onDevice) {
-            double* stage = hPinnedPos + 3*(size_t) n;
-            CUDA_CHECK(cudaMemcpyAsync(stage, dForcesOut.p, bytes, cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaStreamSynchronize(stream));
-            for (size_t k = 0; k < 3*(size_t) n; k++) forces[k] += stage[k];   // accumulate (MPIDReferenceKernels.cpp:229-238)
+        readbackPending = includeForces && !onDevice;
+        try { evaluate(dp, includeForces, includeEnergy, energy, df, false); }
+        catch (...) { readbackPending = false; throw; }
+        if (readbackPending) {
+            readbackPending = false;
+            const double* stage = hPinnedPos + count;
+            for (int c = 0; c < kHostChunks; c++) {
+                size_t b, e;
+                chunkRange(count, c, b, e);
+                CUDA_CHECK(cudaEventSynchronize(evChunk[c]));
+                for (size_t k = b; k < e; k++) forces[k] += stage[k];   // accumulate (MPIDReferenceKernels.cpp:229-238)
+            }
         }
     }
 

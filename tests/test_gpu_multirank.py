@@ -1,0 +1,30 @@
+"""Several ranks against one (needs >= 2 visible GPUs; skipped on a single-GPU box): tools/multirank_check.py under
+torch.distributed.run compares forces, induced dipoles and energy of the row-partitioned engine -- both reciprocal-pass
+strategies, all three polarization types -- with the single-GPU engine on the same box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ranks_reproduce_the_single_gpu_evaluation(world):
+    if _gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    # 64^3 grid at 2x2x2 tiles: divisible by 2 and 4, so the slab pass is exercised at both rank counts
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29530 + world), os.path.join(ROOT, "tools", "multirank_check.py"), "2x2x2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert len(lines) == 6 and all(l["ok"] for l in lines), lines

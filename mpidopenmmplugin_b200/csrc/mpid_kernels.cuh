@@ -1343,7 +1343,9 @@ __global__ void k_eterm_table(DevParams P, const double* __restrict__ modX, cons
 // k_spline_weights (record recBase + t, LEVEL <= 2); otherwise weights are built here from the positions.
 // (A six-lanes-per-atom variant, one x plane per lane with a shuffle reduction, was measured slower on B200 -- 22 us
 // against 16 us for the field-only gather, 79 us against 40 us for all 35 derivatives -- although it exposes six
-// times the loads: the kernel is bound by L1 sector traffic, 36 sectors per atom whichever way they are issued.)
+// times the loads: the kernel is bound by L1 sector traffic, 36 sectors per atom whichever way they are issued.
+// Reading each row as the two or three aligned quads that cover it, with z weights shifted to the quad origin, was
+// measured too: 1.628 ms per evaluation against 1.546 ms -- 94 instead of 80 registers for the field-only gather.)
 //   reference: computeFixedPotentialFromGrid (:3368-3530), computeInducedPotentialFromGrid (:3575-3737)
 template <typename real, int LEVEL, bool POL>
 __global__ void __launch_bounds__(128)

@@ -94,8 +94,17 @@ class MPIDForce:
         self._scale14 = 1.0
         self._coefs = [-0.154, 0.017, 0.658, 0.474]
         self._multipoles = []
+        self._force_group = 0          # OpenMM::Force::getForceGroup / setForceGroup
 
     # ---- global settings ----------------------------------------------------------------------------
+    def getForceGroup(self):
+        return self._force_group
+
+    def setForceGroup(self, group):
+        if group < 0 or group > 31:
+            raise MPIDB200Error("Force group must be between 0 and 31")
+        self._force_group = int(group)
+
     def getNonbondedMethod(self):
         return self._method
 

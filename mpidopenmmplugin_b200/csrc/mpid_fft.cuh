@@ -311,6 +311,8 @@ __device__ __forceinline__ void fft2LoadTable(float2* dst, int len, const float2
 }
 
 // real grid plane x -> half-complex plane x.  Dynamic shared memory: (2 NY MC + NY + 2 M) float2, M = NZ/2, MC = M+1.
+// (Clearing each plane here after it is read, so that the next spreading pass needs no memset in front of it and the
+// backward transform writes to a second grid, was measured: 1.639 ms per evaluation against 1.546 ms with the memset.)
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
 k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw) {

@@ -382,6 +382,9 @@ k_neighbor_list(DevParams P, const float4* __restrict__ posF, const double* __re
 // cell.  All atoms of a cell share the same candidate set, so the CTA stages the (image-shifted) candidate
 // positions of the neighbouring cells in shared memory once and each warp then scans them for one atom of the
 // cell with full lane utilisation.  Output layout and pair set are identical to k_neighbor_list.
+// (Eight warps per CTA: a cell of liquid water holds 6.6 atoms, 78 % of the cells finish in one round.  Twelve warps --
+// 98 % in one round, queue in dynamic shared memory -- was measured slower, 1.619 against 1.546 ms per evaluation: the
+// extra warps mostly idle at the barrier and cost a resident CTA per SM.)
 #define MPID_NL_MAXC 1280
 #define MPID_NL_MAXI 64
 __global__ void __launch_bounds__(256)

@@ -238,6 +238,14 @@ class MPIDForce:
     def getPMEParametersInContext(self, kernel):
         return kernel.getPMEParameters()
 
+    def getElectrostaticPotential(self, inputGrid, kernel, positions):
+        """MPIDForce::getElectrostaticPotential(inputGrid, context, out) (MPIDForce.h): potential at the grid points, kJ/mol/e."""
+        return kernel.getElectrostaticPotential(positions, inputGrid)
+
+    def getSystemMultipoleMoments(self, kernel, positions, masses):
+        """MPIDForce::getSystemMultipoleMoments(context, out): charge, dipole (Debye), quadrupole (Debye.Angstrom), 13 values."""
+        return kernel.getSystemMultipoleMoments(positions, masses)
+
     def updateParametersInContext(self, kernel):
         kernel.copyParametersToContext(self)
 

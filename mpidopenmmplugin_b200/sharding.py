@@ -116,3 +116,90 @@ def max_over_ranks(dist, values, device=None):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(v) for v in t.cpu()]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Next step for the reciprocal pass: halo exchange instead of reduce-scatter + all-gather of the full grid.
+# Host-side model of the partition and the data movement; the device path is not built yet.
+# ---------------------------------------------------------------------------------------------------------------------
+PME_ORDER = 6
+
+
+def grid_plane_of(frac, nx):
+    """Last of the six x planes an atom with wrapped fractional coordinate `frac` in [0,1) spreads to.  The reference shifts
+    the grid origin by half a box: fr = nx (f - round(f) + 0.5) (computeMPIDBsplines, MPIDReferenceForce.cpp:3049-3075;
+    mpid_math.h: pmeAtomCell), so plane = floor(nx ((frac + 0.5) mod 1)); the support is plane-5 .. plane (mod nx)."""
+    u = (np.asarray(frac, dtype=float) + 0.5) % 1.0
+    return np.minimum((u*nx).astype(int), nx - 1)
+
+
+def halo_plan(nx, ncx, world):
+    """Plane-aligned partition for `world` ranks: rank r takes the cell columns [cell_lo[r], cell_hi[r]) of the x-major
+    sort (so its atoms are one contiguous range of sorted rows, as now) and owns the nx/world planes starting at
+    block_start[r] -- the uniform blocks of the slab transform, rotated by half a box like the grid origin.  halo_lo /
+    halo_hi = how many planes below / above its block the atoms of a rank can reach (spline support + one cell column of
+    slack from rounding the cell boundaries), which is what has to be exchanged with the neighbouring ranks."""
+    if nx % world or world % 2:
+        raise ValueError("halo plan needs an even rank count that divides nx")
+    nxl = nx//world
+    rot = nx//2                                            # = (world/2) blocks: block r of the transform is rank r's
+    cell_lo = [(r*ncx)//world for r in range(world)]
+    cell_hi = cell_lo[1:] + [ncx]
+    block_start = [(r*nxl + rot) % nx for r in range(world)]
+    lo = hi = 0
+    for r in range(world):
+        # extreme fractional coordinates of the rank's cells (upper end exclusive)
+        first = grid_plane_of(cell_lo[r]/ncx, nx) - (PME_ORDER - 1)
+        last = grid_plane_of(np.nextafter(cell_hi[r]/ncx, 0.0), nx)
+        lo = max(lo, (block_start[r] - first) % nx if first != block_start[r] else 0)
+        hi = max(hi, (last - (block_start[r] + nxl - 1)) % nx if (last - block_start[r]) % nx >= nxl else 0)
+    if max(lo, hi) > nxl:
+        raise ValueError("halo wider than a slab: too many ranks for this grid")
+    return dict(world=world, nx=nx, nxl=nxl, rot=rot, cell_lo=cell_lo, cell_hi=cell_hi, block_start=block_start, halo_lo=int(lo), halo_hi=int(hi))
+
+
+def halo_reciprocal_pass(partial_grids, eterm, plan):
+    """numpy model of the reciprocal pass with halo exchange.  partial_grids[r]: rank r's full-size array holding its own
+    atoms' spread (non-zero only on its block and halo).  Steps: (1) every rank adds the halo planes its two neighbours
+    spread into its block; (2) slab transform on the owned blocks (2-D transforms, all-to-all, x transforms + influence
+    function, all-to-all back); (3) every rank fetches the halo planes of the result from its neighbours.  Returns, per
+    rank, a full-size array that is valid on that rank's block and halo (NaN elsewhere)."""
+    R, nx, nxl = plan["world"], plan["nx"], plan["nxl"]
+    lo, hi, start = plan["halo_lo"], plan["halo_hi"], plan["block_start"]
+    ny, nz = partial_grids[0].shape[1:]
+    planes = lambda first, count: [(first + k) % nx for k in range(count)]
+    # (1) halo reduce: rank r's block receives what rank r+1 spread below its own block and rank r-1 above its own
+    owned = []
+    for r in range(R):
+        block = planes(start[r], nxl)
+        acc = partial_grids[r][block].copy()
+        up, down = (r + 1) % R, (r - 1) % R
+        send_from_up = planes(start[up] - lo, lo)                       # the low halo of rank r+1 = top planes of block r
+        acc[nxl - lo:] += partial_grids[up][send_from_up]
+        send_from_down = planes(start[down] + nxl, hi)                  # the high halo of rank r-1 = first planes of block r
+        acc[:hi] += partial_grids[down][send_from_down]
+        owned.append(acc)
+    # (2) slab transform; block r holds planes start[r].. so the natural x order is a rotation of the rank order
+    spec = [np.fft.rfft2(b, axes=(1, 2)) for b in owned]
+    nzc = nz//2 + 1
+    nyl = ny//R
+    full = np.empty((nx, ny, nzc), dtype=complex)
+    for r in range(R):
+        full[planes(start[r], nxl)] = spec[r]                            # what the all-to-all assembles, ky rows split below
+    out_blocks = [np.empty((nxl, ny, nzc), dtype=complex) for _ in range(R)]
+    for q in range(R):                                                   # rank q transforms its ky rows along x
+        rows = slice(q*nyl, (q + 1)*nyl)
+        f = np.fft.ifft(np.fft.fft(full[:, rows, :], axis=0)*eterm[:, rows, :], axis=0)*nx
+        for r in range(R):
+            out_blocks[r][:, rows, :] = f[planes(start[r], nxl)]         # all-to-all back
+    real_blocks = [np.fft.irfft2(b, s=(ny, nz), axes=(1, 2))*(ny*nz) for b in out_blocks]
+    # (3) halo gather
+    result = []
+    for r in range(R):
+        g = np.full((nx, ny, nz), np.nan)
+        g[planes(start[r], nxl)] = real_blocks[r]
+        down, up = (r - 1) % R, (r + 1) % R
+        g[planes(start[r] - lo, lo)] = real_blocks[down][nxl - lo:]
+        g[planes(start[r] + nxl, hi)] = real_blocks[up][:hi]
+        result.append(g)
+    return result

@@ -100,3 +100,47 @@ def test_slab_reciprocal_pass_equals_the_full_transform(world, shape):
     # irfftn drops the imaginary parts a C2R transform drops, so both sides treat a non-Hermitian product alike
     got = sharding.slab_reciprocal_pass(parts, eterm)
     assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("world,nx,ncx", [(2, 32, 7), (4, 32, 9), (8, 224, 54), (4, 64, 15)])
+def test_halo_plan_covers_every_atom_of_a_rank(world, nx, ncx):
+    """The plane-aligned partition planned for the halo-exchange reciprocal pass: every plane an atom of rank r spreads to
+    lies in r's block or its halo, the halo is the spline support plus at most one cell column, and it fits in a slab."""
+    plan = sharding.halo_plan(nx, ncx, world)
+    assert plan["halo_lo"] <= sharding.PME_ORDER - 1 + -(-nx//ncx) + 1 and plan["halo_hi"] <= 1
+    rng = np.random.default_rng(3)
+    f = rng.random(20000)
+    cell = np.minimum((f*ncx).astype(int), ncx - 1)
+    last = sharding.grid_plane_of(f, nx)
+    for r in range(world):
+        mine = (cell >= plan["cell_lo"][r]) & (cell < plan["cell_hi"][r])
+        allowed = {(plan["block_start"][r] - plan["halo_lo"] + k) % nx for k in range(plan["halo_lo"] + plan["nxl"] + plan["halo_hi"])}
+        touched = {int((p - k) % nx) for p in last[mine] for k in range(sharding.PME_ORDER)}
+        assert touched <= allowed, (r, sorted(touched - allowed))
+    assert sorted(plan["cell_lo"]) == plan["cell_lo"] and plan["cell_hi"][-1] == ncx
+    if world == 8 and nx == 224:
+        assert plan["halo_lo"] <= 11 and plan["nxl"] == 28          # 1,024,884-atom box: 11 + 28 + 1 planes instead of 224
+
+
+@pytest.mark.parametrize("world,nx,ncx", [(2, 32, 7), (4, 32, 9), (4, 64, 15)])
+def test_halo_reciprocal_pass_equals_the_full_transform(world, nx, ncx):
+    """Halo reduce -> slab transform on rotated blocks -> halo gather reproduces the full reciprocal pass on every plane a
+    rank needs (its block and halo), for atoms spread with a 6-point support under the planned partition."""
+    plan = sharding.halo_plan(nx, ncx, world)
+    ny, nz = 4*world, 6
+    rng = np.random.default_rng(11)
+    f = rng.random(300)
+    cell = np.minimum((f*ncx).astype(int), ncx - 1)
+    last = sharding.grid_plane_of(f, nx)
+    parts = [np.zeros((nx, ny, nz)) for _ in range(world)]
+    for a in range(len(f)):
+        r = next(q for q in range(world) if plan["cell_lo"][q] <= cell[a] < plan["cell_hi"][q])
+        for k in range(sharding.PME_ORDER):
+            parts[r][(last[a] - k) % nx] += rng.normal(size=(ny, nz))
+    eterm = rng.uniform(0.1, 1.0, size=(nx, ny, nz//2 + 1))
+    ref = np.fft.irfftn(eterm*np.fft.rfftn(np.sum(parts, axis=0)), s=(nx, ny, nz), axes=(0, 1, 2))*(nx*ny*nz)
+    got = sharding.halo_reciprocal_pass(parts, eterm, plan)
+    for r in range(world):
+        need = [(plan["block_start"][r] - plan["halo_lo"] + k) % nx for k in range(plan["halo_lo"] + plan["nxl"] + plan["halo_hi"])]
+        assert np.allclose(got[r][need], ref[need], rtol=1e-9, atol=1e-9), r
+        assert np.isnan(got[r]).sum() == (nx - len(set(need)))*ny*nz

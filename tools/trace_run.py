@@ -10,7 +10,7 @@ import torch
 from mpidopenmmplugin_b200.workloads import water_box, make_kernel
 
 tiles = {"996": (1, 1, 1), "96k": (4, 4, 2), "1m": (7, 7, 7)}[sys.argv[1] if len(sys.argv) > 1 else "96k"]
-s = water_box(tiles, polarization=0, epsilon=1e-5)
+s = water_box(tiles, polarization=int(os.environ.get("MPIDB200_POL", "0")), epsilon=1e-5)      # 0 Mutual, 1 Direct, 2 Extrapolated
 k = make_kernel(s, solver=os.environ.get("MPIDB200_SOLVER", "diis"))
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)

@@ -226,6 +226,7 @@ class ForceField:
         for i, j in bonds:
             adj[local[i]].add(local[j]); adj[local[j]].add(local[i])
         elems = [top.elements[a] for a in atoms]
+        found = []
         for tpl in self.templates.values():
             if len(tpl.atoms) != len(atoms) or len(tpl.bonds) != len(bonds):
                 continue
@@ -237,8 +238,17 @@ class ForceField:
                 tadj[i].add(j); tadj[j].add(i)
             assign = self._isomorphism(telems, tadj, elems, adj)
             if assign is not None:
-                return tpl, [atoms[k] for k in assign]
-        return None, None
+                found.append((tpl, [atoms[k] for k in assign]))
+        if not found:
+            return None, None
+        # several templates with the same graph are fine only if they give every atom the same type (openmm.app refuses
+        # to choose between templates as well)
+        def typing(match):
+            tpl, order = match
+            return sorted(zip(order, (t for _, t in tpl.atoms)))
+        if any(typing(m) != typing(found[0]) for m in found[1:]):
+            raise ValueError("Multiple matching templates found for a residue: " + ", ".join(m[0].name for m in found))
+        return found[0]
 
     @staticmethod
     def _isomorphism(telems, tadj, elems, adj):

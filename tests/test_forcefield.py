@@ -137,6 +137,21 @@ def test_residue_matched_by_its_bond_graph():
     assert f.getMultipoleParameters(1)[4] == MPIDForce.ThreeFold and sorted(f.getMultipoleParameters(1)[5:8]) == [0, 2, 3]
 
 
+def test_ambiguous_templates_are_refused():
+    """Two templates with the same bond graph but different atom types: nothing decides between them."""
+    twin = XML.replace('<Residue name="AR"><Atom name="AR" type="X"/></Residue>',
+                       '<Residue name="AR"><Atom name="AR" type="X"/></Residue>'
+                       '<Residue name="ND3"><Atom name="N" type="N"/><Atom name="D1" type="HO"/><Atom name="D2" type="HN"/><Atom name="D3" type="HN"/>'
+                       '<Bond from="0" to="1"/><Bond from="0" to="2"/><Bond from="0" to="3"/></Residue>')
+    top = FF.Topology()
+    idx = top.add_residue("UNK", [("Q2", "N", None), ("Q1", "H", None), ("Q3", "H", None), ("Q4", "H", None)])
+    for h in idx[1:]:
+        top.add_bond(idx[0], h)
+    with pytest.raises(ValueError, match="Multiple matching templates"):
+        FF.ForceField(twin).create_mpid_force(top)
+    FF.ForceField(XML).create_mpid_force(top)          # with one candidate the same residue is fine
+
+
 def _same_force(f, g):
     assert f.getNumMultipoles() == g.getNumMultipoles()
     for i in range(f.getNumMultipoles()):

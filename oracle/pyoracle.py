@@ -113,3 +113,66 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+
+class CellOracle:
+    """The reference's PME pair functions driven from a cell list (oracle/cell_driver.cpp): same arithmetic as `Oracle`,
+    O(N) pair enumeration, optionally several threads.  PME with explicit parameters only."""
+
+    def __init__(self, s, threads=1):
+        L = lib()
+        L.mpidcell_last_error.restype = ctypes.c_char_p
+        self.lib = L
+        self.s = s
+        self.threads = int(threads)
+        if s.method != 1 or s.alpha == 0.0 or int(s.grid[0]) == 0:
+            raise ValueError("CellOracle: PME with explicit alpha/grid only")
+        off, idx = s.cov_csr()
+        off = np.ascontiguousarray(off, dtype=np.int32); idx = np.ascontiguousarray(idx, dtype=np.int32)
+        box = np.ascontiguousarray(s.box, dtype=np.float64).reshape(-1)
+        coefs = np.ascontiguousarray(s.coefs, dtype=np.float64)
+        c = np.ascontiguousarray
+        h = ctypes.c_void_p()
+        rc = L.mpidcell_create(ctypes.c_int(s.n), _dp(c(s.charges)), _dp(c(s.dipoles)), _dp(c(s.quadrupoles)), _dp(c(s.octopoles)),
+                               _ip(c(s.axis)), _ip(c(s.atomZ)), _ip(c(s.atomX)), _ip(c(s.atomY)), _dp(c(s.tholes)), _dp(c(s.alphas)),
+                               _ip(off), _ip(idx), ctypes.c_int(s.polarization), ctypes.c_double(s.cutoff),
+                               ctypes.c_double(s.alpha), ctypes.c_int(int(s.grid[0])), ctypes.c_int(int(s.grid[1])), ctypes.c_int(int(s.grid[2])),
+                               ctypes.c_double(s.default_thole), ctypes.c_double(s.scale14),
+                               ctypes.c_int(s.max_iter), ctypes.c_double(s.epsilon), ctypes.c_int(len(coefs)), _dp(coefs), _dp(box),
+                               ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(L.mpidcell_last_error().decode())
+        self.h = h
+
+    def execute(self, pos=None, threads=None):
+        pos = np.ascontiguousarray(self.s.pos if pos is None else pos, dtype=np.float64)
+        e = ctypes.c_double()
+        f = np.zeros((self.s.n, 3))
+        t = self.threads if threads is None else int(threads)
+        if self.lib.mpidcell_execute(self.h, _dp(pos), ctypes.c_int(t), ctypes.byref(e), _dp(f)) != 0:
+            raise RuntimeError(self.lib.mpidcell_last_error().decode())
+        return e.value, f
+
+    def induced(self):
+        out = np.zeros((self.s.n, 3))
+        if self.lib.mpidcell_get_induced(self.h, _dp(out)) != 0:
+            raise RuntimeError(self.lib.mpidcell_last_error().decode())
+        return out
+
+    def profile(self):
+        sec = np.zeros(5)
+        st = np.zeros(4, dtype=np.int64)
+        self.lib.mpidcell_get_profile(self.h, _dp(sec), st.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+        return dict(candidates_s=sec[0], fixed_field_s=sec[1], induced_fields_s=sec[2], electrostatics_s=sec[3], total_s=sec[4],
+                    candidate_pairs=int(st[0]), induced_field_evaluations=int(st[1]), iterations=int(st[2]), threads=int(st[3]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpidcell_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -3,11 +3,18 @@
 synthetic SWM6-MPID water boxes named by BASELINE.json.
 
   python bench.py --gpus N --steps K --warmup W            # our engine (N=1: 95,616 atoms; N>1: 1,024,884 atoms, sharded)
-  python bench.py --impl reference ...                     # the reference's own CPU path (oracle/_ref) on a bounded sample
+  python bench.py --impl reference ...                     # the reference's own CPU pair functions on the SAME box
 
-One "step" = one MPIDForce energy+force evaluation (PME, mutual polarization to eps=1e-5, octopoles) on one
-coordinate set.  `value`: positions and forces resident in HBM (mpidb200_execute_device).  `e2e`: the same
-evaluation through mpidb200_execute with host buffers (H2D of positions and D2H of forces inside the call).
+One "step" = one MPIDForce energy+force evaluation (PME, mutual polarization to eps=1e-5, octopoles, anisotropic
+polarizability on O) on one coordinate set of a short synthetic trajectory (every water is translated rigidly by a
+seeded N(0, 0.001 nm) vector per step, so no step sees the coordinates of the one before).
+`value`: positions and forces resident in HBM (mpidb200_execute_device).  `e2e`: the same evaluation through
+mpidb200_execute with HOST buffers (H2D of positions, H2D + D2H of the accumulated forces inside the timed call).
+`roofline` / `roofline_kernels`: per KERNEL, from a third pass in which every launch runs alone between two CUDA
+events (mpidb200_set_kernel_profiling); work = the pairs / bytes that kernel actually processes.
+`cpu_baseline` / `--impl reference`: the reference's own pair functions driven from a cell list (oracle/cell_driver.cpp,
+bit-identical to the Reference platform's O(N^2) loops) on the same coordinates, all host threads, measured -- not
+extrapolated; `parity` compares the GPU result with it.
 """
 import argparse
 import json
@@ -28,6 +35,12 @@ WORKLOADS = {
     "96k":  dict(tiles=(4, 4, 2), name="synthetic SWM6-MPID water box, N=95616, 12.5156x12.5156x6.2578 nm, grid 128x128x64"),
     "1m":   dict(tiles=(7, 7, 7), name="synthetic SWM6-MPID water box, N=1024884, L=21.9023 nm, grid 224^3"),
 }
+METRIC = "ns/day (force-evaluation limited, 2 fs) of one MPIDForce eval, waterbox PME + mutual induced"
+STEP_SIGMA_NM = 0.001              # per-step rigid displacement of every water in the timed trajectory
+# Algorithmic flops per unit.  2240 / 430 / 150: SURVEY.md 8(d), counted from the oracle's generic
+# routines (430 and 150 cover both directions of a pair; the gather kernels evaluate directions: 215 / 75 each).
+# 325 / 48: the pair classes the oracle has no routine for, counted the same way (tools/count_flops.cpp).
+FLOP_FULL_FULL, FLOP_FIXED_DIRECTED, FLOP_INDUCED_PAIR, FLOP_FULL_CHARGE, FLOP_CHARGE_CHARGE = 2240.0, 215.0, 150.0, 325.0, 48.0
 
 
 def peaks():
@@ -67,65 +80,154 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
 
 
-def stage_rooflines(stats, n, G, pairs, n_f, pk, es_pairs=None):
-    """Algorithmic flops / bytes per stage over the measured CUDA-event time of that stage.
-    es_pairs: pairs evaluated by the kernels the electrostatics stage timer brackets (full-full + full-charge); the
-    charge-charge pairs run beside the solver on another stream and are not credited to it."""
-    ms = stats["stage_ms"]
-    fp32_peak = 148*128*2*pk["sm_max_mhz"]*1e6/1e12     # TFLOP/s, nominal FP32 FMA peak at max SM clock
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def build_system(args, world):
+    from mpidopenmmplugin_b200.workloads import water_box
+    wl = args.workload or ("96k" if world == 1 else "1m")
+    s = water_box(WORKLOADS[wl]["tiles"], polarization=0, epsilon=1e-5, anisotropic=(args.variant == "aniso"))
+    name = WORKLOADS[wl]["name"] + (", anisotropic polarizability on O (north-star target variant)" if args.variant == "aniso" else ", isotropic polarizability")
+    return wl, s, name
+
+
+def trajectory_shifts(s, count, seed=777):
+    """Per-step rigid displacement of every water (cumulative): step k uses s.pos + cumulative[k]."""
+    rng = np.random.default_rng(seed)
+    nw = s.n//3
+    out = [np.zeros((s.n, 3))]
+    acc = np.zeros((nw, 3))
+    for _ in range(count - 1):
+        acc = acc + rng.normal(0.0, STEP_SIGMA_NM, size=(nw, 3))
+        out.append(np.repeat(acc, 3, axis=0))
+    return out
+
+
+def kernel_rooflines(kprof, work, n, n_pol, rows, G, n_f, hbm_peak, fp32_peak):
+    """Per-kernel rooflines.  kprof: {name: (launches per evaluation, us per evaluation)} from the kernel-profile pass
+    (each launch alone on the device).  Work per evaluation = what the kernel's launches process (this rank's share)."""
+    def find(sub, excl=()):
+        hits = [(k, v) for k, v in kprof.items() if sub in k and not any(x in k for x in excl)]
+        if not hits:
+            return None
+        return (sum(v[0] for _, v in hits), sum(v[1] for _, v in hits))
+
     out = {}
 
-    def add(name, bound, work, unit_scale, peak, unit):
-        t = ms.get(name, 0.0)
-        if t <= 0:
+    def add(label, key, bound, work_amount, note=None, excl=()):
+        r = find(key, excl)
+        if r is None or r[1] <= 0:
             return
-        achieved = work/(t*1e-3)/unit_scale
-        out[name] = dict(bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved/peak, ms=t)
+        launches, us = r
+        if bound == "fp32":
+            achieved, peak, unit = work_amount/(us*1e-6)/1e12, fp32_peak, "TFLOP/s"
+        else:
+            achieved, peak, unit = work_amount/(us*1e-6)/1e9, hbm_peak, "GB/s"
+        d = dict(bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved/peak, us_per_evaluation=us, launches_per_evaluation=launches,
+                 us_per_launch=us/max(launches, 1), work_per_evaluation=work_amount)
+        if note:
+            d["note"] = note
+        out[label] = d
 
-    add("electrostatics", "fp32", (pairs if es_pairs is None else es_pairs)*2240.0, 1e12, fp32_peak, "TFLOP/s")
-    add("fixed_real", "fp32", pairs*430.0, 1e12, fp32_peak, "TFLOP/s")
-    add("ind_real", "fp32", n_f*pairs*150.0, 1e12, fp32_peak, "TFLOP/s")
-    add("fixed_spread", "hbm", n*(16+19*4) + 4.0*G + 4.0*G, 1e9, pk["hbm_gbs"], "GB/s")          # + grid clear
-    add("ind_spread", "hbm", n_f*(n*(16+12) + 4.0*G + 4.0*G), 1e9, pk["hbm_gbs"], "GB/s")
-    add("fft", "hbm", (n_f+1)*(8.0*G + 8.0*G + 8.0*G), 1e9, pk["hbm_gbs"], "GB/s")             # R2C + convolution + C2R
-    add("fixed_gather", "hbm", 4.0*G + n*(16+35*4), 1e9, pk["hbm_gbs"], "GB/s")
-    add("ind_gather", "hbm", n_f*(4.0*G + n*(16+12)) + n*35*4, 1e9, pk["hbm_gbs"], "GB/s")
+    P = float(work["pairs"])
+    # pair kernels: FP32 FMA bound
+    add("k_electrostatics", "k_electrostatics<", "fp32", work["full_full"]*FLOP_FULL_FULL, "full x full pairs x 2240 flop (quasi-internal frame)", excl=("special",))
+    add("k_charge_site_pairs", "k_charge_site_pairs", "fp32", work["full_charge"]*FLOP_FULL_CHARGE, "full x bare-charge pairs x 325 flop (tools/count_flops.cpp)")
+    add("k_simple_pairs", "k_simple_pairs", "fp32", work["charge_charge"]*FLOP_CHARGE_CHARGE, "charge x charge pairs x 48 flop (tools/count_flops.cpp)")
+    add("k_fixed_field", "k_fixed_field", "fp32", work["fixed_field_directed"]*FLOP_FIXED_DIRECTED, "polarizable sites x their neighbours x 215 flop (one direction of SURVEY's 430)")
+    add("k_induced_field", "k_induced_field", "fp32", n_f*work["pol_pol"]*FLOP_INDUCED_PAIR, "%d field evaluations x polarizable x polarizable pairs x 150 flop" % n_f)
+    # neighbour search: integer / FP32 issue bound; the bytes figure is the floor (positions in, two list entries per pair + the
+    # polarizable list out)
+    add("k_neighbor_list_cell", "k_neighbor_list", "hbm", 16.0*rows + 8.0*P + 8.0*work["pol_pol"] + 16.0*rows,
+        "issue-slot bound integer/FP32 search (ncu: 66 % issue active); bytes = float4 positions in + 2 list entries per pair + polarizable list out")
+    add("cub_radix_sort", "cub_radix_sort", "hbm", 4*16.0*n, "4 onesweep passes over (key, index) pairs")
+    # reciprocal space: HBM class (the grid lives in L2 at these sizes)
+    add("k_spread_fixed", "k_spread<real, true>", "hbm", rows*(16 + 19*4) + 4.0*G, "N x (position + 19 fractional moments) + grid")
+    add("k_spread_induced", "k_spread<real, false>", "hbm", n_f*(n_pol*(16 + 12) + 4.0*G), "per pass: polarizable sites x (position + dipole) + grid")
+    add("k_fft2_planes_forward", "k_fft2_planes_forward", "hbm", (n_f + 1)*8.0*G, "per pass: real grid in, half-complex grid out")
+    add("k_fft2_x_convolve", "k_fft2_x_convolve", "hbm", (n_f + 1)*10.0*G, "per pass: half-complex grid in and out + influence function")
+    add("k_fft2_planes_backward", "k_fft2_planes_backward", "hbm", (n_f + 1)*8.0*G, "per pass: half-complex grid in, real grid out")
+    add("cufft_forward", "cufft_forward", "hbm", (n_f + 1)*8.0*G)
+    add("cufft_backward", "cufft_backward", "hbm", (n_f + 1)*8.0*G)
+    add("k_convolution", "k_convolution", "hbm", (n_f + 1)*10.0*G)
+    add("k_gather_35", "k_gather<real, 4, false>", "hbm", 2*(4.0*G + rows*(16 + 35*4)), "2 launches: grid + 35 derivatives per site")
+    add("k_gather_field", "k_gather<real, 1, true>", "hbm", n_f*(4.0*G + n_pol*(16 + 12)), "per pass: grid + field at polarizable sites")
+    add("k_diis_step", "k_diis_step", "hbm", n_f*n_pol*(12 + 48 + 24 + 24 + 48 + 48 + 24.0*(n_f + 1)/2),
+        "per iteration per polarizable site: reciprocal field, alpha, E_fixed, E_induced, mu in/out, history in/out, error overlaps")
+    add("k_lab_frame", "k_lab_frame", "hbm", n*(24 + 20*8 + 16 + 20*8 + 16*8 + 20*4 + 16*4 + 16*8 + 48 + 4.0), "per atom: parameters in, both moment packings (FP64 + FP32), alpha tensor out")
+    add("k_reciprocal_terms", "k_reciprocal_terms", "hbm", rows*(2*35*4 + 20*8 + 16*8 + 24 + 48.0), "per atom: phi, phi_dp, moments in; force/torque atomics out")
     return out
 
 
 def run_reference(args, rank, real_stdout):
-    """The reference's own CPU implementation (Reference platform, compiled unmodified into oracle/_ref) on a
-    bounded sample of the workload: the 996-water box the synthetic boxes are tiled from."""
+    """The reference's own CPU implementation of the path on the SAME box and coordinates as the GPU arm: its PME pair
+    functions, reciprocal-space and solver code (oracle/_ref, compiled unmodified) with the three O(N^2) pair loops replaced
+    by a cell list that visits the same pairs in the same order (oracle/cell_driver.cpp), on every host thread."""
     if rank != 0:
         return
-    from oracle.pyoracle import Oracle
+    from oracle.pyoracle import CellOracle, Oracle
     from mpidopenmmplugin_b200.workloads import water_box
-    wl = args.workload or ("96k" if args.gpus == 1 else "1m")
-    full_n = 2988*int(np.prod(WORKLOADS[wl]["tiles"]))
-    s = water_box((1, 1, 1), polarization=0, epsilon=1e-5)
-    o = Oracle(s)
-    steps = max(1, min(args.steps, 20))
-    for _ in range(min(args.warmup, 1)):
-        o.execute()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        e, f = o.execute()
-    ms = (time.perf_counter() - t0)*1e3/steps
-    scale = (full_n/2988.0)**2         # the Reference platform is O(N^2): no neighbour list (MPIDReferenceForce.cpp:919-933)
-    ms_full = ms*scale
-    value = NS_PER_DAY_PER_MS/ms_full
-    sample = "N=2988 (996-water box, same density/parameters), %d evaluations at %.1f ms; extrapolated x(N/2988)^2=%.0f to N=%d because the Reference platform visits all pairs" % (steps, ms, scale, full_n)
-    line = dict(metric="ns/day (force-evaluation limited, 2 fs) of one MPIDForce eval, waterbox PME + mutual induced", value=value, unit="ns/day",
-                impl="reference", n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 1), ms_per_step=ms_full, higher_is_better=True,
+    world = args.gpus
+    wl, s, name = build_system(args, world)
+    threads = host_threads() if args.ref_threads <= 0 else args.ref_threads
+    o = CellOracle(s, threads=threads)
+    shifts = trajectory_shifts(s, 4)
+    budget = float(os.environ.get("MPIDB200_REF_BUDGET_S", "240"))
+    t_begin = time.perf_counter()
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        o.execute(s.pos)
+    t_warm = time.perf_counter() - t_begin
+    per = t_warm if warm else None
+    steps_wanted = max(1, args.steps)
+    times = []
+    for k in range(steps_wanted):
+        if times and (time.perf_counter() - t_begin) + np.mean(times) > budget:
+            break                                  # bounded: the whole run has to end within minutes (1M box: ~2.5 min per step)
+        t0 = time.perf_counter()
+        e, f = o.execute(s.pos + shifts[k % len(shifts)])
+        times.append(time.perf_counter() - t0)
+    steps = len(times)
+    ms = float(np.mean(times))*1e3
+    prof = o.profile()
+    value = NS_PER_DAY_PER_MS/ms
+    # the stock O(N^2) loops, for the record: measured on the 996-water box, law checked at N=11,952 (profiles/r02_reference_arm.md)
+    stock = None
+    if not args.no_stock_sample:
+        sb = water_box((1, 1, 1), polarization=0, epsilon=1e-5, anisotropic=(args.variant == "aniso"))
+        ob = Oracle(sb)
+        ob.execute()
+        t0 = time.perf_counter()
+        ob.execute()
+        t_stock = (time.perf_counter() - t0)*1e3
+        stock = dict(measured_ms_at_N2988=t_stock, extrapolated=True, same_config=False,
+                     extrapolated_ms_at_this_N=t_stock*(s.n/2988.0)**2,
+                     note="stock Reference-platform loops visit all N^2/2 pairs (MPIDReferenceForce.cpp:919-933, 4084-4088, 4932-4946); "
+                          "(N/2988)^2 extrapolation, NOT used for value")
+    sample = ("full %d-atom box, %d evaluation(s) of %d requested (budget %.0f s), %d host threads, cell-list driver around the reference's own pair functions "
+              "(bit-identical to the stock loops with 1 thread: tests/test_oracle_cell.py)" % (s.n, steps, steps_wanted, budget, threads))
+    line = dict(metric=METRIC, value=value, unit="ns/day",
+                impl="reference", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms, higher_is_better=True,
                 scaling="strong" if args.gpus > 1 else "weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=WORKLOADS[wl]["name"], polarization="Mutual eps=1e-5 (DIIS)", sample=sample),
-                cpu_baseline=dict(value=value, unit="ns/day", cores=1, kind="reference", sample=sample, sample_ms_per_eval=ms),
-                e2e=dict(value=value, unit="ns/day", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                config=dict(workload=name, polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % prof["induced_field_evaluations"],
+                            cutoff_nm=s.cutoff, ewald_alpha=s.alpha, trajectory="rigid per-water N(0, %.3f nm) displacement per step (seed 777)" % STEP_SIGMA_NM),
+                cpu_baseline=dict(value=value, unit="ns/day", cores=threads, kind="reference", sample=sample, ms_per_eval=ms,
+                                  seconds_by_part={k: float(prof[k]) for k in ("candidates_s", "fixed_field_s", "induced_fields_s", "electrostatics_s", "total_s")}),
+                e2e=dict(value=value, unit="ns/day", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                energy_kj_mol=e, stock_loops=stock, wall_s=time.perf_counter() - t_begin)
     emit(line, real_stdout)
 
 
 def emit(line, real_stdout):
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(a - b)/max(np.linalg.norm(b), 1e-300))
 
 
 def main():
@@ -140,8 +242,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS.keys()))
+    ap.add_argument("--variant", default="aniso", choices=["aniso", "iso"], help="polarizability of the O site (north star: anisotropic)")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "double"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock-sample", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--ref-threads", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -154,7 +260,7 @@ def main():
     import torch
     import torch.distributed as dist
     from mpidopenmmplugin_b200 import MPIDB200Kernel
-    from mpidopenmmplugin_b200.workloads import water_box, make_kernel
+    from mpidopenmmplugin_b200.workloads import make_kernel
     from mpidopenmmplugin_b200 import sharding
 
     if not torch.cuda.is_available():
@@ -162,8 +268,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = args.workload or ("96k" if world == 1 else "1m")
-    s = water_box(WORKLOADS[wl]["tiles"], polarization=0, epsilon=1e-5)
+    wl, s, wl_name = build_system(args, world)
     n = s.n
     G = float(np.prod(s.grid))
     k = make_kernel(s, precision=args.precision, device=local_rank)
@@ -176,11 +281,14 @@ def main():
         k.commInit(rank, world, bytes(uid.cpu().tolist()))
     # One explicit (non-default) stream for everything: the engine runs its main work on it (mpidb200_set_stream), so
     # the L2 flush, the zeroing of the force buffer, the timing events and the evaluation are ordered on the device.
-    # (Handle 0, torch's legacy default stream, would make the engine fall back to its private stream.)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     k.setStream(stream.cuda_stream)
-    pos_d = torch.tensor(s.pos, dtype=torch.float64, device="cuda").contiguous()
+    # the timed trajectory: warm-up and timed steps all see different coordinates
+    total = args.warmup + args.steps
+    shifts = trajectory_shifts(s, total)
+    pos_h = [np.ascontiguousarray(s.pos + sh) for sh in shifts]
+    pos_d = [torch.tensor(p, dtype=torch.float64, device="cuda").contiguous() for p in pos_h]
     f_d = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
     flush = torch.empty(256*1024*1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     torch.cuda.synchronize()
@@ -190,129 +298,192 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         f_d.zero_()
-        k.execute_device(pos_d.data_ptr(), True, True, f_d.data_ptr())
+        k.execute_device(pos_d[i].data_ptr(), True, True, f_d.data_ptr())
     # ---- timed region: device-resident ----------------------------------------------------------------
-    # The engine's per-stage timers are CUDA events recorded around every stage on three streams; they cost ~15 % at
-    # this size, so the headline loop runs with them off and a second loop of the same steps (reported separately as
-    # ms_per_step_with_stage_timers) provides the per-stage times the rooflines are computed from.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     energy = 0.0
+    iters = []
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()                    # L2 flush between timed iterations (not timed)
         f_d.zero_()
         ev[i][0].record(stream)
-        energy = k.execute_device(pos_d.data_ptr(), True, True, f_d.data_ptr())
+        energy = k.execute_device(pos_d[args.warmup + i].data_ptr(), True, True, f_d.data_ptr())
         ev[i][1].record(stream)
-        launches += k.getStats()["launches"]
+        st = k.getStats()
+        launches += st["launches"]
+        iters.append(st["iterations"])
     barrier()
     t_wall = (time.perf_counter() - t_wall0)*1e3
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)/args.steps
-    # ---- same steps again with the stage timers on: per-stage CUDA-event times for the rooflines --------
+    stats = k.getStats()
+    work = k.getWorkCounts()
+    # ---- same steps with the stage timers on (intervals on three co-resident streams: informational) ----
     k.setProfiling(True)
     stage_sum = {}
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
     for i in range(args.steps):
         flush.zero_()
         f_d.zero_()
-        ev2[i][0].record(stream)
-        k.execute_device(pos_d.data_ptr(), True, True, f_d.data_ptr())
-        ev2[i][1].record(stream)
+        k.execute_device(pos_d[args.warmup + i].data_ptr(), True, True, f_d.data_ptr())
         for kk, v in k.getStats()["stage_ms"].items():
             stage_sum[kk] = stage_sum.get(kk, 0.0) + v
     barrier()
-    prof_ms = sum(a.elapsed_time(b) for a, b in ev2)/args.steps
     k.setProfiling(False)
+    # ---- per-kernel times: every launch alone on the device between two events ---------------------------
+    kprof = {}
+    if not args.no_kernel_profile:
+        k.setKernelProfiling(True)
+        for i in range(min(args.steps, 5)):
+            f_d.zero_()
+            k.execute_device(pos_d[args.warmup + i].data_ptr(), True, True, f_d.data_ptr())
+        kprof = k.getKernelProfile()
+        k.setKernelProfiling(False)
+        barrier()
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------
+    # The caller's arrays are page-locked once (mpidb200_pin_host_buffer), as the platform kernel does for the Context's
+    # position / force vectors; every step copies that step's coordinates into the pinned array first (inside the timed
+    # region: it stands for the integrator writing new positions), then H2D, evaluation, D2H of the accumulated forces.
+    pos_pin = np.zeros((n, 3))
     f_h = np.zeros((n, 3))
-    for _ in range(2):
-        k.execute(s.pos, True, True, f_h)
+    k.pinHostBuffer(pos_pin)
+    k.pinHostBuffer(f_h)
+    for i in range(2):
+        pos_pin[:] = pos_h[i]
+        f_h[:] = 0.0
+        k.execute(pos_pin, True, True, f_h)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
+        pos_pin[:] = pos_h[args.warmup + i]
         f_h[:] = 0.0
-        e_h = k.execute(s.pos, True, True, f_h)
+        e_h = k.execute(pos_pin, True, True, f_h)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0)*1e3/args.steps
     barrier()
+    # pageable (not pinned) caller arrays, for comparison
+    f_p = np.zeros((n, 3))
+    t0 = time.perf_counter()
+    for i in range(min(args.steps, 5)):
+        f_p[:] = 0.0
+        k.execute(pos_h[args.warmup + i], True, True, f_p)
+    torch.cuda.synchronize()
+    e2e_pageable_ms = (time.perf_counter() - t0)*1e3/min(args.steps, 5)
+    barrier()
     sampler.stop_flag = True
+    # ---- several ranks: the same workload on ONE GPU in the same run, and parity of the sharded result against it ----
+    single = None
+    if world > 1:
+        f_ref = np.zeros((n, 3))
+        f_sh = np.zeros((n, 3))
+        e_sh = k.execute(s.pos, True, True, f_sh)
+        mu_sh = k.getInducedDipoles(s.pos)
+        k1 = make_kernel(s, precision=args.precision, device=local_rank)
+        k1.setStream(stream.cuda_stream)
+        for i in range(3):
+            f_d.zero_()
+            k1.execute_device(pos_d[i].data_ptr(), True, True, f_d.data_ptr())
+        ev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for i in range(5):
+            flush.zero_()
+            f_d.zero_()
+            ev1[i][0].record(stream)
+            k1.execute_device(pos_d[args.warmup + i].data_ptr(), True, True, f_d.data_ptr())
+            ev1[i][1].record(stream)
+        torch.cuda.synchronize()
+        one_ms = sum(a.elapsed_time(b) for a, b in ev1)/5
+        e_one = k1.execute(s.pos, True, True, f_ref)
+        mu_one = k1.getInducedDipoles(s.pos)
+        k1.close()
+        single = dict(ms_per_step=one_ms, value=NS_PER_DAY_PER_MS/one_ms, unit="ns/day", steps=5,
+                      note="same box, same coordinates, one engine without a communicator on this rank's GPU, measured in this run",
+                      parity_of_sharded_result=dict(dF=rel_err(f_sh, f_ref), dmu=rel_err(mu_sh, mu_one), dE=abs(e_sh - e_one)/abs(e_one)))
+        barrier()
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_ms, e2e_pageable_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    stats = k.getStats()
+    dev_ms, e2e_ms, e2e_pageable_ms = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         pk = peaks()
+        fp32_peak = MPIDB200Kernel.measureFp32Peak(local_rank)
         stage_avg = {kk: v/args.steps for kk, v in stage_sum.items()}
         n_f = stats["iterations"] + 1
-        pc = stats["pair_classes"]
-        roofs = stage_rooflines(dict(stage_ms=stage_avg), n/world, G, float(stats["pairs"]), n_f, pk, es_pairs=float(pc["full_full"] + pc["full_charge"]))   # rank 0's share of the work over rank 0's stage times
-        dominant = max(roofs.items(), key=lambda kv: kv[1]["ms"])[0] if roofs else None
-        roof = dict(roofs[dominant]) if dominant else None
-        if roof:
-            roof["kernel"] = dominant
-            # DRAM traffic of the dominant stage's kernels from the committed `ncu --set full` capture of this workload
-            # (profiles/traffic.json: bytes per evaluation), null when no capture exists for it
+        rows = n//world if world > 1 else n
+        roofs = kernel_rooflines(kprof, work, n, work["polarizable_sites"], rows, G, n_f, pk["hbm_gbs"], fp32_peak)
+        # dominant kernel = the one with the most device time per evaluation, whatever its bound
+        roof = None
+        if roofs:
+            dom = max(roofs, key=lambda kk: roofs[kk]["us_per_evaluation"])
+            roof = dict(roofs[dom], kernel=dom)
+            roof["achieved_definition"] = "algorithmic work of the kernel's launches in one evaluation / their summed duration, each launch alone on the device (CUDA events, warm L2)"
+            roof["peak_source"] = (pk["source"] if roof["bound"] == "hbm" else
+                                   "measured in this run: FP32 FMA-chain micro-benchmark (mpidb200_measure_fp32_peak), nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f" % (pk["sm_max_mhz"], 148*128*2*pk["sm_max_mhz"]*1e-6))
             roof["traffic"] = None
             tpath = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tpath) and world == 1:
-                t = json.load(open(tpath)).get(wl, {}).get(dominant)
-                if t:
-                    roof["traffic"] = t["bytes"]
-                    roof["traffic_source"] = t["source"]
-            roof["peak_source"] = pk["source"] if roof["bound"] == "hbm" else "nominal FP32 FMA peak 148 SM x 128 lanes x 2 x %.0f MHz (pair kernels are FMA-pipe bound, not HBM or tensor bound)" % pk["sm_max_mhz"]
-            roof["algorithmic_work"] = "SURVEY.md 8(d): 2240 flop per in-cutoff pair (electrostatics; pairs of the timed kernels only: full-full + full-charge), 430 (fixed field), 150 per field evaluation (induced field)"
-            roof["pairs"] = dict(stats["pair_classes"], total=int(stats["pairs"]))
-            # the contract's enum is hbm | tensor; the dominant stage here is FP32-FMA bound, so the longest HBM-class stage
-            # (spread / FFT / gather) is given next to it with the same fields
-            hbm = {kk: v for kk, v in roofs.items() if v["bound"] == "hbm"}
-            if hbm:
-                hk = max(hbm, key=lambda kk: hbm[kk]["ms"])
-                hroof = dict(hbm[hk], kernel=hk, traffic=None, peak_source=pk["source"])
-                if os.path.exists(tpath) and world == 1:
-                    t = json.load(open(tpath)).get(wl, {}).get(hk)
-                    if t:
-                        hroof["traffic"] = t["bytes"]
-                        hroof["traffic_source"] = t["source"]
-                roof["hbm_dominant"] = hroof
-        line = dict(metric="ns/day (force-evaluation limited, 2 fs) of one MPIDForce eval, waterbox PME + mutual induced",
+                tj = json.load(open(tpath)).get(wl, {}).get(dom)
+                if tj:
+                    roof["traffic"] = tj["bytes"]
+                    roof["traffic_source"] = tj["source"]
+            fp = {kk: v for kk, v in roofs.items() if v["bound"] == "fp32"}
+            hb = {kk: v for kk, v in roofs.items() if v["bound"] == "hbm" and kk != dom}
+            if fp:
+                kk = max(fp, key=lambda q: fp[q]["us_per_evaluation"])
+                roof["fp32_dominant"] = dict(fp[kk], kernel=kk)
+            if hb:
+                kk = max(hb, key=lambda q: hb[q]["us_per_evaluation"])
+                roof["hbm_next"] = dict(hb[kk], kernel=kk)
+        kernel_us = {kk: dict(launches=v[0], us=v[1]) for kk, v in sorted(kprof.items(), key=lambda kv: -kv[1][1])}
+        line = dict(metric=METRIC,
                     value=NS_PER_DAY_PER_MS/dev_ms, unit="ns/day", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=dev_ms, higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None,
                     dtype="f32 pair/grid math, f64 accumulation" if args.precision == "mixed" else "f64", data="synthetic",
-                    config=dict(workload=WORKLOADS[wl]["name"], polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % n_f,
+                    config=dict(workload=wl_name, polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % n_f,
                                 cutoff_nm=s.cutoff, ewald_alpha=s.alpha, l2="256 MB buffer written between timed iterations",
+                                trajectory="rigid per-water N(0, %.3f nm) displacement per step (seed 777): every warm-up and timed step has its own coordinates" % STEP_SIGMA_NM,
                                 parallelism=("atom-block rows x%d: NCCL all-reduce of the partial induced field every solver iteration and of forces/torques once; "
-                                             "reciprocal pass on a second communicator / stream: %s" % (world, (
-                                                 "slab decomposition (reduce-scatter, 2-D FFT on own x planes, all-to-all, x FFT + influence function on own ky rows, "
-                                                 "all-to-all back, all-gather)" if sharding.uses_slab_fft(world, s.grid) else
-                                                 "all-reduce of the charge grid, FFT replicated"))) if world > 1 else "1 GPU",
+                                             "reciprocal pass on a second communicator / stream: %s" % (world, sharding.reciprocal_mode(world, s.grid)))
+                                if world > 1 else "1 GPU",
                                 note=("N>1 runs the 1,024,884-atom box of BASELINE.json config 5 (strong scaling of ONE system); the N=1 default runs the "
-                                      "95,616-atom box of config 4, so values at N=1 and N>1 are different workloads -- run `--gpus 1 --workload 1m` for the "
-                                      "single-GPU point of the same system") if world > 1 else "N=1 default = BASELINE.json config 4 (96k atoms, 1 B200)"),
-                    e2e=dict(value=NS_PER_DAY_PER_MS/e2e_ms, unit="ns/day", ms_per_step=e2e_ms, h2d_bytes_per_step=24*n, d2h_bytes_per_step=24*n + 8),
-                    gpu_launches=int(launches), energy_kj_mol=energy, wall_ms_per_step=t_wall/args.steps, ms_per_step_with_stage_timers=prof_ms,
-                    clocks=sampler.summary(), roofline=roof, roofline_stages=roofs, stage_ms=stage_avg)
+                                      "95,616-atom box of config 4, so the same-workload single-GPU time is measured in THIS run: single_gpu_same_workload") if world > 1
+                                else "N=1 default = BASELINE.json config 4 (96k atoms, 1 B200)"),
+                    e2e=dict(value=NS_PER_DAY_PER_MS/e2e_ms, unit="ns/day", ms_per_step=e2e_ms, h2d_bytes_per_step=48*n, d2h_bytes_per_step=24*n + 8,
+                             ms_per_step_pageable_arrays=e2e_pageable_ms,
+                             note="host arrays page-locked once with mpidb200_pin_host_buffer; per step: positions H2D, caller's forces H2D (accumulated on the device), forces D2H, energy D2H"),
+                    gpu_launches=int(launches), energy_kj_mol=energy, wall_ms_per_step=t_wall/args.steps,
+                    solver_field_evaluations=[int(i) + 1 for i in iters],
+                    clocks=sampler.summary(), roofline=roof, roofline_kernels=roofs, kernel_us_per_evaluation=kernel_us,
+                    work_counts=work, fp32_peak_measured_tflops=fp32_peak,
+                    stage_ms_coresident_intervals=stage_avg)
+        if single:
+            line["single_gpu_same_workload"] = single
         if world == 1 and not args.no_cpu_baseline:
-            from oracle.pyoracle import Oracle
-            sb = water_box((1, 1, 1), polarization=0, epsilon=1e-5)
-            o = Oracle(sb)
-            reps = 4
+            # the reference's own pair functions (cell-list driven) on the SAME coordinates, all host threads: measured baseline
+            # and parity of the GPU result in one go
+            from oracle.pyoracle import CellOracle
+            threads = host_threads()
+            o = CellOracle(s, threads=threads)
             t0 = time.perf_counter()
-            for _ in range(reps):
-                o.execute()
-            ms = (time.perf_counter() - t0)*1e3/reps
-            scale = (n/2988.0)**2
-            line["cpu_baseline"] = dict(value=NS_PER_DAY_PER_MS/(ms*scale), unit="ns/day", cores=1, kind="reference", sample_ms_per_eval=ms,
-                                        sample="oracle/_ref (reference Reference-platform code, unmodified) on N=2988 (996-water box), %d evaluations at %.0f ms; x(N/2988)^2=%.0f extrapolation to N=%d (O(N^2) pair loops)" % (reps, ms, scale, n))
+            e_ref, f_ref = o.execute(s.pos)
+            cpu_ms = (time.perf_counter() - t0)*1e3
+            mu_ref = o.induced()
+            prof = o.profile()
+            f_g = np.zeros((n, 3))
+            e_g = k.execute(s.pos, True, True, f_g)
+            mu_g = k.getInducedDipoles(s.pos)
+            line["cpu_baseline"] = dict(value=NS_PER_DAY_PER_MS/cpu_ms, unit="ns/day", cores=threads, kind="reference", ms_per_eval=cpu_ms,
+                                        sample="one evaluation of the full %d-atom box (same coordinates as step 0), %d host threads: the reference's own PME pair functions, "
+                                               "reciprocal-space and DIIS code (oracle/_ref, unmodified) driven from a cell list (oracle/cell_driver.cpp)" % (n, threads),
+                                        seconds_by_part={kk: float(prof[kk]) for kk in ("candidates_s", "fixed_field_s", "induced_fields_s", "electrostatics_s", "total_s")})
+            line["parity"] = dict(against="cpu_baseline evaluation (reference arithmetic, FP64), both at eps=1e-5", dF=rel_err(f_g, f_ref), dmu=rel_err(mu_g, mu_ref),
+                                  dE=abs(e_g - e_ref)/abs(e_ref), energy_reference=e_ref, energy_gpu=e_g, tolerance_mixed=1e-5)
         emit(line, real_stdout)
     k.close()
     if world > 1:

@@ -92,6 +92,14 @@ int mpidb200_execute(mpidb200_handle h, const double* positions, int include_for
 int mpidb200_execute_device(mpidb200_handle h, const double* d_positions, int include_forces, int include_energy,
                             double* energy, double* d_forces);
 
+/* Page-lock a caller-owned host array (cudaHostRegister) so that mpidb200_execute moves it by DMA without a staging
+ * copy: positions straight from the caller's array, forces uploaded beside the evaluation, accumulated ON THE DEVICE and
+ * written back by one DMA.  The platform kernel calls this once for the Context's position and force vectors (they
+ * live as long as the Context: platforms/reference/src/MPIDReferenceKernels.cpp:43-66).  The buffer must stay
+ * allocated until mpidb200_unpin_host_buffer / mpidb200_destroy.  Arrays that were not pinned still work (staged). */
+int mpidb200_pin_host_buffer(mpidb200_handle h, void* buffer, unsigned long long bytes);
+int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer);
+
 /* Run the engine on a caller-owned CUDA stream (e.g. the host framework's current stream) instead of its
  * own; pass NULL to return to the private stream.  The caller keeps ownership. */
 int mpidb200_set_stream(mpidb200_handle h, void* cuda_stream);
@@ -137,6 +145,18 @@ int mpidb200_get_pair_class_counts(mpidb200_handle h, long long* out3);
 /* per-stage CUDA-event timing: events are recorded on the engine's stream around each stage and read
  * after the call's final synchronisation (no extra synchronisation is added); off by default */
 int mpidb200_set_profiling(mpidb200_handle h, int enabled);
+/* Per-kernel timing: while enabled every launch of an evaluation runs alone (device drained first) between two CUDA
+ * events and the durations are accumulated per kernel name; mpidb200_get_kernel_profile returns them as CSV text
+ * "kernel,launches,total_us,evaluations" (call with buffer == NULL to get the size).  Measurement aid: slow. */
+int mpidb200_set_kernel_profiling(mpidb200_handle h, int enabled);
+int mpidb200_get_kernel_profile(mpidb200_handle h, char* buffer, long long capacity, long long* needed);
+/* Work the kernels of the last execute did (this rank's share), for the rooflines:
+ * out8 = { ordinary pairs, full x full, full x bare charge, charge x charge, polarizable x polarizable pairs,
+ *          directed site x neighbour evaluations of the permanent-field kernel, covalently scaled pairs, polarizable sites } */
+int mpidb200_get_work_counts(mpidb200_handle h, long long* out8);
+/* FP32 FMA throughput of `device` measured with a register-resident FMA-chain kernel (TFLOP/s, 2 flop per FMA):
+ * the denominator of the pair kernels' rooflines. */
+int mpidb200_measure_fp32_peak(int device, double* tflops, double* seconds_per_launch);
 /* number of kernel launches issued by the last execute */
 long long mpidb200_last_launch_count(mpidb200_handle h);
 

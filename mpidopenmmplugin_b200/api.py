@@ -439,6 +439,44 @@ class MPIDB200Kernel:
                     stage_ms={k: ms[i] for i, k in enumerate(names)},
                     launches=int(self._lib.mpidb200_last_launch_count(self._h)))
 
+    def pinHostBuffer(self, array):
+        """Page-lock a numpy array the caller keeps alive (positions / forces passed to execute): mpidb200_pin_host_buffer."""
+        self._check(self._lib.mpidb200_pin_host_buffer(self._h, ctypes.c_void_p(array.ctypes.data), ctypes.c_ulonglong(array.nbytes)))
+
+    def unpinHostBuffer(self, array):
+        self._check(self._lib.mpidb200_unpin_host_buffer(self._h, ctypes.c_void_p(array.ctypes.data)))
+
+    def getWorkCounts(self):
+        out = (ctypes.c_longlong*8)()
+        self._check(self._lib.mpidb200_get_work_counts(self._h, out))
+        names = ("pairs", "full_full", "full_charge", "charge_charge", "pol_pol", "fixed_field_directed", "covalent_pairs", "polarizable_sites")
+        return {k: int(out[i]) for i, k in enumerate(names)}
+
+    def setKernelProfiling(self, enabled):
+        self._check(self._lib.mpidb200_set_kernel_profiling(self._h, ctypes.c_int(1 if enabled else 0)))
+
+    def getKernelProfile(self):
+        """{kernel name: (launches per evaluation, microseconds per evaluation)} accumulated since setKernelProfiling(True)."""
+        need = ctypes.c_longlong()
+        self._check(self._lib.mpidb200_get_kernel_profile(self._h, None, ctypes.c_longlong(0), ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value + 1)
+        self._check(self._lib.mpidb200_get_kernel_profile(self._h, buf, ctypes.c_longlong(need.value + 1), ctypes.byref(need)))
+        out = {}
+        for line in buf.value.decode().splitlines()[1:]:
+            name, rest = line.rsplit('",', 1)
+            launches, us, evals = rest.split(",")
+            ev = max(int(evals), 1)
+            out[name.strip('"')] = (int(launches)/ev, float(us)/ev)
+        return out
+
+    @staticmethod
+    def measureFp32Peak(device=0):
+        lib = load_library()
+        t = ctypes.c_double(); sec = ctypes.c_double()
+        if lib.mpidb200_measure_fp32_peak(ctypes.c_int(device), ctypes.byref(t), ctypes.byref(sec)) != 0:
+            raise MPIDB200Error(lib.mpidb200_last_error().decode())
+        return t.value
+
     def getPairList(self):
         cnt = ctypes.c_longlong()
         self._check(self._lib.mpidb200_get_pair_list(self._h, ctypes.c_longlong(0), None, None, None, ctypes.byref(cnt)))

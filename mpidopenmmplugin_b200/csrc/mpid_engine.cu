@@ -116,6 +116,11 @@ struct EngineBase {
     virtual void setStream(void* st) = 0;
     virtual void systemMoments(const double* pos, const double* masses, double* out13) = 0;
     virtual void potential(const double* pos, int npts, const double* pts, double* out) = 0;
+    virtual void pinHost(void* ptr, size_t bytes) = 0;
+    virtual void unpinHost(void* ptr) = 0;
+    virtual void workCounts(long long* out8) = 0;
+    virtual void setKernelProfiling(bool on) = 0;
+    virtual std::string kernelProfileCsv() = 0;
     bool profiling = false;
     long long launches = 0;
 };
@@ -251,6 +256,8 @@ struct Engine : public EngineBase {
         destroySlabPlans();
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
+        for (const PinnedRange& r : pinnedRanges) cudaHostUnregister(r.p);
+        if (streamCopy) { cudaStreamDestroy(streamCopy); cudaEventDestroy(evForcesUp); }
         if (evEnergyDone) { cudaEventDestroy(evEnergyDone); for (int c = 0; c < kHostChunks; c++) cudaEventDestroy(evChunk[c]); }
         if (hDiis) cudaFreeHost(hDiis);
         if (hCg) cudaFreeHost(hCg);
@@ -312,10 +319,26 @@ struct Engine : public EngineBase {
     const char* tracePath = getenv("MPIDB200_TRACE");
     bool tracing = false;
     long long evalCounter = 0;
+    // Kernel-profile mode (mpidb200_set_kernel_profiling): every launch of an evaluation runs ALONE -- the device is
+    // drained before it starts -- between two events, and the durations are summed per kernel name.  Unlike the stage
+    // timers (which bracket intervals in which kernels of three streams are co-resident) these are per-kernel times;
+    // unlike ncu's they are taken with the L2 contents the preceding kernels left.  Slow (a host sync per launch).
+    bool kernelProfile = false;
+    struct KernelTime { long long launches = 0; double us = 0; };
+    std::map<std::string, KernelTime> kernelTimes;
+    long long kernelProfileEvals = 0;
+    void setKernelProfiling(bool on) override { kernelProfile = on; if (on) { kernelTimes.clear(); kernelProfileEvals = 0; } }
+    std::string kernelProfileCsv() override {
+        std::string out = "kernel,launches,total_us,evaluations\n";
+        for (auto& kv : kernelTimes)
+            out += "\"" + kv.first + "\"," + std::to_string(kv.second.launches) + "," + std::to_string(kv.second.us) + "," + std::to_string(kernelProfileEvals) + "\n";
+        return out;
+    }
     int streamId(cudaStream_t st) const { return st == stream ? 1 : (st == stream2 ? 2 : 3); }
     void traceBegin(const char* name) {
         if (!tracing) return;
         TraceRec r; r.name = name; r.streamId = streamId(cur);
+        if (kernelProfile) cudaDeviceSynchronize();
         cudaEventCreate(&r.a); cudaEventCreate(&r.b);
         cudaEventRecord(r.a, cur);
         trace.push_back(r);
@@ -324,7 +347,16 @@ struct Engine : public EngineBase {
     void traceDump() {
         if (!tracing || trace.empty()) return;
         cudaDeviceSynchronize();
-        FILE* f = fopen(tracePath, "w");
+        if (kernelProfile) {
+            for (const TraceRec& r : trace) {
+                float t = 0;
+                cudaEventElapsedTime(&t, r.a, r.b);
+                KernelTime& k = kernelTimes[r.name];
+                k.launches++; k.us += t*1e3;
+            }
+            kernelProfileEvals++;
+        }
+        FILE* f = (tracePath && !kernelProfile) ? fopen(tracePath, "w") : nullptr;
         if (f) {
             fprintf(f, "stream,name,start_us,end_us\n");
             for (const TraceRec& r : trace) {
@@ -1082,35 +1114,6 @@ struct Engine : public EngineBase {
         stageEnd();
     }
 
-    // Gauss-Jordan with partial pivoting for the (m+1)x(m+1) DIIS system (:1254-1291 solves the same
-    // system through an SVD)
-    static void solveDiis(int m, const std::vector<double>& Bm, int ld, std::vector<double>& coef) {
-        int rank = m + 1, w = rank + 1;
-        std::vector<double> a((size_t) rank*w, 0.0);
-        for (int i = 0; i < rank; i++)
-            for (int j = 0; j < rank; j++)
-                a[(size_t) i*w + j] = (i == 0 && j == 0) ? 0.0 : ((i == 0 || j == 0) ? -1.0 : Bm[(size_t) (i-1)*ld + (j-1)]);
-        a[rank] = -1.0;
-        for (int c = 0; c < rank; c++) {
-            int piv = c;
-            for (int r = c+1; r < rank; r++) if (fabs(a[(size_t) r*w + c]) > fabs(a[(size_t) piv*w + c])) piv = r;
-            if (piv != c) for (int k = 0; k < w; k++) std::swap(a[(size_t) c*w + k], a[(size_t) piv*w + k]);
-            double d = a[(size_t) c*w + c];
-            if (d == 0.0) continue;
-            for (int r = 0; r < rank; r++) {
-                if (r == c) continue;
-                double f = a[(size_t) r*w + c]/d;
-                if (f == 0.0) continue;
-                for (int k = c; k < w; k++) a[(size_t) r*w + k] -= f*a[(size_t) c*w + k];
-            }
-        }
-        coef.assign(m, 0.0);
-        for (int i = 0; i < m; i++) {
-            double d = a[(size_t) (i+1)*w + (i+1)];
-            coef[i] = d != 0.0 ? a[(size_t) (i+1)*w + rank]/d : 0.0;
-        }
-    }
-
     void dots(const double* vec, const VecList& list, int m, double* hostOut) {
         const int nb = 296;   // 2 x 148 SMs
         dDotPartial.ensure((size_t) nb*(MPID_MAX_HISTORY + 1)); dDots.ensure(MPID_MAX_HISTORY + 1);
@@ -1319,7 +1322,7 @@ struct Engine : public EngineBase {
         if (forked3) { CUDA_CHECK(cudaStreamSynchronize(stream3)); forked3 = false; }     // a previous call ended early (exception)
         launches = 0;
         evalCounter++;
-        tracing = tracePath != nullptr && evalCounter == 4 && !dipolesOnly;     // one warmed-up evaluation
+        tracing = (tracePath != nullptr && evalCounter == 4 && !dipolesOnly) || (kernelProfile && !dipolesOnly);     // one warmed-up evaluation
         lastPosDevice = dPosIn;
         memset(stageMs, 0, sizeof(stageMs));
         const bool pme = P.method == PME;
@@ -1434,6 +1437,7 @@ struct Engine : public EngineBase {
         }
         if (includeForces) {
             LAUNCH(k_torque_to_force, blocksFor(n, 128), 128, P, particleParams(), dOrder.p, dInv.p, dPosIn, torqueP(), forceP());
+            if (forcesUploadPending) { CUDA_CHECK(cudaStreamWaitEvent(stream, evForcesUp, 0)); forcesUploadPending = false; }
             LAUNCH(k_output_forces, blocksFor(n, 256), 256, n, dOrder.p, forceP(), dForcesOut);
         }
         unsigned long long* he = (unsigned long long*) hPinned;
@@ -1451,10 +1455,42 @@ struct Engine : public EngineBase {
         if (energy) *energy = includeEnergy ? (double) ((long long) he[0])*(1.0/MPID_FIXED_SCALE) : 0.0;
     }
 
-    // ---- host-buffer entry (mpidb200_execute): positions in, forces accumulated out, both pipelined in chunks ----
+    // ---- host-buffer entry (mpidb200_execute): positions in, forces accumulated out ------------------------------
+    // Two paths.  (1) The caller has pinned its arrays (mpidb200_pin_host_buffer; the platform kernel does that once
+    // for the Context's position and force vectors): positions are DMA-ed straight from the caller's array, the
+    // caller's current forces are uploaded on a copy stream while the evaluation runs, the engine adds its forces to
+    // them on the device, and one DMA writes the sum back -- no staging copy, no host loop.  (2) Pageable arrays: both
+    // directions are staged through the engine's pinned buffer in chunks so that the host copy / add of chunk k
+    // overlaps the transfer of chunk k+1.
     static const int kHostChunks = 4;
     cudaEvent_t evEnergyDone = nullptr, evChunk[kHostChunks] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t streamCopy = nullptr;
+    cudaEvent_t evForcesUp = nullptr;
     bool readbackPending = false;
+    double* readbackDirect = nullptr;       // pinned destination of the force read-back (path 1), else staged
+    struct PinnedRange { char* p; size_t bytes; };
+    std::vector<PinnedRange> pinnedRanges;
+    void pinHost(void* ptr, size_t bytes) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        if (!ptr || bytes == 0) throw std::runtime_error("mpidb200_pin_host_buffer: null buffer");
+        for (const PinnedRange& r : pinnedRanges) if (r.p == (char*) ptr && r.bytes >= bytes) return;
+        unpinHost(ptr);
+        CUDA_CHECK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+        pinnedRanges.push_back(PinnedRange{(char*) ptr, bytes});
+    }
+    void unpinHost(void* ptr) override {
+        for (size_t k = 0; k < pinnedRanges.size(); k++)
+            if (pinnedRanges[k].p == (char*) ptr) {
+                cudaHostUnregister(ptr);
+                pinnedRanges.erase(pinnedRanges.begin() + k);
+                return;
+            }
+    }
+    bool isPinned(const void* ptr, size_t bytes) const {
+        for (const PinnedRange& r : pinnedRanges)
+            if ((const char*) ptr >= r.p && (const char*) ptr + bytes <= r.p + r.bytes) return true;
+        return false;
+    }
     static void chunkRange(size_t count, int c, size_t& begin, size_t& end) {
         const int chunks = count >= 65536 ? kHostChunks : 1;
         begin = c < chunks ? count*c/chunks : count;
@@ -1474,8 +1510,12 @@ struct Engine : public EngineBase {
     const double* stagePositions(const double* pos, bool onDevice) {
         if (onDevice) return pos;
         const size_t count = 3*(size_t) n;
-        ensureHostStage(count*sizeof(double));
         dPos.ensure(count);
+        if (isPinned(pos, count*sizeof(double))) {
+            CUDA_CHECK(cudaMemcpyAsync(dPos.p, pos, count*sizeof(double), cudaMemcpyHostToDevice, stream));
+            return dPos.p;
+        }
+        ensureHostStage(count*sizeof(double));
         // the copy of chunk k into pinned memory overlaps the transfer of chunk k-1
         for (int c = 0; c < kHostChunks; c++) {
             size_t b, e;
@@ -1488,6 +1528,11 @@ struct Engine : public EngineBase {
     }
     void enqueueForceReadback(const double* dSrc) {
         const size_t count = 3*(size_t) n;
+        if (readbackDirect) {
+            CUDA_CHECK(cudaMemcpyAsync(readbackDirect, dSrc, count*sizeof(double), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaEventRecord(evChunk[0], stream));
+            return;
+        }
         double* stage = hPinnedPos + count;
         for (int c = 0; c < kHostChunks; c++) {
             size_t b, e;
@@ -1499,30 +1544,84 @@ struct Engine : public EngineBase {
 
     void execute(const double* pos, bool onDevice, bool includeForces, bool includeEnergy, double* energy, double* forces) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
-        const double* dp = stagePositions(pos, onDevice);
         const size_t count = 3*(size_t) n;
+        const double* dp = stagePositions(pos, onDevice);
         double* df = nullptr;
+        readbackDirect = nullptr;
+        forcesUploadPending = false;
         if (includeForces) {
             if (onDevice) df = forces;
             else {
                 dForcesOut.ensure(count);
-                CUDA_CHECK(cudaMemsetAsync(dForcesOut.p, 0, count*sizeof(double), stream));
+                ensureHostStage(count*sizeof(double));
                 df = dForcesOut.p;
+                if (isPinned(forces, count*sizeof(double))) {
+                    // the caller's forces travel up beside the evaluation; k_output_forces adds to them on the device
+                    if (!streamCopy) {
+                        CUDA_CHECK(cudaStreamCreateWithFlags(&streamCopy, cudaStreamNonBlocking));
+                        CUDA_CHECK(cudaEventCreateWithFlags(&evForcesUp, cudaEventDisableTiming));
+                    }
+                    CUDA_CHECK(cudaEventRecord(evFork3, stream));          // orders the copy after earlier use of dForcesOut
+                    CUDA_CHECK(cudaStreamWaitEvent(streamCopy, evFork3, 0));
+                    CUDA_CHECK(cudaMemcpyAsync(dForcesOut.p, forces, count*sizeof(double), cudaMemcpyHostToDevice, streamCopy));
+                    CUDA_CHECK(cudaEventRecord(evForcesUp, streamCopy));
+                    forcesUploadPending = true;
+                    readbackDirect = forces;
+                } else {
+                    CUDA_CHECK(cudaMemsetAsync(dForcesOut.p, 0, count*sizeof(double), stream));
+                }
             }
         }
         readbackPending = includeForces && !onDevice;
         try { evaluate(dp, includeForces, includeEnergy, energy, df, false); }
-        catch (...) { readbackPending = false; throw; }
+        catch (...) { readbackPending = false; forcesUploadPending = false; throw; }
         if (readbackPending) {
             readbackPending = false;
+            if (readbackDirect) {
+                CUDA_CHECK(cudaEventSynchronize(evChunk[0]));
+                readbackDirect = nullptr;
+                return;
+            }
             const double* stage = hPinnedPos + count;
             for (int c = 0; c < kHostChunks; c++) {
                 size_t b, e;
                 chunkRange(count, c, b, e);
                 CUDA_CHECK(cudaEventSynchronize(evChunk[c]));
-                for (size_t k = b; k < e; k++) forces[k] += stage[k];   // accumulate (MPIDReferenceKernels.cpp:229-238)
+                const double* __restrict__ src = stage;
+                double* __restrict__ dst = forces;
+                for (size_t k = b; k < e; k++) dst[k] += src[k];   // accumulate (MPIDReferenceKernels.cpp:229-238)
             }
         }
+    }
+    bool forcesUploadPending = false;
+
+    // Work the kernels of the last evaluation did, for the rooflines (off the timed path: copies the counters back).
+    //   [0] ordinary in-cutoff pairs (i<j)   [1] full x full   [2] full x bare charge   [3] charge x charge
+    //   [4] polarizable x polarizable pairs (k_induced_field walks both directions of each)
+    //   [5] directed site x neighbour evaluations of k_fixed_field (polarizable sites x all their neighbours)
+    //   [6] covalently scaled pairs (static list)   [7] polarizable sites
+    void workCounts(long long* out) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        long long pc[3];
+        getPairClassCounts(pc);
+        out[0] = lastPairs; out[1] = pc[0]; out[2] = pc[1]; out[3] = pc[2];
+        const int rows = P.rowEnd - P.rowBegin;
+        std::vector<unsigned> polCnt(std::max(numPol, 1));
+        std::vector<int> polList(std::max(numPol, 1));
+        std::vector<uint4> cnt(std::max(rows, 1));
+        if (numPol > 0) {
+            CUDA_CHECK(cudaMemcpy(polCnt.data(), dPolCount.p, numPol*sizeof(unsigned), cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(polList.data(), dPolList.p + polBegin, numPol*sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        if (rows > 0) CUDA_CHECK(cudaMemcpy(cnt.data(), dCounts.p, rows*sizeof(uint4), cudaMemcpyDeviceToHost));
+        long long polDirected = 0, fixedDirected = 0;
+        for (int k = 0; k < numPol; k++) {
+            polDirected += polCnt[k];
+            const uint4 c = cnt[polList[k] - P.rowBegin];
+            fixedDirected += (long long) c.x + c.y;
+        }
+        out[4] = polDirected/2; out[5] = fixedDirected; out[6] = (long long) hSpLo.size(); out[7] = numPol;
     }
 
     void getDipoles(const double* pos, int which, double* out) override {
@@ -1685,6 +1784,23 @@ struct Engine : public EngineBase {
 
 EngineBase* asEngine(mpidb200_handle h) { return reinterpret_cast<EngineBase*>(h); }
 
+// FP32 FMA micro-benchmark: the measured denominator of the pair kernels' rooflines (mpidb200_measure_fp32_peak).
+// Every thread runs 16 independent FMA chains (enough ILP to cover the 4-cycle FMA latency at 8 warps per scheduler).
+__global__ void __launch_bounds__(256) k_fma_peak(int iters, float seed, float* __restrict__ out) {
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = seed + (float) (threadIdx.x + k);
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) a[k] = fmaf(a[k], m, c);
+    }
+    float sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) sum += a[k];
+    if (sum == 123.456f) out[blockIdx.x*blockDim.x + threadIdx.x] = sum;      // never true: keeps the chains alive
+}
+
 template <typename F> int guarded(F f) {
     try { f(); return 0; }
     catch (const std::exception& e) { g_lastError = e.what(); return 1; }
@@ -1777,6 +1893,55 @@ int mpidb200_get_pair_list(mpidb200_handle h, long long capacity, int* pairs_i, 
 }
 int mpidb200_set_stream(mpidb200_handle h, void* cuda_stream) {
     return guarded([&] { asEngine(h)->setStream(cuda_stream); });
+}
+int mpidb200_pin_host_buffer(mpidb200_handle h, void* buffer, unsigned long long bytes) {
+    return guarded([&] { asEngine(h)->pinHost(buffer, (size_t) bytes); });
+}
+int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer) {
+    return guarded([&] { asEngine(h)->unpinHost(buffer); });
+}
+int mpidb200_get_work_counts(mpidb200_handle h, long long* out8) {
+    return guarded([&] { asEngine(h)->workCounts(out8); });
+}
+int mpidb200_set_kernel_profiling(mpidb200_handle h, int enabled) {
+    return guarded([&] { asEngine(h)->setKernelProfiling(enabled != 0); });
+}
+int mpidb200_get_kernel_profile(mpidb200_handle h, char* buffer, long long capacity, long long* needed) {
+    return guarded([&] {
+        const std::string csv = asEngine(h)->kernelProfileCsv();
+        if (needed) *needed = (long long) csv.size() + 1;
+        if (buffer && capacity > 0) {
+            const size_t len = std::min<size_t>(csv.size(), (size_t) capacity - 1);
+            memcpy(buffer, csv.data(), len);
+            buffer[len] = 0;
+        }
+    });
+}
+int mpidb200_measure_fp32_peak(int device, double* tflops, double* seconds_per_launch) {
+    return guarded([&] {
+        CUDA_CHECK(cudaSetDevice(device));
+        int sms = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const int blocks = sms*8, threads = 256, iters = 8192;
+        float* d = nullptr;
+        CUDA_CHECK(cudaMalloc((void**) &d, (size_t) blocks*threads*sizeof(float)));
+        cudaEvent_t a, b;
+        CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+        double best = 1e30;
+        for (int rep = 0; rep < 8; rep++) {
+            CUDA_CHECK(cudaEventRecord(a, 0));
+            k_fma_peak<<<blocks, threads>>>(iters, 1.0f, d);
+            CUDA_CHECK(cudaEventRecord(b, 0));
+            CUDA_CHECK(cudaEventSynchronize(b));
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+            if (rep >= 2) best = std::min(best, (double) ms*1e-3);
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+        const double flops = 2.0*16.0*iters*(double) blocks*threads;
+        if (tflops) *tflops = flops/best*1e-12;
+        if (seconds_per_launch) *seconds_per_launch = best;
+    });
 }
 int mpidb200_nccl_unique_id(unsigned char* out128) {
     return guarded([&] {

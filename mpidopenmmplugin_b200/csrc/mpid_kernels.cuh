@@ -1680,15 +1680,31 @@ __device__ __forceinline__ void diisSolveBlock(int numBlocks, int m, const SlotL
     if (converged) return;
     if (m == 1) { if (tid == 0) status->coef[0] = 1.0; return; }
     __threadfence_block();
+    // The error overlaps span 20+ orders of magnitude near convergence, so the overlap block is scaled to a unit diagonal
+    // (B'_ij = B_ij d_i d_j, d_i = 1/sqrt(B_ii); the border -1 becomes -d_i) before the elimination, and pivots below 1e-12
+    // are dropped (their coefficient is 0): the rank truncation the reference gets from its SVD (:1276-1289).
+    // tests/host_emul/emul.cpp carries the same algorithm and is checked against the oracle down to eps = 1e-12.
     const int rank = m + 1, w = rank + 1;
     const int r = tid / W, c = tid % W;
     const bool inside = r < rank && c < w && tid < R*W;
+    __shared__ double dscale[R];
+    __shared__ int dropped[R];
+    if (tid < rank) {
+        dropped[tid] = 0;
+        if (tid == 0) dscale[0] = 1.0;
+        else {
+            const double bii = status->B[slots.s[tid-1]*H + slots.s[tid-1]];
+            dscale[tid] = bii > 0.0 ? rsqrt(bii) : 1.0;
+        }
+    }
+    __syncthreads();
     if (inside) {
         double v;
         if (c == rank) v = r == 0 ? -1.0 : 0.0;
         else if (r == 0 && c == 0) v = 0.0;
-        else if (r == 0 || c == 0) v = -1.0;
-        else v = status->B[slots.s[r-1]*H + slots.s[c-1]];
+        else if (r == 0) v = -dscale[c];
+        else if (c == 0) v = -dscale[r];
+        else v = status->B[slots.s[r-1]*H + slots.s[c-1]]*dscale[r]*dscale[c];
         a[r][c] = v;
     }
     __syncthreads();
@@ -1708,15 +1724,17 @@ __device__ __forceinline__ void diisSolveBlock(int numBlocks, int m, const SlotL
         if (sw) a[r][c] = other;
         __syncthreads();
         const double d = a[col][col];
+        const bool usable = fabs(d) >= 1e-12;
+        if (!usable && tid == 0) dropped[col] = 1;
         double f = 0.0, pc = 0.0;
-        if (inside && r != col && d != 0.0) { f = a[r][col]/d; pc = a[col][c]; }
+        if (inside && r != col && usable) { f = a[r][col]/d; pc = a[col][c]; }
         __syncthreads();
-        if (inside && r != col && d != 0.0 && f != 0.0 && c >= col) a[r][c] -= f*pc;
+        if (inside && r != col && usable && f != 0.0 && c >= col) a[r][c] -= f*pc;
         __syncthreads();
     }
     if (tid < m) {
         const double d = a[tid+1][tid+1];
-        status->coef[tid] = d != 0.0 ? a[tid+1][rank]/d : 0.0;
+        status->coef[tid] = (!dropped[tid+1] && d != 0.0) ? dscale[tid+1]*a[tid+1][rank]/d : 0.0;
     }
 }
 

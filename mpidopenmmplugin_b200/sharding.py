@@ -27,6 +27,16 @@ def uses_slab_fft(world, grid):
     return world >= SLAB_FFT_MIN_RANKS and grid[0] % world == 0 and grid[1] % world == 0
 
 
+def reciprocal_mode(world, grid):
+    """One-line description of how the reciprocal pass is partitioned at this rank count (bench.py's config line)."""
+    if world <= 1:
+        return "single GPU"
+    if uses_slab_fft(world, grid):
+        return ("slab decomposition (reduce-scatter, 2-D FFT on own x planes, all-to-all, x FFT + influence function on own ky rows, "
+                "all-to-all back, all-gather)")
+    return "all-reduce of the charge grid, FFT replicated"
+
+
 def collectives_per_evaluation(polarization, field_evaluations, pme=True, world=2, grid=(224, 224, 224)):
     """Collectives one evaluation issues per rank, by payload (used for the scaling model in DESIGN.md 5):
     list of (what, element count per atom or 'grid' / 'slab', dtype bytes).  A reciprocal pass is one all-reduce of

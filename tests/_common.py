@@ -98,6 +98,18 @@ def rel_err(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b))/max(np.linalg.norm(np.asarray(b)), 1e-300))
 
 
+def record_parity(test, **values):
+    """Append the errors a parity test achieved to gpurun_out/parity_achieved.jsonl (copied to profiles/ per round) so that
+    the margin under each tolerance is on record, not just pass/fail."""
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_achieved.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=test, **{k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in values.items()})) + "\n")
+    except OSError:
+        pass
+
+
 # ---------------------------------------------------------------------------------------------------
 # the reference's own test configurations (platforms/reference/tests/TestReferenceMPIDForce.cpp)
 # ---------------------------------------------------------------------------------------------------

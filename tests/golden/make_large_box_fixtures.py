@@ -20,12 +20,12 @@ from oracle.pyoracle import CellOracle  # noqa: E402
 
 CASES = {
     # name: (tiles, polarization, anisotropic, epsilon)
-    "96k_mutual": ((4, 4, 2), 0, False, 1e-8),
-    "96k_mutual_aniso": ((4, 4, 2), 0, True, 1e-8),
+    "96k_mutual": ((4, 4, 2), 0, False, 1e-12),
+    "96k_mutual_aniso": ((4, 4, 2), 0, True, 1e-12),
     "96k_direct": ((4, 4, 2), 1, False, 1e-5),
     "96k_extrapolated": ((4, 4, 2), 2, False, 1e-5),
     "96k_extrapolated_aniso": ((4, 4, 2), 2, True, 1e-5),
-    "1m_mutual": ((7, 7, 7), 0, False, 1e-8),
+    "1m_mutual": ((7, 7, 7), 0, False, 1e-12),
 }
 SUBSET = 4096
 

@@ -276,27 +276,33 @@ template <typename T> struct Emul {
 
     // small dense solve for the DIIS coefficients (:1254-1291 uses an SVD; any stable solver agrees)
     static void solveDiis(int m, const std::vector<double>& Bm, std::vector<double>& coef) {
+        // Same algorithm as the device solve (mpid_kernels.cuh: diisSolveScaled): the error-overlap block is scaled to a unit
+        // diagonal (its entries span 20+ orders of magnitude near convergence), Gauss-Jordan with partial pivoting, and pivots
+        // below 1e-12 are dropped (coefficient 0) -- the rank truncation the reference gets from its SVD (:1276-1289).
         int rank = m + 1;
-        std::vector<double> a(rank*(rank+1), 0.0);
+        std::vector<double> a(rank*(rank+1), 0.0), d(m, 1.0);
+        for (int i = 0; i < m; i++) d[i] = Bm[i*m+i] > 0 ? 1.0/sqrt(Bm[i*m+i]) : 1.0;
         for (int i = 0; i < rank; i++) for (int j = 0; j < rank; j++) {
             double v;
-            if (i == 0 && j == 0) v = 0; else if (i == 0 || j == 0) v = -1; else v = Bm[(i-1)*m + (j-1)];
+            if (i == 0 && j == 0) v = 0; else if (i == 0) v = -d[j-1]; else if (j == 0) v = -d[i-1]; else v = Bm[(i-1)*m + (j-1)]*d[i-1]*d[j-1];
             a[i*(rank+1)+j] = v;
         }
         a[0*(rank+1)+rank] = -1;
+        std::vector<char> dropped(rank, 0);
         for (int c = 0; c < rank; c++) {
             int piv = c;
             for (int r = c+1; r < rank; r++) if (fabs(a[r*(rank+1)+c]) > fabs(a[piv*(rank+1)+c])) piv = r;
             if (piv != c) for (int k = 0; k <= rank; k++) std::swap(a[c*(rank+1)+k], a[piv*(rank+1)+k]);
-            double d = a[c*(rank+1)+c];
+            double dd = a[c*(rank+1)+c];
+            if (fabs(dd) < 1e-12) { dropped[c] = 1; continue; }
             for (int r = 0; r < rank; r++) {
                 if (r == c) continue;
-                double f = a[r*(rank+1)+c]/d;
+                double f = a[r*(rank+1)+c]/dd;
                 for (int k = c; k <= rank; k++) a[r*(rank+1)+k] -= f*a[c*(rank+1)+k];
             }
         }
         coef.resize(m);
-        for (int i = 0; i < m; i++) coef[i] = a[(i+1)*(rank+1)+rank]/a[(i+1)*(rank+1)+(i+1)];
+        for (int i = 0; i < m; i++) coef[i] = dropped[i+1] ? 0.0 : d[i]*a[(i+1)*(rank+1)+rank]/a[(i+1)*(rank+1)+(i+1)];
     }
 
     // OPT storage

@@ -3,7 +3,7 @@ error 1e-5 in mixed precision, 1e-8 in double; neighbour list / exclusion classe
 import numpy as np
 import pytest
 
-from _common import (Oracle, load_fixture, make_kernel, methanol_dimer, pair_set_reference, random_molecule_box, rel_err, water_box,
+from _common import (Oracle, load_fixture, make_kernel, methanol_dimer, pair_set_reference, random_molecule_box, record_parity, rel_err, water_box,
                      water_dimer)
 from mpidopenmmplugin_b200 import MPIDB200Error, MPIDForce, MPIDB200Kernel
 from mpidopenmmplugin_b200.workloads import ANISO_ALPHA_O
@@ -12,9 +12,18 @@ from test_oracle_golden import GOLDEN, MAKERS, assert_equal_tol
 pytestmark = pytest.mark.gpu
 
 FTOL = {"mixed": 1e-5, "double": 1e-8}
-# mutual polarization: both sides iterate to eps (1e-8/1e-9 in the reference's tests) with different linear
-# solvers for the DIIS step, so the converged dipoles agree to ~eps, not to round-off
-MU_TOL_MUTUAL = 2e-6
+# Mutual polarization: the two sides stop at "eps < target" along slightly different DIIS paths (SVD there, scaled
+# Gauss-Jordan here), so at the reference's own test settings (eps = 1e-8 / 1e-9) the converged dipoles agree to ~eps,
+# not to round-off.  The double-precision parity runs therefore converge BOTH sides to eps = 1e-12, where the north
+# star's 1e-8 is asserted as it stands; the mixed-precision runs keep the reference's settings.
+EPS_TIGHT = 1e-12
+
+
+def tighten(s, prec):
+    if prec == "double" and s.polarization == 0:
+        s.epsilon = EPS_TIGHT
+        s.max_iter = 500
+    return s
 
 
 def run(s, prec):
@@ -29,16 +38,16 @@ def run(s, prec):
 @pytest.mark.parametrize("key", sorted(GOLDEN.keys()))
 def test_reference_golden_configurations(key, prec):
     name, method, pol = key
-    s = MAKERS[name](method, pol)
+    s = tighten(MAKERS[name](method, pol), prec)
     k, e, f, mu = run(s, prec)
     assert_equal_tol(GOLDEN[key], e, 1e-4)                 # the reference's own assertion
     o = Oracle(s)
     e0, f0 = o.execute()
     mu0 = o.dipoles(0)
-    ftol = FTOL[prec] if pol != 0 else max(FTOL[prec], 5e-7)
-    assert rel_err(f, f0) < ftol
+    record_parity("golden/%s/method%d/pol%d/%s" % (name, method, pol, prec), dF=rel_err(f, f0), dmu=rel_err(mu, mu0), dE=abs(e - e0)/max(1.0, abs(e0)), eps=s.epsilon)
+    assert rel_err(f, f0) < FTOL[prec]
     # FP32 fields at sites where large intramolecular contributions cancel: the north-star bound itself
-    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else (MU_TOL_MUTUAL if pol == 0 else 1e-7))
+    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else 1e-8)
     assert abs(e - e0) <= (1e-5 if prec == "mixed" else 1e-8)*max(1.0, abs(e0))
     if pol == 0:
         assert k.getStats()["epsilon"] < s.epsilon
@@ -68,13 +77,14 @@ def test_14_scaling(scale, expected, method):
 @pytest.mark.parametrize("pol,eps", [(1, 1e-5), (2, 1e-5), (0, 1e-7)])
 def test_waterbox_996(pol, eps, prec):
     """examples/waterbox coordinates, SWM6, PME alpha=3.2853, 32^3, rc=0.8 nm (BASELINE config 3)."""
-    s = water_box((1, 1, 1), polarization=pol, epsilon=eps)
+    s = tighten(water_box((1, 1, 1), polarization=pol, epsilon=eps), prec)
     k, e, f, mu = run(s, prec)
     o = Oracle(s)
     e0, f0 = o.execute()
     mu0 = o.dipoles(0)
+    record_parity("waterbox996/pol%d/%s" % (pol, prec), dF=rel_err(f, f0), dmu=rel_err(mu, mu0), dE=abs(e - e0)/abs(e0), eps=s.epsilon)
     assert rel_err(f, f0) < FTOL[prec]
-    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else (1e-6 if pol == 0 else 1e-9))
+    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else 1e-8)
     assert abs(e - e0) < (1e-5 if prec == "mixed" else 1e-8)*abs(e0)
     per_atom = np.linalg.norm(f - f0, axis=1)/np.sqrt(np.mean(np.sum(f0*f0, axis=1)))
     assert per_atom.max() < 20*FTOL[prec]
@@ -83,10 +93,15 @@ def test_waterbox_996(pol, eps, prec):
 
 @pytest.mark.parametrize("prec", ["double", "mixed"])
 def test_anisotropic_mutual_waterbox(prec):
-    s = water_box((1, 1, 1), polarization=0, epsilon=1e-7, anisotropic=True)
+    s = tighten(water_box((1, 1, 1), polarization=0, epsilon=1e-7, anisotropic=True), prec)
     k, e, f, mu = run(s, prec)
-    e0, f0 = Oracle(s).execute()
-    assert rel_err(f, f0) < FTOL[prec]*(1 if prec == "mixed" else 10)
+    o = Oracle(s)
+    e0, f0 = o.execute()
+    mu0 = o.dipoles(0)
+    record_parity("waterbox996-aniso/pol0/%s" % prec, dF=rel_err(f, f0), dmu=rel_err(mu, mu0), dE=abs(e - e0)/abs(e0), eps=s.epsilon)
+    assert rel_err(f, f0) < FTOL[prec]
+    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else 1e-8)
+    assert abs(e - e0) < (1e-5 if prec == "mixed" else 1e-8)*abs(e0)
     k.close()
 
 
@@ -140,13 +155,14 @@ def test_all_axis_types_and_triclinic_box(prec):
     """ZBisect, ThreeFold, ZOnly, NoAxisType and chirality flips are not covered by the reference's fixtures;
     the compiled oracle is the authority.  Random but traceless moments on 125 'molecules' of 4 atoms in a
     reduced triclinic box (builder: _common.random_molecule_box)."""
-    s = random_molecule_box()
+    s = tighten(random_molecule_box(), prec)
     k, e, f, mu = run(s, prec)
     o = Oracle(s)
     e0, f0 = o.execute()
     mu0 = o.dipoles(0)
-    assert rel_err(f, f0) < FTOL[prec]*(1 if prec == "mixed" else 30)
-    assert rel_err(mu, mu0) < 1e-5
+    record_parity("axis-types-triclinic/%s" % prec, dF=rel_err(f, f0), dmu=rel_err(mu, mu0), dE=abs(e - e0)/max(1.0, abs(e0)), eps=s.epsilon)
+    assert rel_err(f, f0) < FTOL[prec]
+    assert rel_err(mu, mu0) < (1e-5 if prec == "mixed" else 1e-8)
     assert abs(e - e0) < (1e-5 if prec == "mixed" else 1e-8)*max(1.0, abs(e0))
     pi, pj, pc = k.getPairList()
     assert set(zip(pi.tolist(), pj.tolist(), pc.tolist())) == set(pair_set_reference(s))

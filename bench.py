@@ -6,8 +6,8 @@ synthetic SWM6-MPID water boxes named by BASELINE.json.
   python bench.py --impl reference ...                     # the reference's own CPU pair functions on the SAME box
 
 One "step" = one MPIDForce energy+force evaluation (PME, mutual polarization to eps=1e-5, octopoles, anisotropic
-polarizability on O) on one coordinate set of a short synthetic trajectory (every water is translated rigidly by a
-seeded N(0, 0.001 nm) vector per step, so no step sees the coordinates of the one before).
+polarizability on O) on one coordinate set of a short synthetic ballistic trajectory (every water moves rigidly with
+its own seeded thermal velocity, so no step sees the coordinates of the one before).
 `value`: positions and forces resident in HBM (mpidb200_execute_device).  `e2e`: the same evaluation through
 mpidb200_execute with HOST buffers (H2D of positions, H2D + D2H of the accumulated forces inside the timed call).
 `roofline` / `roofline_kernels`: per KERNEL, from a third pass in which every launch runs alone between two CUDA
@@ -36,7 +36,8 @@ WORKLOADS = {
     "1m":   dict(tiles=(7, 7, 7), name="synthetic SWM6-MPID water box, N=1024884, L=21.9023 nm, grid 224^3"),
 }
 METRIC = "ns/day (force-evaluation limited, 2 fs) of one MPIDForce eval, waterbox PME + mutual induced"
-STEP_SIGMA_NM = 0.001              # per-step rigid displacement of every water in the timed trajectory
+STEP_SIGMA_NM = 0.00074            # per-step, per-component displacement of every water in the timed trajectory: thermal
+                                   # velocity of a water molecule at 300 K, sqrt(kT/m) = 0.37 nm/ps, times the 2 fs step
 # Algorithmic flops per unit.  2240 / 430 / 150: SURVEY.md 8(d), counted from the oracle's generic
 # routines (430 and 150 cover both directions of a pair; the gather kernels evaluate directions: 215 / 75 each).
 # 325 / 48: the pair classes the oracle has no routine for, counted the same way (tools/count_flops.cpp).
@@ -96,15 +97,11 @@ def build_system(args, world):
 
 
 def trajectory_shifts(s, count, seed=777):
-    """Per-step rigid displacement of every water (cumulative): step k uses s.pos + cumulative[k]."""
+    """Ballistic synthetic trajectory: every water moves rigidly with a constant seeded thermal velocity; step k uses
+    s.pos + k*v.  (Displacements grow linearly, as between two neighbour-list rebuilds of a real MD run.)"""
     rng = np.random.default_rng(seed)
-    nw = s.n//3
-    out = [np.zeros((s.n, 3))]
-    acc = np.zeros((nw, 3))
-    for _ in range(count - 1):
-        acc = acc + rng.normal(0.0, STEP_SIGMA_NM, size=(nw, 3))
-        out.append(np.repeat(acc, 3, axis=0))
-    return out
+    v = np.repeat(rng.normal(0.0, STEP_SIGMA_NM, size=(s.n//3, 3)), 3, axis=0)
+    return [k*v for k in range(count)]
 
 
 def kernel_rooflines(kprof, work, n, n_pol, rows, G, n_f, hbm_peak, fp32_peak):
@@ -214,7 +211,7 @@ def run_reference(args, rank, real_stdout):
                 impl="reference", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms, higher_is_better=True,
                 scaling="strong" if args.gpus > 1 else "weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=name, polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % prof["induced_field_evaluations"],
-                            cutoff_nm=s.cutoff, ewald_alpha=s.alpha, trajectory="rigid per-water N(0, %.3f nm) displacement per step (seed 777)" % STEP_SIGMA_NM),
+                            cutoff_nm=s.cutoff, ewald_alpha=s.alpha, trajectory="ballistic: every water moves rigidly with its own N(0, %.5f nm/step) thermal velocity (seed 777)" % STEP_SIGMA_NM),
                 cpu_baseline=dict(value=value, unit="ns/day", cores=threads, kind="reference", sample=sample, ms_per_eval=ms,
                                   seconds_by_part={k: float(prof[k]) for k in ("candidates_s", "fixed_field_s", "induced_fields_s", "electrostatics_s", "total_s")}),
                 e2e=dict(value=value, unit="ns/day", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -348,30 +345,30 @@ def main():
         barrier()
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------
     # The caller's arrays are page-locked once (mpidb200_pin_host_buffer), as the platform kernel does for the Context's
-    # position / force vectors; every step copies that step's coordinates into the pinned array first (inside the timed
-    # region: it stands for the integrator writing new positions), then H2D, evaluation, D2H of the accumulated forces.
-    pos_pin = np.zeros((n, 3))
+    # position / force vectors; every step: H2D of that step's coordinates and of the caller's (zeroed) forces, the
+    # evaluation, D2H of the accumulated forces and of the energy.
     f_h = np.zeros((n, 3))
-    k.pinHostBuffer(pos_pin)
     k.pinHostBuffer(f_h)
+    for p in pos_h:
+        k.pinHostBuffer(p)
     for i in range(2):
-        pos_pin[:] = pos_h[i]
-        f_h[:] = 0.0
-        k.execute(pos_pin, True, True, f_h)
+        f_h.fill(0.0)
+        k.execute(pos_h[i], True, True, f_h)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        pos_pin[:] = pos_h[args.warmup + i]
-        f_h[:] = 0.0
-        e_h = k.execute(pos_pin, True, True, f_h)
+        f_h.fill(0.0)                    # the host framework's force array starts every step at zero (the engine accumulates)
+        e_h = k.execute(pos_h[args.warmup + i], True, True, f_h)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0)*1e3/args.steps
     barrier()
+    for p in pos_h:
+        k.unpinHostBuffer(p)
     # pageable (not pinned) caller arrays, for comparison
     f_p = np.zeros((n, 3))
     t0 = time.perf_counter()
     for i in range(min(args.steps, 5)):
-        f_p[:] = 0.0
+        f_p.fill(0.0)
         k.execute(pos_h[args.warmup + i], True, True, f_p)
     torch.cuda.synchronize()
     e2e_pageable_ms = (time.perf_counter() - t0)*1e3/min(args.steps, 5)
@@ -447,7 +444,7 @@ def main():
                     dtype="f32 pair/grid math, f64 accumulation" if args.precision == "mixed" else "f64", data="synthetic",
                     config=dict(workload=wl_name, polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % n_f,
                                 cutoff_nm=s.cutoff, ewald_alpha=s.alpha, l2="256 MB buffer written between timed iterations",
-                                trajectory="rigid per-water N(0, %.3f nm) displacement per step (seed 777): every warm-up and timed step has its own coordinates" % STEP_SIGMA_NM,
+                                trajectory="ballistic: every water moves rigidly with its own N(0, %.5f nm/step) thermal velocity (seed 777); every warm-up and timed step has its own coordinates" % STEP_SIGMA_NM,
                                 parallelism=("atom-block rows x%d: NCCL all-reduce of the partial induced field every solver iteration and of forces/torques once; "
                                              "reciprocal pass on a second communicator / stream: %s" % (world, sharding.reciprocal_mode(world, s.grid)))
                                 if world > 1 else "1 GPU",

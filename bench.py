@@ -141,6 +141,8 @@ def kernel_rooflines(kprof, work, n, n_pol, rows, G, n_f, hbm_peak, fp32_peak):
     # polarizable list out)
     add("k_neighbor_list_cell", "k_neighbor_list", "hbm", 16.0*rows + 8.0*P + 8.0*work["pol_pol"] + 16.0*rows,
         "issue-slot bound integer/FP32 search (ncu: 66 % issue active); bytes = float4 positions in + 2 list entries per pair + polarizable list out")
+    add("k_filter_list", "k_filter_list", "hbm", 4.0*work.get("candidate_entries", 0) + 16.0*rows + 8.0*P + 8.0*work["pol_pol"] + 16.0*rows,
+        "candidate entries in + float4 positions + 2 list entries per pair + polarizable list out")
     add("cub_radix_sort", "cub_radix_sort", "hbm", 4*16.0*n, "4 onesweep passes over (key, index) pairs")
     # reciprocal space: HBM class (the grid lives in L2 at these sizes)
     add("k_spread_fixed", "k_spread<real, true>", "hbm", rows*(16 + 19*4) + 4.0*G, "N x (position + 19 fractional moments) + grid")
@@ -322,6 +324,9 @@ def main():
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)/args.steps
     stats = k.getStats()
     work = k.getWorkCounts()
+    ls = k.getListStats()
+    list_stats = dict(ls, note="evaluations of warm-up + timed loop that sorted and searched (builds) / reused the order and the skin-padded candidate list "
+                               "(reuses); skin 0.1 nm, rebuild when an atom has moved skin/2; the exact in-cutoff list is re-derived every evaluation")
     # ---- same steps with the stage timers on (intervals on three co-resident streams: informational) ----
     k.setProfiling(True)
     stage_sum = {}
@@ -457,7 +462,7 @@ def main():
                     gpu_launches=int(launches), energy_kj_mol=energy, wall_ms_per_step=t_wall/args.steps,
                     solver_field_evaluations=[int(i) + 1 for i in iters],
                     clocks=sampler.summary(), roofline=roof, roofline_kernels=roofs, kernel_us_per_evaluation=kernel_us,
-                    work_counts=work, fp32_peak_measured_tflops=fp32_peak,
+                    work_counts=work, fp32_peak_measured_tflops=fp32_peak, neighbour_list=list_stats,
                     stage_ms_coresident_intervals=stage_avg)
         if single:
             line["single_gpu_same_workload"] = single

@@ -154,6 +154,10 @@ int mpidb200_get_kernel_profile(mpidb200_handle h, char* buffer, long long capac
  * out8 = { ordinary pairs, full x full, full x bare charge, charge x charge, polarizable x polarizable pairs,
  *          directed site x neighbour evaluations of the permanent-field kernel, covalently scaled pairs, polarizable sites } */
 int mpidb200_get_work_counts(mpidb200_handle h, long long* out8);
+/* Neighbour-list reuse: out2[0] = evaluations that sorted and searched (built the skin-padded candidate list),
+ * out2[1] = evaluations that reused the order and the candidates (positions moved less than skin/2 since the build;
+ * MPIDB200_SKIN, default 0.1 nm; MPIDB200_NO_LIST_REUSE=1 disables).  The pair set is exact either way. */
+int mpidb200_get_list_stats(mpidb200_handle h, long long* out2);
 /* FP32 FMA throughput of `device` measured with a register-resident FMA-chain kernel (TFLOP/s, 2 flop per FMA):
  * the denominator of the pair kernels' rooflines. */
 int mpidb200_measure_fp32_peak(int device, double* tflops, double* seconds_per_launch);

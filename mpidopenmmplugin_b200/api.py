@@ -452,6 +452,11 @@ class MPIDB200Kernel:
         names = ("pairs", "full_full", "full_charge", "charge_charge", "pol_pol", "fixed_field_directed", "covalent_pairs", "polarizable_sites")
         return {k: int(out[i]) for i, k in enumerate(names)}
 
+    def getListStats(self):
+        out = (ctypes.c_longlong*2)()
+        self._check(self._lib.mpidb200_get_list_stats(self._h, out))
+        return dict(builds=int(out[0]), reuses=int(out[1]))
+
     def setKernelProfiling(self, enabled):
         self._check(self._lib.mpidb200_set_kernel_profiling(self._h, ctypes.c_int(1 if enabled else 0)))
 

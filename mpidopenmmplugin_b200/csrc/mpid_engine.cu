@@ -119,6 +119,7 @@ struct EngineBase {
     virtual void pinHost(void* ptr, size_t bytes) = 0;
     virtual void unpinHost(void* ptr) = 0;
     virtual void workCounts(long long* out8) = 0;
+    virtual void listStats(long long* out2) = 0;
     virtual void setKernelProfiling(bool on) = 0;
     virtual std::string kernelProfileCsv() = 0;
     bool profiling = false;
@@ -187,6 +188,14 @@ struct Engine : public EngineBase {
     int numSimpleTotal = 0, numSimple = 0, simpleBegin = 0;
     int numFull = 0, fullBegin = 0;       // sites that are not bare charges, among this rank's rows
     int nbrCap = 0;
+    // Verlet-skin reuse of the sorted order and the candidate list (k_regather_sites / k_filter_list)
+    double skin = 0.0;                  // nm; 0 = every evaluation sorts and searches (no-cutoff, boxes under 2(rc+skin), MPIDB200_SKIN=0)
+    bool listValid = false;             // order, class lists and candidates of an earlier evaluation are usable
+    bool reusing = false;               // this evaluation runs on them
+    int candCap = 0;
+    DevBuf<unsigned> dCand; DevBuf<uint4> dCandCounts; DevBuf<unsigned> dDisp; DevBuf<double> dPosBuild;
+    float lastDisp2 = 0.f, prevDisp2 = 0.f;
+    long long listBuilds = 0, listReuses = 0;
     int numPolTotal = 0;            // polarizable sites (static: follows from the parameters)
     int numPol = 0, polBegin = 0;   // polarizable sites among this rank's rows
     long long typeBegin[6] = {0, 0, 0, 0, 0, 0};   // boundaries of the four pair-class lists inside pairI/pairJ
@@ -417,7 +426,7 @@ struct Engine : public EngineBase {
         dThole.upload(hThole, stream); dAlpha.upload(hAlpha, stream); dDamp.upload(hDamp, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         haveParticles = true;
-        nlCapsKnown = false;
+        nlCapsKnown = false; listValid = false;
         if (hSpStart.empty()) {   // no covalent maps yet: empty special lists
             std::vector<int> off(8*(size_t) (n+1), 0), idx(1, 0);
             setCovalent(off.data(), idx.data());
@@ -458,6 +467,7 @@ struct Engine : public EngineBase {
         dSpStart.upload(hSpStart, stream); dSpPartner.upload(hSpPartner, stream); dSpClass.upload(hSpClass, stream);
         dSpLo.upload(hSpLo, stream); dSpHi.upload(hSpHi, stream); dSpPairClass.upload(hSpPairClass, stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
+        listValid = false;
     }
 
     // B-spline moduli, identical construction to initializeBSplineModuli (MPIDReferenceForce.cpp:2720-2810)
@@ -516,6 +526,7 @@ struct Engine : public EngineBase {
         P.cutoff = cfg.cutoff; P.cutoff2 = cfg.cutoff*cfg.cutoff;
         P.defaultThole = cfg.default_thole_width; P.scale14 = cfg.scale14;
         makeBox(P.box, a, b, c);
+        listValid = false; skin = 0.0;
         for (int sx = -1; sx <= 1; sx++) for (int sy = -1; sy <= 1; sy++) for (int sz = -1; sz <= 1; sz++) {
             int code = (sx+1)*9 + (sy+1)*3 + (sz+1);
             for (int k = 0; k < 3; k++) P.shift[code][k] = pme ? sx*a[k] + sy*b[k] + sz*c[k] : 0.0;
@@ -550,8 +561,15 @@ struct Engine : public EngineBase {
         double axb[3] = {a[1]*b[2] - a[2]*b[1], a[2]*b[0] - a[0]*b[2], a[0]*b[1] - a[1]*b[0]};
         double w[3] = {vol/sqrt(bxc[0]*bxc[0] + bxc[1]*bxc[1] + bxc[2]*bxc[2]), vol/sqrt(cxa[0]*cxa[0] + cxa[1]*cxa[1] + cxa[2]*cxa[2]),
                        vol/sqrt(axb[0]*axb[0] + axb[1]*axb[1] + axb[2]*axb[2])};
+        // list reuse needs the recorded image of a candidate to stay THE minimum image: rc + skin below half of every box width
+        {
+            const char* env = getenv("MPIDB200_SKIN");
+            const double want = env ? atof(env) : 0.1;
+            skin = (want > 0.0 && 2.0*(cfg.cutoff + want) <= std::min(w[0], std::min(w[1], w[2]))) ? want : 0.0;
+        }
+        const double rcList = cfg.cutoff + skin;           // the cell search runs with the skin-padded cutoff
         for (int d = 0; d < 3; d++) {
-            int n2 = (int) floor(w[d]/(0.5*cfg.cutoff*1.0001)), n1 = (int) floor(w[d]/(cfg.cutoff*1.0001));
+            int n2 = (int) floor(w[d]/(0.5*rcList*1.0001)), n1 = (int) floor(w[d]/(rcList*1.0001));
             if (n2 >= 5) { P.ncell[d] = std::min(n2, 1024); P.reach[d] = 2; }
             else if (n1 >= 3) { P.ncell[d] = n1; P.reach[d] = 1; }
             else { P.ncell[d] = 1; P.reach[d] = 0; }
@@ -575,6 +593,7 @@ struct Engine : public EngineBase {
         LAUNCH((k_eterm_table<real>), blocksFor((long long) GC, 256), 256, P, dModX.p, dModY.p, dModZ.p, dEterm.p);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         haveBox = true;
+        planHalo();
     }
 
     // Fused reciprocal pass (mpid_fft.cuh): single precision, power-of-two grid whose y-z and x-z slabs fit in shared
@@ -664,6 +683,48 @@ struct Engine : public EngineBase {
         return pp;
     }
 
+    // Reuse step: same sorted order, class lists and candidate list as the evaluation that built them; only the sorted
+    // positions (and the lab frames, which follow the atoms) are refreshed.
+    bool regatherAndFrames(const double* dPosIn) {
+        const int B = 256;
+        real* cartR; real* pkR;
+        if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
+        else { cartR = dCartR.p; pkR = dPkR.p; }
+        CUDA_CHECK(cudaMemsetAsync(dDisp.p, 0, sizeof(unsigned), stream));
+        LAUNCH((k_regather_sites<real>), blocksFor(n, B), B, n, dOrder.p, dPosIn, dPosBuild.p, dPosW.p, dFlagS.p, dDampThole.p,
+               dPosS.p, dPosF.p, dMud.p, dDisp.p);
+        CUDA_CHECK(cudaEventRecord(evFork, stream));
+        CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
+        stageEnd();
+        cur = stream2;
+        stageBegin(MPIDB200_STAGE_SORT);
+        LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn,
+               dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p);
+        stageEnd();
+        CUDA_CHECK(cudaEventRecord(evFrames, stream2));
+        cur = stream;
+        if (numRanks > 1) {
+            // several ranks decide together (every rank sees every atom): a host check before anything else is queued
+            unsigned* bits = (unsigned*) hPinned + 32;
+            CUDA_CHECK(cudaMemcpyAsync(bits, dDisp.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            float d2; memcpy(&d2, bits, sizeof(float));
+            return noteDisplacement(d2);
+        }
+        return true;
+    }
+    // Largest squared displacement since the list was built: beyond (skin/2)^2 the candidates no longer cover the cutoff
+    // sphere (this evaluation must be redone on a fresh list); when the next step is likely to get there, rebuild next time.
+    bool noteDisplacement(float d2) {
+        prevDisp2 = lastDisp2; lastDisp2 = d2;
+        const double lim = 0.5*skin;
+        const double now = sqrt((double) d2), before = sqrt((double) prevDisp2);
+        const bool ok = now <= lim;
+        const double step = std::max(now - before, 0.0);
+        if (!ok || now + 1.5*step > lim) listValid = false;
+        return ok;
+    }
+
     // wrap, cell sort, lab-frame moments, site-class lists (everything the reciprocal-space pass needs)
     void sortAndFrames(const double* dPosIn) {
         const int B = 256;
@@ -671,6 +732,11 @@ struct Engine : public EngineBase {
         dPosW.ensure(3*(size_t) n); dCellKey.ensure(n); dAtomIdx.ensure(n); dSortedKey.ensure(n); dOrder.ensure(n); dInv.ensure(n);
         dCellStart.ensure((size_t) numCells + 2);
         LAUNCH(k_wrap_cells, blocksFor(n, B), B, P, dPosIn, dPosW.p, dCellKey.p, dAtomIdx.p);
+        if (skin > 0.0) {      // the positions this order and the candidate list belong to
+            dPosBuild.ensure(3*(size_t) n); dDisp.ensure(1);
+            CUDA_CHECK(cudaMemcpyAsync(dPosBuild.p, dPosIn, 3*(size_t) n*sizeof(double), cudaMemcpyDeviceToDevice, stream));
+            lastDisp2 = prevDisp2 = 0.f;
+        }
         if (numCells > 1) {
             int bits = 1;
             while ((1 << bits) < numCells) bits++;
@@ -685,7 +751,8 @@ struct Engine : public EngineBase {
             CUDA_CHECK(cudaMemcpyAsync(dSortedKey.p, dCellKey.p, n*sizeof(int), cudaMemcpyDeviceToDevice, stream));
             CUDA_CHECK(cudaMemcpyAsync(dOrder.p, dAtomIdx.p, n*sizeof(int), cudaMemcpyDeviceToDevice, stream));
         }
-        // row partition of the sorted atoms across ranks
+        // row partition of the sorted atoms across ranks: equal counts, or (halo mode) whole x cell columns -- set below,
+        // once the cell starts are known
         P.rowBegin = (int) ((long long) n*rank/numRanks);
         P.rowEnd = (int) ((long long) n*(rank+1)/numRanks);
         dPosS.ensure(n); dPosF.ensure(n); dCartD.ensure(20*(size_t) n); dPkD.ensure(16*(size_t) n); dSphD.ensure(16*(size_t) n);
@@ -729,6 +796,16 @@ struct Engine : public EngineBase {
             CUDA_CHECK(cudaEventRecord(evFrames, stream2));
             cur = stream;
             stageBegin(MPIDB200_STAGE_SORT);
+        }
+        if (haloMode) {
+            // rows of rank r = the atoms of its x cell columns [xCellLo[r], xCellLo[r+1]): contiguous in the x-major sorted
+            // order, and every one of them spreads into rank r's block of x planes or its halo (planHalo)
+            int* cs = (int*) hPinned + 8;
+            const int colCells = P.ncell[1]*P.ncell[2];
+            CUDA_CHECK(cudaMemcpyAsync(&cs[0], dCellStart.p + (size_t) xCellLo[rank]*colCells, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&cs[1], dCellStart.p + (size_t) xCellLo[rank+1]*colCells, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            P.rowBegin = cs[0]; P.rowEnd = cs[1];
         }
         if (numRanks > 1) {
             int* pr = (int*) hPinned;
@@ -775,7 +852,13 @@ struct Engine : public EngineBase {
             dNbr.ensure((size_t) std::max(rows, 1)*nbrCap);
             dPolNbr.ensure((size_t) std::max(numPol, 1)*nbrCap);
             CUDA_CHECK(cudaMemsetAsync(dMaxCount.p, 0, 2*sizeof(unsigned), stream));
-            if (rows > 0) {
+            if (skin > 0.0) {
+                // (a) when the list is (re)built: cell search with the cutoff padded by the skin, into the candidate list;
+                // (b) always: exact list = candidates inside the cutoff at the current positions
+                if (!reusing && attempt == 0) searchCandidates(dPosIn, rows, roundMode, numCells);
+                if (rows > 0) LAUNCH(k_filter_list, blocksFor((long long) rows*32, B), B, P, candCap, dPosF.p, dPosIn, dOrder.p, dCand.p, dCandCounts.p,
+                                     dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
+            } else if (rows > 0) {
                 if (roundMode) LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, P, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
                                       dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
                 else LAUNCH(k_neighbor_list_cell, numCells, 256, P, dPosF.p, dPosIn, dOrder.p, dCellStart.p,
@@ -799,17 +882,20 @@ struct Engine : public EngineBase {
                 LAUNCH(k_collect_totals, 1, 32, rows, dMaxCount.p, dTypeStart.p, dTotals.p);
                 cur = keep;
                 CUDA_CHECK(cudaMemcpyAsync(totals, dTotals.p, 7*sizeof(unsigned), cudaMemcpyDeviceToHost, stream3));
+                if (reusing) CUDA_CHECK(cudaMemcpyAsync(totals + 7, dDisp.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream3));
                 CUDA_CHECK(cudaEventRecord(evNlTotals, stream3));
                 break;
             }
             LAUNCH(k_collect_totals, 1, 32, rows, dMaxCount.p, dTypeStart.p, dTotals.p);
             CUDA_CHECK(cudaMemcpyAsync(totals, dTotals.p, 7*sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            if (reusing && numRanks == 1) CUDA_CHECK(cudaMemcpyAsync(totals + 7, dDisp.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaEventRecord(evNlTotals, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             if ((int) totals[0] <= nbrCap) break;
             if (attempt > 3) throw std::runtime_error("mpidb200: neighbour list capacity could not be established");
             nbrCap = (int) (totals[0]*1.2) + 16;       // rare: density fluctuation beyond the guess
         }
+        if (skin > 0.0 && !reusing) listValid = true;      // a fresh candidate list: later evaluations may run on it
         if (!nlSpeculative) {
             adoptNlistTotals();
             // flat full-full list: 10 % head room so that the next evaluations can run speculatively
@@ -819,10 +905,43 @@ struct Engine : public EngineBase {
         }
         stageEnd();
     }
+    // Cell search with the padded cutoff into the candidate list (same kernels, same layout as the exact list); the
+    // capacity is checked on the host right away -- this runs once per list life time, not once per evaluation.
+    void searchCandidates(const double* dPosIn, int rows, bool roundMode, int numCells) {
+        const int B = 256;
+        const double rcList = cfg.cutoff + skin;
+        if (candCap == 0) {
+            const double grow = (rcList/cfg.cutoff)*(rcList/cfg.cutoff)*(rcList/cfg.cutoff);
+            candCap = std::min(std::max((int) (nbrCap*grow*1.05) + 32, 32), std::max(n, 32));
+        }
+        dCandCounts.ensure((size_t) rows + 1);
+        DevParams Pb = P;
+        Pb.cutoff = rcList; Pb.cutoff2 = rcList*rcList;
+        unsigned* mx = (unsigned*) hPinned + 34;
+        for (int attempt = 0; ; attempt++) {
+            Pb.nbrCap = candCap;
+            dCand.ensure((size_t) std::max(rows, 1)*candCap);
+            dPolNbr.ensure((size_t) std::max(numPol, 1)*std::max(candCap, nbrCap));     // scratch for the search's polarizable rows
+            CUDA_CHECK(cudaMemsetAsync(dMaxCount.p + 1, 0, sizeof(unsigned), stream));
+            if (rows > 0) {
+                if (roundMode) LAUNCH((k_neighbor_list<true>), blocksFor((long long) rows*32, B), B, Pb, dPosF.p, dPosIn, dOrder.p, dSortedKey.p, dCellStart.p,
+                                      dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dCand.p, dCandCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p + 1);
+                else LAUNCH(k_neighbor_list_cell, numCells, 256, Pb, dPosF.p, dPosIn, dOrder.p, dCellStart.p,
+                            dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dCand.p, dCandCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p + 1);
+            }
+            CUDA_CHECK(cudaMemcpyAsync(mx, dMaxCount.p + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            if ((int) mx[0] <= candCap) break;
+            if (attempt > 3) throw std::runtime_error("mpidb200: candidate list capacity could not be established");
+            candCap = (int) (mx[0]*1.15) + 16;
+        }
+        listBuilds++;
+    }
     unsigned* hNlTotals = nullptr;
     DevBuf<unsigned> dTotals;
     cudaEvent_t evNlTotals = nullptr;
     bool nlSpeculative = false, nlCapsKnown = false;
+    const bool noReuse = getenv("MPIDB200_NO_LIST_REUSE") != nullptr;
     size_t pairCap = 0;
     void adoptNlistTotals() {
         for (int t = 0; t < 5; t++) typeBegin[t] = hNlTotals[1 + t];
@@ -830,9 +949,20 @@ struct Engine : public EngineBase {
     }
     // Speculative evaluations: wait for the (long finished) read-back and verify the capacities that were assumed.
     bool nlistTotalsOk() {
-        if (!nlSpeculative) return true;
+        if (!nlSpeculative) {
+            // synchronous path: capacities were checked on the spot; a single-rank reuse step still owes its displacement check
+            if (reusing && numRanks == 1) {
+                float d2; memcpy(&d2, hNlTotals + 7, sizeof(float));
+                if (!noteDisplacement(d2)) return false;
+            }
+            return true;
+        }
         CUDA_CHECK(cudaEventSynchronize(evNlTotals));
-        const bool ok = (int) hNlTotals[0] <= nbrCap && (size_t) hNlTotals[2] <= pairCap;
+        bool ok = (int) hNlTotals[0] <= nbrCap && (size_t) hNlTotals[2] <= pairCap;
+        if (reusing) {
+            float d2; memcpy(&d2, hNlTotals + 7, sizeof(float));
+            if (!noteDisplacement(d2)) ok = false;           // an atom left its skin: redo on a fresh list
+        }
         if (ok) adoptNlistTotals();
         else {
             nlCapsKnown = false;                     // the repeat runs synchronously and re-establishes the capacities
@@ -889,6 +1019,112 @@ struct Engine : public EngineBase {
     //   all-gather       : every rank gets the full real grid back for its gather kernels
     // The spread and gather kernels are unchanged (no halo logic), and a pass moves half the bytes of the all-reduce
     // version over NVLink while the transform itself is divided by R.  Needs nx and ny divisible by R.
+    // ---- reciprocal pass with halo exchange (several ranks) -------------------------------------------------------
+    // Rank r owns the block of nx/R x planes that starts at plane r nx/R + nx/2 (the reference's grid origin sits half a
+    // box away from the coordinate origin: computeMPIDBsplines, MPIDReferenceForce.cpp:3049-3075) and the atoms of the x cell
+    // columns [xCellLo[r], xCellLo[r+1]).  Such an atom spreads into the block or at most haloLo planes below / haloHi
+    // planes above it, so a pass exchanges those few planes with the two neighbouring ranks instead of reduce-scattering
+    // and all-gathering the whole grid:
+    //   halo reduce (send the planes spread outside the own block, add what the neighbours spread into it)
+    //   2-D R2C on the own planes, all-to-all, 1-D C2C along x + influence function + C2C back on the own ky rows,
+    //   all-to-all back, 2-D C2R                                                (the slab transform, blocks rotated by R/2)
+    //   halo gather (fetch the result on the halo planes from the neighbours)
+    // The spread and gather kernels are the single-GPU ones: they address the full-size grid array, of which a rank only
+    // ever touches its block and halo.  sharding.halo_plan / halo_reciprocal_pass restate plan and data movement in numpy.
+    bool haloMode = false;
+    int haloLo = 0, haloHi = 0;
+    std::vector<int> xCellLo;
+    DevBuf<real> dHaloIn;
+    const bool haloEnabled = !(getenv("MPIDB200_HALO") && atoi(getenv("MPIDB200_HALO")) == 0);
+    void planHalo() {
+        haloMode = false;
+        const int R = numRanks, nx = grid[0];
+        if (!haloEnabled || R < 2 || (R % 2) != 0 || cfg.nonbonded_method != MPIDB200_PME || !haveBox) return;
+        if (nx % R != 0 || grid[1] % R != 0 || P.ncell[0] < R) return;
+        if (!(g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd)) return;
+        const int nxl = nx/R, ncx = P.ncell[0];
+        xCellLo.assign(R + 1, 0);
+        for (int r = 0; r <= R; r++) xCellLo[r] = (int) ((long long) r*ncx/R);
+        // fractional drift an atom may have picked up since the list was built (skin/2), plus rounding slack
+        const double drift = 0.5*skin*sqrt(P.box.ra[0]*P.box.ra[0] + P.box.rb[0]*P.box.rb[0] + P.box.rc[0]*P.box.rc[0]) + 1e-9;
+        int lo = 0, hi = 0;
+        for (int r = 0; r < R; r++) {
+            const double f0 = (double) xCellLo[r]/ncx - drift, f1 = (double) xCellLo[r+1]/ncx + drift;
+            const long long first = (long long) floor(nx*(f0 + 0.5)) - (MPID_PME_ORDER - 1);      // unwrapped plane numbers
+            const long long last = (long long) floor(nx*(f1 + 0.5));
+            const long long blockFirst = (long long) r*nxl + nx/2;
+            lo = std::max(lo, (int) std::max(0LL, blockFirst - first));
+            hi = std::max(hi, (int) std::max(0LL, last - (blockFirst + nxl - 1)));
+        }
+        if (lo + hi > nxl) return;          // halos of the two neighbours must not overlap inside a block
+        haloLo = lo; haloHi = hi; haloMode = true;
+    }
+    void haloReciprocalPass() {
+        const int R = numRanks, nx = grid[0], ny = grid[1], nz = grid[2], nzc = nz/2 + 1;
+        const int nxl = nx/R, nyl = ny/R;
+        const size_t plane = (size_t) ny*nz, slabCplx = (size_t) nxl*ny*nzc, blk = (size_t) nxl*nyl*nzc;
+        ensureSlabPlans(R);
+        dSlabC.ensure(slabCplx); dSlabPack.ensure(slabCplx); dSlabT.ensure(slabCplx);
+        dHaloIn.ensure(std::max<size_t>((size_t) (haloLo + haloHi)*plane, 1));
+        void* c = (cur == stream2 && commPme) ? commPme : comm;
+        const int dt = sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
+        const int up = (rank + 1) % R, down = (rank + R - 1) % R;
+        const int myStart = (rank*nxl + nx/2) % nx;
+        real* own = dGrid.p + (size_t) myStart*plane;
+        real* lowHalo = dGrid.p + (size_t) ((myStart - haloLo + nx) % nx)*plane;
+        real* highHalo = dGrid.p + (size_t) ((myStart + nxl) % nx)*plane;
+        const size_t nLo = (size_t) haloLo*plane, nHi = (size_t) haloHi*plane;
+        // halo reduce
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        if (nLo) ncclCheck(g_nccl.Send(lowHalo, nLo, dt, down, c, cur), "ncclSend");
+        if (nHi) ncclCheck(g_nccl.Send(highHalo, nHi, dt, up, c, cur), "ncclSend");
+        if (nLo) ncclCheck(g_nccl.Recv(dHaloIn.p, nLo, dt, up, c, cur), "ncclRecv");
+        if (nHi) ncclCheck(g_nccl.Recv(dHaloIn.p + nLo, nHi, dt, down, c, cur), "ncclRecv");
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        if (nLo + nHi) LAUNCH((k_halo_add<real>), blocksFor((long long) (nLo + nHi), 256), 256, nLo, nHi, dHaloIn.p, own + (size_t) (nxl - haloLo)*plane, own);
+        // slab transform on the own block; block r sits at x position (r + R/2) mod R of the transform
+        CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, own, dSlabC.p));
+        launches += 1;
+        LAUNCH((k_slab_transpose<cplx, true>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabC.p, dSlabPack.p);
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < R; r++) {
+            ncclCheck(g_nccl.Send(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
+            ncclCheck(g_nccl.Recv(dSlabT.p + (size_t) ((r + R/2) % R)*blk, 2*blk, dt, r, c, cur), "ncclRecv");
+        }
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_FORWARD));
+        LAUNCH((k_slab_convolution<cplx, real>), blocksFor((long long) slabCplx, 256), 256, nx, ny, nyl, rank*nyl, nzc, dEterm.p, dSlabT.p);
+        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_INVERSE));
+        launches += 2;
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < R; r++) {
+            ncclCheck(g_nccl.Send(dSlabT.p + (size_t) ((r + R/2) % R)*blk, 2*blk, dt, r, c, cur), "ncclSend");
+            ncclCheck(g_nccl.Recv(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
+        }
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
+        CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, dSlabC.p, own));
+        launches += 1;
+        // halo gather: my top planes are the low halo of the rank above, my first planes the high halo of the rank below
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        if (nLo) ncclCheck(g_nccl.Send(own + (size_t) (nxl - haloLo)*plane, nLo, dt, up, c, cur), "ncclSend");
+        if (nHi) ncclCheck(g_nccl.Send(own, nHi, dt, down, c, cur), "ncclSend");
+        if (nLo) ncclCheck(g_nccl.Recv(lowHalo, nLo, dt, down, c, cur), "ncclRecv");
+        if (nHi) ncclCheck(g_nccl.Recv(highHalo, nHi, dt, up, c, cur), "ncclRecv");
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+    }
+    void ensureSlabPlans(int R) {
+        const int nx = grid[0], ny = grid[1], nz = grid[2], nzc = nz/2 + 1, nxl = nx/R, nyl = ny/R;
+        if (slabPlansMade && slabRanks == R) return;
+        destroySlabPlans();
+        int n2[2] = {ny, nz};
+        CUFFT_CHECK(cufftPlanMany(&planSlabF, 2, n2, nullptr, 1, 0, nullptr, 1, 0, FftTraits<real>::fwdType, nxl));
+        CUFFT_CHECK(cufftPlanMany(&planSlabB, 2, n2, nullptr, 1, 0, nullptr, 1, 0, FftTraits<real>::bwdType, nxl));
+        int n1[1] = {nx}, embed[1] = {nx};
+        CUFFT_CHECK(cufftPlanMany(&planSlabX, 1, n1, embed, nyl*nzc, 1, embed, nyl*nzc, 1, FftTraits<real>::c2cType, nyl*nzc));
+        slabPlansMade = true; slabRanks = R;
+        setPlanStreams();
+    }
     void destroySlabPlans() {
         if (slabPlansMade) { cufftDestroy(planSlabF); cufftDestroy(planSlabB); cufftDestroy(planSlabX); slabPlansMade = false; }
     }
@@ -906,16 +1142,7 @@ struct Engine : public EngineBase {
         const int R = numRanks, nx = grid[0], ny = grid[1], nz = grid[2], nzc = nz/2 + 1;
         const int nxl = nx/R, nyl = ny/R;
         const size_t slabReal = (size_t) nxl*ny*nz, slabCplx = (size_t) nxl*ny*nzc, blk = (size_t) nxl*nyl*nzc;
-        if (!slabPlansMade || slabRanks != R) {
-            destroySlabPlans();
-            int n2[2] = {ny, nz};
-            CUFFT_CHECK(cufftPlanMany(&planSlabF, 2, n2, nullptr, 1, 0, nullptr, 1, 0, FftTraits<real>::fwdType, nxl));
-            CUFFT_CHECK(cufftPlanMany(&planSlabB, 2, n2, nullptr, 1, 0, nullptr, 1, 0, FftTraits<real>::bwdType, nxl));
-            int n1[1] = {nx}, embed[1] = {nx};
-            CUFFT_CHECK(cufftPlanMany(&planSlabX, 1, n1, embed, nyl*nzc, 1, embed, nyl*nzc, 1, FftTraits<real>::c2cType, nyl*nzc));
-            slabPlansMade = true; slabRanks = R;
-            setPlanStreams();
-        }
+        ensureSlabPlans(R);
         dSlabR.ensure(slabReal); dSlabC.ensure(slabCplx); dSlabPack.ensure(slabCplx); dSlabT.ensure(slabCplx);
         void* c = (cur == stream2 && commPme) ? commPme : comm;
         const int dt = sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
@@ -949,6 +1176,7 @@ struct Engine : public EngineBase {
     void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
         size_t GC = (size_t) grid[0]*grid[1]*(grid[2]/2 + 1);
         stageBegin(MPIDB200_STAGE_FFT);
+        if (haloMode) { haloReciprocalPass(); stageEnd(); return; }
         if (useSlabFft()) { slabReciprocalPass(); stageEnd(); return; }
         if (numRanks > 1) allReduce(dGrid.p, (size_t) grid[0]*grid[1]*grid[2], sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64);
         if (fft2.ok) {
@@ -1328,7 +1556,15 @@ struct Engine : public EngineBase {
         const bool pme = P.method == PME;
         P.numRanks = numRanks; P.rank = rank;
         stageBegin(MPIDB200_STAGE_SORT);
-        sortAndFrames(dPosIn);
+        reusing = listValid && skin > 0.0 && !noReuse;
+        if (reusing && !regatherAndFrames(dPosIn)) {
+            // (several ranks) an atom has left its skin: this evaluation sorts and searches again
+            CUDA_CHECK(cudaStreamSynchronize(stream2));
+            reusing = false;
+            stageBegin(MPIDB200_STAGE_SORT);
+        }
+        if (!reusing) sortAndFrames(dPosIn);
+        else { stageBegin(MPIDB200_STAGE_SORT); stageEnd(); listReuses++; }
         fixedReciprocalStart();                    // stream 2, beside the neighbour search
         buildNeighborList(dPosIn);
         CUDA_CHECK(cudaStreamWaitEvent(stream, evFrames, 0));      // lab-frame moments (second stream) before any pair kernel
@@ -1600,6 +1836,7 @@ struct Engine : public EngineBase {
     //   [4] polarizable x polarizable pairs (k_induced_field walks both directions of each)
     //   [5] directed site x neighbour evaluations of k_fixed_field (polarizable sites x all their neighbours)
     //   [6] covalently scaled pairs (static list)   [7] polarizable sites
+    void listStats(long long* out2) override { out2[0] = listBuilds; out2[1] = listReuses; }
     void workCounts(long long* out) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
         CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1779,6 +2016,8 @@ struct Engine : public EngineBase {
         rank = rk; numRanks = nr;
         P.rank = rk; P.numRanks = nr;
         setPlanStreams();
+        listValid = false;
+        planHalo();
     }
 };
 
@@ -1902,6 +2141,9 @@ int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer) {
 }
 int mpidb200_get_work_counts(mpidb200_handle h, long long* out8) {
     return guarded([&] { asEngine(h)->workCounts(out8); });
+}
+int mpidb200_get_list_stats(mpidb200_handle h, long long* out2) {
+    return guarded([&] { asEngine(h)->listStats(out2); });
 }
 int mpidb200_set_kernel_profiling(mpidb200_handle h, int enabled) {
     return guarded([&] { asEngine(h)->setKernelProfiling(enabled != 0); });

@@ -555,6 +555,126 @@ k_neighbor_list_cell(DevParams P, const float4* __restrict__ posF, const double*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Neighbour-list reuse (Verlet skin).  The cell search above is run with the cutoff enlarged by a skin and its output
+// kept as the CANDIDATE list; every evaluation -- the one that built it and the ones that reuse it -- derives the exact
+// list from the candidates with k_filter_list: same FP32 pre-test, same FP64 re-test of the borderline pairs on the raw
+// positions with the oracle's own formula, so the pair set is still exactly { i<j : |minimg(r_j - r_i)|^2 <= rc^2 }.
+// While no atom has moved more than skin/2 since the search, every pair inside the cutoff is among the candidates, the
+// sorted order is kept (no sort, no cell bookkeeping) and the periodic image recorded for a candidate is still the
+// minimum image (|d| <= rc + skin < L/2).
+// ---------------------------------------------------------------------------------------------------
+// Sorted positions of a reuse step: the atom keeps the lattice translation it was wrapped with when the list was built,
+// so pair vectors stay continuous.  Also the largest squared displacement since the build (atomicMax on float bits).
+template <typename real>
+__global__ void k_regather_sites(int n, const int* __restrict__ order, const double* __restrict__ posNow, const double* __restrict__ posBuild,
+                                 const double* __restrict__ poswBuild, const int* __restrict__ flagS, const double2* __restrict__ dampTholeD,
+                                 double4* __restrict__ posS, float4* __restrict__ posF, typename Real4<real>::type* __restrict__ mud,
+                                 unsigned* __restrict__ maxDisp2Bits) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    float d2 = 0.f;
+    if (s < n) {
+        const int o = order[s];
+        const double dx = posNow[3*(size_t) o] - posBuild[3*(size_t) o], dy = posNow[3*(size_t) o+1] - posBuild[3*(size_t) o+1], dz = posNow[3*(size_t) o+2] - posBuild[3*(size_t) o+2];
+        const double x = poswBuild[3*(size_t) o] + dx, y = poswBuild[3*(size_t) o+1] + dy, z = poswBuild[3*(size_t) o+2] + dz;
+        const int flag = flagS[s];
+        posS[s] = make_double4(x, y, z, (double) flag);
+        posF[s] = make_float4((float) x, (float) y, (float) z, (float) flag);
+        const double dmp = dampTholeD[s].x;
+        typename Real4<real>::type m;
+        m.x = 0; m.y = 0; m.z = 0; m.w = dmp != 0.0 ? (real) (1.0/dmp) : real(0);
+        mud[s] = m;
+        d2 = __double2float_ru(dx*dx + dy*dy + dz*dz);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, off));
+    if ((threadIdx.x & 31) == 0 && d2 > 0.f) atomicMax(maxDisp2Bits, __float_as_uint(d2));
+}
+
+// One warp per row: walk the row's candidates (upper run from the front, lower run from the back, the layout of
+// k_neighbor_list) and keep the pairs inside the cutoff, in the same layout and order.
+__global__ void __launch_bounds__(256)
+k_filter_list(DevParams P, int candCap, const float4* __restrict__ posF, const double* __restrict__ posOrig, const int* __restrict__ order,
+              const unsigned* __restrict__ cand, const uint4* __restrict__ candCounts, const int* __restrict__ polRank, int polBegin,
+              unsigned* __restrict__ nbr, uint4* __restrict__ counts, unsigned* __restrict__ polNbr, unsigned* __restrict__ polCount,
+              unsigned* __restrict__ maxCount) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int rows = P.rowEnd - P.rowBegin;
+    if (row >= rows) return;
+    const int i = P.rowBegin + row;
+    const float4 pi = posF[i];
+    const bool pme = P.method == PME;
+    const float rcLo = (float) P.cutoff - 1.0e-4f, rcHi = (float) P.cutoff + 1.0e-4f;
+    const float rcLo2 = rcLo > 0.f ? rcLo*rcLo : 0.f, rcHi2 = rcHi*rcHi;
+    const unsigned cap = (unsigned) P.nbrCap;
+    const uint4 cc = candCounts[row];
+    const unsigned* cbase = cand + (size_t) row*candCap;
+    unsigned* base = nbr + (size_t) row*cap;
+    const bool iPol = ((int) pi.w & 1) != 0;
+    unsigned* polBase = polNbr + (iPol ? (size_t) (polRank[i] - polBegin)*cap : 0);
+    unsigned nUp = 0, nLow = 0, nUpSimple = 0, nPol = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    int oi = -1;
+    // Four candidates per lane and trip: the four list entries, then the four (dependent) position gathers are in flight
+    // together -- the kernel is bound by that latency, not by arithmetic.  Sub-blocks are committed in order, so the
+    // output keeps the candidate order.
+    constexpr int U = 4;
+    for (int run = 0; run < 2; run++) {
+        const unsigned len = run == 0 ? cc.x : cc.y;
+        for (unsigned k0 = 0; k0 < len; k0 += 32*U) {
+            unsigned e[U];
+            float4 pj[U];
+            bool in[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned k = k0 + 32*u + lane;
+                in[u] = k < len;
+                e[u] = in[u] ? (run == 0 ? cbase[k] : cbase[candCap - 1 - k]) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) pj[u] = posF[e[u] & MPID_JMASK];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int jflag = (int) pj[u].w;
+                if (in[u] && pme) {
+                    const unsigned code = e[u] >> MPID_CODE_SHIFT;
+                    const float ddx = (pj[u].x - pi.x) - (float) P.shift[code][0], ddy = (pj[u].y - pi.y) - (float) P.shift[code][1], ddz = (pj[u].z - pi.z) - (float) P.shift[code][2];
+                    const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
+                    if (r2 > rcHi2) in[u] = false;
+                    else if (r2 >= rcLo2) {
+                        // borderline: the oracle's test, bit for bit, on the raw positions
+                        if (oi < 0) oi = order[i];
+                        const int oj = order[e[u] & MPID_JMASK];
+                        const int lo = min(oi, oj), hi = max(oi, oj);
+                        double ex = posOrig[3*(size_t) hi] - posOrig[3*(size_t) lo], ey = posOrig[3*(size_t) hi+1] - posOrig[3*(size_t) lo+1], ez = posOrig[3*(size_t) hi+2] - posOrig[3*(size_t) lo+2];
+                        periodicDelta(P.box, ex, ey, ez);
+                        in[u] = !(dist2Exact(ex, ey, ez) > P.cutoff2);
+                    }
+                }
+                const unsigned maskIn = __ballot_sync(FULL, in[u]);
+                const unsigned maskS = __ballot_sync(FULL, in[u] && run == 0 && (jflag & 2));
+                const unsigned maskP = __ballot_sync(FULL, in[u] && iPol && (jflag & 1));
+                const unsigned cnt = __popc(maskIn);
+                if (in[u] && nUp + nLow + cnt <= cap) {
+                    if (run == 0) base[nUp + __popc(maskIn & lt)] = e[u];
+                    else base[cap - 1 - (nLow + __popc(maskIn & lt))] = e[u];
+                    if (iPol && (jflag & 1)) polBase[nPol + __popc(maskP & lt)] = e[u];
+                }
+                if (run == 0) nUp += cnt; else nLow += cnt;
+                nUpSimple += __popc(maskS); nPol += __popc(maskP);
+            }
+        }
+    }
+    if (lane == 0) {
+        const bool fits = nUp + nLow <= cap;       // see k_neighbor_list
+        counts[row] = fits ? make_uint4(nUp, nLow, nUpSimple, nPol) : make_uint4(0u, 0u, 0u, 0u);
+        if (iPol) polCount[polRank[i] - polBegin] = fits ? nPol : 0u;
+        atomicMax(maxCount, nUp + nLow);
+    }
+}
+
 // Pair classes of the energy kernel: type = 2*simple(i) + simple(j).  typeCount[t*(rows+1) + r] = number of
 // upper neighbours of row r that fall in class t (scanned per class to place the runs of the four flat lists).
 __global__ void k_half_counts(DevParams P, int rows, const uint4* __restrict__ counts, const int* __restrict__ flagS,
@@ -1305,6 +1425,15 @@ __global__ void k_slab_transpose(int nxl, int R, int rowLen, const cplx* __restr
     if (PACK) dst[packed] = src[idx]; else dst[idx] = src[packed];
 }
 // influence function on this rank's ky rows: data[x][kyl][kz] *= eterm[x][ky0 + kyl][kz]
+// halo reduce of the partitioned reciprocal pass: what the neighbours spread into this rank's block
+//   top[0..nLo) += in[0..nLo)   (low halo of the rank above)      bottom[0..nHi) += in[nLo..nLo+nHi)   (high halo of the rank below)
+template <typename real>
+__global__ void k_halo_add(size_t nLo, size_t nHi, const real* __restrict__ in, real* __restrict__ top, real* __restrict__ bottom) {
+    const size_t t = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (t < nLo) top[t] += in[t];
+    else if (t < nLo + nHi) bottom[t - nLo] += in[t];
+}
+
 template <typename cplx, typename real>
 __global__ void k_slab_convolution(int nx, int ny, int nyl, int ky0, int nzc, const real* __restrict__ eterm, cplx* __restrict__ data) {
     const size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x;

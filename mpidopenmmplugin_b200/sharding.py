@@ -27,10 +27,22 @@ def uses_slab_fft(world, grid):
     return world >= SLAB_FFT_MIN_RANKS and grid[0] % world == 0 and grid[1] % world == 0
 
 
+def uses_halo_exchange(world, grid, ncell_x=None):
+    """mpid_engine.cu: planHalo() -- an even rank count that divides nx and ny, at least one x cell column per rank and
+    halos that fit into a block (checked by the engine; MPIDB200_HALO=0 switches it off)."""
+    import os
+    if os.environ.get("MPIDB200_HALO", "1") == "0":
+        return False
+    return world >= 2 and world % 2 == 0 and grid[0] % world == 0 and grid[1] % world == 0 and (ncell_x is None or ncell_x >= world)
+
+
 def reciprocal_mode(world, grid):
     """One-line description of how the reciprocal pass is partitioned at this rank count (bench.py's config line)."""
     if world <= 1:
         return "single GPU"
+    if uses_halo_exchange(world, grid):
+        return ("slab decomposition with halo exchange: rows = whole x cell columns, every rank spreads into its block of nx/R planes + halo; "
+                "halo reduce with the two neighbours, 2-D FFT on own planes, all-to-all, x FFT + influence function on own ky rows, all-to-all back, halo gather")
     if uses_slab_fft(world, grid):
         return ("slab decomposition (reduce-scatter, 2-D FFT on own x planes, all-to-all, x FFT + influence function on own ky rows, "
                 "all-to-all back, all-gather)")

@@ -394,3 +394,53 @@ def test_conjugate_gradient_reports_non_convergence():
     with pytest.raises(MPIDB200Error, match="Induced dipoles did not converge"):
         k.execute(s.pos, True, True, np.zeros((s.n, 3)))
     k.close()
+
+
+def test_neighbour_list_reuse_keeps_the_pair_set_exact():
+    """Verlet-skin reuse (k_regather_sites / k_filter_list): evaluations that reuse the sorted order and the skin-padded
+    candidate list must give the oracle's pair set and a fresh engine's forces, step after step; an atom that leaves its
+    skin (more than skin/2 from where the list was built) must be noticed, and the evaluation redone on a fresh list."""
+    s = water_box((1, 1, 1), polarization=1)
+    rng = np.random.default_rng(5)
+    v = np.repeat(rng.normal(0.0, 0.004, size=(s.n//3, 3)), 3, axis=0)      # rigid per-water drift, 0.004 nm per step
+    k = make_kernel(s, precision="double")
+    for step in range(9):
+        t = s.copy()
+        t.pos = s.pos + step*v
+        if step == 7:
+            t.pos[300:303] += np.array([0.0, 0.31, 0.0])                   # one water jumps 0.31 nm between two steps
+        f = np.zeros((s.n, 3))
+        e = k.execute(t.pos, True, True, f)
+        pi, pj, pc = k.getPairList()
+        assert set(zip(pi.tolist(), pj.tolist(), pc.tolist())) == set(pair_set_reference(t)), step
+        kf = make_kernel(t, precision="double")                             # fresh engine: sorts and searches from scratch
+        g = np.zeros((s.n, 3))
+        eg = kf.execute(t.pos, True, True, g)
+        kf.close()
+        assert abs(e - eg) < 1e-11*abs(eg), step
+        assert rel_err(f, g) < 1e-11, step
+    st = k.getListStats()
+    # 0.004 nm/step x up to 4 sigma: the 0.05 nm limit is reached after a few steps -> several builds AND several reuses
+    assert st["reuses"] >= 3 and st["builds"] >= 3, st
+    k.close()
+    e0, f0 = Oracle(t).execute()
+    assert rel_err(f, f0) < 1e-8
+
+
+def test_neighbour_list_reuse_can_be_disabled(monkeypatch):
+    s = water_box((1, 1, 1), polarization=1)
+    monkeypatch.setenv("MPIDB200_NO_LIST_REUSE", "1")
+    k = make_kernel(s, precision="mixed")
+    f = np.zeros((s.n, 3))
+    for _ in range(3):
+        k.execute(s.pos, True, True, f)
+    assert k.getListStats()["reuses"] == 0
+    k.close()
+    monkeypatch.setenv("MPIDB200_SKIN", "0")
+    monkeypatch.delenv("MPIDB200_NO_LIST_REUSE")
+    k = make_kernel(s, precision="mixed")
+    g = np.zeros((s.n, 3))
+    k.execute(s.pos, True, True, g)
+    k.execute(s.pos, True, True, np.zeros((s.n, 3)))
+    assert k.getListStats() == dict(builds=0, reuses=0)            # no skin: the search writes the exact list directly
+    k.close()

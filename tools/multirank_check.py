@@ -1,6 +1,8 @@
 """Multi-rank parity check (run under torch.distributed.run, one rank per GPU): the row-partitioned engine with its
-NCCL collectives against the same engine on one GPU, same box, for every polarization type and both reciprocal-pass
-strategies (all-reduce + replicated FFT, slab decomposition).  Rank 0 prints one JSON line per case and exits
+NCCL collectives against the same engine on one GPU, same box, for every polarization type and every reciprocal-pass
+strategy (all-reduce + replicated FFT, slab decomposition, slab decomposition with halo exchange), over a short
+trajectory so that the neighbour-list reuse path runs too.  With tiles 4x4x2 the sharded result is also compared with the
+reference's own pair functions (tests/golden/large_box_96k_*.npz).  Rank 0 prints one JSON line per case and exits
 non-zero on a mismatch.  Usage: python -m torch.distributed.run --nproc-per-node N tools/multirank_check.py [tiles]"""
 import json
 import os
@@ -22,15 +24,24 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tiles = tuple(int(v) for v in sys.argv[1].split("x")) if len(sys.argv) > 1 else (2, 2, 2)
     ok = True
+    fixtures = {0: "96k_mutual", 1: "96k_direct", 2: "96k_extrapolated"} if tiles == (4, 4, 2) else {}
     for pol, eps in ((0, 1e-6), (1, 1e-6), (2, 1e-6)):          # Mutual, Direct, Extrapolated
         s = water_box(tiles, polarization=pol, epsilon=eps)
+        rng = np.random.default_rng(11)
+        drift = np.repeat(rng.normal(0.0, 0.003, size=(s.n//3, 3)), 3, axis=0)
         ref_f = np.zeros((s.n, 3))
         k1 = make_kernel(s, precision="mixed", device=local)       # every rank computes the single-GPU answer itself
         ref_e = k1.execute(s.pos, True, True, ref_f)
         ref_mu = k1.getInducedDipoles(s.pos)
+        ref_f2 = np.zeros((s.n, 3))
+        ref_e2 = k1.execute(s.pos + 2*drift, True, True, ref_f2)
         k1.close()
-        for slab in (0, 2):                                       # MPIDB200_SLAB_FFT: never / from 2 ranks on
+        gold = None
+        if pol in fixtures:
+            gold = np.load(os.path.join(ROOT, "tests", "golden", "large_box_%s.npz" % fixtures[pol]))
+        for mode, slab, halo in (("allreduce", 0, 0), ("slab", 2, 0), ("halo", 0, 1)):
             os.environ["MPIDB200_SLAB_FFT"] = str(slab)
+            os.environ["MPIDB200_HALO"] = str(halo)
             k = make_kernel(s, precision="mixed", device=local)
             if rank == 0:
                 uid = torch.tensor(list(MPIDB200Kernel.ncclUniqueId()), dtype=torch.uint8, device="cuda")
@@ -42,13 +53,26 @@ def main():
             e = k.execute(s.pos, True, True, f)
             e2 = k.execute(s.pos, True, True, np.zeros((s.n, 3)))          # second call: speculative capacities, same answer
             mu = k.getInducedDipoles(s.pos)
+            # two more steps along a drift: the ranks reuse the sorted order and the candidate list
+            k.execute(s.pos + drift, True, True, np.zeros((s.n, 3)))
+            f3 = np.zeros((s.n, 3))
+            e3 = k.execute(s.pos + 2*drift, True, True, f3)
+            reuse = k.getListStats()
             k.close()
             df = float(np.linalg.norm(f - ref_f)/np.linalg.norm(ref_f))
             dmu = float(np.linalg.norm(mu - ref_mu)/max(np.linalg.norm(ref_mu), 1e-300))
             de = abs(e - ref_e)/abs(ref_e)
-            rec = dict(world=world, n=s.n, grid=list(s.grid), polarization=pol, slab_fft=slab, dF=df, dmu=dmu, dE=de, repeat_dE=abs(e2 - e)/abs(e))
+            df3 = float(np.linalg.norm(f3 - ref_f2)/np.linalg.norm(ref_f2))
+            rec = dict(world=world, n=s.n, grid=list(s.grid), polarization=pol, reciprocal=mode, dF=df, dmu=dmu, dE=de, repeat_dE=abs(e2 - e)/abs(e),
+                       drift_dF=df3, drift_dE=abs(e3 - ref_e2)/abs(ref_e2), list=reuse)
             # the grid is summed with single-precision atomics, so a repeated evaluation agrees to ~1e-9, not bitwise
-            good = df < 2e-6 and dmu < 2e-6 and de < 1e-8 and rec["repeat_dE"] < 1e-8
+            good = df < 2e-6 and dmu < 2e-6 and de < 1e-8 and rec["repeat_dE"] < 1e-8 and df3 < 2e-6 and rec["drift_dE"] < 1e-8 and reuse["reuses"] >= 3
+            if gold is not None:
+                idx = gold["subset"]
+                rec["oracle_dF"] = float(np.linalg.norm(f[idx] - gold["forces"])/np.linalg.norm(gold["forces"]))
+                rec["oracle_dmu"] = float(np.linalg.norm(mu[idx] - gold["induced"])/max(np.linalg.norm(gold["induced"]), 1e-300))
+                rec["oracle_dE"] = abs(e - float(gold["energy"]))/abs(float(gold["energy"]))
+                good = good and rec["oracle_dF"] < 1e-5 and rec["oracle_dmu"] < 1e-5 and rec["oracle_dE"] < 1e-5
             ok = ok and good
             if rank == 0:
                 print(json.dumps(dict(rec, ok=good)), flush=True)

@@ -158,6 +158,10 @@ int mpidb200_get_work_counts(mpidb200_handle h, long long* out8);
  * out2[1] = evaluations that reused the order and the candidates (positions moved less than skin/2 since the build;
  * MPIDB200_SKIN, default 0.1 nm; MPIDB200_NO_LIST_REUSE=1 disables).  The pair set is exact either way. */
 int mpidb200_get_list_stats(mpidb200_handle h, long long* out2);
+/* Test hook: one reciprocal pass (R2C, influence function, C2R; unnormalised) of a caller-supplied real grid
+ * [nx][ny][nz] in place, through the hand-written transform kernels (use_library = 0) or cuFFT (1).  Mixed precision,
+ * one rank.  reference stage: fftpack_exec_3d + performMPIDReciprocalConvolution, MPIDReferenceForce.cpp:2931-2933, 3329-3366 */
+int mpidb200_debug_reciprocal_pass(mpidb200_handle h, float* host_grid, int use_library);
 /* FP32 FMA throughput of `device` measured with a register-resident FMA-chain kernel (TFLOP/s, 2 flop per FMA):
  * the denominator of the pair kernels' rooflines. */
 int mpidb200_measure_fp32_peak(int device, double* tflops, double* seconds_per_launch);

@@ -452,6 +452,12 @@ class MPIDB200Kernel:
         names = ("pairs", "full_full", "full_charge", "charge_charge", "pol_pol", "fixed_field_directed", "covalent_pairs", "polarizable_sites")
         return {k: int(out[i]) for i, k in enumerate(names)}
 
+    def debugReciprocalPass(self, grid, use_library=False):
+        """One reciprocal pass of a float32 [nx][ny][nz] array (copy returned): hand-written kernels or cuFFT."""
+        g = np.ascontiguousarray(grid, dtype=np.float32).copy()
+        self._check(self._lib.mpidb200_debug_reciprocal_pass(self._h, g.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.c_int(1 if use_library else 0)))
+        return g
+
     def getListStats(self):
         out = (ctypes.c_longlong*2)()
         self._check(self._lib.mpidb200_get_list_stats(self._h, out))

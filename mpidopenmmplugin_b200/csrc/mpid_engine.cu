@@ -120,6 +120,7 @@ struct EngineBase {
     virtual void unpinHost(void* ptr) = 0;
     virtual void workCounts(long long* out8) = 0;
     virtual void listStats(long long* out2) = 0;
+    virtual void debugReciprocalPass(float* hostGrid, bool library) = 0;
     virtual void setKernelProfiling(bool on) = 0;
     virtual std::string kernelProfileCsv() = 0;
     bool profiling = false;
@@ -166,6 +167,7 @@ struct Engine : public EngineBase {
     double boxA[3], boxB[3], boxC[3];
     DevParams P;
     double alphaEwald = 0; int grid[3] = {0, 0, 0};
+    double autoAlpha = 0; int autoGrid[3] = {0, 0, 0};      // automatic PME parameters, fixed at the first set_box
     // static device data
     DevBuf<double> dCharge, dDipole, dQuad, dOct, dThole, dAlpha, dDamp;
     DevBuf<int> dAxis, dZ, dX, dY, dFlagOrig;
@@ -202,9 +204,10 @@ struct Engine : public EngineBase {
     DevBuf<double> dField, dEfix, dMu, dIfield, dGrad;
     // force[3n], torque[3n], energy[2] in ONE allocation: one memset per evaluation, one all-reduce with several ranks
     DevBuf<unsigned long long> dAccum;
-    unsigned long long* forceP() { return dAccum.p; }
-    unsigned long long* torqueP() { return dAccum.p + 3*(size_t) n; }
-    unsigned long long* energyP() { return dAccum.p + 6*(size_t) n; }
+    // layout [energy 2 | force 3n | torque 3n]: energy and forces are contiguous for the one all-reduce of the last stage
+    unsigned long long* energyP() { return dAccum.p; }
+    unsigned long long* forceP() { return dAccum.p + 2; }
+    unsigned long long* torqueP() { return dAccum.p + 2 + 3*(size_t) n; }
     DevBuf<real> dFrac, dGrid, dEterm, dPhi, dPhidp, dThetaPol;
     DevBuf<int4> dIgridPol;
     DevBuf<cplx> dGridC;
@@ -543,10 +546,16 @@ struct Engine : public EngineBase {
         // (NonbondedForceImpl::calcPMEParameters; call site MPIDReferenceKernels.cpp:161-170)
         double al = cfg.ewald_alpha; int g[3] = {cfg.grid[0], cfg.grid[1], cfg.grid[2]};
         if (al == 0.0 || g[0] == 0) {
-            double tol = cfg.ewald_tolerance;
-            al = sqrt(-log(2.0*tol))/cfg.cutoff;
-            double len[3] = {a[0], b[1], c[2]};
-            for (int d = 0; d < 3; d++) g[d] = legalFftSize(std::max((int) ceil(2.0*al*len[d]/(3.0*pow(tol, 0.2))), 6));
+            // Resolved ONCE, from the first box this engine sees (the reference derives them in initialize from the System's
+            // default box and keeps them: MPIDReferenceKernels.cpp:161-170); later box changes -- a barostat -- only rebuild
+            // the reciprocal tables, so getPMEParametersInContext stays constant and the energy continuous.
+            if (autoAlpha == 0.0) {
+                double tol = cfg.ewald_tolerance;
+                autoAlpha = sqrt(-log(2.0*tol))/cfg.cutoff;
+                double len[3] = {a[0], b[1], c[2]};
+                for (int d = 0; d < 3; d++) autoGrid[d] = legalFftSize(std::max((int) ceil(2.0*autoAlpha*len[d]/(3.0*pow(tol, 0.2))), 6));
+            }
+            al = autoAlpha; g[0] = autoGrid[0]; g[1] = autoGrid[1]; g[2] = autoGrid[2];
         }
         bool gridChanged = !(g[0] == grid[0] && g[1] == grid[1] && g[2] == grid[2]);
         alphaEwald = al; grid[0] = g[0]; grid[1] = g[1]; grid[2] = g[2];
@@ -605,25 +614,30 @@ struct Engine : public EngineBase {
         const char* env = getenv("MPIDB200_FFT");
         const std::string mode = env ? env : "";
         if (mode == "cufft") return;
-        for (int d = 0; d < 3; d++) if (g[d] < 8 || g[d] > MPID_FFT_MAXLEN || (g[d] & (g[d] - 1)) != 0) return;
         auto uploadTwiddles = [&]() {
             if (dTwiddle.p) return;
-            std::vector<float2> tw(MPID_FFT_MAXLEN);
+            // exp(-2 pi i t/512), t < 512, then exp(-2 pi i t/448), t < 448 (mpid_fft.cuh: fft2LoadTablePart)
+            std::vector<float2> tw(MPID_FFT_TABLE);
             for (int t = 0; t < MPID_FFT_MAXLEN; t++) {
                 const double a = -2.0*MPID_PI*t/MPID_FFT_MAXLEN;
                 tw[t] = make_float2((float) cos(a), (float) sin(a));
             }
+            for (int t = 0; t < MPID_FFT_LEN7; t++) {
+                const double a = -2.0*MPID_PI*t/MPID_FFT_LEN7;
+                tw[MPID_FFT_MAXLEN + t] = make_float2((float) cos(a), (float) sin(a));
+            }
             dTwiddle.upload(tw, stream);
         };
         if (mode != "fused") {
-            // register-radix kernels (x, y in {32,64,128,256}, z in {32,64,128}): MPIDB200_FFT=fused2, or the default when
-            // the grid qualifies
-            if (mode == "fused2" || (mode.empty() && MPIDB200_FFT2_DEFAULT)) {
-                fft2 = fft2MakePlan(g[0], g[1], g[2]);
+            // register-radix kernels (x, y in {32,64,128,224,256}, z in {32,64,128,224}): the default when the grid qualifies;
+            // MPIDB200_FFT=fused3 selects the single-buffer plane kernels for every size (they are the only ones for 224)
+            if (mode == "fused2" || mode == "fused3" || (mode.empty() && MPIDB200_FFT2_DEFAULT)) {
+                fft2 = fft2MakePlan(g[0], g[1], g[2], mode == "fused3");
                 if (fft2.ok) uploadTwiddles();
             }
             return;
         }
+        for (int d = 0; d < 3; d++) if (g[d] < 8 || g[d] > MPID_FFT_MAXLEN || (g[d] & (g[d] - 1)) != 0) return;
         const size_t nzc = (size_t) g[2]/2 + 1;
         fftSmemPlane = 2*(size_t) g[1]*nzc*sizeof(float2);
         fftSmemX = 2*(size_t) g[0]*nzc*sizeof(float2);
@@ -687,22 +701,11 @@ struct Engine : public EngineBase {
     // positions (and the lab frames, which follow the atoms) are refreshed.
     bool regatherAndFrames(const double* dPosIn) {
         const int B = 256;
-        real* cartR; real* pkR;
-        if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
-        else { cartR = dCartR.p; pkR = dPkR.p; }
         CUDA_CHECK(cudaMemsetAsync(dDisp.p, 0, sizeof(unsigned), stream));
         LAUNCH((k_regather_sites<real>), blocksFor(n, B), B, n, dOrder.p, dPosIn, dPosBuild.p, dPosW.p, dFlagS.p, dDampThole.p,
                dPosS.p, dPosF.p, dMud.p, dDisp.p);
-        CUDA_CHECK(cudaEventRecord(evFork, stream));
-        CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
+        launchLabFrames(dPosIn);
         stageEnd();
-        cur = stream2;
-        stageBegin(MPIDB200_STAGE_SORT);
-        LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn,
-               dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p);
-        stageEnd();
-        CUDA_CHECK(cudaEventRecord(evFrames, stream2));
-        cur = stream;
         if (numRanks > 1) {
             // several ranks decide together (every rank sees every atom): a host check before anything else is queued
             unsigned* bits = (unsigned*) hPinned + 32;
@@ -780,32 +783,29 @@ struct Engine : public EngineBase {
             LAUNCH(k_class_lists, blocksFor(n + 1, B), B, n, dFlagS.p, dClassScan.p, dPolRank.p, dSimpleRank.p, dFullRank.p,
                    dPolList.p, dSimpleList.p, dFullList.p, dOrder.p, dInv.p, dSpStart.p, dSpPartner.p, dSpSorted.p);
         }
-        // ... while the lab-frame moments (needed by the reciprocal pass first, by the pair kernels after the neighbour
-        // search) are built on the second stream; evaluate() makes the main stream wait for evFrames.  Forked after
-        // the class lists so that its blocks (higher-priority stream) do not delay the short kernels the neighbour
-        // search is waiting for.
-        {
-            CUDA_CHECK(cudaEventRecord(evFork, stream));
-            CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
-            stageEnd();
-            cur = stream2;
-            stageBegin(MPIDB200_STAGE_SORT);
-            LAUNCH((k_lab_frame<real>), blocksFor(n, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn,
-                   dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p);
-            stageEnd();
-            CUDA_CHECK(cudaEventRecord(evFrames, stream2));
-            cur = stream;
-            stageBegin(MPIDB200_STAGE_SORT);
-        }
+        if (numRanks == 1) launchLabFrames(dPosIn);       // forked right after the class lists (see launchLabFrames)
+        frameSeg[0][0] = 0; frameSeg[0][1] = n; frameSeg[1][0] = frameSeg[1][1] = 0;
         if (haloMode) {
             // rows of rank r = the atoms of its x cell columns [xCellLo[r], xCellLo[r+1]): contiguous in the x-major sorted
-            // order, and every one of them spreads into rank r's block of x planes or its halo (planHalo)
+            // order, and every one of them spreads into rank r's block of x planes or its halo (planHalo).  The only
+            // atoms whose moments and dipoles this rank ever reads are those rows plus the cell columns its neighbour
+            // search reaches into: frameSeg = that range of the sorted order (two pieces when it wraps around the box).
             int* cs = (int*) hPinned + 8;
-            const int colCells = P.ncell[1]*P.ncell[2];
+            const int colCells = P.ncell[1]*P.ncell[2], ncx = P.ncell[0];
+            const int lo = xCellLo[rank] - P.reach[0], hi = xCellLo[rank+1] + P.reach[0];
+            const bool all = hi - lo >= ncx;
+            const int loW = ((lo % ncx) + ncx) % ncx, hiW = ((hi % ncx) + ncx) % ncx;       // hiW == 0 means "up to the end"
             CUDA_CHECK(cudaMemcpyAsync(&cs[0], dCellStart.p + (size_t) xCellLo[rank]*colCells, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaMemcpyAsync(&cs[1], dCellStart.p + (size_t) xCellLo[rank+1]*colCells, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&cs[2], dCellStart.p + (size_t) loW*colCells, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(&cs[3], dCellStart.p + (size_t) hiW*colCells, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             P.rowBegin = cs[0]; P.rowEnd = cs[1];
+            if (!all) {
+                const int a = cs[2], b = hiW == 0 ? n : cs[3];
+                if (lo >= 0 && hi <= ncx) { frameSeg[0][0] = a; frameSeg[0][1] = b; }
+                else { frameSeg[0][0] = a; frameSeg[0][1] = n; frameSeg[1][0] = 0; frameSeg[1][1] = hiW == 0 ? 0 : cs[3]; }
+            }
         }
         if (numRanks > 1) {
             int* pr = (int*) hPinned;
@@ -813,15 +813,84 @@ struct Engine : public EngineBase {
             CUDA_CHECK(cudaMemcpyAsync(&pr[1], dPolRank.p + P.rowEnd, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaMemcpyAsync(&pr[2], dSimpleRank.p + P.rowBegin, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaMemcpyAsync(&pr[3], dSimpleRank.p + P.rowEnd, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            // the covalently scaled pairs this rank owns in the energy stage (lower atom among its rows)
+            const int ns = (int) hSpLo.size();
+            dSpOwn.ensure(std::max(ns, 1)); dSpOwnCount.ensure(1);
+            CUDA_CHECK(cudaMemsetAsync(dSpOwnCount.p, 0, sizeof(unsigned), stream));
+            if (ns > 0) LAUNCH(k_own_special, blocksFor(ns, 256), 256, ns, dSpLo.p, dInv.p, P.rowBegin, P.rowEnd, dSpOwn.p, dSpOwnCount.p);
+            CUDA_CHECK(cudaMemcpyAsync(&pr[4], dSpOwnCount.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             polBegin = pr[0]; numPol = pr[1] - pr[0];
             simpleBegin = pr[2]; numSimple = pr[3] - pr[2];
+            numSpOwn = pr[4];
+            exchangePolPartition();
+            launchLabFrames(dPosIn);
         } else {
             polBegin = 0; numPol = numPolTotal; simpleBegin = 0; numSimple = numSimpleTotal;
         }
         // full = complement of simple within the same row range
         fullBegin = P.rowBegin - simpleBegin; numFull = (P.rowEnd - P.rowBegin) - numSimple;
         stageEnd();
+    }
+    // Lab-frame moments (needed by the reciprocal pass first, by the pair kernels after the neighbour search) are built on
+    // the second stream; evaluate() makes the main stream wait for evFrames.  Forked after the class lists so that its
+    // blocks (higher-priority stream) do not delay the short kernels the neighbour search is waiting for.  With several
+    // ranks only the atoms of frameSeg are done (a query evaluation, which reports per-atom values, does them all).
+    int frameSeg[2][2] = {{0, 0}, {0, 0}};
+    bool allFramesWanted = false;
+    DevBuf<int> dSpOwn; DevBuf<unsigned> dSpOwnCount; int numSpOwn = 0;
+    void launchLabFrames(const double* dPosIn) {
+        real* cartR; real* pkR;
+        if (sizeof(real) == sizeof(double)) { cartR = (real*) dCartD.p; pkR = (real*) dPkD.p; }
+        else { cartR = dCartR.p; pkR = dPkR.p; }
+        CUDA_CHECK(cudaEventRecord(evFork, stream));
+        CUDA_CHECK(cudaStreamWaitEvent(stream2, evFork, 0));
+        stageEnd();
+        cur = stream2;
+        stageBegin(MPIDB200_STAGE_SORT);
+        for (int q = 0; q < 2; q++) {
+            int b = frameSeg[q][0], e = frameSeg[q][1];
+            if (allFramesWanted || numRanks == 1) { if (q == 1) break; b = 0; e = n; }
+            if (e > b) LAUNCH((k_lab_frame<real>), blocksFor(e - b, 128), 128, P, particleParams(), cfg.frameless_alpha_fix, dOrder.p, dPosIn,
+                              dCartD.p, dPkD.p, cartR, pkR, dSphD.p, dAlphaLab.p, dAniso.p, b, e);
+        }
+        stageEnd();
+        CUDA_CHECK(cudaEventRecord(evFrames, stream2));
+        cur = stream;
+        stageBegin(MPIDB200_STAGE_SORT);
+    }
+    // Every rank's share of the polarizable-site list (offset, count), gathered once per list build: the solver exchanges
+    // the dipoles of the sites a rank owns with all-to-all sends of exactly those pieces (gatherDipoles).
+    std::vector<int> polBeginOf, numPolOf;
+    DevBuf<int> dPolPart;
+    void exchangePolPartition() {
+        polBeginOf.assign(numRanks, 0); numPolOf.assign(numRanks, 0);
+        if (!g_nccl.AllGather) throw std::runtime_error("mpidb200: ncclAllGather is not available");
+        dPolPart.ensure(2*(size_t) numRanks);
+        int mine[2] = {polBegin, numPol};
+        CUDA_CHECK(cudaMemcpyAsync(dPolPart.p + 2*rank, mine, 2*sizeof(int), cudaMemcpyHostToDevice, stream));
+        ncclCheck(g_nccl.AllGather(dPolPart.p + 2*rank, dPolPart.p, 2, /*ncclInt32*/ 2, comm, stream), "ncclAllGather");
+        std::vector<int> all(2*(size_t) numRanks);
+        CUDA_CHECK(cudaMemcpyAsync(all.data(), dPolPart.p, all.size()*sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int r = 0; r < numRanks; r++) { polBeginOf[r] = all[2*r]; numPolOf[r] = all[2*r+1]; }
+    }
+    // Owner computes: after a rank has new dipoles for the polarizable sites among its rows, every rank needs them (the
+    // field kernels read the dipoles of neighbours).  Compact pieces, one grouped send/receive per pair of ranks, then one
+    // pass that writes the per-atom arrays.  This is the per-iteration exchange of the partitioned solver.
+    DevBuf<double> dMuCompact, dDotsLocal;
+    void gatherDipoles() {
+        if (numRanks <= 1 || numPolTotal == 0) return;
+        dMuCompact.ensure(3*(size_t) numPolTotal);
+        if (numPol > 0) LAUNCH(k_pack_sites, blocksFor(3*(long long) numPol, 256), 256, numPol, (const int*) dPolList.p + polBegin, dMu.p, dMuCompact.p + 3*(size_t) polBegin);
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < numRanks; r++) {
+            if (r == rank) continue;
+            if (numPol > 0) ncclCheck(g_nccl.Send(dMuCompact.p + 3*(size_t) polBegin, 3*(size_t) numPol, NCCL_FLOAT64, r, comm, cur), "ncclSend");
+            if (numPolOf[r] > 0) ncclCheck(g_nccl.Recv(dMuCompact.p + 3*(size_t) polBeginOf[r], 3*(size_t) numPolOf[r], NCCL_FLOAT64, r, comm, cur), "ncclRecv");
+        }
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        LAUNCH((k_unpack_mu<real>), blocksFor(numPolTotal, 256), 256, numPolTotal, (const int*) dPolList.p, dMuCompact.p, dMu.p, dMud.p);
     }
 
     // neighbour list: single pass into per-atom runs, then the flat half list for the energy kernel
@@ -839,6 +908,10 @@ struct Engine : public EngineBase {
             nbrCap = P.method == PME ? (int) (1.35*expected) + 48 : n;
             nbrCap = std::min(std::max(nbrCap, 32), std::max(n, 32));
         }
+        // pair offsets and totals are 32-bit (cub scans over unsigned): refuse systems that could overflow them instead of
+        // wrapping silently (reached near 25 M atoms of liquid water per rank at rc = 0.8 nm)
+        if (0.5*(double) std::max(rows, 1)*nbrCap > 4.0e9)
+            throw std::runtime_error("mpidb200: this system needs more than 2^32 neighbour-list entries per rank; partition it over more ranks");
         const bool roundMode = P.method != PME || P.reach[0] == 0 || P.reach[1] == 0 || P.reach[2] == 0;
         if (!hNlTotals) CUDA_CHECK(cudaMallocHost((void**) &hNlTotals, 8*sizeof(unsigned)));
         if (!evNlTotals) CUDA_CHECK(cudaEventCreateWithFlags(&evNlTotals, cudaEventDisableTiming));
@@ -1083,8 +1156,7 @@ struct Engine : public EngineBase {
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
         if (nLo + nHi) LAUNCH((k_halo_add<real>), blocksFor((long long) (nLo + nHi), 256), 256, nLo, nHi, dHaloIn.p, own + (size_t) (nxl - haloLo)*plane, own);
         // slab transform on the own block; block r sits at x position (r + R/2) mod R of the transform
-        CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, own, dSlabC.p));
-        launches += 1;
+        slabPlanesForward(own, dSlabC.p, nxl);
         LAUNCH((k_slab_transpose<cplx, true>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabC.p, dSlabPack.p);
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         for (int r = 0; r < R; r++) {
@@ -1092,10 +1164,7 @@ struct Engine : public EngineBase {
             ncclCheck(g_nccl.Recv(dSlabT.p + (size_t) ((r + R/2) % R)*blk, 2*blk, dt, r, c, cur), "ncclRecv");
         }
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
-        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_FORWARD));
-        LAUNCH((k_slab_convolution<cplx, real>), blocksFor((long long) slabCplx, 256), 256, nx, ny, nyl, rank*nyl, nzc, dEterm.p, dSlabT.p);
-        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_INVERSE));
-        launches += 2;
+        slabXConvolve(dSlabT.p, nyl, slabCplx);
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         for (int r = 0; r < R; r++) {
             ncclCheck(g_nccl.Send(dSlabT.p + (size_t) ((r + R/2) % R)*blk, 2*blk, dt, r, c, cur), "ncclSend");
@@ -1103,8 +1172,7 @@ struct Engine : public EngineBase {
         }
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
         LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
-        CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, dSlabC.p, own));
-        launches += 1;
+        slabPlanesBackward(dSlabC.p, own, nxl);
         // halo gather: my top planes are the low halo of the rank above, my first planes the high halo of the rank below
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         if (nLo) ncclCheck(g_nccl.Send(own + (size_t) (nxl - haloLo)*plane, nLo, dt, up, c, cur), "ncclSend");
@@ -1147,8 +1215,7 @@ struct Engine : public EngineBase {
         void* c = (cur == stream2 && commPme) ? commPme : comm;
         const int dt = sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
         ncclCheck(g_nccl.ReduceScatter(dGrid.p, dSlabR.p, slabReal, dt, NCCL_SUM, c, cur), "ncclReduceScatter");
-        CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, dSlabR.p, dSlabC.p));
-        launches += 1;
+        slabPlanesForward(dSlabR.p, dSlabC.p, nxl);
         LAUNCH((k_slab_transpose<cplx, true>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabC.p, dSlabPack.p);
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         for (int r = 0; r < R; r++) {
@@ -1157,10 +1224,7 @@ struct Engine : public EngineBase {
         }
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
         // dSlabT = [x = 0..nx-1][ky own][kz]
-        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_FORWARD));
-        LAUNCH((k_slab_convolution<cplx, real>), blocksFor((long long) slabCplx, 256), 256, nx, ny, nyl, rank*nyl, nzc, dEterm.p, dSlabT.p);
-        CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, dSlabT.p, CUFFT_INVERSE));
-        launches += 2;
+        slabXConvolve(dSlabT.p, nyl, slabCplx);
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         for (int r = 0; r < R; r++) {
             ncclCheck(g_nccl.Send(dSlabT.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
@@ -1168,25 +1232,60 @@ struct Engine : public EngineBase {
         }
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
         LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
-        CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, dSlabC.p, dSlabR.p));
-        launches += 1;
+        slabPlanesBackward(dSlabC.p, dSlabR.p, nxl);
         ncclCheck(g_nccl.AllGather(dSlabR.p, dGrid.p, slabReal, dt, c, cur), "ncclAllGather");
     }
 
+    bool forceLibraryFft = false;       // debug entry: run the pass through cuFFT whatever the plan says
+    // The three transform steps of a slab-decomposed pass on this rank's planes / ky rows: the hand-written kernels of
+    // mpid_fft.cuh when the grid qualifies (mixed precision), else batched cuFFT plans.
+    void slabPlanesForward(real* ownPlanes, cplx* out, int nxl) {
+        if (fft2.ok && !forceLibraryFft) {
+            traceBegin("k_fft2_planes_forward");
+            fft2.fwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float*) (const void*) ownPlanes, (float2*) (void*) out, dTwiddle.p);
+            traceEnd();
+        } else CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, ownPlanes, out));
+        launches += 1;
+    }
+    void slabPlanesBackward(cplx* in, real* ownPlanes, int nxl) {
+        if (fft2.ok && !forceLibraryFft) {
+            traceBegin("k_fft2_planes_backward");
+            fft2.bwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float2*) (const void*) in, (float*) (void*) ownPlanes, dTwiddle.p);
+            traceEnd();
+        } else CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, in, ownPlanes));
+        launches += 1;
+    }
+    void slabXConvolve(cplx* data, int nyl, size_t slabCplx) {      // data = [x = 0..nx-1][ky own][kz]
+        const int nx = grid[0], ny = grid[1], nzc = grid[2]/2 + 1;
+        if (fft2.ok && !forceLibraryFft) {
+            traceBegin("k_fft2_x_convolve");
+            fft2.xcv<<<dim3(nyl, fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(nyl, nzc, fft2.chunk, (const float*) (const void*) dEterm.p, (float2*) (void*) data,
+                                                                                dTwiddle.p, ny, rank*nyl);
+            traceEnd();
+            launches += 1;
+        } else {
+            CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, data, CUFFT_FORWARD));
+            LAUNCH((k_slab_convolution<cplx, real>), blocksFor((long long) slabCplx, 256), 256, nx, ny, nyl, rank*nyl, nzc, dEterm.p, data);
+            CUFFT_CHECK(FftTraits<real>::c2c(planSlabX, data, CUFFT_INVERSE));
+            launches += 2;
+        }
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) throw CudaError(std::string("launch of the slab transform failed: ") + cudaGetErrorString(le));
+    }
     void reciprocalPass() {   // forward FFT, convolution, backward FFT of dGrid in place (through dGridC)
         size_t GC = (size_t) grid[0]*grid[1]*(grid[2]/2 + 1);
         stageBegin(MPIDB200_STAGE_FFT);
         if (haloMode) { haloReciprocalPass(); stageEnd(); return; }
         if (useSlabFft()) { slabReciprocalPass(); stageEnd(); return; }
         if (numRanks > 1) allReduce(dGrid.p, (size_t) grid[0]*grid[1]*grid[2], sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64);
-        if (fft2.ok) {
+        if (fft2.ok && !forceLibraryFft) {
             const float* g = (const float*) (const void*) dGrid.p;
             float2* c = (float2*) (void*) dGridC.p;
             traceBegin("k_fft2_planes_forward");
             fft2.fwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(g, c, dTwiddle.p);
             traceEnd();
             traceBegin("k_fft2_x_convolve");
-            fft2.xcv<<<dim3(grid[1], fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(grid[1], grid[2]/2 + 1, fft2.chunk, (const float*) (const void*) dEterm.p, c, dTwiddle.p);
+            fft2.xcv<<<dim3(grid[1], fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(grid[1], grid[2]/2 + 1, fft2.chunk, (const float*) (const void*) dEterm.p, c, dTwiddle.p, grid[1], 0);
             traceEnd();
             traceBegin("k_fft2_planes_backward");
             fft2.bwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(c, (float*) (void*) dGrid.p, dTwiddle.p);
@@ -1194,7 +1293,7 @@ struct Engine : public EngineBase {
             launches += 3;
             cudaError_t le = cudaGetLastError();
             if (le != cudaSuccess) throw CudaError(std::string("launch of the fused reciprocal pass failed: ") + cudaGetErrorString(le));
-        } else if (customFft) {
+        } else if (customFft && !forceLibraryFft) {
             // (only instantiated for real = float; the casts keep the double engine compiling)
             LAUNCH_SMEM(k_fft_planes_forward, grid[0], MPID_FFT_THREADS, fftSmemPlane, grid[1], grid[2], (const float*) (const void*) dGrid.p, (float2*) (void*) dGridC.p, dTwiddle.p);
             LAUNCH_SMEM(k_fft_x_convolve, grid[1], MPID_FFT_THREADS, fftSmemX, grid[0], grid[1], grid[2]/2 + 1, (const float*) (const void*) dEterm.p, (float2*) (void*) dGridC.p, dTwiddle.p);
@@ -1228,7 +1327,7 @@ struct Engine : public EngineBase {
         if (!overlapPme()) CUDA_CHECK(cudaStreamWaitEvent(stream, evFrames, 0));   // single-stream mode: moments come from stream2
         stageBegin(MPIDB200_STAGE_FIXED_SPREAD);
         dFrac.ensure(20*(size_t) n);
-        LAUNCH((k_fractional_multipoles<real>), blocksFor(n, 128), 128, P, cartR(), dFrac.p);
+        if (rows > 0) LAUNCH((k_fractional_multipoles<real>), blocksFor(rows, 128), 128, P, cartR(), dFrac.p);
         // B-spline weights of this rank's polarizable rows, once per evaluation: every induced-dipole pass reads them
         dThetaPol.ensure((size_t) std::max(numPolTotal, 1)*MPID_THETA_POL); dIgridPol.ensure(std::max(numPolTotal, 1));
         if (numPol > 0)
@@ -1272,9 +1371,13 @@ struct Engine : public EngineBase {
         } else if (numRanks == 1) {
             LAUNCH((k_fixed_recip_mu<real>), blocksFor(n, 256), 256, P, dPhi.p, dCartD.p, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
         } else {
+            // several ranks: the gather kernels leave the COMPLETE permanent field at this rank's rows (real space over
+            // the full neighbour list, covalent partners, reciprocal space at its own sites), so mu0 = alpha.E needs no
+            // reduction -- only the exchange of the dipoles themselves
             if (rows > 0 && pme) LAUNCH((k_fixed_recip<real>), blocksFor(rows, 256), 256, P, dPhi.p, dCartD.p, dField.p);
-            allReduce(dField.p, 3*(size_t) n, NCCL_FLOAT64);
-            LAUNCH((k_fixed_mu<real>), blocksFor(n, 256), 256, P, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p);
+            CUDA_CHECK(cudaMemsetAsync(dMu.p, 0, 3*(size_t) n*sizeof(double), cur));
+            if (rows > 0) LAUNCH((k_fixed_mu<real>), blocksFor(rows, 256), 256, P, dAlphaLab.p, dField.p, dEfix.p, dMu.p, dMud.p, P.rowBegin, P.rowEnd);
+            gatherDipoles();
         }
         stageEnd();
     }
@@ -1282,7 +1385,8 @@ struct Engine : public EngineBase {
     // compactReduce (several ranks, DIIS): only the polarizable entries of the partial field are all-reduced, into
     // dFieldCompact (indexed like dPolList); otherwise the whole per-atom vector is reduced in place.
     DevBuf<double> dFieldCompact;
-    void inducedFieldPass(const double* dPosIn, int level, double* grad, bool realSpace, bool callerFinishes = false, bool compactReduce = false) {
+    void inducedFieldPass(const double* dPosIn, int level, double* grad, bool realSpace, bool callerFinishes = false, bool compactReduce = false,
+                          bool ownerComputes = false) {
         const bool pme = P.method == PME;
         const int rows = P.rowEnd - P.rowBegin;
         size_t G = (size_t) grid[0]*grid[1]*grid[2];
@@ -1332,7 +1436,9 @@ struct Engine : public EngineBase {
             if (grad) LAUNCH((k_induced_finish<real, true>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, grad);
             else LAUNCH((k_induced_finish<real, false>), blocksFor(numPol, 256), 256, P, numPol, polRows, dPhidp.p, dMu.p, dIfield.p, (double*) nullptr);
         }
-        // the per-iteration collective of the partitioned solver: partial induced fields -> full field
+        // the per-iteration collective of the partitioned solver: partial induced fields -> full field.  (ownerComputes:
+        // the caller only needs the field at this rank's own sites, where it is already complete -- see solveMutualDiis.)
+        if (ownerComputes) { stageEnd(); return; }
         if (compactReduce && numRanks > 1 && numPolTotal > 0) {
             dFieldCompact.ensure(3*(size_t) numPolTotal);
             LAUNCH(k_pack_sites, blocksFor(3*(long long) numPolTotal, 256), 256, numPolTotal, (const int*) dPolList.p, dIfield.p, dFieldCompact.p);
@@ -1429,8 +1535,12 @@ struct Engine : public EngineBase {
             } else if (fused) {
                 launchSolverStep(dPosIn, it, !last);
             } else {
-                const bool compact = numPolTotal > 0;
-                inducedFieldPass(dPosIn, 1, nullptr, true, false, compact);
+                // Several ranks, owner computes: the gather kernels leave the complete induced field at the polarizable sites
+                // among this rank's rows, so each rank records newDip / err and the error overlaps for ITS sites only; the
+                // overlaps (<= 21 numbers) are all-reduced, every rank solves the same small DIIS system, combines the
+                // history of its own sites and the new dipoles are exchanged (gatherDipoles).  Per iteration that is one
+                // scalar all-reduce and one all-to-all of the dipoles; nothing per-atom is replicated.
+                inducedFieldPass(dPosIn, 1, nullptr, true, false, false, true);
                 stageBegin(MPIDB200_STAGE_SOLVER);
                 const int m = std::min(it + 1, H);
                 VecList el; SlotList sl;
@@ -1440,14 +1550,15 @@ struct Engine : public EngineBase {
                 }
                 double* hd = dHistDip.p + (size_t) sl.s[m-1]*3*n;
                 double* he = dHistErr.p + (size_t) sl.s[m-1]*3*n;
-                // the solver vectors are replicated, but only their polarizable entries are ever non-zero: walk those
-                if (compact) LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dFieldCompact.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p,
-                                    numPolTotal, (const int*) dPolList.p, 1);
-                else LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p, n, (const int*) nullptr, 0);
-                LAUNCH(k_diis_solve, 1, 512, nb, m, sl, it, n, cfg.target_epsilon, dDotPartial.p, dDiis.p);
+                dDotsLocal.ensure(MPID_MAX_HISTORY + 1);
+                LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p,
+                       numPol, (const int*) dPolList.p + polBegin, 0);
+                LAUNCH(k_sum_partials, 1, 32, nb, m, dDotPartial.p, dDotsLocal.p);
+                allReduce(dDotsLocal.p, (size_t) m, NCCL_FLOAT64);
+                LAUNCH(k_diis_solve, 1, 512, 1, m, sl, it, n, cfg.target_epsilon, dDotsLocal.p, dDiis.p);
                 if (!last) {
-                    if (compact) LAUNCH((k_diis_combine_ring<real>), blocksFor(numPolTotal, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, numPolTotal, (const int*) dPolList.p);
-                    else LAUNCH((k_diis_combine_ring<real>), blocksFor(n, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, n, (const int*) nullptr);
+                    if (numPol > 0) LAUNCH((k_diis_combine_ring<real>), blocksFor(numPol, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, numPol, (const int*) dPolList.p + polBegin);
+                    gatherDipoles();
                 }
                 stageEnd();
             }
@@ -1556,6 +1667,7 @@ struct Engine : public EngineBase {
         const bool pme = P.method == PME;
         P.numRanks = numRanks; P.rank = rank;
         stageBegin(MPIDB200_STAGE_SORT);
+        allFramesWanted = dipolesOnly;
         reusing = listValid && skin > 0.0 && !noReuse;
         if (reusing && !regatherAndFrames(dPosIn)) {
             // (several ranks) an atom has left its skin: this evaluation sorts and searches again
@@ -1617,11 +1729,13 @@ struct Engine : public EngineBase {
         {
             const int ns = (int) hSpLo.size();
             cur = stream3;
-            if (ns > 0) {
-                if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                                   dPkD.p, dDampThole.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP());
-                else LAUNCH((k_special_electrostatics<false>), blocksFor(ns, 128), 128, P, ns, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
-                            dPkD.p, dDampThole.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP());
+            const int nsRun = numRanks > 1 ? numSpOwn : ns;
+            const int* ownList = numRanks > 1 ? dSpOwn.p : nullptr;
+            if (nsRun > 0) {
+                if (mutual) LAUNCH((k_special_electrostatics<true>), blocksFor(nsRun, 128), 128, P, nsRun, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                                   dPkD.p, dDampThole.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP(), ownList);
+                else LAUNCH((k_special_electrostatics<false>), blocksFor(nsRun, 128), 128, P, nsRun, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
+                            dPkD.p, dDampThole.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP(), ownList);
             }
             cur = stream2;
             if (pme && rows > 0)
@@ -1668,11 +1782,20 @@ struct Engine : public EngineBase {
             }
             LAUNCH(k_opt_force, blocksFor(rows, 128), 128, P, L, dAniso.p, forceP(), torqueP());
         }
+        if (includeForces) {
+            // torques -> forces on the atom and its frame anchors; with several ranks on each rank's partial torques (the
+            // atoms of frameSeg are the only ones it accumulated into), so that only energy + forces are summed across ranks
+            for (int q = 0; q < 2; q++) {
+                int b = frameSeg[q][0], e = frameSeg[q][1];
+                if (numRanks == 1) { if (q == 1) break; b = 0; e = n; }
+                if (e > b) LAUNCH(k_torque_to_force, blocksFor(e - b, 128), 128, P, particleParams(), dOrder.p, dInv.p, dPosIn, torqueP(), forceP(), b, e);
+            }
+        }
         if (numRanks > 1) {
-            allReduce(dAccum.p, 6*(size_t) n + 1, NCCL_UINT64);      // forces, torques, energy: 64-bit integers, order independent
+            // energy + forces: 64-bit integers, order independent
+            allReduce(dAccum.p, includeForces ? 2 + 3*(size_t) n : 2, NCCL_UINT64);
         }
         if (includeForces) {
-            LAUNCH(k_torque_to_force, blocksFor(n, 128), 128, P, particleParams(), dOrder.p, dInv.p, dPosIn, torqueP(), forceP());
             if (forcesUploadPending) { CUDA_CHECK(cudaStreamWaitEvent(stream, evForcesUp, 0)); forcesUploadPending = false; }
             LAUNCH(k_output_forces, blocksFor(n, 256), 256, n, dOrder.p, forceP(), dForcesOut);
         }
@@ -1836,6 +1959,25 @@ struct Engine : public EngineBase {
     //   [4] polarizable x polarizable pairs (k_induced_field walks both directions of each)
     //   [5] directed site x neighbour evaluations of k_fixed_field (polarizable sites x all their neighbours)
     //   [6] covalently scaled pairs (static list)   [7] polarizable sites
+    // Test hook: one reciprocal pass (forward transform, influence function, backward transform) of a caller-supplied real
+    // grid, through the hand-written kernels or through cuFFT (single rank, mixed precision).
+    void debugReciprocalPass(float* hostGrid, bool library) override {
+        if (sizeof(real) != sizeof(float)) throw std::runtime_error("mpidb200_debug_reciprocal_pass: mixed-precision engines only");
+        if (!haveBox || cfg.nonbonded_method != MPIDB200_PME || numRanks != 1) throw std::runtime_error("mpidb200_debug_reciprocal_pass: needs a PME box on one rank");
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        const size_t G = (size_t) grid[0]*grid[1]*grid[2];
+        CUDA_CHECK(cudaMemcpyAsync(dGrid.p, hostGrid, G*sizeof(float), cudaMemcpyHostToDevice, stream));
+        forceLibraryFft = library;
+        cur = stream;
+        cudaStream_t keep2 = stream2;
+        if (plansMade) { CUFFT_CHECK(cufftSetStream(planF, stream)); CUFFT_CHECK(cufftSetStream(planB, stream)); }
+        try { reciprocalPass(); } catch (...) { forceLibraryFft = false; setPlanStreams(); throw; }
+        forceLibraryFft = false;
+        (void) keep2;
+        CUDA_CHECK(cudaMemcpyAsync(hostGrid, dGrid.p, G*sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        setPlanStreams();
+    }
     void listStats(long long* out2) override { out2[0] = listBuilds; out2[1] = listReuses; }
     void workCounts(long long* out) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
@@ -2141,6 +2283,9 @@ int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer) {
 }
 int mpidb200_get_work_counts(mpidb200_handle h, long long* out8) {
     return guarded([&] { asEngine(h)->workCounts(out8); });
+}
+int mpidb200_debug_reciprocal_pass(mpidb200_handle h, float* host_grid, int use_library) {
+    return guarded([&] { asEngine(h)->debugReciprocalPass(host_grid, use_library != 0); });
 }
 int mpidb200_get_list_stats(mpidb200_handle h, long long* out2) {
     return guarded([&] { asEngine(h)->listStats(out2); });

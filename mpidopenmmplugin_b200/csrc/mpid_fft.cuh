@@ -237,9 +237,51 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 // R-point DFT in registers (R = 2, 4, 8, 16), natural order in and out, decimation in time; INV conjugates.
+// 7-point DFT from the (n, 7-n) symmetry: three sums and three differences, 18 real multiplies per output pair.
+template <bool INV>
+__device__ __forceinline__ void dft7(float2* v) {
+    constexpr float c1 = 0.62348980185873353f, c2 = -0.22252093395631440f, c3 = -0.90096886790241913f;     // cos(2 pi k/7)
+    constexpr float s1 = 0.78183148246802981f, s2 = 0.97492791218182361f, s3 = 0.43388373911755812f;       // sin(2 pi k/7)
+    const float2 a1 = cadd(v[1], v[6]), a2 = cadd(v[2], v[5]), a3 = cadd(v[3], v[4]);
+    const float2 b1 = csub(v[1], v[6]), b2 = csub(v[2], v[5]), b3 = csub(v[3], v[4]);
+    const float2 x0 = v[0];
+    v[0] = make_float2(x0.x + a1.x + a2.x + a3.x, x0.y + a1.y + a2.y + a3.y);
+    // X_k = R_k -+ i I_k,  X_{7-k} = R_k +- i I_k  (upper sign: forward)
+    const float cc[3][3] = {{c1, c2, c3}, {c2, c3, c1}, {c3, c1, c2}};
+    const float ss[3][3] = {{s1, s2, s3}, {s2, -s3, -s1}, {s3, -s1, s2}};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float2 r = make_float2(x0.x + cc[k][0]*a1.x + cc[k][1]*a2.x + cc[k][2]*a3.x, x0.y + cc[k][0]*a1.y + cc[k][1]*a2.y + cc[k][2]*a3.y);
+        const float2 q = make_float2(ss[k][0]*b1.x + ss[k][1]*b2.x + ss[k][2]*b3.x, ss[k][0]*b1.y + ss[k][1]*b2.y + ss[k][2]*b3.y);
+        const float2 miq = make_float2(q.y, -q.x);          // -i q
+        if (INV) { v[k+1] = csub(r, miq); v[6-k] = cadd(r, miq); }
+        else     { v[k+1] = cadd(r, miq); v[6-k] = csub(r, miq); }
+    }
+}
+
 template <int R, bool INV>
 __device__ __forceinline__ void dftReg(float2* v) {
-    if constexpr (R == 2) {
+    if constexpr (R == 7) {
+        dft7<INV>(v);
+    } else if constexpr (R == 14) {
+        float2 e[7], o[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) { e[k] = v[2*k]; o[k] = v[2*k+1]; }
+        dft7<INV>(e);
+        dft7<INV>(o);
+        // exp(-2 pi i k/14), k = 0..6
+        const float c14[7] = {1.f, 0.90096886790241913f, 0.62348980185873353f, 0.22252093395631440f,
+                              -0.22252093395631440f, -0.62348980185873353f, -0.90096886790241913f};
+        const float s14[7] = {0.f, -0.43388373911755812f, -0.78183148246802981f, -0.97492791218182361f,
+                              -0.97492791218182361f, -0.78183148246802981f, -0.43388373911755812f};
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const float wr = c14[k], wi = INV ? -s14[k] : s14[k];
+            const float2 t = k == 0 ? o[0] : make_float2(o[k].x*wr - o[k].y*wi, o[k].x*wi + o[k].y*wr);
+            v[k] = cadd(e[k], t);
+            v[k + 7] = csub(e[k], t);
+        }
+    } else if constexpr (R == 2) {
         const float2 a = v[0], b = v[1];
         v[0] = cadd(a, b);
         v[1] = csub(a, b);
@@ -305,10 +347,21 @@ __device__ __forceinline__ void fft2Pass2(const float2* buf, int count, int sE, 
         for (int p = 0; p < R2; p++) store(b, q + R1*p, v[p]);
     }
 }
-__device__ __forceinline__ void fft2LoadTable(float2* dst, int len, const float2* __restrict__ tw) {
-    const int step = MPID_FFT_MAXLEN/len;
-    for (int t = threadIdx.x; t < len; t += blockDim.x) dst[t] = tw[t*step];
+// The device table holds exp(-2 pi i t/512), t < 512, followed by exp(-2 pi i t/448), t < 448: the first serves the
+// power-of-two lengths, the second the lengths that divide 448 = 2^6 x 7 (224, 112, 56, ...).
+#define MPID_FFT_LEN7 448
+#define MPID_FFT_TABLE (MPID_FFT_MAXLEN + MPID_FFT_LEN7)
+__device__ __forceinline__ void fft2LoadTablePart(float2* dst, int len, int count, const float2* __restrict__ tw) {
+    // dst[t] = exp(-2 pi i t/len), t < count
+    if (MPID_FFT_MAXLEN % len == 0) {
+        const int step = MPID_FFT_MAXLEN/len;
+        for (int t = threadIdx.x; t < count; t += blockDim.x) dst[t] = tw[t*step];
+    } else {
+        const int step = MPID_FFT_LEN7/len;
+        for (int t = threadIdx.x; t < count; t += blockDim.x) dst[t] = tw[MPID_FFT_MAXLEN + t*step];
+    }
 }
+__device__ __forceinline__ void fft2LoadTable(float2* dst, int len, const float2* __restrict__ tw) { fft2LoadTablePart(dst, len, len, tw); }
 
 // real grid plane x -> half-complex plane x.  Dynamic shared memory: (2 NY MC + NY + 2 M) float2, M = NZ/2, MC = M+1.
 // (Clearing each plane here after it is read, so that the next spreading pass needs no memset in front of it and the
@@ -395,9 +448,12 @@ k_fft2_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, 
 
 // For one ky and a chunk of kz: forward transform along x, multiply by the influence function, backward transform
 // along x, in place.  grid = (ny, ceil(nzc/chunk)).  Dynamic shared memory: (2 NX S + NX) float2, S = chunk | 1.
+// (Slab-decomposed passes hand in this rank's ky rows only: data holds nyData rows per x, the influence function all
+// nyEterm of them, and row 0 of the data is row ky0 of the influence function.)
 template <int NX, int R1, int R2>
 __global__ void __launch_bounds__(256)
-k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, float2* __restrict__ data, const float2* __restrict__ tw) {
+k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, float2* __restrict__ data, const float2* __restrict__ tw,
+                  int nyEterm, int ky0) {
     static_assert(R1*R2 == NX, "radix split");
     extern __shared__ float2 fftsm[];
     const int S = chunk | 1;
@@ -408,6 +464,7 @@ k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, f
     const int ky = blockIdx.x, kz0 = blockIdx.y*chunk;
     const int count = min(chunk, nzc - kz0);
     const size_t line = (size_t) ky*nzc + kz0, xStride = (size_t) ny*nzc;
+    const size_t lineE = (size_t) (ky0 + ky)*nzc + kz0, xStrideE = (size_t) nyEterm*nzc;
     for (int t = threadIdx.x; t < NX*count; t += blockDim.x) {
         const int x = t / count, c = t - x*count;
         buf0[x*S + c] = data[x*xStride + line + c];
@@ -416,7 +473,7 @@ k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, f
     fft2Pass1<R1, R2, false>(buf0, count, S, 1, twX);
     __syncthreads();
     fft2Pass2<R1, R2, false>(buf0, count, S, 1, [&](int c, int kx, float2 v) {
-        const float e = eterm[kx*xStride + line + c];
+        const float e = eterm[kx*xStrideE + lineE + c];
         buf1[kx*S + c] = make_float2(v.x*e, v.y*e);
     });
     __syncthreads();
@@ -425,7 +482,180 @@ k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, f
     fft2Pass2<R1, R2, true>(buf1, count, S, 1, [&](int c, int x, float2 v) { data[x*xStride + line + c] = v; });
 }
 
-// ---- host-side dispatch over the supported sizes: x, y in {32, 64, 128, 256}, z in {32, 64, 128} -------------------------------
+// =====================================================================================================
+// Third generation: the plane kernels with ONE shared-memory buffer (a 224 x 224 plane is 200 KB: two do not fit), and
+// lengths with a factor 7 (224 = 16 x 14, 112 = 16 x 7) through the 7- and 14-point register DFTs above.
+//
+// Pass 2 of a transform writes its R2 results back into the R2 slots it read (task-local, so no second buffer and no
+// extra barrier): element k = q + R1 p of the result then sits at slot q R2 + p.  Whoever consumes the result maps
+// element -> slot (slotOf) or slot -> element (elemOf); the real/half-complex "untangle" step works on the pair
+// (k, M - k) at once, which is what makes it safe in place.
+// =====================================================================================================
+template <int R1, int R2> __device__ __forceinline__ int slotOf(int k) { return (k % R1)*R2 + k / R1; }
+template <int R1, int R2> __device__ __forceinline__ int elemOf(int s) { return (s % R2)*R1 + s / R2; }
+
+// transform b's element at slot e sits at buf[off(b) + e*sE]
+template <int R1, int R2, bool INV, typename Off>
+__device__ __forceinline__ void fft3Pass1(float2* buf, int count, int sE, Off off, const float2* twL) {
+    const int tasks = count*R2;
+    for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+        const int j = t / count, b = t - j*count;
+        float2* base = buf + off(b) + j*sE;
+        float2 v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; r++) v[r] = base[r*R2*sE];
+        dftReg<R1, INV>(v);
+#pragma unroll
+        for (int q = 1; q < R1; q++) {
+            float2 w = twL[j*q];
+            if (INV) w.y = -w.y;
+            v[q] = cmul(v[q], w);
+        }
+#pragma unroll
+        for (int q = 0; q < R1; q++) base[q*R2*sE] = v[q];
+    }
+}
+template <int R1, int R2, bool INV, typename Off>
+__device__ __forceinline__ void fft3Pass2InPlace(float2* buf, int count, int sE, Off off) {
+    const int tasks = count*R1;
+    for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+        const int q = t / count, b = t - q*count;
+        float2* base = buf + off(b) + q*R2*sE;
+        float2 v[R2];
+#pragma unroll
+        for (int j = 0; j < R2; j++) v[j] = base[j*sE];
+        dftReg<R2, INV>(v);
+#pragma unroll
+        for (int p = 0; p < R2; p++) base[p*sE] = v[p];
+    }
+}
+// QFAST: consecutive threads take consecutive q of one transform (results q + R1 p are then contiguous per p);
+// otherwise consecutive transforms.
+template <int R1, int R2, bool INV, bool QFAST, typename Off, typename Store>
+__device__ __forceinline__ void fft3Pass2Store(const float2* buf, int count, int sE, Off off, Store store) {
+    const int tasks = count*R1;
+    for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+        int q, b;
+        if (QFAST) { b = t / R1; q = t - b*R1; } else { q = t / count; b = t - q*count; }
+        const float2* base = buf + off(b) + q*R2*sE;
+        float2 v[R2];
+#pragma unroll
+        for (int j = 0; j < R2; j++) v[j] = base[j*sE];
+        dftReg<R2, INV>(v);
+#pragma unroll
+        for (int p = 0; p < R2; p++) store(b, q + R1*p, v[p]);
+    }
+}
+
+// real grid plane x -> half-complex plane x.  Dynamic shared memory: (NY MC + NY + 2 M) float2, M = NZ/2, MC = M + 1.
+template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
+__global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
+k_fft3_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw) {
+    constexpr int M = NZ/2, MC = M + 1;
+    static_assert(R1Y*R2Y == NY && R1Z*R2Z == M, "radix split");
+    extern __shared__ float2 fftsm[];
+    float2* buf = fftsm;
+    float2* twY = buf + NY*MC;
+    float2* twZ = twY + NY;
+    float2* twU = twZ + M;
+    fft2LoadTable(twY, NY, tw);
+    fft2LoadTable(twZ, M, tw);
+    fft2LoadTablePart(twU, NZ, M, tw);
+    // rows of NZ reals read as M complex numbers z_j = x_{2j} + i x_{2j+1}
+    const float2* plane = reinterpret_cast<const float2*>(grid + (size_t) blockIdx.x*NY*NZ);
+    for (int t = threadIdx.x; t < NY*M; t += blockDim.x) buf[(t / M)*MC + (t % M)] = plane[t];
+    __syncthreads();
+    auto rowOff = [](int y) { return y*MC; };
+    fft3Pass1<R1Z, R2Z, false>(buf, NY, 1, rowOff, twZ);
+    __syncthreads();
+    fft3Pass2InPlace<R1Z, R2Z, false>(buf, NY, 1, rowOff);
+    __syncthreads();
+    // untangle, pairwise in place: X[k] = E[k] + w^k O[k], E = (Z[k] + conj Z[M-k])/2, O = -i (Z[k] - conj Z[M-k])/2;
+    // Z[k] sits at slot slotOf(k); X[M] (from Z[0]) takes the extra column M
+    for (int t = threadIdx.x; t < NY*(M/2 + 1); t += blockDim.x) {
+        const int k = t / NY, y = t - k*NY;
+        float2* row = buf + y*MC;
+        if (k == 0) {
+            const float2 z0 = row[0];
+            row[0] = make_float2(z0.x + z0.y, 0.f);
+            row[M] = make_float2(z0.x - z0.y, 0.f);
+        } else {
+            const int k2 = M - k, sk = slotOf<R1Z, R2Z>(k), sk2 = slotOf<R1Z, R2Z>(k2);
+            const float2 zk = row[sk], zk2 = row[sk2];
+            {
+                const float2 zr = cconj(zk2);
+                const float2 e = make_float2(0.5f*(zk.x + zr.x), 0.5f*(zk.y + zr.y));
+                const float2 d = make_float2(0.5f*(zk.x - zr.x), 0.5f*(zk.y - zr.y));
+                row[sk] = cadd(e, cmul(twU[k], make_float2(d.y, -d.x)));
+            }
+            if (k2 != k) {
+                const float2 zr = cconj(zk);
+                const float2 e = make_float2(0.5f*(zk2.x + zr.x), 0.5f*(zk2.y + zr.y));
+                const float2 d = make_float2(0.5f*(zk2.x - zr.x), 0.5f*(zk2.y - zr.y));
+                row[sk2] = cadd(e, cmul(twU[k2], make_float2(d.y, -d.x)));
+            }
+        }
+    }
+    __syncthreads();
+    // y transform of the MC columns; column kz lives at slot slotOf(kz) (column M at M)
+    auto colOff = [](int kz) { return kz == M ? M : slotOf<R1Z, R2Z>(kz); };
+    fft3Pass1<R1Y, R2Y, false>(buf, MC, MC, colOff, twY);
+    __syncthreads();
+    float2* dstp = out + (size_t) blockIdx.x*NY*MC;
+    fft3Pass2Store<R1Y, R2Y, false, false>(buf, MC, MC, colOff, [&](int kz, int ky, float2 v) { dstp[ky*MC + kz] = v; });
+}
+
+// half-complex plane x -> real grid plane x (unnormalised, like cufftExecC2R).  Same shared memory as the forward kernel.
+template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
+__global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
+k_fft3_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, const float2* __restrict__ tw) {
+    constexpr int M = NZ/2, MC = M + 1;
+    extern __shared__ float2 fftsm[];
+    float2* buf = fftsm;
+    float2* twY = buf + NY*MC;
+    float2* twZ = twY + NY;
+    float2* twU = twZ + M;
+    fft2LoadTable(twY, NY, tw);
+    fft2LoadTable(twZ, M, tw);
+    fft2LoadTablePart(twU, NZ, M, tw);
+    const float2* src = in + (size_t) blockIdx.x*NY*MC;
+    for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) buf[t] = src[t];
+    __syncthreads();
+    auto colOff = [](int kz) { return kz; };
+    fft3Pass1<R1Y, R2Y, true>(buf, MC, MC, colOff, twY);
+    __syncthreads();
+    fft3Pass2InPlace<R1Y, R2Y, true>(buf, MC, MC, colOff);          // row slot r now holds y = elemOf<R1Y, R2Y>(r)
+    __syncthreads();
+    // Z[k] = (X[k] + conj X[M-k]) + i w^-k (X[k] - conj X[M-k]), k = 0..M-1, pairwise in place (k = 0 pairs with column M);
+    // a length-M backward transform then gives x_{2j} + i x_{2j+1} scaled by NZ, the unnormalised C2R result
+    for (int t = threadIdx.x; t < NY*(M/2 + 1); t += blockDim.x) {
+        const int k = t / NY, r = t - k*NY;
+        float2* row = buf + r*MC;
+        const int k2 = M - k;
+        const float2 xk = row[k], xk2 = row[k2];
+        {
+            const float2 b = cconj(xk2);
+            const float2 s = cadd(xk, b), d = csub(xk, b);
+            const float2 wd = k == 0 ? d : cmul(cconj(twU[k]), d);
+            row[k] = make_float2(s.x - wd.y, s.y + wd.x);
+        }
+        if (k != 0 && k2 != k) {
+            const float2 b = cconj(xk);
+            const float2 s = cadd(xk2, b), d = csub(xk2, b);
+            const float2 wd = cmul(cconj(twU[k2]), d);
+            row[k2] = make_float2(s.x - wd.y, s.y + wd.x);
+        }
+    }
+    __syncthreads();
+    auto rowOff = [](int r) { return r*MC; };
+    fft3Pass1<R1Z, R2Z, true>(buf, NY, 1, rowOff, twZ);
+    __syncthreads();
+    float2* plane = reinterpret_cast<float2*>(grid + (size_t) blockIdx.x*NY*NZ);
+    fft3Pass2Store<R1Z, R2Z, true, true>(buf, NY, 1, rowOff, [&](int r, int j, float2 v) { plane[elemOf<R1Y, R2Y>(r)*M + j] = v; });
+}
+
+// ---- host-side dispatch over the supported sizes: x, y in {32, 64, 128, 224, 256}, z in {32, 64, 128, 224} ----------------
+// Power-of-two planes use the two-buffer kernels (k_fft2_*); a plane with a 224 edge uses the single-buffer ones (k_fft3_*).
 struct Fft2Plan {
     bool ok = false;
     int nx = 0, ny = 0, nz = 0, chunk = 0, chunks = 0;
@@ -433,7 +663,7 @@ struct Fft2Plan {
     size_t planeSmem = 0, xSmem = 0;
     void (*fwd)(const float*, float2*, const float2*) = nullptr;
     void (*bwd)(const float2*, float*, const float2*) = nullptr;
-    void (*xcv)(int, int, int, const float*, float2*, const float2*) = nullptr;
+    void (*xcv)(int, int, int, const float*, float2*, const float2*, int, int) = nullptr;
 };
 template <int NY, int R1Y, int R2Y> inline bool fft2PickPlanes(Fft2Plan& p, int nz) {
     if (nz == 32)  { p.fwd = k_fft2_planes_forward<NY, R1Y, R2Y, 32, 4, 4>;  p.bwd = k_fft2_planes_backward<NY, R1Y, R2Y, 32, 4, 4>;  return true; }
@@ -441,23 +671,40 @@ template <int NY, int R1Y, int R2Y> inline bool fft2PickPlanes(Fft2Plan& p, int 
     if (nz == 128) { p.fwd = k_fft2_planes_forward<NY, R1Y, R2Y, 128, 8, 8>; p.bwd = k_fft2_planes_backward<NY, R1Y, R2Y, 128, 8, 8>; return true; }
     return false;
 }
-inline Fft2Plan fft2MakePlan(int nx, int ny, int nz) {
+template <int NY, int R1Y, int R2Y> inline bool fft3PickPlanes(Fft2Plan& p, int nz) {
+    if (nz == 32)  { p.fwd = k_fft3_planes_forward<NY, R1Y, R2Y, 32, 4, 4>;   p.bwd = k_fft3_planes_backward<NY, R1Y, R2Y, 32, 4, 4>;   return true; }
+    if (nz == 64)  { p.fwd = k_fft3_planes_forward<NY, R1Y, R2Y, 64, 8, 4>;   p.bwd = k_fft3_planes_backward<NY, R1Y, R2Y, 64, 8, 4>;   return true; }
+    if (nz == 128) { p.fwd = k_fft3_planes_forward<NY, R1Y, R2Y, 128, 8, 8>;  p.bwd = k_fft3_planes_backward<NY, R1Y, R2Y, 128, 8, 8>;  return true; }
+    if (nz == 224) { p.fwd = k_fft3_planes_forward<NY, R1Y, R2Y, 224, 16, 7>; p.bwd = k_fft3_planes_backward<NY, R1Y, R2Y, 224, 16, 7>; return true; }
+    return false;
+}
+inline Fft2Plan fft2MakePlan(int nx, int ny, int nz, bool singleBuffer = false) {
     Fft2Plan p;
     p.nx = nx; p.ny = ny; p.nz = nz;
     int r2y = 0, r1x = 0;
     bool okP = false;
-    if (ny == 32)  { okP = fft2PickPlanes<32, 8, 4>(p, nz);    r2y = 4; }
-    if (ny == 64)  { okP = fft2PickPlanes<64, 8, 8>(p, nz);    r2y = 8; }
-    if (ny == 128) { okP = fft2PickPlanes<128, 16, 8>(p, nz);  r2y = 8; }
-    if (ny == 256) { okP = fft2PickPlanes<256, 16, 16>(p, nz); r2y = 16; }
+    const bool gen3 = singleBuffer || ny == 224 || nz == 224;
+    if (gen3) {
+        if (ny == 32)  { okP = fft3PickPlanes<32, 8, 4>(p, nz);    r2y = 4; }
+        if (ny == 64)  { okP = fft3PickPlanes<64, 8, 8>(p, nz);    r2y = 8; }
+        if (ny == 128) { okP = fft3PickPlanes<128, 16, 8>(p, nz);  r2y = 8; }
+        if (ny == 224) { okP = fft3PickPlanes<224, 16, 14>(p, nz); r2y = 14; }
+        if (ny == 256) { okP = fft3PickPlanes<256, 16, 16>(p, nz); r2y = 16; }
+    } else {
+        if (ny == 32)  { okP = fft2PickPlanes<32, 8, 4>(p, nz);    r2y = 4; }
+        if (ny == 64)  { okP = fft2PickPlanes<64, 8, 8>(p, nz);    r2y = 8; }
+        if (ny == 128) { okP = fft2PickPlanes<128, 16, 8>(p, nz);  r2y = 8; }
+        if (ny == 256) { okP = fft2PickPlanes<256, 16, 16>(p, nz); r2y = 16; }
+    }
     if (nx == 32)  { p.xcv = k_fft2_x_convolve<32, 8, 4>;    r1x = 8; }
     if (nx == 64)  { p.xcv = k_fft2_x_convolve<64, 8, 8>;    r1x = 8; }
     if (nx == 128) { p.xcv = k_fft2_x_convolve<128, 16, 8>;  r1x = 16; }
+    if (nx == 224) { p.xcv = k_fft2_x_convolve<224, 16, 14>; r1x = 16; }
     if (nx == 256) { p.xcv = k_fft2_x_convolve<256, 16, 16>; r1x = 16; }
     if (!okP || !p.xcv) return p;
     const int m = nz/2, mc = m + 1;
-    p.planeSmem = ((size_t) 2*ny*mc + ny + 2*m)*sizeof(float2);
-    if (p.planeSmem > 200*1024) return p;
+    p.planeSmem = ((size_t) (gen3 ? 1 : 2)*ny*mc + ny + 2*m)*sizeof(float2);
+    if (p.planeSmem > 226*1024) return p;
     // one round of the widest y pass per block when it fits, else two
     int tasks = mc*r2y;
     if (tasks > MPID_FFT2_MAX_THREADS) tasks = (tasks + 1)/2;

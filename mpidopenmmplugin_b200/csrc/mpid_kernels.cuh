@@ -150,14 +150,16 @@ __global__ void __launch_bounds__(128)
 k_lab_frame(DevParams P, ParticleParams pp, int framelessFix, const int* __restrict__ order,
             const double* __restrict__ posOrig,
             double* __restrict__ cartD, double* __restrict__ pkD, real* __restrict__ cartR, real* __restrict__ pkR,
-            double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso) {
+            double* __restrict__ sphD, double* __restrict__ alphaLab, int* __restrict__ aniso, int sBegin, int sEnd) {
+    // sorted atoms [sBegin, sEnd): everything on one rank; with several ranks the rows a rank owns plus the cell columns
+    // its neighbour search reaches into (nobody else's moments are ever read there)
     __shared__ double tiles[4][32][21];
-    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    const int s = sBegin + blockIdx.x*blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s0 = s - lane;                                  // first atom of this warp
-    if (s0 >= P.n) return;
-    const int nValid = min(32, P.n - s0);
-    const bool valid = s < P.n;
+    if (s0 >= sEnd) return;
+    const int nValid = min(32, sEnd - s0);
+    const bool valid = s < sEnd;
     double c[20], pk[16], sph[16], alpha[6];
     if (valid) {
         const int o = order[s];
@@ -592,13 +594,81 @@ __global__ void k_regather_sites(int n, const int* __restrict__ order, const dou
 }
 
 // One warp per row: walk the row's candidates (upper run from the front, lower run from the back, the layout of
-// k_neighbor_list) and keep the pairs inside the cutoff, in the same layout and order.
+// k_neighbor_list) and keep the pairs inside the cutoff, in the same layout and order.  The kernel is issue bound
+// (ncu, profiles/r02e: 65 % issue utilisation), so the inner loop is kept lean: image shifts come from a float table in
+// shared memory, the rare borderline re-test sits behind a warp-uniform branch, the bare-charge count is only taken on
+// the upper run and the polarizable list only for polarizable rows (both warp-uniform conditions).
+template <int RUN, bool IPOL>
+__device__ __forceinline__ void filterRun(const DevParams& P, const float (*shiftF)[4], const float4* __restrict__ posF, const double* __restrict__ posOrig,
+                                          const int* __restrict__ order, int i, const float4 pi, float rcLo2, float rcHi2,
+                                          const unsigned* __restrict__ src, int step, unsigned len, unsigned cap, unsigned* __restrict__ base,
+                                          unsigned* __restrict__ polBase, int lane, unsigned lt,
+                                          unsigned& nOut, unsigned otherCount, unsigned& nUpSimple, unsigned& nPol) {
+    const unsigned FULL = 0xffffffffu;
+    constexpr int U = 4;
+    for (unsigned k0 = 0; k0 < len; k0 += 32*U) {
+        unsigned e[U];
+        float4 pj[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned k = k0 + 32*u + lane;
+            e[u] = k < len ? src[(long long) step*(long long) k] : (31u << MPID_CODE_SHIFT);   // padding: atom 0 with image code 31 = far away
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) pj[u] = posF[e[u] & MPID_JMASK];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (k0 + 32*u >= len) break;            // warp-uniform: the rest of this trip is padding
+            const unsigned code = e[u] >> MPID_CODE_SHIFT;
+            const float4 sh = *reinterpret_cast<const float4*>(shiftF[code]);
+            const float ddx = (pj[u].x - pi.x) - sh.x, ddy = (pj[u].y - pi.y) - sh.y, ddz = (pj[u].z - pi.z) - sh.z;
+            const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
+            bool in = r2 <= rcHi2;
+            if (__any_sync(FULL, in && r2 >= rcLo2)) {
+                if (in && r2 >= rcLo2) {
+                    // borderline: the oracle's test, bit for bit, on the raw positions
+                    const int oi = order[i], oj = order[e[u] & MPID_JMASK];
+                    const int lo = min(oi, oj), hi = max(oi, oj);
+                    double ex = posOrig[3*(size_t) hi] - posOrig[3*(size_t) lo], ey = posOrig[3*(size_t) hi+1] - posOrig[3*(size_t) lo+1], ez = posOrig[3*(size_t) hi+2] - posOrig[3*(size_t) lo+2];
+                    periodicDelta(P.box, ex, ey, ez);
+                    in = !(dist2Exact(ex, ey, ez) > P.cutoff2);
+                }
+            }
+            const unsigned maskIn = __ballot_sync(FULL, in);
+            const unsigned cnt = __popc(maskIn);
+            const bool room = nOut + otherCount + cnt <= cap;
+            if (in && room) {
+                const unsigned slot = nOut + __popc(maskIn & lt);
+                if (RUN == 0) base[slot] = e[u]; else base[cap - 1 - slot] = e[u];
+            }
+            nOut += cnt;
+            if (RUN == 0) nUpSimple += __popc(__ballot_sync(FULL, in && (e[u] & MPID_SIMPLE_BIT)));
+            if (IPOL) {
+                const bool jp = in && (((int) pj[u].w) & 1);
+                const unsigned maskP = __ballot_sync(FULL, jp);
+                if (jp && room) polBase[nPol + __popc(maskP & lt)] = e[u];
+                nPol += __popc(maskP);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_filter_list(DevParams P, int candCap, const float4* __restrict__ posF, const double* __restrict__ posOrig, const int* __restrict__ order,
               const unsigned* __restrict__ cand, const uint4* __restrict__ candCounts, const int* __restrict__ polRank, int polBegin,
               unsigned* __restrict__ nbr, uint4* __restrict__ counts, unsigned* __restrict__ polNbr, unsigned* __restrict__ polCount,
               unsigned* __restrict__ maxCount) {
-    const unsigned FULL = 0xffffffffu;
+    __shared__ __align__(16) float shiftF[32][4];
+    if (threadIdx.x < 32) {
+        const int c = threadIdx.x;
+        const bool real = c < 27 && P.method == PME;
+        // entries 27..31 are never produced by the search; 31 marks the padding lanes and throws them far outside the cutoff
+        shiftF[c][0] = real ? (float) P.shift[c][0] : (c == 31 ? 1.0e18f : 0.f);
+        shiftF[c][1] = real ? (float) P.shift[c][1] : 0.f;
+        shiftF[c][2] = real ? (float) P.shift[c][2] : 0.f;
+        shiftF[c][3] = 0.f;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int row = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int rows = P.rowEnd - P.rowBegin;
@@ -607,7 +677,8 @@ k_filter_list(DevParams P, int candCap, const float4* __restrict__ posF, const d
     const float4 pi = posF[i];
     const bool pme = P.method == PME;
     const float rcLo = (float) P.cutoff - 1.0e-4f, rcHi = (float) P.cutoff + 1.0e-4f;
-    const float rcLo2 = rcLo > 0.f ? rcLo*rcLo : 0.f, rcHi2 = rcHi*rcHi;
+    // without a cutoff everything is inside and nothing is borderline
+    const float rcLo2 = pme ? (rcLo > 0.f ? rcLo*rcLo : 0.f) : 3.0e38f, rcHi2 = pme ? rcHi*rcHi : 1.0e30f;
     const unsigned cap = (unsigned) P.nbrCap;
     const uint4 cc = candCounts[row];
     const unsigned* cbase = cand + (size_t) row*candCap;
@@ -616,56 +687,12 @@ k_filter_list(DevParams P, int candCap, const float4* __restrict__ posF, const d
     unsigned* polBase = polNbr + (iPol ? (size_t) (polRank[i] - polBegin)*cap : 0);
     unsigned nUp = 0, nLow = 0, nUpSimple = 0, nPol = 0;
     const unsigned lt = (1u << lane) - 1u;
-    int oi = -1;
-    // Four candidates per lane and trip: the four list entries, then the four (dependent) position gathers are in flight
-    // together -- the kernel is bound by that latency, not by arithmetic.  Sub-blocks are committed in order, so the
-    // output keeps the candidate order.
-    constexpr int U = 4;
-    for (int run = 0; run < 2; run++) {
-        const unsigned len = run == 0 ? cc.x : cc.y;
-        for (unsigned k0 = 0; k0 < len; k0 += 32*U) {
-            unsigned e[U];
-            float4 pj[U];
-            bool in[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const unsigned k = k0 + 32*u + lane;
-                in[u] = k < len;
-                e[u] = in[u] ? (run == 0 ? cbase[k] : cbase[candCap - 1 - k]) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) pj[u] = posF[e[u] & MPID_JMASK];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int jflag = (int) pj[u].w;
-                if (in[u] && pme) {
-                    const unsigned code = e[u] >> MPID_CODE_SHIFT;
-                    const float ddx = (pj[u].x - pi.x) - (float) P.shift[code][0], ddy = (pj[u].y - pi.y) - (float) P.shift[code][1], ddz = (pj[u].z - pi.z) - (float) P.shift[code][2];
-                    const float r2 = ddx*ddx + ddy*ddy + ddz*ddz;
-                    if (r2 > rcHi2) in[u] = false;
-                    else if (r2 >= rcLo2) {
-                        // borderline: the oracle's test, bit for bit, on the raw positions
-                        if (oi < 0) oi = order[i];
-                        const int oj = order[e[u] & MPID_JMASK];
-                        const int lo = min(oi, oj), hi = max(oi, oj);
-                        double ex = posOrig[3*(size_t) hi] - posOrig[3*(size_t) lo], ey = posOrig[3*(size_t) hi+1] - posOrig[3*(size_t) lo+1], ez = posOrig[3*(size_t) hi+2] - posOrig[3*(size_t) lo+2];
-                        periodicDelta(P.box, ex, ey, ez);
-                        in[u] = !(dist2Exact(ex, ey, ez) > P.cutoff2);
-                    }
-                }
-                const unsigned maskIn = __ballot_sync(FULL, in[u]);
-                const unsigned maskS = __ballot_sync(FULL, in[u] && run == 0 && (jflag & 2));
-                const unsigned maskP = __ballot_sync(FULL, in[u] && iPol && (jflag & 1));
-                const unsigned cnt = __popc(maskIn);
-                if (in[u] && nUp + nLow + cnt <= cap) {
-                    if (run == 0) base[nUp + __popc(maskIn & lt)] = e[u];
-                    else base[cap - 1 - (nLow + __popc(maskIn & lt))] = e[u];
-                    if (iPol && (jflag & 1)) polBase[nPol + __popc(maskP & lt)] = e[u];
-                }
-                if (run == 0) nUp += cnt; else nLow += cnt;
-                nUpSimple += __popc(maskS); nPol += __popc(maskP);
-            }
-        }
+    if (iPol) {
+        filterRun<0, true>(P, shiftF, posF, posOrig, order, i, pi, rcLo2, rcHi2, cbase, 1, cc.x, cap, base, polBase, lane, lt, nUp, 0u, nUpSimple, nPol);
+        filterRun<1, true>(P, shiftF, posF, posOrig, order, i, pi, rcLo2, rcHi2, cbase + candCap - 1, -1, cc.y, cap, base, polBase, lane, lt, nLow, nUp, nUpSimple, nPol);
+    } else {
+        filterRun<0, false>(P, shiftF, posF, posOrig, order, i, pi, rcLo2, rcHi2, cbase, 1, cc.x, cap, base, polBase, lane, lt, nUp, 0u, nUpSimple, nPol);
+        filterRun<1, false>(P, shiftF, posF, posOrig, order, i, pi, rcLo2, rcHi2, cbase + candCap - 1, -1, cc.y, cap, base, polBase, lane, lt, nLow, nUp, nUpSimple, nPol);
     }
     if (lane == 0) {
         const bool fits = nUp + nLow <= cap;       // see k_neighbor_list
@@ -1198,11 +1225,13 @@ __global__ void k_special_electrostatics(DevParams P, int numSpecial, const int*
                                          const double* __restrict__ posOrig, const double* __restrict__ pkD,
                                          const double2* __restrict__ dampTholeD, const double* __restrict__ mu, const int* __restrict__ aniso,
                                          unsigned long long* __restrict__ force, unsigned long long* __restrict__ torque,
-                                         unsigned long long* __restrict__ energy) {
-    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+                                         unsigned long long* __restrict__ energy, const int* __restrict__ ownList) {
+    // ownList (several ranks): the pairs whose lower atom sits in this rank's rows (k_own_special), numSpecial of them
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
     // no early return: the pair energies of a warp are summed with shuffles and leave through ONE atomic per warp
     // (one atomic per pair on the single energy word serialises at the L2: 95,616 of them at 95,616 atoms)
-    bool active = k < numSpecial && (k % P.numRanks) == P.rank;
+    const bool active = t < numSpecial;
+    const int k = active ? (ownList ? ownList[t] : t) : 0;
     double e = 0.0;
     if (active) {
         const int lo = spPairLo[k], hi = spPairHi[k];
@@ -1241,8 +1270,8 @@ __global__ void k_special_electrostatics(DevParams P, int numSpecial, const int*
 // Scaled-fractional multipoles of the permanent moments (20 per atom).  reference: :3077-3169
 template <typename real>
 __global__ void k_fractional_multipoles(DevParams P, const real* __restrict__ cart, real* __restrict__ frac) {
-    const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= P.n) return;
+    const int s = P.rowBegin + blockIdx.x*blockDim.x + threadIdx.x;      // this rank's rows: only they are spread
+    if (s >= P.rowEnd) return;
     real m[20], f[20];
     for (int k = 0; k < 20; k++) m[k] = cart[20*(size_t) s + k];
     multipolesToFractional<real>(P.geom.A, m, f);
@@ -1578,9 +1607,9 @@ __global__ void k_fixed_recip(DevParams P, const real* __restrict__ phi, const d
 // efix = alpha.E_fixed ; mu = efix       (:1305-1316, :936-946)
 template <typename real>
 __global__ void k_fixed_mu(DevParams P, const double* __restrict__ alphaLab, const double* __restrict__ field,
-                           double* __restrict__ efix, double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud) {
-    const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= P.n) return;
+                           double* __restrict__ efix, double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud, int sBegin, int sEnd) {
+    const int s = sBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= sEnd) return;
     double ox, oy, oz;
     applyAlphaLab(alphaLab + 6*(size_t) s, field[3*(size_t) s], field[3*(size_t) s+1], field[3*(size_t) s+2], ox, oy, oz);
     efix[3*(size_t) s] = ox; efix[3*(size_t) s+1] = oy; efix[3*(size_t) s+2] = oz;
@@ -1716,6 +1745,39 @@ struct SlotList { int s[MPID_MAX_HISTORY + 1]; };
 // products <err_new, err_k> over the m vectors of the history (the last one being err_new itself).
 // dst[3 idx + c] = src[3 siteList[idx] + c]: the polarizable entries of a per-atom vector, contiguous -- what the
 // per-iteration all-reduce of the partial induced field moves (a third of the atoms in water).
+// Covalently scaled pairs this rank evaluates in the energy stage: those whose lower atom is one of its rows (their
+// moments are then among the ones it builds).  Order is whatever the atomics give: every consumer accumulates in fixed point.
+__global__ void k_own_special(int numSpecial, const int* __restrict__ spPairLo, const int* __restrict__ inv, int rowBegin, int rowEnd,
+                              int* __restrict__ ownList, unsigned* __restrict__ count) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= numSpecial) return;
+    const int s = inv[spPairLo[k]];
+    if (s >= rowBegin && s < rowEnd) ownList[atomicAdd(count, 1u)] = k;
+}
+
+// compact dipoles of ALL polarizable sites (order of siteList) -> per-atom mu and the float copy the field kernels read
+template <typename real>
+__global__ void k_unpack_mu(int numSites, const int* __restrict__ siteList, const double* __restrict__ compact,
+                            double* __restrict__ mu, typename Real4<real>::type* __restrict__ mud) {
+    const int idx = blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= numSites) return;
+    const int s = siteList[idx];
+    const double x = compact[3*(size_t) idx], y = compact[3*(size_t) idx+1], z = compact[3*(size_t) idx+2];
+    mu[3*(size_t) s] = x; mu[3*(size_t) s+1] = y; mu[3*(size_t) s+2] = z;
+    typename Real4<real>::type m = mud[s];
+    m.x = (real) x; m.y = (real) y; m.z = (real) z;
+    mud[s] = m;
+}
+
+// column sums of the per-block partial error overlaps (fixed order: deterministic), ready for the all-reduce
+__global__ void k_sum_partials(int numBlocks, int m, const double* __restrict__ partial, double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= m) return;
+    double v = 0;
+    for (int b = 0; b < numBlocks; b++) v += partial[(size_t) b*(MPID_MAX_HISTORY + 1) + k];
+    out[k] = v;
+}
+
 __global__ void k_pack_sites(int numSites, const int* __restrict__ siteList, const double* __restrict__ src, double* __restrict__ dst) {
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     if (t >= 3*numSites) return;
@@ -2295,9 +2357,11 @@ __global__ void k_opt_force(DevParams P, OptLists L, const int* __restrict__ ani
 // torque -> forces on the frame atoms (:2112-2131, :1895-2110); one thread per sorted atom
 __global__ void k_torque_to_force(DevParams P, ParticleParams pp, const int* __restrict__ order, const int* __restrict__ inv,
                                   const double* __restrict__ posOrig, const unsigned long long* __restrict__ torque,
-                                  unsigned long long* __restrict__ force) {
-    const int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= P.n) return;
+                                  unsigned long long* __restrict__ force, int sBegin, int sEnd) {
+    // The map torque -> forces is linear in the torque, so with several ranks it is applied to each rank's PARTIAL torques
+    // (atoms [sBegin, sEnd): the only ones it can have touched) before the forces are summed across ranks.
+    const int s = sBegin + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= sEnd) return;
     const int o = order[s];
     const int axis = pp.axis[o];
     if (axis == NoAxisType) return;

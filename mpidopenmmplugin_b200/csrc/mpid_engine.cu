@@ -1156,8 +1156,7 @@ struct Engine : public EngineBase {
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
         if (nLo + nHi) LAUNCH((k_halo_add<real>), blocksFor((long long) (nLo + nHi), 256), 256, nLo, nHi, dHaloIn.p, own + (size_t) (nxl - haloLo)*plane, own);
         // slab transform on the own block; block r sits at x position (r + R/2) mod R of the transform
-        slabPlanesForward(own, dSlabC.p, nxl);
-        LAUNCH((k_slab_transpose<cplx, true>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabC.p, dSlabPack.p);
+        slabPlanesForward(own, nxl, nyl, slabCplx);
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         for (int r = 0; r < R; r++) {
             ncclCheck(g_nccl.Send(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
@@ -1171,8 +1170,7 @@ struct Engine : public EngineBase {
             ncclCheck(g_nccl.Recv(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
         }
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
-        LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
-        slabPlanesBackward(dSlabC.p, own, nxl);
+        slabPlanesBackward(own, nxl, nyl, slabCplx);
         // halo gather: my top planes are the low halo of the rank above, my first planes the high halo of the rank below
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         if (nLo) ncclCheck(g_nccl.Send(own + (size_t) (nxl - haloLo)*plane, nLo, dt, up, c, cur), "ncclSend");
@@ -1215,8 +1213,7 @@ struct Engine : public EngineBase {
         void* c = (cur == stream2 && commPme) ? commPme : comm;
         const int dt = sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
         ncclCheck(g_nccl.ReduceScatter(dGrid.p, dSlabR.p, slabReal, dt, NCCL_SUM, c, cur), "ncclReduceScatter");
-        slabPlanesForward(dSlabR.p, dSlabC.p, nxl);
-        LAUNCH((k_slab_transpose<cplx, true>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabC.p, dSlabPack.p);
+        slabPlanesForward(dSlabR.p, nxl, nyl, slabCplx);
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         for (int r = 0; r < R; r++) {
             ncclCheck(g_nccl.Send(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
@@ -1231,29 +1228,42 @@ struct Engine : public EngineBase {
             ncclCheck(g_nccl.Recv(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
         }
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
-        LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
-        slabPlanesBackward(dSlabC.p, dSlabR.p, nxl);
+        slabPlanesBackward(dSlabR.p, nxl, nyl, slabCplx);
         ncclCheck(g_nccl.AllGather(dSlabR.p, dGrid.p, slabReal, dt, c, cur), "ncclAllGather");
     }
 
     bool forceLibraryFft = false;       // debug entry: run the pass through cuFFT whatever the plan says
     // The three transform steps of a slab-decomposed pass on this rank's planes / ky rows: the hand-written kernels of
     // mpid_fft.cuh when the grid qualifies (mixed precision), else batched cuFFT plans.
-    void slabPlanesForward(real* ownPlanes, cplx* out, int nxl) {
-        if (fft2.ok && !forceLibraryFft) {
+    // Forward: own real planes -> dSlabPack in the send layout of the all-to-all.  The hand-written kernel stores that
+    // layout directly; the library path transforms into dSlabC and packs with k_slab_transpose.
+    bool slabNative() const { return fft2.ok && !forceLibraryFft; }
+    void slabPlanesForward(real* ownPlanes, int nxl, int nyl, size_t slabCplx) {
+        const int R = numRanks, nzc = grid[2]/2 + 1;
+        if (slabNative()) {
             traceBegin("k_fft2_planes_forward");
-            fft2.fwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float*) (const void*) ownPlanes, (float2*) (void*) out, dTwiddle.p);
+            fft2.fwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float*) (const void*) ownPlanes, (float2*) (void*) dSlabPack.p, dTwiddle.p, nxl, nyl);
             traceEnd();
-        } else CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, ownPlanes, out));
-        launches += 1;
+            launches += 1;
+        } else {
+            CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, ownPlanes, dSlabC.p));
+            launches += 1;
+            LAUNCH((k_slab_transpose<cplx, true>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabC.p, dSlabPack.p);
+        }
     }
-    void slabPlanesBackward(cplx* in, real* ownPlanes, int nxl) {
-        if (fft2.ok && !forceLibraryFft) {
+    // Backward: dSlabPack (receive layout of the all-to-all back) -> own real planes.
+    void slabPlanesBackward(real* ownPlanes, int nxl, int nyl, size_t slabCplx) {
+        const int R = numRanks, nzc = grid[2]/2 + 1;
+        if (slabNative()) {
             traceBegin("k_fft2_planes_backward");
-            fft2.bwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float2*) (const void*) in, (float*) (void*) ownPlanes, dTwiddle.p);
+            fft2.bwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float2*) (const void*) dSlabPack.p, (float*) (void*) ownPlanes, dTwiddle.p, nxl, nyl);
             traceEnd();
-        } else CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, in, ownPlanes));
-        launches += 1;
+            launches += 1;
+        } else {
+            LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
+            CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, dSlabC.p, ownPlanes));
+            launches += 1;
+        }
     }
     void slabXConvolve(cplx* data, int nyl, size_t slabCplx) {      // data = [x = 0..nx-1][ky own][kz]
         const int nx = grid[0], ny = grid[1], nzc = grid[2]/2 + 1;
@@ -1282,13 +1292,13 @@ struct Engine : public EngineBase {
             const float* g = (const float*) (const void*) dGrid.p;
             float2* c = (float2*) (void*) dGridC.p;
             traceBegin("k_fft2_planes_forward");
-            fft2.fwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(g, c, dTwiddle.p);
+            fft2.fwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(g, c, dTwiddle.p, 0, 0);
             traceEnd();
             traceBegin("k_fft2_x_convolve");
             fft2.xcv<<<dim3(grid[1], fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(grid[1], grid[2]/2 + 1, fft2.chunk, (const float*) (const void*) dEterm.p, c, dTwiddle.p, grid[1], 0);
             traceEnd();
             traceBegin("k_fft2_planes_backward");
-            fft2.bwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(c, (float*) (void*) dGrid.p, dTwiddle.p);
+            fft2.bwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(c, (float*) (void*) dGrid.p, dTwiddle.p, 0, 0);
             traceEnd();
             launches += 3;
             cudaError_t le = cudaGetLastError();

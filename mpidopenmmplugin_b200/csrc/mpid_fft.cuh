@@ -366,9 +366,16 @@ __device__ __forceinline__ void fft2LoadTable(float2* dst, int len, const float2
 // real grid plane x -> half-complex plane x.  Dynamic shared memory: (2 NY MC + NY + 2 M) float2, M = NZ/2, MC = M+1.
 // (Clearing each plane here after it is read, so that the next spreading pass needs no memset in front of it and the
 // backward transform writes to a second grid, was measured: 1.639 ms per evaluation against 1.546 ms with the memset.)
+// Slab-decomposed passes (several ranks) hand in nxl > 0: the half-complex result of plane xl then goes straight into the
+// send layout of the all-to-all, [destination rank q][xl][ky - q nyl][kz] with nyl = NY/ranks rows per rank, and the
+// backward kernels read that layout -- no separate transpose kernels.
+__device__ __forceinline__ size_t slabIndex(int nxl, int nyl, int xl, int ky, int mc) {
+    const int q = ky / nyl;
+    return (((size_t) q*nxl + xl)*nyl + (ky - q*nyl))*mc;
+}
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
-k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw) {
+k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl) {
     constexpr int M = NZ/2, MC = M + 1;
     static_assert(R1Y*R2Y == NY && R1Z*R2Z == M, "radix split");
     extern __shared__ float2 fftsm[];
@@ -402,14 +409,18 @@ k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, 
     __syncthreads();
     fft2Pass1<R1Y, R2Y, false>(buf0, MC, MC, 1, twY);
     __syncthreads();
-    float2* dstp = out + (size_t) blockIdx.x*NY*MC;
-    fft2Pass2<R1Y, R2Y, false>(buf0, MC, MC, 1, [&](int kz, int ky, float2 v) { dstp[ky*MC + kz] = v; });
+    if (nxl > 0) {
+        fft2Pass2<R1Y, R2Y, false>(buf0, MC, MC, 1, [&](int kz, int ky, float2 v) { out[slabIndex(nxl, nyl, blockIdx.x, ky, MC) + kz] = v; });
+    } else {
+        float2* dstp = out + (size_t) blockIdx.x*NY*MC;
+        fft2Pass2<R1Y, R2Y, false>(buf0, MC, MC, 1, [&](int kz, int ky, float2 v) { dstp[ky*MC + kz] = v; });
+    }
 }
 
 // half-complex plane x -> real grid plane x (unnormalised, like cufftExecC2R).  Same shared memory as the forward kernel.
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
-k_fft2_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, const float2* __restrict__ tw) {
+k_fft2_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, const float2* __restrict__ tw, int nxl, int nyl) {
     constexpr int M = NZ/2, MC = M + 1;
     extern __shared__ float2 fftsm[];
     float2* buf0 = fftsm;
@@ -420,8 +431,12 @@ k_fft2_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, 
     fft2LoadTable(twY, NY, tw);
     fft2LoadTable(twZ, M, tw);
     for (int t = threadIdx.x; t < M; t += blockDim.x) twU[t] = tw[t*(MPID_FFT_MAXLEN/NZ)];
-    const float2* src = in + (size_t) blockIdx.x*NY*MC;
-    for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) buf0[t] = src[t];
+    if (nxl > 0) {
+        for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) { const int ky = t / MC; buf0[t] = in[slabIndex(nxl, nyl, blockIdx.x, ky, MC) + (t - ky*MC)]; }
+    } else {
+        const float2* src = in + (size_t) blockIdx.x*NY*MC;
+        for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) buf0[t] = src[t];
+    }
     __syncthreads();
     fft2Pass1<R1Y, R2Y, true>(buf0, MC, MC, 1, twY);
     __syncthreads();
@@ -550,7 +565,7 @@ __device__ __forceinline__ void fft3Pass2Store(const float2* buf, int count, int
 // real grid plane x -> half-complex plane x.  Dynamic shared memory: (NY MC + NY + 2 M) float2, M = NZ/2, MC = M + 1.
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
-k_fft3_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw) {
+k_fft3_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl) {
     constexpr int M = NZ/2, MC = M + 1;
     static_assert(R1Y*R2Y == NY && R1Z*R2Z == M, "radix split");
     extern __shared__ float2 fftsm[];
@@ -601,14 +616,18 @@ k_fft3_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, 
     auto colOff = [](int kz) { return kz == M ? M : slotOf<R1Z, R2Z>(kz); };
     fft3Pass1<R1Y, R2Y, false>(buf, MC, MC, colOff, twY);
     __syncthreads();
-    float2* dstp = out + (size_t) blockIdx.x*NY*MC;
-    fft3Pass2Store<R1Y, R2Y, false, false>(buf, MC, MC, colOff, [&](int kz, int ky, float2 v) { dstp[ky*MC + kz] = v; });
+    if (nxl > 0) {
+        fft3Pass2Store<R1Y, R2Y, false, false>(buf, MC, MC, colOff, [&](int kz, int ky, float2 v) { out[slabIndex(nxl, nyl, blockIdx.x, ky, MC) + kz] = v; });
+    } else {
+        float2* dstp = out + (size_t) blockIdx.x*NY*MC;
+        fft3Pass2Store<R1Y, R2Y, false, false>(buf, MC, MC, colOff, [&](int kz, int ky, float2 v) { dstp[ky*MC + kz] = v; });
+    }
 }
 
 // half-complex plane x -> real grid plane x (unnormalised, like cufftExecC2R).  Same shared memory as the forward kernel.
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
-k_fft3_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, const float2* __restrict__ tw) {
+k_fft3_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, const float2* __restrict__ tw, int nxl, int nyl) {
     constexpr int M = NZ/2, MC = M + 1;
     extern __shared__ float2 fftsm[];
     float2* buf = fftsm;
@@ -618,8 +637,12 @@ k_fft3_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, 
     fft2LoadTable(twY, NY, tw);
     fft2LoadTable(twZ, M, tw);
     fft2LoadTablePart(twU, NZ, M, tw);
-    const float2* src = in + (size_t) blockIdx.x*NY*MC;
-    for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) buf[t] = src[t];
+    if (nxl > 0) {
+        for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) { const int ky = t / MC; buf[t] = in[slabIndex(nxl, nyl, blockIdx.x, ky, MC) + (t - ky*MC)]; }
+    } else {
+        const float2* src = in + (size_t) blockIdx.x*NY*MC;
+        for (int t = threadIdx.x; t < NY*MC; t += blockDim.x) buf[t] = src[t];
+    }
     __syncthreads();
     auto colOff = [](int kz) { return kz; };
     fft3Pass1<R1Y, R2Y, true>(buf, MC, MC, colOff, twY);
@@ -661,8 +684,8 @@ struct Fft2Plan {
     int nx = 0, ny = 0, nz = 0, chunk = 0, chunks = 0;
     int planeThreads = 0, xThreads = 0;
     size_t planeSmem = 0, xSmem = 0;
-    void (*fwd)(const float*, float2*, const float2*) = nullptr;
-    void (*bwd)(const float2*, float*, const float2*) = nullptr;
+    void (*fwd)(const float*, float2*, const float2*, int, int) = nullptr;
+    void (*bwd)(const float2*, float*, const float2*, int, int) = nullptr;
     void (*xcv)(int, int, int, const float*, float2*, const float2*, int, int) = nullptr;
 };
 template <int NY, int R1Y, int R2Y> inline bool fft2PickPlanes(Fft2Plan& p, int nz) {

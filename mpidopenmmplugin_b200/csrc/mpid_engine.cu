@@ -608,6 +608,27 @@ struct Engine : public EngineBase {
     // Fused reciprocal pass (mpid_fft.cuh): single precision, power-of-two grid whose y-z and x-z slabs fit in shared
     // memory.  Opt-in with MPIDB200_FFT=fused: measured on B200 at 128x128x64 it only ties the library path (three
     // 16-20 us single-wave kernels against seven ~6 us ones, profiles/r01_fft_experiment.md), so cuFFT stays the default.
+    // measured choice between the plane-kernel generations when MPIDB200_FFT is not set (profiles/r02_fft.md)
+    int fftDefaultMode(const int* g) const { (void) g; return 0; }
+    // plane kernels: plain launch, or one cluster of fft2.cluster CTAs per plane
+    void launchPlanes(bool forward, int planes, const void* in, void* out, int nxl, int nyl) {
+        traceBegin(forward ? "k_fft2_planes_forward" : "k_fft2_planes_backward");
+        if (fft2.cluster > 1) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(planes*fft2.cluster); lc.blockDim = dim3(fft2.planeThreads);
+            lc.dynamicSmemBytes = fft2.planeSmem; lc.stream = cur;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = fft2.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            const float2* twp = dTwiddle.p;
+            if (forward) CUDA_CHECK(cudaLaunchKernelEx(&lc, fft2.fwd, (const float*) in, (float2*) out, twp, nxl, nyl));
+            else CUDA_CHECK(cudaLaunchKernelEx(&lc, fft2.bwd, (const float2*) in, (float*) out, twp, nxl, nyl));
+        } else if (forward) fft2.fwd<<<planes, fft2.planeThreads, fft2.planeSmem, cur>>>((const float*) in, (float2*) out, dTwiddle.p, nxl, nyl);
+        else fft2.bwd<<<planes, fft2.planeThreads, fft2.planeSmem, cur>>>((const float2*) in, (float*) out, dTwiddle.p, nxl, nyl);
+        traceEnd();
+        launches += 1;
+    }
     void setupCustomFft(const int* g) {
         customFft = false; fft2 = Fft2Plan();
         if (sizeof(real) != sizeof(float)) return;
@@ -631,8 +652,9 @@ struct Engine : public EngineBase {
         if (mode != "fused") {
             // register-radix kernels (x, y in {32,64,128,224,256}, z in {32,64,128,224}): the default when the grid qualifies;
             // MPIDB200_FFT=fused3 selects the single-buffer plane kernels for every size (they are the only ones for 224)
-            if (mode == "fused2" || mode == "fused3" || (mode.empty() && MPIDB200_FFT2_DEFAULT)) {
-                fft2 = fft2MakePlan(g[0], g[1], g[2], mode == "fused3");
+            // MPIDB200_FFT=cluster: one plane per thread-block cluster of 4 CTAs, transposition through distributed shared memory
+            if (mode == "fused2" || mode == "fused3" || mode == "cluster" || (mode.empty() && MPIDB200_FFT2_DEFAULT)) {
+                fft2 = fft2MakePlan(g[0], g[1], g[2], mode == "fused3" ? 3 : (mode == "cluster" ? 4 : fftDefaultMode(g)));
                 if (fft2.ok) uploadTwiddles();
             }
             return;
@@ -1241,10 +1263,7 @@ struct Engine : public EngineBase {
     void slabPlanesForward(real* ownPlanes, int nxl, int nyl, size_t slabCplx) {
         const int R = numRanks, nzc = grid[2]/2 + 1;
         if (slabNative()) {
-            traceBegin("k_fft2_planes_forward");
-            fft2.fwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float*) (const void*) ownPlanes, (float2*) (void*) dSlabPack.p, dTwiddle.p, nxl, nyl);
-            traceEnd();
-            launches += 1;
+            launchPlanes(true, nxl, ownPlanes, dSlabPack.p, nxl, nyl);
         } else {
             CUFFT_CHECK(FftTraits<real>::fwd(planSlabF, ownPlanes, dSlabC.p));
             launches += 1;
@@ -1255,10 +1274,7 @@ struct Engine : public EngineBase {
     void slabPlanesBackward(real* ownPlanes, int nxl, int nyl, size_t slabCplx) {
         const int R = numRanks, nzc = grid[2]/2 + 1;
         if (slabNative()) {
-            traceBegin("k_fft2_planes_backward");
-            fft2.bwd<<<nxl, fft2.planeThreads, fft2.planeSmem, cur>>>((const float2*) (const void*) dSlabPack.p, (float*) (void*) ownPlanes, dTwiddle.p, nxl, nyl);
-            traceEnd();
-            launches += 1;
+            launchPlanes(false, nxl, dSlabPack.p, ownPlanes, nxl, nyl);
         } else {
             LAUNCH((k_slab_transpose<cplx, false>), blocksFor((long long) slabCplx, 256), 256, nxl, R, nyl*nzc, dSlabPack.p, dSlabC.p);
             CUFFT_CHECK(FftTraits<real>::bwd(planSlabB, dSlabC.p, ownPlanes));
@@ -1291,16 +1307,12 @@ struct Engine : public EngineBase {
         if (fft2.ok && !forceLibraryFft) {
             const float* g = (const float*) (const void*) dGrid.p;
             float2* c = (float2*) (void*) dGridC.p;
-            traceBegin("k_fft2_planes_forward");
-            fft2.fwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(g, c, dTwiddle.p, 0, 0);
-            traceEnd();
+            launchPlanes(true, grid[0], g, c, 0, 0);
             traceBegin("k_fft2_x_convolve");
             fft2.xcv<<<dim3(grid[1], fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(grid[1], grid[2]/2 + 1, fft2.chunk, (const float*) (const void*) dEterm.p, c, dTwiddle.p, grid[1], 0);
             traceEnd();
-            traceBegin("k_fft2_planes_backward");
-            fft2.bwd<<<grid[0], fft2.planeThreads, fft2.planeSmem, cur>>>(c, (float*) (void*) dGrid.p, dTwiddle.p, 0, 0);
-            traceEnd();
-            launches += 3;
+            launchPlanes(false, grid[0], c, dGrid.p, 0, 0);
+            launches += 1;
             cudaError_t le = cudaGetLastError();
             if (le != cudaSuccess) throw CudaError(std::string("launch of the fused reciprocal pass failed: ") + cudaGetErrorString(le));
         } else if (customFft && !forceLibraryFft) {

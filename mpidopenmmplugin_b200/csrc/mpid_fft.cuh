@@ -15,6 +15,7 @@
 #define MPIDB200_FFT_CUH_
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <algorithm>
 
 namespace mpid {
@@ -677,10 +678,155 @@ k_fft3_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, 
     fft3Pass2Store<R1Z, R2Z, true, true>(buf, NY, 1, rowOff, [&](int r, int j, float2 v) { plane[elemOf<R1Y, R2Y>(r)*M + j] = v; });
 }
 
+// =====================================================================================================
+// Fourth generation: one x plane per thread-block CLUSTER.  The C CTAs of a cluster split the plane's rows for the z
+// transforms and its kz columns for the y transforms; the transposition between the two goes through distributed shared
+// memory (every CTA reads the column block it owns out of the row blocks of its C-1 neighbours with ld.shared::cluster).
+// A 224 x 224 plane then needs 2 x 52 KB per CTA instead of 206 KB in one, four times as many warps work on a plane, and
+// a rank that holds only 28 planes of a slab-decomposed pass still fills 112 SMs.
+//   forward :  rows -> A, z passes in A, untangle A -> B (natural kz order) | cluster.sync | columns of all B -> A,
+//              y passes in A -> global | cluster.sync (nobody leaves while its B is still being read)
+//   backward:  columns -> A, y passes in A (row slots) | cluster.sync | rows of all A -> B, untangle in B, z passes -> global
+//              | cluster.sync
+// =====================================================================================================
+template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z, int C>
+__global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
+k_fft4_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl) {
+    namespace cg = cooperative_groups;
+    constexpr int M = NZ/2, MC = M + 1, NYC = NY/C, W = (MC + C - 1)/C;
+    constexpr int REGION = (NYC*MC > NY*W ? NYC*MC : NY*W);
+    static_assert(R1Y*R2Y == NY && R1Z*R2Z == M && NY % C == 0, "radix split");
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int) cluster.block_rank();
+    const int plane = blockIdx.x / C;
+    extern __shared__ float2 fftsm[];
+    float2* A = fftsm;
+    float2* B = A + REGION;
+    float2* twY = B + REGION;
+    float2* twZ = twY + NY;
+    float2* twU = twZ + M;
+    fft2LoadTable(twY, NY, tw);
+    fft2LoadTable(twZ, M, tw);
+    fft2LoadTablePart(twU, NZ, M, tw);
+    // this CTA's rows y = c NYC .. (c+1) NYC - 1, NZ reals read as M complex numbers
+    const float2* src = reinterpret_cast<const float2*>(grid + ((size_t) plane*NY + (size_t) c*NYC)*NZ);
+    for (int t = threadIdx.x; t < NYC*M; t += blockDim.x) A[(t / M)*MC + (t % M)] = src[t];
+    __syncthreads();
+    auto rowOff = [](int y) { return y*MC; };
+    fft3Pass1<R1Z, R2Z, false>(A, NYC, 1, rowOff, twZ);
+    __syncthreads();
+    fft3Pass2InPlace<R1Z, R2Z, false>(A, NYC, 1, rowOff);
+    __syncthreads();
+    // untangle A (element k at slot slotOf(k)) -> B in natural kz order
+    for (int t = threadIdx.x; t < NYC*MC; t += blockDim.x) {
+        const int k = t / NYC, y = t - k*NYC;
+        const float2* row = A + y*MC;
+        const float2 zk = row[k == M ? 0 : slotOf<R1Z, R2Z>(k)];
+        const float2 zr = cconj(row[k == 0 ? 0 : slotOf<R1Z, R2Z>(M - k)]);
+        const float2 e = make_float2(0.5f*(zk.x + zr.x), 0.5f*(zk.y + zr.y));
+        const float2 d = make_float2(0.5f*(zk.x - zr.x), 0.5f*(zk.y - zr.y));
+        const float2 w = k == M ? make_float2(-1.f, 0.f) : twU[k];
+        B[y*MC + k] = cadd(e, cmul(w, make_float2(d.y, -d.x)));
+    }
+    cluster.sync();
+    // this CTA's columns kz = c W .. : gather them from the row blocks of all C CTAs (distributed shared memory)
+    const int kz0 = c*W, ncol = min(W, MC - kz0);
+    for (int r = 0; r < C; r++) {
+        const float2* rb = cluster.map_shared_rank(B, (unsigned) r);
+        for (int t = threadIdx.x; t < NYC*ncol; t += blockDim.x) {
+            const int y = t / ncol, q = t - y*ncol;
+            A[(r*NYC + y)*W + q] = rb[y*MC + kz0 + q];
+        }
+    }
+    __syncthreads();
+    auto colOff = [](int q) { return q; };
+    fft3Pass1<R1Y, R2Y, false>(A, ncol, W, colOff, twY);
+    __syncthreads();
+    if (nxl > 0) {
+        fft3Pass2Store<R1Y, R2Y, false, false>(A, ncol, W, colOff, [&](int q, int ky, float2 v) { out[slabIndex(nxl, nyl, plane, ky, MC) + kz0 + q] = v; });
+    } else {
+        float2* dstp = out + (size_t) plane*NY*MC;
+        fft3Pass2Store<R1Y, R2Y, false, false>(A, ncol, W, colOff, [&](int q, int ky, float2 v) { dstp[ky*MC + kz0 + q] = v; });
+    }
+    cluster.sync();
+}
+
+template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z, int C>
+__global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
+k_fft4_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, const float2* __restrict__ tw, int nxl, int nyl) {
+    namespace cg = cooperative_groups;
+    constexpr int M = NZ/2, MC = M + 1, NYC = NY/C, W = (MC + C - 1)/C;
+    constexpr int REGION = (NYC*MC > NY*W ? NYC*MC : NY*W);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int) cluster.block_rank();
+    const int plane = blockIdx.x / C;
+    extern __shared__ float2 fftsm[];
+    float2* A = fftsm;
+    float2* B = A + REGION;
+    float2* twY = B + REGION;
+    float2* twZ = twY + NY;
+    float2* twU = twZ + M;
+    fft2LoadTable(twY, NY, tw);
+    fft2LoadTable(twZ, M, tw);
+    fft2LoadTablePart(twU, NZ, M, tw);
+    // this CTA's columns kz = c W .., all ky
+    const int kz0 = c*W, ncol = min(W, MC - kz0);
+    if (nxl > 0) {
+        for (int t = threadIdx.x; t < NY*ncol; t += blockDim.x) { const int ky = t / ncol, q = t - ky*ncol; A[ky*W + q] = in[slabIndex(nxl, nyl, plane, ky, MC) + kz0 + q]; }
+    } else {
+        const float2* src = in + (size_t) plane*NY*MC;
+        for (int t = threadIdx.x; t < NY*ncol; t += blockDim.x) { const int ky = t / ncol, q = t - ky*ncol; A[ky*W + q] = src[ky*MC + kz0 + q]; }
+    }
+    __syncthreads();
+    auto colOff = [](int q) { return q; };
+    fft3Pass1<R1Y, R2Y, true>(A, ncol, W, colOff, twY);
+    __syncthreads();
+    fft3Pass2InPlace<R1Y, R2Y, true>(A, ncol, W, colOff);           // row slot s now holds y = elemOf<R1Y, R2Y>(s)
+    cluster.sync();
+    // this CTA's row slots s = c NYC .. : gather them from the column blocks of all C CTAs
+    for (int r = 0; r < C; r++) {
+        const float2* cb = cluster.map_shared_rank(A, (unsigned) r);
+        const int rk0 = r*W, rn = min(W, MC - rk0);
+        for (int t = threadIdx.x; t < NYC*rn; t += blockDim.x) {
+            const int y = t / rn, q = t - y*rn;
+            B[y*MC + rk0 + q] = cb[(c*NYC + y)*W + q];
+        }
+    }
+    __syncthreads();
+    // Z[k] = (X[k] + conj X[M-k]) + i w^-k (X[k] - conj X[M-k]), pairwise in place (k = 0 pairs with column M)
+    for (int t = threadIdx.x; t < NYC*(M/2 + 1); t += blockDim.x) {
+        const int k = t / NYC, r = t - k*NYC;
+        float2* row = B + r*MC;
+        const int k2 = M - k;
+        const float2 xk = row[k], xk2 = row[k2];
+        {
+            const float2 b = cconj(xk2);
+            const float2 s = cadd(xk, b), d = csub(xk, b);
+            const float2 wd = k == 0 ? d : cmul(cconj(twU[k]), d);
+            row[k] = make_float2(s.x - wd.y, s.y + wd.x);
+        }
+        if (k != 0 && k2 != k) {
+            const float2 b = cconj(xk);
+            const float2 s = cadd(xk2, b), d = csub(xk2, b);
+            const float2 wd = cmul(cconj(twU[k2]), d);
+            row[k2] = make_float2(s.x - wd.y, s.y + wd.x);
+        }
+    }
+    __syncthreads();
+    auto rowOff = [](int r) { return r*MC; };
+    fft3Pass1<R1Z, R2Z, true>(B, NYC, 1, rowOff, twZ);
+    __syncthreads();
+    float2* dst = reinterpret_cast<float2*>(grid + (size_t) plane*NY*NZ);
+    fft3Pass2Store<R1Z, R2Z, true, true>(B, NYC, 1, rowOff, [&](int r, int j, float2 v) { dst[elemOf<R1Y, R2Y>(c*NYC + r)*M + j] = v; });
+    cluster.sync();
+}
+
 // ---- host-side dispatch over the supported sizes: x, y in {32, 64, 128, 224, 256}, z in {32, 64, 128, 224} ----------------
 // Power-of-two planes use the two-buffer kernels (k_fft2_*); a plane with a 224 edge uses the single-buffer ones (k_fft3_*).
+#define MPID_FFT_CLUSTER 4
 struct Fft2Plan {
     bool ok = false;
+    int cluster = 1;                    // CTAs per plane (k_fft4_*: thread-block cluster with DSMEM transposition)
     int nx = 0, ny = 0, nz = 0, chunk = 0, chunks = 0;
     int planeThreads = 0, xThreads = 0;
     size_t planeSmem = 0, xSmem = 0;
@@ -701,13 +847,32 @@ template <int NY, int R1Y, int R2Y> inline bool fft3PickPlanes(Fft2Plan& p, int 
     if (nz == 224) { p.fwd = k_fft3_planes_forward<NY, R1Y, R2Y, 224, 16, 7>; p.bwd = k_fft3_planes_backward<NY, R1Y, R2Y, 224, 16, 7>; return true; }
     return false;
 }
-inline Fft2Plan fft2MakePlan(int nx, int ny, int nz, bool singleBuffer = false) {
+template <int NY, int R1Y, int R2Y> inline bool fft4PickPlanes(Fft2Plan& p, int nz) {
+    constexpr int C = MPID_FFT_CLUSTER;
+    if (nz == 32)  { p.fwd = k_fft4_planes_forward<NY, R1Y, R2Y, 32, 4, 4, C>;   p.bwd = k_fft4_planes_backward<NY, R1Y, R2Y, 32, 4, 4, C>;   return true; }
+    if (nz == 64)  { p.fwd = k_fft4_planes_forward<NY, R1Y, R2Y, 64, 8, 4, C>;   p.bwd = k_fft4_planes_backward<NY, R1Y, R2Y, 64, 8, 4, C>;   return true; }
+    if (nz == 128) { p.fwd = k_fft4_planes_forward<NY, R1Y, R2Y, 128, 8, 8, C>;  p.bwd = k_fft4_planes_backward<NY, R1Y, R2Y, 128, 8, 8, C>;  return true; }
+    if (nz == 224) { p.fwd = k_fft4_planes_forward<NY, R1Y, R2Y, 224, 16, 7, C>; p.bwd = k_fft4_planes_backward<NY, R1Y, R2Y, 224, 16, 7, C>; return true; }
+    return false;
+}
+// mode: 0 = default (two-buffer planes for power-of-two grids, single-buffer for 224), 3 = single-buffer everywhere,
+// 4 = cluster planes everywhere
+inline Fft2Plan fft2MakePlan(int nx, int ny, int nz, int mode = 0) {
     Fft2Plan p;
     p.nx = nx; p.ny = ny; p.nz = nz;
-    int r2y = 0, r1x = 0;
+    int r2y = 0, r1x = 0, r2z = 0;
     bool okP = false;
-    const bool gen3 = singleBuffer || ny == 224 || nz == 224;
-    if (gen3) {
+    const bool gen4 = mode == 4;
+    const bool gen3 = !gen4 && (mode == 3 || ny == 224 || nz == 224);
+    if (gen4) {
+        p.cluster = MPID_FFT_CLUSTER;
+        if (ny == 32)  { okP = fft4PickPlanes<32, 8, 4>(p, nz);    r2y = 4; }
+        if (ny == 64)  { okP = fft4PickPlanes<64, 8, 8>(p, nz);    r2y = 8; }
+        if (ny == 128) { okP = fft4PickPlanes<128, 16, 8>(p, nz);  r2y = 8; }
+        if (ny == 224) { okP = fft4PickPlanes<224, 16, 14>(p, nz); r2y = 14; }
+        if (ny == 256) { okP = fft4PickPlanes<256, 16, 16>(p, nz); r2y = 16; }
+        r2z = nz == 224 ? 7 : (nz == 128 ? 8 : 4);
+    } else if (gen3) {
         if (ny == 32)  { okP = fft3PickPlanes<32, 8, 4>(p, nz);    r2y = 4; }
         if (ny == 64)  { okP = fft3PickPlanes<64, 8, 8>(p, nz);    r2y = 8; }
         if (ny == 128) { okP = fft3PickPlanes<128, 16, 8>(p, nz);  r2y = 8; }
@@ -726,12 +891,20 @@ inline Fft2Plan fft2MakePlan(int nx, int ny, int nz, bool singleBuffer = false) 
     if (nx == 256) { p.xcv = k_fft2_x_convolve<256, 16, 16>; r1x = 16; }
     if (!okP || !p.xcv) return p;
     const int m = nz/2, mc = m + 1;
-    p.planeSmem = ((size_t) (gen3 ? 1 : 2)*ny*mc + ny + 2*m)*sizeof(float2);
+    if (gen4) {
+        const int C = MPID_FFT_CLUSTER, nyc = ny/C, w = (mc + C - 1)/C;
+        const size_t region = std::max((size_t) nyc*mc, (size_t) ny*w);
+        p.planeSmem = (2*region + ny + 2*m)*sizeof(float2);
+        const int tasks = std::max(std::max(nyc*r2z, w*r2y), 64);
+        p.planeThreads = std::min(MPID_FFT2_MAX_THREADS, (tasks + 31)/32*32);
+    } else {
+        p.planeSmem = ((size_t) (gen3 ? 1 : 2)*ny*mc + ny + 2*m)*sizeof(float2);
+        // one round of the widest y pass per block when it fits, else two
+        int tasks = mc*r2y;
+        if (tasks > MPID_FFT2_MAX_THREADS) tasks = (tasks + 1)/2;
+        p.planeThreads = std::min(MPID_FFT2_MAX_THREADS, (tasks + 31)/32*32);
+    }
     if (p.planeSmem > 226*1024) return p;
-    // one round of the widest y pass per block when it fits, else two
-    int tasks = mc*r2y;
-    if (tasks > MPID_FFT2_MAX_THREADS) tasks = (tasks + 1)/2;
-    p.planeThreads = std::min(MPID_FFT2_MAX_THREADS, (tasks + 31)/32*32);
     p.chunks = (mc + 11)/12;
     p.chunk = (mc + p.chunks - 1)/p.chunks;
     p.chunks = (mc + p.chunk - 1)/p.chunk;

@@ -449,12 +449,15 @@ def test_neighbour_list_reuse_can_be_disabled(monkeypatch):
 
 
 @pytest.mark.parametrize("grid,mode", [((224, 32, 32), ""), ((32, 224, 32), ""), ((32, 32, 224), ""), ((224, 224, 224), ""), ((64, 224, 128), ""),
-                                       ((128, 128, 64), "fused3"), ((256, 32, 128), "fused3"), ((128, 128, 64), "fused2")])
+                                       ((128, 128, 64), "fused3"), ((256, 32, 128), "fused3"), ((128, 128, 64), "fused2"),
+                                       ((128, 128, 64), "cluster"), ((224, 224, 224), "cluster"), ((32, 64, 32), "cluster"), ((256, 32, 128), "cluster"),
+                                       ((64, 224, 64), "cluster"), ((32, 256, 224), "cluster")])
 def test_hand_written_reciprocal_pass_equals_the_library_transform(grid, mode, monkeypatch):
     """One reciprocal pass (R2C, influence function, C2R) of a random real grid through the kernels of mpid_fft.cuh and
     through cuFFT + k_convolution (mpidb200_debug_reciprocal_pass): the register-radix kernels with two plane buffers
-    (power-of-two grids), and the single-buffer kernels with the 7- and 14-point DFTs that serve the 224^3 grid of the
-    1,024,884-atom box (BASELINE.json config 5)."""
+    (power-of-two grids), the single-buffer kernels with the 7- and 14-point DFTs that serve the 224^3 grid of the
+    1,024,884-atom box (BASELINE.json config 5), and the thread-block-cluster kernels that split a plane over four CTAs and
+    transpose it through distributed shared memory (MPIDB200_FFT=cluster)."""
     s = water_box((1, 1, 1), polarization=1, grid=grid)
     if mode:
         monkeypatch.setenv("MPIDB200_FFT", mode)

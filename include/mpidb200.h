@@ -100,6 +100,20 @@ int mpidb200_execute_device(mpidb200_handle h, const double* d_positions, int in
 int mpidb200_pin_host_buffer(mpidb200_handle h, void* buffer, unsigned long long bytes);
 int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer);
 
+/* The same evaluation on the device-resident data of an OpenMM CudaContext, for a kernel registered on the "CUDA"
+ * platform -- no host copies at all:
+ *   d_posq            cu.getPosq().getDevicePointer(): float4 (posq_is_double = 0) or double4 (1) per atom, in the
+ *                     context's reordered atom order (reference: platforms/cuda/src/MPIDCudaKernels.cpp:216)
+ *   d_posq_correction cu.getPosqCorrection() in mixed precision, else NULL
+ *   d_atom_index      cu.getAtomIndexArray(): slot i holds atom d_atom_index[i] (MPIDCudaKernels.cpp:1089)
+ *   d_force_buffer    cu.getForce(): signed 64-bit fixed point, scale 2^32, [x | y | z] x padded_num_atoms by slot;
+ *                     our forces are ADDED with atomicAdd like the reference's kernels do
+ *                     (platforms/cuda/src/kernels/multipoleElectrostatics.cu:708-710)
+ * Run it on the context's stream with mpidb200_set_stream(h, cu.getCurrentStream()). */
+int mpidb200_execute_cuda_context(mpidb200_handle h, const void* d_posq, int posq_is_double, const void* d_posq_correction,
+                                  const int* d_atom_index, int padded_num_atoms, int include_forces, int include_energy,
+                                  double* energy, void* d_force_buffer);
+
 /* Run the engine on a caller-owned CUDA stream (e.g. the host framework's current stream) instead of its
  * own; pass NULL to return to the private stream.  The caller keeps ownership. */
 int mpidb200_set_stream(mpidb200_handle h, void* cuda_stream);

@@ -390,6 +390,15 @@ class MPIDB200Kernel:
                                                       ctypes.c_void_p(d_forces)))
         return e.value
 
+    def execute_cuda_context(self, d_posq, posq_is_double, d_posq_correction, d_atom_index, padded_num_atoms, includeForces, includeEnergy, d_force_buffer):
+        """mpidb200_execute_cuda_context: raw device pointers (ints) in the layouts of an OpenMM CudaContext."""
+        e = ctypes.c_double(0.0)
+        self._check(self._lib.mpidb200_execute_cuda_context(self._h, ctypes.c_void_p(d_posq), ctypes.c_int(1 if posq_is_double else 0),
+                                                            ctypes.c_void_p(d_posq_correction if d_posq_correction else None), ctypes.c_void_p(d_atom_index),
+                                                            ctypes.c_int(padded_num_atoms), ctypes.c_int(1 if includeForces else 0),
+                                                            ctypes.c_int(1 if includeEnergy else 0), ctypes.byref(e), ctypes.c_void_p(d_force_buffer if d_force_buffer else None)))
+        return e.value
+
     def _dipoles(self, positions, which):
         pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1)
         out = np.zeros((self._n, 3))

@@ -120,6 +120,8 @@ struct EngineBase {
     virtual void unpinHost(void* ptr) = 0;
     virtual void workCounts(long long* out8) = 0;
     virtual void listStats(long long* out2) = 0;
+    virtual void executeCudaContext(const void* posq, int posqIsDouble, const void* posqCorrection, const int* atomIndex, int paddedNumAtoms,
+                                    bool includeForces, bool includeEnergy, double* energy, void* forceBuffer) = 0;
     virtual void debugReciprocalPass(float* hostGrid, bool library) = 0;
     virtual void setKernelProfiling(bool on) = 0;
     virtual std::string kernelProfileCsv() = 0;
@@ -266,6 +268,7 @@ struct Engine : public EngineBase {
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); }
         destroySlabPlans();
+        closePeers();
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
         for (const PinnedRange& r : pinnedRanges) cudaHostUnregister(r.p);
@@ -611,7 +614,9 @@ struct Engine : public EngineBase {
     // measured choice between the plane-kernel generations when MPIDB200_FFT is not set (profiles/r02_fft.md)
     int fftDefaultMode(const int* g) const { (void) g; return 0; }
     // plane kernels: plain launch, or one cluster of fft2.cluster CTAs per plane
-    void launchPlanes(bool forward, int planes, const void* in, void* out, int nxl, int nyl) {
+    void launchPlanes(bool forward, int planes, const void* in, void* out, int nxl, int nyl, const SlabPeers* peersIn = nullptr) {
+        SlabPeers peers; memset(&peers, 0, sizeof(peers));
+        if (peersIn) peers = *peersIn;
         traceBegin(forward ? "k_fft2_planes_forward" : "k_fft2_planes_backward");
         if (fft2.cluster > 1) {
             cudaLaunchConfig_t lc = {};
@@ -622,9 +627,9 @@ struct Engine : public EngineBase {
             at[0].val.clusterDim.x = fft2.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             lc.attrs = at; lc.numAttrs = 1;
             const float2* twp = dTwiddle.p;
-            if (forward) CUDA_CHECK(cudaLaunchKernelEx(&lc, fft2.fwd, (const float*) in, (float2*) out, twp, nxl, nyl));
+            if (forward) CUDA_CHECK(cudaLaunchKernelEx(&lc, fft2.fwd, (const float*) in, (float2*) out, twp, nxl, nyl, peers));
             else CUDA_CHECK(cudaLaunchKernelEx(&lc, fft2.bwd, (const float2*) in, (float*) out, twp, nxl, nyl));
-        } else if (forward) fft2.fwd<<<planes, fft2.planeThreads, fft2.planeSmem, cur>>>((const float*) in, (float2*) out, dTwiddle.p, nxl, nyl);
+        } else if (forward) fft2.fwd<<<planes, fft2.planeThreads, fft2.planeSmem, cur>>>((const float*) in, (float2*) out, dTwiddle.p, nxl, nyl, peers);
         else fft2.bwd<<<planes, fft2.planeThreads, fft2.planeSmem, cur>>>((const float2*) in, (float*) out, dTwiddle.p, nxl, nyl);
         traceEnd();
         launches += 1;
@@ -1157,7 +1162,7 @@ struct Engine : public EngineBase {
     void haloReciprocalPass() {
         const int R = numRanks, nx = grid[0], ny = grid[1], nz = grid[2], nzc = nz/2 + 1;
         const int nxl = nx/R, nyl = ny/R;
-        const size_t plane = (size_t) ny*nz, slabCplx = (size_t) nxl*ny*nzc, blk = (size_t) nxl*nyl*nzc;
+        const size_t plane = (size_t) ny*nz, slabCplx = (size_t) nxl*ny*nzc;
         ensureSlabPlans(R);
         dSlabC.ensure(slabCplx); dSlabPack.ensure(slabCplx); dSlabT.ensure(slabCplx);
         dHaloIn.ensure(std::max<size_t>((size_t) (haloLo + haloHi)*plane, 1));
@@ -1178,21 +1183,7 @@ struct Engine : public EngineBase {
         ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
         if (nLo + nHi) LAUNCH((k_halo_add<real>), blocksFor((long long) (nLo + nHi), 256), 256, nLo, nHi, dHaloIn.p, own + (size_t) (nxl - haloLo)*plane, own);
         // slab transform on the own block; block r sits at x position (r + R/2) mod R of the transform
-        slabPlanesForward(own, nxl, nyl, slabCplx);
-        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
-        for (int r = 0; r < R; r++) {
-            ncclCheck(g_nccl.Send(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
-            ncclCheck(g_nccl.Recv(dSlabT.p + (size_t) ((r + R/2) % R)*blk, 2*blk, dt, r, c, cur), "ncclRecv");
-        }
-        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
-        slabXConvolve(dSlabT.p, nyl, slabCplx);
-        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
-        for (int r = 0; r < R; r++) {
-            ncclCheck(g_nccl.Send(dSlabT.p + (size_t) ((r + R/2) % R)*blk, 2*blk, dt, r, c, cur), "ncclSend");
-            ncclCheck(g_nccl.Recv(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
-        }
-        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
-        slabPlanesBackward(own, nxl, nyl, slabCplx);
+        slabTransform(own, R/2);
         // halo gather: my top planes are the low halo of the rank above, my first planes the high halo of the rank below
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         if (nLo) ncclCheck(g_nccl.Send(own + (size_t) (nxl - haloLo)*plane, nLo, dt, up, c, cur), "ncclSend");
@@ -1229,28 +1220,13 @@ struct Engine : public EngineBase {
     void slabReciprocalPass() {
         const int R = numRanks, nx = grid[0], ny = grid[1], nz = grid[2], nzc = nz/2 + 1;
         const int nxl = nx/R, nyl = ny/R;
-        const size_t slabReal = (size_t) nxl*ny*nz, slabCplx = (size_t) nxl*ny*nzc, blk = (size_t) nxl*nyl*nzc;
+        const size_t slabReal = (size_t) nxl*ny*nz, slabCplx = (size_t) nxl*ny*nzc;
         ensureSlabPlans(R);
         dSlabR.ensure(slabReal); dSlabC.ensure(slabCplx); dSlabPack.ensure(slabCplx); dSlabT.ensure(slabCplx);
         void* c = (cur == stream2 && commPme) ? commPme : comm;
         const int dt = sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
         ncclCheck(g_nccl.ReduceScatter(dGrid.p, dSlabR.p, slabReal, dt, NCCL_SUM, c, cur), "ncclReduceScatter");
-        slabPlanesForward(dSlabR.p, nxl, nyl, slabCplx);
-        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
-        for (int r = 0; r < R; r++) {
-            ncclCheck(g_nccl.Send(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
-            ncclCheck(g_nccl.Recv(dSlabT.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
-        }
-        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
-        // dSlabT = [x = 0..nx-1][ky own][kz]
-        slabXConvolve(dSlabT.p, nyl, slabCplx);
-        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
-        for (int r = 0; r < R; r++) {
-            ncclCheck(g_nccl.Send(dSlabT.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
-            ncclCheck(g_nccl.Recv(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
-        }
-        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
-        slabPlanesBackward(dSlabR.p, nxl, nyl, slabCplx);
+        slabTransform(dSlabR.p, 0);
         ncclCheck(g_nccl.AllGather(dSlabR.p, dGrid.p, slabReal, dt, c, cur), "ncclAllGather");
     }
 
@@ -1260,6 +1236,129 @@ struct Engine : public EngineBase {
     // Forward: own real planes -> dSlabPack in the send layout of the all-to-all.  The hand-written kernel stores that
     // layout directly; the library path transforms into dSlabC and packs with k_slab_transpose.
     bool slabNative() const { return fft2.ok && !forceLibraryFft; }
+    // ---- peer-to-peer all-to-all (MPIDB200_P2P, default on): the slab buffers of all ranks are mapped into every process
+    // (CUDA IPC; the ranks share one NVLink/NVSwitch node), the forward plane kernel and the x kernel store their results
+    // directly into the receivers' buffers, and a flag barrier (k_cross_barrier) replaces the collective.
+    const bool p2pEnabled = !(getenv("MPIDB200_P2P") && atoi(getenv("MPIDB200_P2P")) == 0);
+    bool p2pReady = false, p2pTried = false;
+    int p2pRanks = 0;
+    size_t p2pSlabCplx = 0;
+    std::vector<void*> peerSlabT, peerSlabPack, peerFlags, ipcOpened;
+    DevBuf<int> dBarFlags, dBarTimeout;
+    int barEpoch = 0;
+    void closePeers() {
+        for (void* p : ipcOpened) cudaIpcCloseMemHandle(p);
+        ipcOpened.clear(); peerSlabT.clear(); peerSlabPack.clear(); peerFlags.clear();
+        p2pReady = false;
+    }
+    // exchange IPC handles of dSlabT, dSlabPack and the flag array (once per allocation of those buffers)
+    void setupPeers(size_t slabCplx) {
+        if (p2pReady && p2pRanks == numRanks && p2pSlabCplx == slabCplx) return;
+        if (p2pTried && p2pRanks == numRanks && p2pSlabCplx == slabCplx) return;         // failed before: stay on NCCL
+        closePeers();
+        p2pTried = true; p2pRanks = numRanks; p2pSlabCplx = slabCplx;
+        if (!p2pEnabled || !slabNative() || !g_nccl.AllGather || numRanks > 16) return;
+        dBarFlags.ensure(16); dBarTimeout.ensure(1);
+        CUDA_CHECK(cudaMemsetAsync(dBarFlags.p, 0, 16*sizeof(int), cur));
+        CUDA_CHECK(cudaMemsetAsync(dBarTimeout.p, 0, sizeof(int), cur));
+        barEpoch = 0;
+        struct Handles { cudaIpcMemHandle_t t, pack, flags; int ok; int pad[3]; };
+        Handles mine; memset(&mine, 0, sizeof(mine));
+        mine.ok = cudaIpcGetMemHandle(&mine.t, dSlabT.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.pack, dSlabPack.p) == cudaSuccess &&
+                  cudaIpcGetMemHandle(&mine.flags, dBarFlags.p) == cudaSuccess;
+        cudaGetLastError();
+        DevBuf<unsigned char> dH;
+        dH.ensure(sizeof(Handles)*(size_t) numRanks);
+        CUDA_CHECK(cudaMemcpyAsync(dH.p + sizeof(Handles)*(size_t) rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, cur));
+        void* c = (cur == stream2 && commPme) ? commPme : comm;
+        ncclCheck(g_nccl.AllGather(dH.p + sizeof(Handles)*(size_t) rank, dH.p, sizeof(Handles), /*ncclUint8*/ 1, c, cur), "ncclAllGather");
+        std::vector<Handles> all(numRanks);
+        CUDA_CHECK(cudaMemcpyAsync(all.data(), dH.p, sizeof(Handles)*(size_t) numRanks, cudaMemcpyDeviceToHost, cur));
+        CUDA_CHECK(cudaStreamSynchronize(cur));
+        bool ok = true;
+        for (int r = 0; r < numRanks; r++) ok = ok && all[r].ok;
+        peerSlabT.assign(numRanks, nullptr); peerSlabPack.assign(numRanks, nullptr); peerFlags.assign(numRanks, nullptr);
+        for (int r = 0; r < numRanks && ok; r++) {
+            if (r == rank) { peerSlabT[r] = dSlabT.p; peerSlabPack[r] = dSlabPack.p; peerFlags[r] = dBarFlags.p; continue; }
+            void* a = nullptr; void* b = nullptr; void* f = nullptr;
+            ok = cudaIpcOpenMemHandle(&a, all[r].t, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (ok) { ipcOpened.push_back(a); ok = cudaIpcOpenMemHandle(&b, all[r].pack, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
+            if (ok) { ipcOpened.push_back(b); ok = cudaIpcOpenMemHandle(&f, all[r].flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
+            if (ok) ipcOpened.push_back(f);
+            peerSlabT[r] = a; peerSlabPack[r] = b; peerFlags[r] = f;
+        }
+        cudaGetLastError();
+        // all ranks must agree (one failed mapping anywhere -> everybody stays on NCCL)
+        int* flag = (int*) hPinned + 40;
+        flag[0] = ok ? 0 : 1;
+        DevBuf<int> dOk; dOk.ensure(1);
+        CUDA_CHECK(cudaMemcpyAsync(dOk.p, flag, sizeof(int), cudaMemcpyHostToDevice, cur));
+        ncclCheck(g_nccl.AllReduce(dOk.p, dOk.p, 1, /*ncclInt32*/ 2, NCCL_SUM, c, cur), "ncclAllReduce");
+        CUDA_CHECK(cudaMemcpyAsync(flag, dOk.p, sizeof(int), cudaMemcpyDeviceToHost, cur));
+        CUDA_CHECK(cudaStreamSynchronize(cur));
+        if (flag[0] != 0) { closePeers(); return; }
+        p2pReady = true;
+    }
+    void crossBarrier() {
+        PeerPtrs pf; memset(&pf, 0, sizeof(pf));
+        for (int r = 0; r < numRanks; r++) pf.p[r] = peerFlags[r];
+        barEpoch++;
+        LAUNCH(k_cross_barrier, 1, 32, numRanks, rank, barEpoch, pf, (volatile int*) dBarFlags.p, dBarTimeout.p);
+    }
+    void checkBarrierTimeout() {
+        if (!p2pReady) return;
+        int* t = (int*) hPinned + 44;
+        CUDA_CHECK(cudaMemcpyAsync(t, dBarTimeout.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (t[0]) throw std::runtime_error("mpidb200: a rank did not reach the peer-to-peer barrier of the reciprocal pass");
+    }
+    // The transform of a slab-decomposed pass from this rank's real planes back to them.  rot = block rotation of the
+    // x order (R/2 with halo exchange, 0 otherwise).  Peer-to-peer: forward planes -> (remote stores into every rank's
+    // dSlabT) | barrier | x transform + influence function -> (remote stores into every rank's dSlabPack) | barrier |
+    // backward planes.  Otherwise the same steps around two grouped ncclSend/ncclRecv all-to-alls.
+    void slabTransform(real* ownPlanes, int rot) {
+        const int R = numRanks, nx = grid[0], ny = grid[1], nzc = grid[2]/2 + 1;
+        const int nxl = nx/R, nyl = ny/R;
+        const size_t slabCplx = (size_t) nxl*ny*nzc, blk = (size_t) nxl*nyl*nzc;
+        void* c = (cur == stream2 && commPme) ? commPme : comm;
+        const int dt = sizeof(real) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
+        setupPeers(slabCplx);
+        if (p2pReady) {
+            SlabPeers toT; memset(&toT, 0, sizeof(toT));
+            SlabPeers toPack = toT;
+            for (int r = 0; r < R; r++) { toT.dst[r] = (float2*) peerSlabT[r]; toPack.dst[r] = (float2*) peerSlabPack[r]; }
+            toT.ranks = toPack.ranks = R; toT.rot = toPack.rot = rot;
+            toT.slot = (rank + rot) % R; toPack.slot = rank;
+            launchPlanes(true, nxl, ownPlanes, dSlabPack.p, nxl, nyl, &toT);
+            crossBarrier();
+            traceBegin("k_fft2_x_convolve");
+            fft2.xcv<<<dim3(nyl, fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(nyl, nzc, fft2.chunk, (const float*) (const void*) dEterm.p, (float2*) (void*) dSlabT.p,
+                                                                                dTwiddle.p, ny, rank*nyl, toPack);
+            traceEnd();
+            launches += 1;
+            crossBarrier();
+            launchPlanes(false, nxl, dSlabPack.p, ownPlanes, nxl, nyl);
+            cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) throw CudaError(std::string("launch of the peer-to-peer slab transform failed: ") + cudaGetErrorString(le));
+            return;
+        }
+        slabPlanesForward(ownPlanes, nxl, nyl, slabCplx);
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < R; r++) {
+            ncclCheck(g_nccl.Send(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclSend");
+            ncclCheck(g_nccl.Recv(dSlabT.p + (size_t) ((r + rot) % R)*blk, 2*blk, dt, r, c, cur), "ncclRecv");
+        }
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        // dSlabT = [x = 0..nx-1][ky own][kz]
+        slabXConvolve(dSlabT.p, nyl, slabCplx);
+        ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < R; r++) {
+            ncclCheck(g_nccl.Send(dSlabT.p + (size_t) ((r + rot) % R)*blk, 2*blk, dt, r, c, cur), "ncclSend");
+            ncclCheck(g_nccl.Recv(dSlabPack.p + (size_t) r*blk, 2*blk, dt, r, c, cur), "ncclRecv");
+        }
+        ncclCheck(g_nccl.GroupEnd(), "ncclGroupEnd");
+        slabPlanesBackward(ownPlanes, nxl, nyl, slabCplx);
+    }
     void slabPlanesForward(real* ownPlanes, int nxl, int nyl, size_t slabCplx) {
         const int R = numRanks, nzc = grid[2]/2 + 1;
         if (slabNative()) {
@@ -1286,7 +1385,7 @@ struct Engine : public EngineBase {
         if (fft2.ok && !forceLibraryFft) {
             traceBegin("k_fft2_x_convolve");
             fft2.xcv<<<dim3(nyl, fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(nyl, nzc, fft2.chunk, (const float*) (const void*) dEterm.p, (float2*) (void*) data,
-                                                                                dTwiddle.p, ny, rank*nyl);
+                                                                                dTwiddle.p, ny, rank*nyl, SlabPeers{});
             traceEnd();
             launches += 1;
         } else {
@@ -1309,7 +1408,7 @@ struct Engine : public EngineBase {
             float2* c = (float2*) (void*) dGridC.p;
             launchPlanes(true, grid[0], g, c, 0, 0);
             traceBegin("k_fft2_x_convolve");
-            fft2.xcv<<<dim3(grid[1], fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(grid[1], grid[2]/2 + 1, fft2.chunk, (const float*) (const void*) dEterm.p, c, dTwiddle.p, grid[1], 0);
+            fft2.xcv<<<dim3(grid[1], fft2.chunks), fft2.xThreads, fft2.xSmem, cur>>>(grid[1], grid[2]/2 + 1, fft2.chunk, (const float*) (const void*) dEterm.p, c, dTwiddle.p, grid[1], 0, SlabPeers{});
             traceEnd();
             launchPlanes(false, grid[0], c, dGrid.p, 0, 0);
             launches += 1;
@@ -1575,7 +1674,7 @@ struct Engine : public EngineBase {
                 dDotsLocal.ensure(MPID_MAX_HISTORY + 1);
                 LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p,
                        numPol, (const int*) dPolList.p + polBegin, 0);
-                LAUNCH(k_sum_partials, 1, 32, nb, m, dDotPartial.p, dDotsLocal.p);
+                LAUNCH(k_sum_partials, 1, 32*m, nb, m, dDotPartial.p, dDotsLocal.p);
                 allReduce(dDotsLocal.p, (size_t) m, NCCL_FLOAT64);
                 LAUNCH(k_diis_solve, 1, 512, 1, m, sl, it, n, cfg.target_epsilon, dDotsLocal.p, dDiis.p);
                 if (!last) {
@@ -1831,6 +1930,7 @@ struct Engine : public EngineBase {
             enqueueForceReadback(dForcesOut);
             CUDA_CHECK(cudaEventSynchronize(evEnergyDone));
         } else CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (numRanks > 1) checkBarrierTimeout();
         collectTimings();
         if (tracing) { traceDump(); tracing = false; }
         if (energy) *energy = includeEnergy ? (double) ((long long) he[0])*(1.0/MPID_FIXED_SCALE) : 0.0;
@@ -1981,6 +2081,35 @@ struct Engine : public EngineBase {
     //   [4] polarizable x polarizable pairs (k_induced_field walks both directions of each)
     //   [5] directed site x neighbour evaluations of k_fixed_field (polarizable sites x all their neighbours)
     //   [6] covalently scaled pairs (static list)   [7] polarizable sites
+    // Device-resident entry for an OpenMM CudaContext (see k_positions_from_cuda_context): everything stays on the GPU and on
+    // the caller's stream (mpidb200_set_stream(h, cu.getCurrentStream())); only the energy comes back to the host.
+    DevBuf<double> dCtxPos, dCtxForce;
+    void executeCudaContext(const void* posq, int posqIsDouble, const void* posqCorrection, const int* atomIndex, int paddedNumAtoms,
+                            bool includeForces, bool includeEnergy, double* energy, void* forceBuffer) override {
+        CUDA_CHECK(cudaSetDevice(cfg.device));
+        if (!posq || !atomIndex) throw std::runtime_error("mpidb200_execute_cuda_context: null posq / atomIndex");
+        if (paddedNumAtoms < n) throw std::runtime_error("mpidb200_execute_cuda_context: paddedNumAtoms is smaller than the number of particles");
+        const size_t count = 3*(size_t) n;
+        dCtxPos.ensure(count);
+        cur = stream;
+        if (posqIsDouble) LAUNCH((k_positions_from_cuda_context<double4>), blocksFor(n, 256), 256, n, (const double4*) posq, (const float4*) nullptr, atomIndex, dCtxPos.p);
+        else LAUNCH((k_positions_from_cuda_context<float4>), blocksFor(n, 256), 256, n, (const float4*) posq, (const float4*) posqCorrection, atomIndex, dCtxPos.p);
+        double* df = nullptr;
+        if (includeForces) {
+            if (!forceBuffer) throw std::runtime_error("mpidb200_execute_cuda_context: a force buffer is required when forces are requested");
+            dCtxForce.ensure(count);
+            CUDA_CHECK(cudaMemsetAsync(dCtxForce.p, 0, count*sizeof(double), stream));
+            df = dCtxForce.p;
+        }
+        readbackPending = false; forcesUploadPending = false;
+        const long long convLaunches = 1;
+        evaluate(dCtxPos.p, includeForces, includeEnergy, energy, df, false);
+        if (includeForces) {
+            cur = stream;
+            LAUNCH(k_forces_to_cuda_context, blocksFor(n, 256), 256, n, paddedNumAtoms, atomIndex, dCtxForce.p, (unsigned long long*) forceBuffer);
+        }
+        launches += convLaunches;
+    }
     // Test hook: one reciprocal pass (forward transform, influence function, backward transform) of a caller-supplied real
     // grid, through the hand-written kernels or through cuFFT (single rank, mixed precision).
     void debugReciprocalPass(float* hostGrid, bool library) override {
@@ -2305,6 +2434,11 @@ int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer) {
 }
 int mpidb200_get_work_counts(mpidb200_handle h, long long* out8) {
     return guarded([&] { asEngine(h)->workCounts(out8); });
+}
+int mpidb200_execute_cuda_context(mpidb200_handle h, const void* d_posq, int posq_is_double, const void* d_posq_correction, const int* d_atom_index,
+                                  int padded_num_atoms, int include_forces, int include_energy, double* energy, void* d_force_buffer) {
+    return guarded([&] { asEngine(h)->executeCudaContext(d_posq, posq_is_double, d_posq_correction, d_atom_index, padded_num_atoms,
+                                                         include_forces != 0, include_energy != 0, energy, d_force_buffer); });
 }
 int mpidb200_debug_reciprocal_pass(mpidb200_handle h, float* host_grid, int use_library) {
     return guarded([&] { asEngine(h)->debugReciprocalPass(host_grid, use_library != 0); });

@@ -370,13 +370,21 @@ __device__ __forceinline__ void fft2LoadTable(float2* dst, int len, const float2
 // Slab-decomposed passes (several ranks) hand in nxl > 0: the half-complex result of plane xl then goes straight into the
 // send layout of the all-to-all, [destination rank q][xl][ky - q nyl][kz] with nyl = NY/ranks rows per rank, and the
 // backward kernels read that layout -- no separate transpose kernels.
+// Peer-to-peer all-to-all fused into the producers (several ranks on one node): dst[q] is rank q's RECEIVE buffer, mapped
+// into this process; a block of nxl x nyl x mc numbers sent by rank r lands at offset slotOfSender * blk there.
+struct SlabPeers {
+    float2* dst[16];
+    int ranks;          // 0 = not peer-to-peer (pack into the local send buffer / write the local array)
+    int slot;           // block position of THIS rank's data in the receivers' buffers
+    int rot;            // block position b of the x transform belongs to rank (b - rot) mod ranks (halo mode: ranks/2)
+};
 __device__ __forceinline__ size_t slabIndex(int nxl, int nyl, int xl, int ky, int mc) {
     const int q = ky / nyl;
     return (((size_t) q*nxl + xl)*nyl + (ky - q*nyl))*mc;
 }
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
-k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl) {
+k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl, SlabPeers peers) {
     constexpr int M = NZ/2, MC = M + 1;
     static_assert(R1Y*R2Y == NY && R1Z*R2Z == M, "radix split");
     extern __shared__ float2 fftsm[];
@@ -410,7 +418,13 @@ k_fft2_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, 
     __syncthreads();
     fft2Pass1<R1Y, R2Y, false>(buf0, MC, MC, 1, twY);
     __syncthreads();
-    if (nxl > 0) {
+    if (peers.ranks > 0) {
+        // the all-to-all of the slab transform, done by the producer: row ky of this plane goes to rank ky / nyl
+        fft2Pass2<R1Y, R2Y, false>(buf0, MC, MC, 1, [&](int kz, int ky, float2 v) {
+            const int q = ky / nyl;
+            peers.dst[q][(((size_t) peers.slot*nxl + blockIdx.x)*nyl + (ky - q*nyl))*MC + kz] = v;
+        });
+    } else if (nxl > 0) {
         fft2Pass2<R1Y, R2Y, false>(buf0, MC, MC, 1, [&](int kz, int ky, float2 v) { out[slabIndex(nxl, nyl, blockIdx.x, ky, MC) + kz] = v; });
     } else {
         float2* dstp = out + (size_t) blockIdx.x*NY*MC;
@@ -469,7 +483,7 @@ k_fft2_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, 
 template <int NX, int R1, int R2>
 __global__ void __launch_bounds__(256)
 k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, float2* __restrict__ data, const float2* __restrict__ tw,
-                  int nyEterm, int ky0) {
+                  int nyEterm, int ky0, SlabPeers peers) {
     static_assert(R1*R2 == NX, "radix split");
     extern __shared__ float2 fftsm[];
     const int S = chunk | 1;
@@ -495,7 +509,17 @@ k_fft2_x_convolve(int ny, int nzc, int chunk, const float* __restrict__ eterm, f
     __syncthreads();
     fft2Pass1<R1, R2, true>(buf1, count, S, 1, twX);
     __syncthreads();
-    fft2Pass2<R1, R2, true>(buf1, count, S, 1, [&](int c, int x, float2 v) { data[x*xStride + line + c] = v; });
+    if (peers.ranks > 0) {
+        // the all-to-all back, done by the producer: the planes x of block position b belong to rank (b - R/2) mod R, whose
+        // receive buffer takes this rank's ky rows at block offset peers.slot (= this rank's number)
+        const int nxl = NX/peers.ranks;
+        fft2Pass2<R1, R2, true>(buf1, count, S, 1, [&](int c, int x, float2 v) {
+            const int b = x / nxl, r = (b + peers.ranks - peers.rot) % peers.ranks;
+            peers.dst[r][(((size_t) peers.slot*nxl + (x - b*nxl))*ny + ky)*nzc + kz0 + c] = v;
+        });
+    } else {
+        fft2Pass2<R1, R2, true>(buf1, count, S, 1, [&](int c, int x, float2 v) { data[x*xStride + line + c] = v; });
+    }
 }
 
 // =====================================================================================================
@@ -566,7 +590,7 @@ __device__ __forceinline__ void fft3Pass2Store(const float2* buf, int count, int
 // real grid plane x -> half-complex plane x.  Dynamic shared memory: (NY MC + NY + 2 M) float2, M = NZ/2, MC = M + 1.
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
-k_fft3_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl) {
+k_fft3_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl, SlabPeers peers) {
     constexpr int M = NZ/2, MC = M + 1;
     static_assert(R1Y*R2Y == NY && R1Z*R2Z == M, "radix split");
     extern __shared__ float2 fftsm[];
@@ -617,7 +641,12 @@ k_fft3_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, 
     auto colOff = [](int kz) { return kz == M ? M : slotOf<R1Z, R2Z>(kz); };
     fft3Pass1<R1Y, R2Y, false>(buf, MC, MC, colOff, twY);
     __syncthreads();
-    if (nxl > 0) {
+    if (peers.ranks > 0) {
+        fft3Pass2Store<R1Y, R2Y, false, false>(buf, MC, MC, colOff, [&](int kz, int ky, float2 v) {
+            const int q = ky / nyl;
+            peers.dst[q][(((size_t) peers.slot*nxl + blockIdx.x)*nyl + (ky - q*nyl))*MC + kz] = v;
+        });
+    } else if (nxl > 0) {
         fft3Pass2Store<R1Y, R2Y, false, false>(buf, MC, MC, colOff, [&](int kz, int ky, float2 v) { out[slabIndex(nxl, nyl, blockIdx.x, ky, MC) + kz] = v; });
     } else {
         float2* dstp = out + (size_t) blockIdx.x*NY*MC;
@@ -691,7 +720,7 @@ k_fft3_planes_backward(const float2* __restrict__ in, float* __restrict__ grid, 
 // =====================================================================================================
 template <int NY, int R1Y, int R2Y, int NZ, int R1Z, int R2Z, int C>
 __global__ void __launch_bounds__(MPID_FFT2_MAX_THREADS)
-k_fft4_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl) {
+k_fft4_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, const float2* __restrict__ tw, int nxl, int nyl, SlabPeers peers) {
     namespace cg = cooperative_groups;
     constexpr int M = NZ/2, MC = M + 1, NYC = NY/C, W = (MC + C - 1)/C;
     constexpr int REGION = (NYC*MC > NY*W ? NYC*MC : NY*W);
@@ -742,7 +771,12 @@ k_fft4_planes_forward(const float* __restrict__ grid, float2* __restrict__ out, 
     auto colOff = [](int q) { return q; };
     fft3Pass1<R1Y, R2Y, false>(A, ncol, W, colOff, twY);
     __syncthreads();
-    if (nxl > 0) {
+    if (peers.ranks > 0) {
+        fft3Pass2Store<R1Y, R2Y, false, false>(A, ncol, W, colOff, [&](int q, int ky, float2 v) {
+            const int dq = ky / nyl;
+            peers.dst[dq][(((size_t) peers.slot*nxl + plane)*nyl + (ky - dq*nyl))*MC + kz0 + q] = v;
+        });
+    } else if (nxl > 0) {
         fft3Pass2Store<R1Y, R2Y, false, false>(A, ncol, W, colOff, [&](int q, int ky, float2 v) { out[slabIndex(nxl, nyl, plane, ky, MC) + kz0 + q] = v; });
     } else {
         float2* dstp = out + (size_t) plane*NY*MC;
@@ -830,9 +864,9 @@ struct Fft2Plan {
     int nx = 0, ny = 0, nz = 0, chunk = 0, chunks = 0;
     int planeThreads = 0, xThreads = 0;
     size_t planeSmem = 0, xSmem = 0;
-    void (*fwd)(const float*, float2*, const float2*, int, int) = nullptr;
+    void (*fwd)(const float*, float2*, const float2*, int, int, SlabPeers) = nullptr;
     void (*bwd)(const float2*, float*, const float2*, int, int) = nullptr;
-    void (*xcv)(int, int, int, const float*, float2*, const float2*, int, int) = nullptr;
+    void (*xcv)(int, int, int, const float*, float2*, const float2*, int, int, SlabPeers) = nullptr;
 };
 template <int NY, int R1Y, int R2Y> inline bool fft2PickPlanes(Fft2Plan& p, int nz) {
     if (nz == 32)  { p.fwd = k_fft2_planes_forward<NY, R1Y, R2Y, 32, 4, 4>;  p.bwd = k_fft2_planes_backward<NY, R1Y, R2Y, 32, 4, 4>;  return true; }

@@ -1769,13 +1769,38 @@ __global__ void k_unpack_mu(int numSites, const int* __restrict__ siteList, cons
     mud[s] = m;
 }
 
-// column sums of the per-block partial error overlaps (fixed order: deterministic), ready for the all-reduce
+// column sums of the per-block partial error overlaps, ready for the all-reduce: warp k sums column k (lanes stride
+// over the blocks, then a shuffle tree -- a fixed order, so deterministic).  Launch with 32*m threads.
 __global__ void k_sum_partials(int numBlocks, int m, const double* __restrict__ partial, double* __restrict__ out) {
-    const int k = threadIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= m) return;
     double v = 0;
-    for (int b = 0; b < numBlocks; b++) v += partial[(size_t) b*(MPID_MAX_HISTORY + 1) + k];
-    out[k] = v;
+    for (int b = lane; b < numBlocks; b += 32) v += partial[(size_t) b*(MPID_MAX_HISTORY + 1) + k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) out[k] = v;
+}
+
+// ---- peer-to-peer pieces of the partitioned reciprocal pass (all ranks on one NVLink/NVSwitch node) ------------------
+// The transform kernels write their results straight into the receive buffers of the other ranks (remote stores through
+// peer mappings of their memory), so the all-to-all happens tile by tile inside the kernel that produces the data; what
+// is left of the collective is this barrier: every rank tells every other that its stores are out, and waits to hear the
+// same from all of them.  flags[r] (in this rank's memory) is written by rank r with a monotonically increasing epoch.
+struct PeerPtrs { void* p[16]; };
+__global__ void k_cross_barrier(int numRanks, int rank, int epoch, PeerPtrs peerFlags, volatile int* __restrict__ myFlags, int* __restrict__ timedOut) {
+    const int r = threadIdx.x;
+    if (r >= numRanks) return;
+    __threadfence_system();                                   // this GPU's earlier stores (previous kernels) before the flag
+    int* remote = reinterpret_cast<int*>(peerFlags.p[r]) + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(remote), "r"(epoch) : "memory");
+    long long spins = 0;
+    for (;;) {
+        int seen;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(myFlags + r) : "memory");
+        if (seen - epoch >= 0) break;
+        if (++spins > 400000000LL) { *timedOut = 1; break; }   // a rank never arrived: report instead of hanging the GPU
+        __nanosleep(100);
+    }
 }
 
 __global__ void k_pack_sites(int numSites, const int* __restrict__ siteList, const double* __restrict__ src, double* __restrict__ dst) {
@@ -2381,6 +2406,32 @@ __global__ void k_torque_to_force(DevParams P, ParticleParams pp, const int* __r
     }
     if (ax >= 0 && axis != ZOnly) { const int sx = inv[ax]; for (int k = 0; k < 3; k++) atomicAddFixed(&force[3*(size_t) sx + k], fX[k]); }
     if (ay >= 0) { const int sy = inv[ay]; for (int k = 0; k < 3; k++) atomicAddFixed(&force[3*(size_t) sy + k], fY[k]); }
+}
+
+// ---- OpenMM CUDA-platform data conventions (reference: platforms/cuda/src/MPIDCudaKernels.cpp) -------------------------
+// posq: real4 per atom in the CudaContext's REORDERED atom order (slot i holds atom atomIndex[i]: cu.getAtomIndex(),
+// MPIDCudaKernels.cpp:1089); float4 in single/mixed precision -- mixed adds the low bits from posqCorrection -- or double4
+// in double precision (cu.getPosq(), :216).  Forces: cu.getForce(), signed 64-bit fixed point, scale 2^32, laid out
+// [x: paddedNumAtoms][y: paddedNumAtoms][z: paddedNumAtoms] by slot and ACCUMULATED with atomicAdd (kernels/
+// multipoleElectrostatics.cu:708-710).
+template <typename T4>
+__global__ void k_positions_from_cuda_context(int n, const T4* __restrict__ posq, const float4* __restrict__ posqCorrection,
+                                              const int* __restrict__ atomIndex, double* __restrict__ posOrig) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T4 p = posq[i];
+    double x = p.x, y = p.y, z = p.z;
+    if (posqCorrection) { const float4 c = posqCorrection[i]; x += (double) c.x; y += (double) c.y; z += (double) c.z; }
+    const int o = atomIndex[i];
+    posOrig[3*(size_t) o] = x; posOrig[3*(size_t) o+1] = y; posOrig[3*(size_t) o+2] = z;
+}
+__global__ void k_forces_to_cuda_context(int n, int paddedNumAtoms, const int* __restrict__ atomIndex, const double* __restrict__ forcesOrig,
+                                         unsigned long long* __restrict__ forceBuffer) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int o = atomIndex[i];
+    for (int k = 0; k < 3; k++)
+        atomicAdd(&forceBuffer[i + (size_t) k*paddedNumAtoms], (unsigned long long) __double2ll_rn(forcesOrig[3*(size_t) o + k]*MPID_FIXED_SCALE));
 }
 
 // forcesOrig[o] += fixed-point force of the sorted slot

@@ -176,8 +176,15 @@ class ForceField:
                 raise ValueError("Found multiple MPIDForce tags with different defaultTholeWidth arguments")
         self.coulomb14scale, self.default_thole_width, self._have_section = c14, thole, True
         for m in element.findall("Multipole"):
-            label = m.attrib.get("type", m.attrib.get("class"))
-            axis, kz, kx, ky = axis_type_from_k(m.attrib.get("kz"), m.attrib.get("kx"), m.attrib.get("ky"))
+            # The reference reads `type` (a <Multipole> keyed by class only raises KeyError there, mpidplugin.i:632) and
+            # collects the k attributes POSITIONALLY: missing or empty ones are skipped and the rest move up, so
+            # kx="H" without kz is treated as kz="H" (:634-640).  Mirror both.
+            if "type" not in m.attrib:
+                raise KeyError("type")
+            label = m.attrib["type"]
+            present = [m.attrib[k] for k in ("kz", "kx", "ky") if m.attrib.get(k)]
+            present += [None]*(3 - len(present))
+            axis, kz, kx, ky = axis_type_from_k(present[0], present[1], present[2])
             entry = dict(label=label, kz=kz, kx=kx, ky=ky, axisType=axis, charge=float(m.attrib["c0"]),
                          dipole=[float(m.get(k, 0.0)) for k in _DIPOLE], quadrupole=[float(m.get(k, 0.0)) for k in _QUADRUPOLE],
                          octopole=[float(m.get(k, 0.0)) for k in _OCTOPOLE])

@@ -32,10 +32,16 @@ public:
 
     // engine statistics of the last execute (iterations of the mutual solver, final epsilon)
     void getSolverStatistics(int& iterations, double& epsilon) const;
-private:
+protected:
+    // shared with the CUDA-platform binding (src/MPIDB200CudaPlatformKernel.cpp)
     void check(int status) const;                       // C-ABI status -> OpenMMException
+    void initializeOn(const System& system, const MPIDForce& force, int precision, int device, int solver);
+    void syncBoxVectors(const Vec3& a, const Vec3& b, const Vec3& c);
+    mpidb200_handle engineHandle() const { return engine; }
+private:
     void uploadParticles(const MPIDForce& force);
     void syncBox(ContextImpl& context);
+    void pinIfMoved(std::vector<double>& buffer, const double*& pinned, size_t& pinnedSize);
     const double* flatPositions(ContextImpl& context);
     void dipoleQuery(ContextImpl& context, int which, std::vector<Vec3>& out);
 
@@ -47,6 +53,7 @@ private:
     double lastBox[9];
     bool haveBox;
     std::vector<double> posFlat, forceFlat;
+    const double* pinnedPos; const double* pinnedForce; size_t pinnedPosSize, pinnedForceSize;
 };
 
 } // namespace OpenMM

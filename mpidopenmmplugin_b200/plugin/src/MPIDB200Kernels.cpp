@@ -28,7 +28,8 @@ int precisionFromProperty(const std::string& value) {
 } // namespace
 
 B200CalcMPIDForceKernel::B200CalcMPIDForceKernel(std::string name, const Platform& platform, const System& system, ContextImpl& context)
-    : CalcMPIDForceKernel(name, platform), system(system), owner(context), engine(0), numMultipoles(0), usePme(false), haveBox(false) {
+    : CalcMPIDForceKernel(name, platform), system(system), owner(context), engine(0), numMultipoles(0), usePme(false), haveBox(false),
+      pinnedPos(0), pinnedForce(0), pinnedPosSize(0), pinnedForceSize(0) {
     memset(lastBox, 0, sizeof(lastBox));
 }
 
@@ -41,10 +42,19 @@ void B200CalcMPIDForceKernel::check(int status) const {
 }
 
 void B200CalcMPIDForceKernel::initialize(const System& sys, const MPIDForce& force) {
+    const MPIDB200Platform::PlatformData& state = stateOf(owner);
+    auto prop = [&](const std::string& key) -> std::string {
+        std::map<std::string, std::string>::const_iterator it = state.properties.find(key);
+        return it != state.properties.end() ? it->second : getPlatform().getPropertyDefaultValue(key);
+    };
+    initializeOn(sys, force, precisionFromProperty(prop(MPIDB200Platform::Precision())), atoi(prop(MPIDB200Platform::DeviceIndex()).c_str()),
+                 prop(MPIDB200Platform::Solver()) == "CG" ? MPIDB200_SOLVER_CG : MPIDB200_SOLVER_DIIS);
+}
+
+void B200CalcMPIDForceKernel::initializeOn(const System& sys, const MPIDForce& force, int precision, int device, int solver) {
     numMultipoles = force.getNumMultipoles();
     if (numMultipoles != sys.getNumParticles())
         throw OpenMMException("MPIDForce must have exactly as many particles as the System it belongs to.");
-    const MPIDB200Platform::PlatformData& state = stateOf(owner);
 
     mpidb200_config cfg;
     mpidb200_default_config(&cfg);
@@ -72,13 +82,9 @@ void B200CalcMPIDForceKernel::initialize(const System& sys, const MPIDForce& for
     cfg.num_extrapolation_coefficients = (int) coefs.size();
     for (size_t k = 0; k < coefs.size(); k++) cfg.extrapolation_coefficients[k] = coefs[k];
 
-    auto prop = [&](const std::string& key) -> std::string {
-        std::map<std::string, std::string>::const_iterator it = state.properties.find(key);
-        return it != state.properties.end() ? it->second : getPlatform().getPropertyDefaultValue(key);
-    };
-    cfg.precision = precisionFromProperty(prop(MPIDB200Platform::Precision()));
-    cfg.device = atoi(prop(MPIDB200Platform::DeviceIndex()).c_str());
-    cfg.solver = prop(MPIDB200Platform::Solver()) == "CG" ? MPIDB200_SOLVER_CG : MPIDB200_SOLVER_DIIS;
+    cfg.precision = precision;
+    cfg.device = device;
+    cfg.solver = solver;
 
     check(mpidb200_create(&cfg, &engine));
     uploadParticles(force);
@@ -120,8 +126,13 @@ void B200CalcMPIDForceKernel::uploadParticles(const MPIDForce& force) {
 void B200CalcMPIDForceKernel::syncBox(ContextImpl& context) {
     if (!usePme) return;
     const Vec3* box = stateOf(context).box;
+    syncBoxVectors(box[0], box[1], box[2]);
+}
+void B200CalcMPIDForceKernel::syncBoxVectors(const Vec3& a, const Vec3& b, const Vec3& c) {
+    if (!usePme) return;
+    const Vec3 box[3] = {a, b, c};
     double flat[9];
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) flat[3*r + c] = box[r][c];
+    for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) flat[3*r + cc] = box[r][cc];
     if (haveBox && memcmp(flat, lastBox, sizeof(flat)) == 0) return;
     check(mpidb200_set_box(engine, flat, flat + 3, flat + 6));
     memcpy(lastBox, flat, sizeof(flat));
@@ -141,11 +152,23 @@ double B200CalcMPIDForceKernel::execute(ContextImpl& context, bool includeForces
     double energy = 0.0;
     std::vector<Vec3>& forces = *stateOf(context).forces;
     if (includeForces) forceFlat.assign(3*forces.size(), 0.0);
+    // the two staging vectors live as long as the kernel: page-lock them once so that the engine moves them by DMA and
+    // accumulates the forces on the device (mpidb200_pin_host_buffer)
+    pinIfMoved(posFlat, pinnedPos, pinnedPosSize);
+    if (includeForces) pinIfMoved(forceFlat, pinnedForce, pinnedForceSize);
     check(mpidb200_execute(engine, pos, includeForces ? 1 : 0, includeEnergy ? 1 : 0, &energy, includeForces ? forceFlat.data() : 0));
     if (includeForces)      // forces are accumulated, never overwritten (MPIDReferenceKernels.cpp:229-238)
         for (size_t i = 0; i < forces.size(); i++)
             forces[i] += Vec3(forceFlat[3*i], forceFlat[3*i+1], forceFlat[3*i+2]);
     return energy;
+}
+
+void B200CalcMPIDForceKernel::pinIfMoved(std::vector<double>& buffer, const double*& pinned, size_t& pinnedSize) {
+    if (buffer.empty() || (pinned == buffer.data() && pinnedSize == buffer.size())) return;
+    if (pinned) mpidb200_unpin_host_buffer(engine, (void*) pinned);
+    // page-locking can be refused (limits on locked memory): the engine then stages the array itself
+    if (mpidb200_pin_host_buffer(engine, buffer.data(), (unsigned long long) (buffer.size()*sizeof(double))) == 0) { pinned = buffer.data(); pinnedSize = buffer.size(); }
+    else { pinned = 0; pinnedSize = 0; }
 }
 
 void B200CalcMPIDForceKernel::dipoleQuery(ContextImpl& context, int which, std::vector<Vec3>& out) {

@@ -37,7 +37,7 @@ XML = """<ForceField>
   <Multipole type="HO" kz="O" kx="C" c0="0.4"/>
   <Multipole type="HC" kz="C" c0="0.03" dZ="-0.002"/>
   <Multipole type="N" kz="-HN" kx="-HN" ky="-HN" c0="-0.9" oZZZ="0.0001"/>
-  <Multipole class="HN" kz="N" kx="HN" c0="0.3"/>
+  <Multipole type="HN" kz="N" kx="HN" c0="0.3"/>
   <Multipole type="X" c0="0.0"/>
   <Polarize type="O" polarizabilityXX="0.0009" polarizabilityYY="0.0008" polarizabilityZZ="0.0007" thole="0.39"/>
   <Polarize type="N" polarizabilityXX="0.001" polarizabilityYY="0.001" polarizabilityZZ="0.001" thole="0.39"/>
@@ -174,3 +174,24 @@ def test_reference_examples_reproduce_the_benchmark_workloads():
     f = ff.create_mpid_force(top, nonbondedMethod=FF.PME, nonbondedCutoff=0.8, polarization="direct", defaultTholeWidth=8)
     assert f.get14ScaleFactor() == 1.0 and f.getPolarizationType() == MPIDForce.Direct
     _same_force(f, ethane_box().to_force())
+
+
+def test_k_attributes_are_collected_positionally_like_the_reference():
+    """mpidplugin.i:632-640 appends the non-empty kz/kx/ky values in that order, so a missing kz makes kx the z anchor;
+    and it indexes attrib['type'], so a <Multipole> without a type attribute is an error."""
+    import io
+    xml = """<ForceField>
+ <AtomTypes><Type name="A" class="A" element="O" mass="16"/><Type name="B" class="B" element="H" mass="1"/></AtomTypes>
+ <Residues><Residue name="XX"><Atom name="A1" type="A"/><Atom name="B1" type="B"/><Bond from="0" to="1"/></Residue></Residues>
+ <MPIDForce>
+  <Multipole type="A" kx="B" c0="-0.5"/>
+  <Multipole type="B" kz="" kx="A" ky="" c0="0.5"/>
+ </MPIDForce>
+</ForceField>"""
+    ff = FF.ForceField(xml)
+    a, b = ff.entries["A"][0], ff.entries["B"][0]
+    assert (a["kz"], a["kx"], a["axisType"]) == ("B", "", FF.MPIDForce.ZOnly)
+    assert (b["kz"], b["kx"], b["axisType"]) == ("A", "", FF.MPIDForce.ZOnly)
+    bad = xml.replace('<Multipole type="A" kx="B"', '<Multipole class="A" kx="B"')
+    with pytest.raises(KeyError):
+        FF.ForceField(bad)

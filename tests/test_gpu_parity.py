@@ -472,3 +472,46 @@ def test_hand_written_reciprocal_pass_equals_the_library_transform(grid, mode, m
     record_parity("reciprocal-pass/%dx%dx%d/%s" % (grid + (mode or "default",)), max_rel_err=err)
     assert err < 5e-6
     k.close()
+
+
+@pytest.mark.parametrize("prec,posq_double,correction", [("mixed", False, True), ("mixed", False, False), ("double", True, False)])
+def test_cuda_context_entry_matches_the_host_entry(prec, posq_double, correction):
+    """mpidb200_execute_cuda_context: positions arrive as the posq array of an OpenMM CudaContext (float4 + correction, or
+    double4, in the context's reordered atom order) and forces leave as 64-bit fixed point, scale 2^32, [x|y|z] x padded
+    atoms, ADDED to what the buffer holds (reference: platforms/cuda/src/MPIDCudaKernels.cpp:216, 1089; kernels/
+    multipoleElectrostatics.cu:708-710).  A stand-in for the CudaContext arrays is built with torch."""
+    import torch
+    s = water_box((1, 1, 1), polarization=2)
+    k = make_kernel(s, precision=prec)
+    f_ref = np.zeros((s.n, 3))
+    e_ref = k.execute(s.pos, True, True, f_ref)
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(s.n).astype(np.int32)                # slot i holds atom perm[i]
+    padded = ((s.n + 31)//32)*32 + 32
+    pos_slots = s.pos[perm]
+    if posq_double:
+        posq = np.zeros((padded, 4)); posq[:s.n, :3] = pos_slots
+        d_posq = torch.tensor(posq, dtype=torch.float64, device="cuda")
+        d_corr = None
+    else:
+        hi = pos_slots.astype(np.float32)
+        posq = np.zeros((padded, 4), dtype=np.float32); posq[:s.n, :3] = hi
+        d_posq = torch.tensor(posq, device="cuda")
+        d_corr = None
+        if correction:
+            corr = np.zeros((padded, 4), dtype=np.float32); corr[:s.n, :3] = (pos_slots - hi.astype(np.float64)).astype(np.float32)
+            d_corr = torch.tensor(corr, device="cuda")
+    d_index = torch.tensor(perm, dtype=torch.int32, device="cuda")
+    start = rng.integers(-2**40, 2**40, size=3*padded)
+    d_force = torch.tensor(start, dtype=torch.int64, device="cuda")
+    e = k.execute_cuda_context(d_posq.data_ptr(), posq_double, d_corr.data_ptr() if d_corr is not None else None, d_index.data_ptr(), padded,
+                               True, True, d_force.data_ptr())
+    torch.cuda.synchronize()
+    got = (d_force.cpu().numpy() - start).reshape(3, padded)[:, :s.n].T/2.0**32       # per slot
+    f = np.zeros((s.n, 3)); f[perm] = got
+    # float4 positions without the correction carry 1e-7 nm of rounding; with it (or in double) the inputs are identical
+    exact = posq_double or correction
+    assert abs(e - e_ref) < (1e-9 if exact else 2e-6)*abs(e_ref)
+    assert rel_err(f, f_ref) < (1e-7 if exact else 3e-5)
+    assert np.all((d_force.cpu().numpy() - start).reshape(3, padded)[:, s.n:] == 0)      # padding slots untouched
+    k.close()

@@ -21,19 +21,43 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
+RECORD = os.path.join(HERE, "build_record.json")     # what the last build() call did (git-ignored)
+
+
+def source_hash():
+    """SHA-256 over the CUDA sources and headers the library is compiled from."""
+    import hashlib
+    h = hashlib.sha256()
     for f in SOURCES + HEADERS:
-        if os.path.getmtime(os.path.join(CSRC, f)) > t:
-            return True
-    return False
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def needs_build():
+    """True unless the library exists AND was compiled from exactly the sources that are in the tree now (the hash of
+    the sources is stored beside the library; file times do not survive a snapshot copy)."""
+    if not os.path.exists(LIB) or not os.path.exists(LIB + ".srchash"):
+        return True
+    with open(LIB + ".srchash") as fh:
+        return fh.read().strip() != source_hash()
+
+
+def _record(mode, seconds=0.0):
+    import json
+    import time
+    with open(RECORD, "w") as fh:
+        json.dump(dict(build_mode=mode, seconds=seconds, source_hash=source_hash(), when=time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
+                       library=os.path.basename(LIB)), fh)
 
 
 def build(force=False, verbose=False):
+    force = force or os.environ.get("MPIDB200_FORCE_BUILD") == "1"
     if not force and not needs_build():
+        _record("up-to-date (library matches the source hash)")
         return LIB
+    import time
+    t0 = time.time()
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared"]
     if verbose:
@@ -41,6 +65,9 @@ def build(force=False, verbose=False):
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-o", LIB, "-lcufft", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
+    with open(LIB + ".srchash", "w") as fh:
+        fh.write(source_hash())
+    _record("compiled with nvcc -gencode arch=compute_100a,code=sm_100a", time.time() - t0)
     return LIB
 
 

@@ -13,10 +13,39 @@ def row_range(n, rank, world):
     return (n*rank)//world, (n*(rank + 1))//world
 
 
-def special_pair_owner(num_special, world):
-    """Owner rank of every covalently scaled (1-2/1-3/1-4) pair: round robin over the static pair list
-    (mpid_kernels.cuh: k_special_electrostatics, `k % numRanks == rank`)."""
-    return np.arange(num_special) % world
+def special_pair_owner(sorted_index_of_lo, row_begins):
+    """Owner rank of every covalently scaled (1-2/1-3/1-4) pair: the rank whose rows hold the pair's lower atom
+    (mpid_kernels.cuh: k_own_special compacts those pairs per rank; the rank then builds the moments of both partners
+    itself).  sorted_index_of_lo[k] = position of pair k's lower atom in the sorted order, row_begins = [b_0, ..., b_R]."""
+    return np.searchsorted(np.asarray(row_begins)[1:], np.asarray(sorted_index_of_lo), side="right")
+
+
+def cell_column_partition(ncx, world):
+    """mpid_engine.cu: planHalo() -- first x cell column of every rank (and ncx at the end): rank r owns the atoms of the
+    columns [lo[r], lo[r+1]), which are contiguous in the x-major sorted order."""
+    return [(r*ncx)//world for r in range(world + 1)]
+
+
+def owner_computes_exchange(dist, own_begin, own_values, counts):
+    """The per-iteration exchange of the partitioned solver (mpid_engine.cu: gatherDipoles): every rank has new values for
+    the polarizable sites among its rows (a contiguous piece of the compact site list, own_begin .. own_begin +
+    counts[rank]) and needs everybody's.  Pieces differ in size, so it is point-to-point sends of exactly those pieces,
+    not a padded all-gather.  Returns the assembled compact array."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    begins = np.concatenate([[0], np.cumsum(counts)])
+    assert begins[rank] == own_begin and len(own_values) == counts[rank]
+    out = torch.zeros((int(begins[-1]),) + tuple(own_values.shape[1:]), dtype=own_values.dtype)
+    out[begins[rank]:begins[rank+1]] = own_values
+    reqs = []
+    for r in range(world):
+        if r == rank:
+            continue
+        reqs.append(dist.isend(own_values.contiguous(), r))
+        reqs.append(dist.irecv(out[begins[r]:begins[r+1]], r))
+    for q in reqs:
+        q.wait()
+    return out
 
 
 SLAB_FFT_MIN_RANKS = 4      # mpid_engine.cu: slabFftMinRanks (MPIDB200_SLAB_FFT)
@@ -49,11 +78,38 @@ def reciprocal_mode(world, grid):
     return "all-reduce of the charge grid, FFT replicated"
 
 
-def collectives_per_evaluation(polarization, field_evaluations, pme=True, world=2, grid=(224, 224, 224)):
+def collectives_per_evaluation(polarization, field_evaluations, pme=True, world=2, grid=(224, 224, 224), halo=False):
     """Collectives one evaluation issues per rank, by payload (used for the scaling model in DESIGN.md 5):
-    list of (what, element count per atom or 'grid' / 'slab', dtype bytes).  A reciprocal pass is one all-reduce of
-    the charge grid (every rank then transforms the whole grid) or, with the slab decomposition, a reduce-scatter,
-    two all-to-all transposes of this rank's slab and an all-gather."""
+    list of (what, element count per atom or 'grid' / 'slab' / 'halo' / 'pol' / 'scalars', dtype bytes).
+
+    halo=False (MPIDB200_HALO=0): a reciprocal pass is one all-reduce of the charge grid (every rank then transforms the
+    whole grid) or, with the slab decomposition, a reduce-scatter, two all-to-all transposes of this rank's slab and an
+    all-gather; partial fields are all-reduced.
+    halo=True (the default when the grid divides): halo reduce with the two neighbours, the two all-to-alls (done by
+    remote stores of the transform kernels + a flag barrier when the ranks can map each other's memory), halo gather; the
+    mutual solver is owner-computes: per iteration a scalar all-reduce of the <= 21 error overlaps and the exchange of
+    the new dipoles of the polarizable sites; energy + forces are one all-reduce of 64-bit integers."""
+    if halo:
+        def hpass(what):
+            return [(what + ": halo reduce", "halo", 4), (what + ": all-to-all", "slab", 8), (what + ": all-to-all back", "slab", 8),
+                    (what + ": halo gather", "halo", 4)]
+        out = []
+        if pme:
+            out += hpass("fixed charge grid")
+        out.append(("dipoles of the polarizable sites (mu0)", "pol", 24))
+        for _ in range(field_evaluations):
+            if pme:
+                out += hpass("induced-dipole grid")
+            if polarization == 0:
+                out.append(("error overlaps", "scalars", 8))
+                out.append(("dipoles of the polarizable sites", "pol", 24))
+            else:
+                out.append(("partial induced field", 3, 8))
+                if polarization == 2:
+                    out.append(("partial induced field gradient", 6, 8))
+        out.append(("energy + forces (one buffer of 64-bit integers)", 3, 8))
+        return out
+
     def grid_pass(what):
         if uses_slab_fft(world, grid):
             return [(what + ": reduce-scatter", "grid", 4), (what + ": all-to-all", "slab", 8), (what + ": all-to-all back", "slab", 8),

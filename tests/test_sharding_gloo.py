@@ -43,11 +43,28 @@ def _worker(rank, world, port, n, out):
         partial[b:e] = torch.from_numpy(contrib[b:e])
         dist.all_reduce(partial)
         assert torch.equal(partial, torch.from_numpy(contrib))
-        # 4. every special pair has exactly one owner
-        own = sharding.special_pair_owner(1001, world)
+        # 4. every special pair has exactly one owner: the rank whose rows hold its lower atom
+        bounds = [sharding.row_range(n, r, world)[0] for r in range(world)] + [n]
+        lo_sorted = rng.integers(0, n, size=1001)
+        own = sharding.special_pair_owner(lo_sorted, bounds)
+        assert np.all((lo_sorted >= np.asarray(bounds)[own]) & (lo_sorted < np.asarray(bounds)[own + 1]))
         mine = torch.from_numpy((own == rank).astype(np.int32))
         dist.all_reduce(mine)
         assert int(mine.min()) == 1 and int(mine.max()) == 1
+        # 4b. owner-computes solver step: each rank owns an uneven piece of the polarizable-site list; the error overlaps
+        #     are partial sums that all-reduce to the global ones, and the new dipoles travel as exactly-sized pieces
+        npol = n//3
+        counts = [npol//world + (3 if r == 0 else 0) for r in range(world)]
+        counts[-1] = npol - sum(counts[:-1])
+        begins = np.concatenate([[0], np.cumsum(counts)])
+        err = np.random.default_rng(99).normal(size=(4, npol, 3))            # 4 history vectors, same on every rank
+        dots = torch.tensor([np.sum(err[3, begins[rank]:begins[rank+1]]*err[k, begins[rank]:begins[rank+1]]) for k in range(4)])
+        dist.all_reduce(dots)
+        assert np.allclose(dots.numpy(), [np.sum(err[3]*err[k]) for k in range(4)], rtol=1e-12)
+        new_mu = torch.from_numpy(err[0, begins[rank]:begins[rank+1]] + rank)
+        full = sharding.owner_computes_exchange(dist, int(begins[rank]), new_mu, counts)
+        expect = np.concatenate([err[0, begins[r]:begins[r+1]] + r for r in range(world)])
+        assert np.array_equal(full.numpy(), expect)
         # 5. timing reduction = max over ranks
         mx = sharding.max_over_ranks(dist, [1.0 + rank, 5.0 - rank])
         assert mx == [float(world), 5.0]
@@ -85,6 +102,13 @@ def test_collective_inventory_matches_the_engine():
     assert len(c) == 1 + 4 + 6*(4 + 1) + 1
     assert sum(1 for w in c if w[0].endswith("all-to-all")) == 7
     assert not sharding.uses_slab_fft(8, (225, 224, 224)) and not sharding.uses_slab_fft(2, (224, 224, 224))
+    # halo exchange + owner-computes solver (the default at 2/4/8 ranks on the 224^3 grid)
+    assert sharding.uses_halo_exchange(8, (224, 224, 224), ncell_x=48) and not sharding.uses_halo_exchange(3, (224, 224, 224))
+    c = sharding.collectives_per_evaluation(0, 6, pme=True, world=8, halo=True)
+    assert len(c) == 4 + 1 + 6*(4 + 2) + 1
+    assert sum(1 for w in c if w[1] == "grid") == 0                  # no full-grid collective is left
+    assert sum(1 for w in c if w[0] == "error overlaps") == 6
+    assert sharding.cell_column_partition(48, 8) == [0, 6, 12, 18, 24, 30, 36, 42, 48]
 
 
 @pytest.mark.parametrize("world,shape", [(2, (8, 6, 10)), (4, (8, 12, 6)), (8, (16, 8, 9))])

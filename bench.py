@@ -125,7 +125,7 @@ def kernel_rooflines(kprof, work, n, n_pol, rows, G, n_f, hbm_peak, fp32_peak):
         else:
             achieved, peak, unit = work_amount/(us*1e-6)/1e9, hbm_peak, "GB/s"
         d = dict(bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved/peak, us_per_evaluation=us, launches_per_evaluation=launches,
-                 us_per_launch=us/max(launches, 1), work_per_evaluation=work_amount)
+                 us_per_launch=us/max(launches, 1), work_per_evaluation=work_amount, work_per_launch=work_amount/max(launches, 1))
         if note:
             d["note"] = note
         out[label] = d
@@ -432,8 +432,9 @@ def main():
             if os.path.exists(tpath) and world == 1:
                 tj = json.load(open(tpath)).get(wl, {}).get(dom)
                 if tj:
-                    roof["traffic"] = tj["bytes"]
+                    roof["traffic"] = tj.get("bytes_per_launch", tj["bytes"])          # DRAM bytes per launch (ncu --set full, cold L2)
                     roof["traffic_source"] = tj["source"]
+                    roof["traffic_over_algorithmic"] = roof["traffic"]/max(roof["work_per_launch"], 1.0) if roof["bound"] == "hbm" else None
             fp = {kk: v for kk, v in roofs.items() if v["bound"] == "fp32"}
             hb = {kk: v for kk, v in roofs.items() if v["bound"] == "hbm" and kk != dom}
             if fp:

@@ -1841,8 +1841,8 @@ struct Engine : public EngineBase {
         // None of them fills the GPU (57-61 % issue utilisation for the FP32 pair kernels, latency-bound FP64 for the
         // rest), so they run side by side on three streams:
         //   main    : full x bare-charge pairs (Cartesian gather kernel)
-        //   stream2 : per-atom reciprocal-space / self terms, then full x full pairs (quasi-internal frame kernel)
-        //   stream3 : covalent (1-2/1-3/1-4) pairs in FP64
+        //   stream2 : full x full pairs (quasi-internal frame kernel)
+        //   stream3 : covalent (1-2/1-3/1-4) pairs in FP64, then the per-atom reciprocal-space / self terms
         stageBegin(MPIDB200_STAGE_ELECTROSTATICS);
         CUDA_CHECK(cudaEventRecord(evFork3, stream));
         CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
@@ -1858,9 +1858,11 @@ struct Engine : public EngineBase {
                 else LAUNCH((k_special_electrostatics<false>), blocksFor(nsRun, 128), 128, P, nsRun, dSpLo.p, dSpHi.p, dSpPairClass.p, dInv.p, dPosIn,
                             dPkD.p, dDampThole.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP(), ownList);
             }
-            cur = stream2;
+            // (per-atom reciprocal / self terms follow the covalent pairs on the side stream: 36 + 55 us there balance the
+            // ~90 us quasi-internal-frame kernel on the second stream and the ~107 us gather kernel on the main one)
             if (pme && rows > 0)
                 LAUNCH((k_reciprocal_terms<real>), blocksFor(rows, 128), 128, P, dPhi.p, dPhidp.p, dCartD.p, dSphD.p, dMu.p, dAniso.p, forceP(), torqueP(), energyP());
+            cur = stream2;
             // full x full pairs: quasi-internal frame kernel over the flat half list
             // launch sized for the capacity of the flat list when the count is still on its way from the device
             const long long cnt = nlSpeculative ? (long long) pairCap : typeBegin[1];

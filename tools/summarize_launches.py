@@ -22,8 +22,9 @@ def main():
     rows = list(csv.DictReader(lines))
     which = int(sys.argv[2]) if len(sys.argv) > 2 else None
     if which is not None:
-        # evaluation `which` (0-based): from its k_wrap_cells launch (first kernel of an evaluation) to the next one
-        starts = [i for i, r in enumerate(rows) if "k_wrap_cells" in r["Kernel Name"]] + [len(rows)]
+        # evaluation `which` (0-based): from its first kernel -- k_wrap_cells when the evaluation sorts and searches,
+        # k_regather_sites when it reuses the order and the candidate list -- to the first kernel of the next one
+        starts = [i for i, r in enumerate(rows) if "k_wrap_cells" in r["Kernel Name"] or "k_regather_sites" in r["Kernel Name"]] + [len(rows)]
         rows = [r for r in rows[starts[which]:starts[which + 1]] if "at::native" not in r["Kernel Name"]]
     agg = collections.OrderedDict()
     for r in rows:

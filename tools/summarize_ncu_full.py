@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` report: one row per captured launch with duration, registers, achieved occupancy,
 issue utilisation, FMA / FP64 pipe utilisation, DRAM bytes, L1/L2 hit rates and the three largest stall reasons.
-Usage: summarize_ncu_full.py report.ncu-rep   (needs ncu on PATH; no GPU required)"""
+Usage: summarize_ncu_full.py report.ncu-rep | report.raw.csv   (a .ncu-rep needs ncu on PATH; the raw CSV is what
+`ncu -i report.ncu-rep --page raw --csv` prints -- the reports themselves are too large to bring back from the GPU box)"""
 import csv
 import io
 import re
@@ -10,10 +11,15 @@ import sys
 
 
 def main():
-    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if sys.argv[1].endswith(".csv"):
+        raw = open(sys.argv[1]).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, data = rows[0], rows[2:]
+    hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
+    # ncu scales a whole column to one unit (row 2 of the CSV): bring times to microseconds and sizes to megabytes
+    unit_scale = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "Tbyte": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
     for i, h in enumerate(hdr):          # newer ncu prefixes some columns with their section ("X.Y.metric"): index by bare metric name too
         m = re.search(r"([a-z0-9_]+__[A-Za-z0-9_.]+)$", h)
         if m and m.group(1) not in idx:
@@ -22,7 +28,7 @@ def main():
 
     def g(d, key, scale=1.0, fmt="%.1f"):
         try:
-            return fmt % (float(d[idx[key]])*scale)
+            return fmt % (float(d[idx[key]])*scale*unit_scale.get(units[idx[key]], 1.0))
         except Exception:
             return "-"
 

@@ -158,6 +158,7 @@ struct Engine : public EngineBase {
     cudaStream_t stream = nullptr, ownStream = nullptr;
     cudaStream_t stream2 = nullptr;     // reciprocal-space work runs here, concurrently with the real-space kernels
     cudaStream_t stream3 = nullptr;     // pair work that does not depend on the induced dipoles (fills the SMs the solver leaves idle)
+    cudaStream_t stream4 = nullptr;     // the permanent field from the candidate list, beside the list filter (same priority as the main stream)
     cudaEvent_t evFork3 = nullptr, evJoin3 = nullptr;
     cudaStream_t cur = nullptr;         // stream the LAUNCH macro / stage timers currently target
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evFrames = nullptr;
@@ -249,6 +250,7 @@ struct Engine : public EngineBase {
         cur = stream;
         CUDA_CHECK(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, prGreatest));
         CUDA_CHECK(cudaStreamCreateWithPriority(&stream3, cudaStreamNonBlocking, prLeast));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&stream4, cudaStreamNonBlocking, prMid));
         CUDA_CHECK(cudaEventCreateWithFlags(&evFork3, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evJoin3, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
@@ -283,10 +285,12 @@ struct Engine : public EngineBase {
         if (evFork) cudaEventDestroy(evFork);
         if (evJoin) cudaEventDestroy(evJoin);
         if (evFrames) cudaEventDestroy(evFrames);
+        if (evFixedDone) cudaEventDestroy(evFixedDone);
         if (stream2) cudaStreamDestroy(stream2);
         if (evFork3) cudaEventDestroy(evFork3);
         if (evJoin3) cudaEventDestroy(evJoin3);
         if (stream3) cudaStreamDestroy(stream3);
+        if (stream4) cudaStreamDestroy(stream4);
         if (ownStream) cudaStreamDestroy(ownStream);
     }
     // Reciprocal space is independent of the real-space pair kernels until their results are combined, and
@@ -349,7 +353,7 @@ struct Engine : public EngineBase {
             out += "\"" + kv.first + "\"," + std::to_string(kv.second.launches) + "," + std::to_string(kv.second.us) + "," + std::to_string(kernelProfileEvals) + "\n";
         return out;
     }
-    int streamId(cudaStream_t st) const { return st == stream ? 1 : (st == stream2 ? 2 : 3); }
+    int streamId(cudaStream_t st) const { return st == stream ? 1 : (st == stream2 ? 2 : (st == stream4 ? 4 : 3)); }
     void traceBegin(const char* name) {
         if (!tracing) return;
         TraceRec r; r.name = name; r.streamId = streamId(cur);
@@ -956,6 +960,7 @@ struct Engine : public EngineBase {
                 // (a) when the list is (re)built: cell search with the cutoff padded by the skin, into the candidate list;
                 // (b) always: exact list = candidates inside the cutoff at the current positions
                 if (!reusing && attempt == 0) searchCandidates(dPosIn, rows, roundMode, numCells);
+                if (attempt == 0 && rows > 0) startEarlyFixedField(dPosIn);
                 if (rows > 0) LAUNCH(k_filter_list, blocksFor((long long) rows*32, B), B, P, candCap, dPosF.p, dPosIn, dOrder.p, dCand.p, dCandCounts.p,
                                      dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
             } else if (rows > 0) {
@@ -964,23 +969,27 @@ struct Engine : public EngineBase {
                 else LAUNCH(k_neighbor_list_cell, numCells, 256, P, dPosF.p, dPosIn, dOrder.p, dCellStart.p,
                             dSpStart.p, dSpPartner.p, dSpSorted.p, dPolRank.p, polBegin, dNbr.p, dCounts.p, dPolNbr.p, dPolCount.p, dMaxCount.p);
             }
-            // one scan over the concatenated per-class count arrays gives absolute offsets into pairI/pairJ
-            LAUNCH(k_half_counts, blocksFor(rows + 1, B), B, P, rows, dCounts.p, dFlagS.p, dTypeCount.p);
-            size_t tempBytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, stream);
-            dScanTemp.ensure(tempBytes + 16);
-            traceBegin("cub_scan_pair_classes");
-            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, stream));
-            traceEnd();
-            launches += 1;
-            // one small kernel + one copy; in speculative mode on the side stream so that the main stream moves on
-            dTotals.ensure(8);
+            // One scan over the concatenated per-class count arrays gives absolute offsets into pairI/pairJ.  Only the flat
+            // pair list and the energy stage consume them, so in speculative mode counts, scan, totals and their copy go
+            // to the side stream and the main stream moves straight on to the field kernels.
+            cudaStream_t keepCur = cur;
             if (nlSpeculative) {
                 CUDA_CHECK(cudaEventRecord(evFork3, stream));
                 CUDA_CHECK(cudaStreamWaitEvent(stream3, evFork3, 0));
-                cudaStream_t keep = cur; cur = stream3;
+                cur = stream3;
+            }
+            LAUNCH(k_half_counts, blocksFor(rows + 1, B), B, P, rows, dCounts.p, dFlagS.p, dTypeCount.p);
+            size_t tempBytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, cur);
+            dScanTemp.ensure(tempBytes + 16);
+            traceBegin("cub_scan_pair_classes");
+            CUDA_CHECK(cub::DeviceScan::ExclusiveSum(dScanTemp.p, tempBytes, dTypeCount.p, dTypeStart.p, (int) tlen, cur));
+            traceEnd();
+            launches += 1;
+            dTotals.ensure(8);
+            if (nlSpeculative) {
                 LAUNCH(k_collect_totals, 1, 32, rows, dMaxCount.p, dTypeStart.p, dTotals.p);
-                cur = keep;
+                cur = keepCur;
                 CUDA_CHECK(cudaMemcpyAsync(totals, dTotals.p, 7*sizeof(unsigned), cudaMemcpyDeviceToHost, stream3));
                 if (reusing) CUDA_CHECK(cudaMemcpyAsync(totals + 7, dDisp.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream3));
                 CUDA_CHECK(cudaEventRecord(evNlTotals, stream3));
@@ -1463,19 +1472,55 @@ struct Engine : public EngineBase {
         backToMain();
     }
 
+    // Real-space permanent field straight from the candidate list, on a stream of its own, while the main stream filters
+    // the list: the kernel applies the cutoff itself (same decisions as k_filter_list).  Opt-in (MPIDB200_EARLY_FIXED=1):
+    // measured on B200 it does NOT pay -- the filter and this kernel are both issue bound and simply share the SMs
+    // (95,616 atoms: 1.719 ms with it, 1.678 ms without; list stage 0.30 -> 0.42 ms; profiles/r02_list_reuse.md).
+    cudaEvent_t evFixedDone = nullptr;
+    bool earlyFixedLaunched = false;
+    const bool earlyFixedEnabled = getenv("MPIDB200_EARLY_FIXED") && atoi(getenv("MPIDB200_EARLY_FIXED")) != 0;
+    void startEarlyFixedField(const double* dPosIn) {
+        earlyFixedLaunched = false;
+        if (!earlyFixedEnabled || skin <= 0.0 || numPol <= 0 || P.method != PME) return;
+        if (!evFixedDone) CUDA_CHECK(cudaEventCreateWithFlags(&evFixedDone, cudaEventDisableTiming));
+        dField.ensure(3*(size_t) n);
+        CUDA_CHECK(cudaEventRecord(evFork3, stream));
+        CUDA_CHECK(cudaStreamWaitEvent(stream4, evFork3, 0));
+        CUDA_CHECK(cudaStreamWaitEvent(stream4, evFrames, 0));         // lab-frame moments come from the second stream
+        cudaStream_t keep = cur;
+        const int keepStage = curStage;
+        cur = stream4;
+        CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
+        LAUNCH((k_fixed_field<real, true, true>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, (const int*) dPolList.p + polBegin, dPosS.p, cartR(), dMud.p,
+               dCandCounts.p, dCand.p, dField.p, candCap, dOrder.p, dPosIn);
+        CUDA_CHECK(cudaEventRecord(evFixedDone, stream4));
+        cur = keep;
+        (void) keepStage;
+        earlyFixedLaunched = true;
+    }
     void fixedFieldStage(const double* dPosIn) {
         const bool pme = P.method == PME;
         const int rows = P.rowEnd - P.rowBegin;
         dField.ensure(3*(size_t) n); dEfix.ensure(3*(size_t) n); dMu.ensure(3*(size_t) n);
         dPhi.ensure(35*(size_t) n); dPhidp.ensure(35*(size_t) n);
         stageBegin(MPIDB200_STAGE_FIXED_REAL);
-        // the field is consumed at polarizable sites only; everything else stays zero
-        CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
         const int* polRows = dPolList.p + polBegin;
         const bool fuseFinish = numRanks == 1 && !hSpPartner.empty();
+        if (earlyFixedLaunched) {
+            // the kernel ran from the candidate list on the side stream, beside the list filter (startEarlyFixedField)
+            CUDA_CHECK(cudaStreamWaitEvent(stream, evFixedDone, 0));
+            earlyFixedLaunched = false;
+        } else {
+            // the field is consumed at polarizable sites only; everything else stays zero
+            CUDA_CHECK(cudaMemsetAsync(dField.p, 0, 3*(size_t) n*sizeof(double), cur));
+            if (numPol > 0) {
+                if (pme) LAUNCH((k_fixed_field<real, true, false>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p,
+                                0, (const int*) nullptr, (const double*) nullptr);
+                else LAUNCH((k_fixed_field<real, false, false>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p,
+                            0, (const int*) nullptr, (const double*) nullptr);
+            }
+        }
         if (numPol > 0) {
-            if (pme) LAUNCH((k_fixed_field<real, true>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
-            else LAUNCH((k_fixed_field<real, false>), blocksFor((long long) numPol*MPID_LANES, 256), 256, P, numPol, polRows, dPosS.p, cartR(), dMud.p, dCounts.p, dNbr.p, dField.p);
             if (!hSpPartner.empty() && !fuseFinish)
                 LAUNCH((k_special_field<0>), blocksFor(rows, 128), 128, P, dOrder.p, dInv.p, dPosIn, dSpStart.p, dSpPartner.p, dSpClass.p,
                        dCartD.p, dDampThole.p, dFlagS.p, (const double*) nullptr, dField.p, (double*) nullptr);
@@ -1789,6 +1834,7 @@ struct Engine : public EngineBase {
         P.numRanks = numRanks; P.rank = rank;
         stageBegin(MPIDB200_STAGE_SORT);
         allFramesWanted = dipolesOnly;
+        if (earlyFixedLaunched) { CUDA_CHECK(cudaStreamSynchronize(stream4)); earlyFixedLaunched = false; }     // a previous call ended early
         reusing = listValid && skin > 0.0 && !noReuse;
         if (reusing && !regatherAndFrames(dPosIn)) {
             // (several ranks) an atom has left its skin: this evaluation sorts and searches again

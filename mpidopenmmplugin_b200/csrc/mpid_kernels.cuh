@@ -776,11 +776,16 @@ __device__ __forceinline__ void pairDelta(const DevParams& P, const double4& pi,
 }
 
 // Permanent-multipole field of the ordinary pairs.   reference stage: :911-934 + :2812-2920
-template <typename real, bool EWALD>
+// FROMCAND: walk the skin-padded CANDIDATE rows (layout of k_neighbor_list, stride listCap = candidate capacity) and
+// apply the cutoff here -- FP32 test, the oracle's FP64 test on the raw positions for pairs within 1e-4 nm of rc, the
+// same decisions k_filter_list takes.  Rows are 1.4x longer, but the kernel then does not wait for the filter.  Opt-in
+// (MPIDB200_EARLY_FIXED=1): measured slower, the two issue-bound kernels only share the SMs (profiles/r02_list_reuse.md).
+template <typename real, bool EWALD, bool FROMCAND>
 __global__ void __launch_bounds__(256)
 k_fixed_field(DevParams P, int numPol, const int* __restrict__ polList, const double4* __restrict__ posS, const real* __restrict__ cart,
               const typename Real4<real>::type* __restrict__ mud,
-              const uint4* __restrict__ counts, const unsigned* __restrict__ nbr, double* __restrict__ field) {
+              const uint4* __restrict__ counts, const unsigned* __restrict__ nbr, double* __restrict__ field,
+              int listCap, const int* __restrict__ order, const double* __restrict__ posOrig) {
     // only polarizable sites need the permanent field (mu = alpha.E); polList holds this rank's polarizable rows
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int rp = t/MPID_LANES;
@@ -793,18 +798,32 @@ k_fixed_field(DevParams P, int numPol, const int* __restrict__ polList, const do
         const real invDampI = mud[i].w;
         const uint4 cnt = counts[i - P.rowBegin];
         const unsigned nUp = cnt.x, nAll = cnt.x + cnt.y;
-        const unsigned* base = nbr + (size_t) (i - P.rowBegin)*P.nbrCap;
+        const unsigned cap = FROMCAND ? (unsigned) listCap : (unsigned) P.nbrCap;
+        const unsigned* base = nbr + (size_t) (i - P.rowBegin)*cap;
+        const real rcLo = (real) P.cutoff - real(1.0e-4), rcHi = (real) P.cutoff + real(1.0e-4);
+        const real rcLo2 = rcLo > real(0) ? rcLo*rcLo : real(0), rcHi2 = rcHi*rcHi;
         // the list entry of the next trip is fetched one trip ahead so that its latency overlaps the arithmetic
-        unsigned eNext = sub < nAll ? (sub < nUp ? base[sub] : base[P.nbrCap - 1 - (sub - nUp)]) : 0u;
+        unsigned eNext = sub < nAll ? (sub < nUp ? base[sub] : base[cap - 1 - (sub - nUp)]) : 0u;
         for (unsigned k = sub; k < nAll; k += MPID_LANES) {
             const unsigned e = eNext;
             const unsigned kn = k + MPID_LANES;
-            if (kn < nAll) eNext = kn < nUp ? base[kn] : base[P.nbrCap - 1 - (kn - nUp)];
+            if (kn < nAll) eNext = kn < nUp ? base[kn] : base[cap - 1 - (kn - nUp)];
             const unsigned j = e & MPID_JMASK;
             const double4 pj = posS[j];
             real dx, dy, dz;
             pairDelta<real>(P, pi, pj, e >> MPID_CODE_SHIFT, dx, dy, dz);
             const real r2 = dx*dx + dy*dy + dz*dz;
+            if (FROMCAND && EWALD) {
+                if (r2 > rcHi2) continue;
+                if (r2 >= rcLo2) {
+                    // borderline: the oracle's test, bit for bit, on the raw positions
+                    const int oi = order[i], oj = order[j];
+                    const int lo = min(oi, oj), hi = max(oi, oj);
+                    double fx_ = posOrig[3*(size_t) hi] - posOrig[3*(size_t) lo], fy_ = posOrig[3*(size_t) hi+1] - posOrig[3*(size_t) lo+1], fz_ = posOrig[3*(size_t) hi+2] - posOrig[3*(size_t) lo+2];
+                    periodicDelta(P.box, fx_, fy_, fz_);
+                    if (dist2Exact(fx_, fy_, fz_) > P.cutoff2) continue;
+                }
+            }
             // (a one-coefficient shortcut for bare-charge partners was tried and measured slower: the 8-lane groups of a
             // warp then diverge between the two partner kinds and pay for both paths, profiles/r01r_ncu_full_96k.md)
             const typename Real4<real>::type* src = reinterpret_cast<const typename Real4<real>::type*>(cart + 20*(size_t) j);

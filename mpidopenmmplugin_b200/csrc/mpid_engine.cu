@@ -609,14 +609,20 @@ struct Engine : public EngineBase {
         LAUNCH((k_eterm_table<real>), blocksFor((long long) GC, 256), 256, P, dModX.p, dModY.p, dModZ.p, dEterm.p);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         haveBox = true;
-        planHalo();
+        planReciprocal();
     }
 
     // Fused reciprocal pass (mpid_fft.cuh): single precision, power-of-two grid whose y-z and x-z slabs fit in shared
     // memory.  Opt-in with MPIDB200_FFT=fused: measured on B200 at 128x128x64 it only ties the library path (three
     // 16-20 us single-wave kernels against seven ~6 us ones, profiles/r01_fft_experiment.md), so cuFFT stays the default.
-    // measured choice between the plane-kernel generations when MPIDB200_FFT is not set (profiles/r02_fft.md)
-    int fftDefaultMode(const int* g) const { (void) g; return 0; }
+    // Measured choice between the plane-kernel generations when MPIDB200_FFT is not set (profiles/r02_fft.md): one CTA per
+    // plane, except for the short slabs of a many-rank pass -- 28 planes per rank at 8 ranks on the 224^3 grid -- where one
+    // 4-CTA cluster per plane puts four times as many SMs to work (34 / 23 us against 40 / 31 us per launch there, while
+    // on full grids the cluster kernels are slower).
+    int fftDefaultMode(const int* g) const {
+        const bool slabbed = numRanks > 1 && (haloMode || useSlabFft());
+        return (slabbed && g[0]/numRanks <= 64) ? 4 : 0;
+    }
     // plane kernels: plain launch, or one cluster of fft2.cluster CTAs per plane
     void launchPlanes(bool forward, int planes, const void* in, void* out, int nxl, int nyl, const SlabPeers* peersIn = nullptr) {
         SlabPeers peers; memset(&peers, 0, sizeof(peers));
@@ -1168,6 +1174,10 @@ struct Engine : public EngineBase {
         if (lo + hi > nxl) return;          // halos of the two neighbours must not overlap inside a block
         haloLo = lo; haloHi = hi; haloMode = true;
     }
+    void planReciprocal() {                 // after the box or the communicator changed
+        planHalo();
+        if (haveBox && cfg.nonbonded_method == MPIDB200_PME) setupCustomFft(grid);      // the plane-kernel choice depends on the slab size
+    }
     void haloReciprocalPass() {
         const int R = numRanks, nx = grid[0], ny = grid[1], nz = grid[2], nzc = nz/2 + 1;
         const int nxl = nx/R, nyl = ny/R;
@@ -1183,6 +1193,32 @@ struct Engine : public EngineBase {
         real* lowHalo = dGrid.p + (size_t) ((myStart - haloLo + nx) % nx)*plane;
         real* highHalo = dGrid.p + (size_t) ((myStart + nxl) % nx)*plane;
         const size_t nLo = (size_t) haloLo*plane, nHi = (size_t) haloHi*plane;
+        setupPeers(slabCplx);
+        const bool push = p2pReady && p2pHalos && p2pHaloEnabled && sizeof(real) == 4 && (plane % 4) == 0;
+        if (push) {
+            // halo reduce by remote stores: my low halo lands in the "from above" part of the lower neighbour's staging
+            // buffer, my high halo in the "from below" part of the upper neighbour's; barrier; add locally
+            const int upStart = (up*nxl + nx/2) % nx, downStart = (down*nxl + nx/2) % nx;
+            if (nLo + nHi) {
+                LAUNCH(k_halo_push, blocksFor((long long) ((nLo + nHi)/4), 256), 256, nLo/4, nHi/4,
+                       (const float4*) (const void*) lowHalo, (float4*) peerHaloIn[down],
+                       (const float4*) (const void*) highHalo, (float4*) ((float*) peerHaloIn[up] + nLo));
+                crossBarrier();
+                LAUNCH((k_halo_add<real>), blocksFor((long long) (nLo + nHi), 256), 256, nLo, nHi, dHaloIn.p, own + (size_t) (nxl - haloLo)*plane, own);
+            }
+            slabTransform(own, R/2);
+            // halo gather by remote stores: my top planes are the low halo of the rank above, my first planes the high
+            // halo of the rank below -- written straight into the halo regions of their grids; barrier
+            if (nLo + nHi) {
+                float* upLow = (float*) peerGrid[up] + (size_t) ((upStart - haloLo + nx) % nx)*plane;
+                float* downHigh = (float*) peerGrid[down] + (size_t) ((downStart + nxl) % nx)*plane;
+                LAUNCH(k_halo_push, blocksFor((long long) ((nLo + nHi)/4), 256), 256, nLo/4, nHi/4,
+                       (const float4*) (const void*) (own + (size_t) (nxl - haloLo)*plane), (float4*) upLow,
+                       (const float4*) (const void*) own, (float4*) downHigh);
+                crossBarrier();
+            }
+            return;
+        }
         // halo reduce
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
         if (nLo) ncclCheck(g_nccl.Send(lowHalo, nLo, dt, down, c, cur), "ncclSend");
@@ -1252,29 +1288,31 @@ struct Engine : public EngineBase {
     bool p2pReady = false, p2pTried = false;
     int p2pRanks = 0;
     size_t p2pSlabCplx = 0;
-    std::vector<void*> peerSlabT, peerSlabPack, peerFlags, ipcOpened;
+    std::vector<void*> peerSlabT, peerSlabPack, peerFlags, peerGrid, peerHaloIn, ipcOpened;
+    const void* p2pGridPtr = nullptr; const void* p2pHaloPtr = nullptr;
     DevBuf<int> dBarFlags, dBarTimeout;
     int barEpoch = 0;
     void closePeers() {
         for (void* p : ipcOpened) cudaIpcCloseMemHandle(p);
-        ipcOpened.clear(); peerSlabT.clear(); peerSlabPack.clear(); peerFlags.clear();
+        ipcOpened.clear(); peerSlabT.clear(); peerSlabPack.clear(); peerFlags.clear(); peerGrid.clear(); peerHaloIn.clear();
         p2pReady = false;
     }
     // exchange IPC handles of dSlabT, dSlabPack and the flag array (once per allocation of those buffers)
     void setupPeers(size_t slabCplx) {
-        if (p2pReady && p2pRanks == numRanks && p2pSlabCplx == slabCplx) return;
-        if (p2pTried && p2pRanks == numRanks && p2pSlabCplx == slabCplx) return;         // failed before: stay on NCCL
+        const bool same = p2pRanks == numRanks && p2pSlabCplx == slabCplx && p2pGridPtr == (const void*) dGrid.p && p2pHaloPtr == (const void*) dHaloIn.p;
+        if ((p2pReady || p2pTried) && same) return;            // mapped already -- or failed before: stay on NCCL
         closePeers();
-        p2pTried = true; p2pRanks = numRanks; p2pSlabCplx = slabCplx;
+        p2pTried = true; p2pRanks = numRanks; p2pSlabCplx = slabCplx; p2pGridPtr = dGrid.p; p2pHaloPtr = dHaloIn.p;
         if (!p2pEnabled || !slabNative() || !g_nccl.AllGather || numRanks > 16) return;
         dBarFlags.ensure(16); dBarTimeout.ensure(1);
         CUDA_CHECK(cudaMemsetAsync(dBarFlags.p, 0, 16*sizeof(int), cur));
         CUDA_CHECK(cudaMemsetAsync(dBarTimeout.p, 0, sizeof(int), cur));
         barEpoch = 0;
-        struct Handles { cudaIpcMemHandle_t t, pack, flags; int ok; int pad[3]; };
+        struct Handles { cudaIpcMemHandle_t t, pack, flags, grid, halo; int ok; int hasHalo; int pad[2]; };
         Handles mine; memset(&mine, 0, sizeof(mine));
         mine.ok = cudaIpcGetMemHandle(&mine.t, dSlabT.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.pack, dSlabPack.p) == cudaSuccess &&
                   cudaIpcGetMemHandle(&mine.flags, dBarFlags.p) == cudaSuccess;
+        mine.hasHalo = haloMode && dHaloIn.p && cudaIpcGetMemHandle(&mine.grid, dGrid.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.halo, dHaloIn.p) == cudaSuccess;
         cudaGetLastError();
         DevBuf<unsigned char> dH;
         dH.ensure(sizeof(Handles)*(size_t) numRanks);
@@ -1287,8 +1325,19 @@ struct Engine : public EngineBase {
         bool ok = true;
         for (int r = 0; r < numRanks; r++) ok = ok && all[r].ok;
         peerSlabT.assign(numRanks, nullptr); peerSlabPack.assign(numRanks, nullptr); peerFlags.assign(numRanks, nullptr);
+        peerGrid.assign(numRanks, nullptr); peerHaloIn.assign(numRanks, nullptr);
+        bool halos = true;
+        for (int r = 0; r < numRanks; r++) halos = halos && all[r].hasHalo;
         for (int r = 0; r < numRanks && ok; r++) {
-            if (r == rank) { peerSlabT[r] = dSlabT.p; peerSlabPack[r] = dSlabPack.p; peerFlags[r] = dBarFlags.p; continue; }
+            if (r == rank) { peerSlabT[r] = dSlabT.p; peerSlabPack[r] = dSlabPack.p; peerFlags[r] = dBarFlags.p; peerGrid[r] = dGrid.p; peerHaloIn[r] = dHaloIn.p; continue; }
+            if (halos) {
+                void* g = nullptr; void* hh = nullptr;
+                ok = cudaIpcOpenMemHandle(&g, all[r].grid, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                if (ok) { ipcOpened.push_back(g); ok = cudaIpcOpenMemHandle(&hh, all[r].halo, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
+                if (ok) ipcOpened.push_back(hh);
+                peerGrid[r] = g; peerHaloIn[r] = hh;
+                if (!ok) break;
+            }
             void* a = nullptr; void* b = nullptr; void* f = nullptr;
             ok = cudaIpcOpenMemHandle(&a, all[r].t, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
             if (ok) { ipcOpened.push_back(a); ok = cudaIpcOpenMemHandle(&b, all[r].pack, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
@@ -1307,7 +1356,10 @@ struct Engine : public EngineBase {
         CUDA_CHECK(cudaStreamSynchronize(cur));
         if (flag[0] != 0) { closePeers(); return; }
         p2pReady = true;
+        p2pHalos = halos;
     }
+    bool p2pHalos = false;                  // the halo planes travel by remote stores too (no NCCL call inside a reciprocal pass)
+    const bool p2pHaloEnabled = !(getenv("MPIDB200_P2P_HALO") && atoi(getenv("MPIDB200_P2P_HALO")) == 0);
     void crossBarrier() {
         PeerPtrs pf; memset(&pf, 0, sizeof(pf));
         for (int r = 0; r < numRanks; r++) pf.p[r] = peerFlags[r];
@@ -2358,7 +2410,7 @@ struct Engine : public EngineBase {
         P.rank = rk; P.numRanks = nr;
         setPlanStreams();
         listValid = false;
-        planHalo();
+        planReciprocal();
     }
 };
 

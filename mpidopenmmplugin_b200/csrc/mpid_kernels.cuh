@@ -1806,6 +1806,15 @@ __global__ void k_sum_partials(int numBlocks, int m, const double* __restrict__ 
 // is left of the collective is this barrier: every rank tells every other that its stores are out, and waits to hear the
 // same from all of them.  flags[r] (in this rank's memory) is written by rank r with a monotonically increasing epoch.
 struct PeerPtrs { void* p[16]; };
+// Halo planes pushed into a neighbour's memory (remote float4 stores over NVLink): two contiguous plane ranges, each to
+// its own destination.  Used for the halo reduce (into the neighbours' staging buffers) and the halo gather (into the halo
+// regions of the neighbours' grids) of the partitioned reciprocal pass.
+__global__ void k_halo_push(size_t nA4, size_t nB4, const float4* __restrict__ srcA, float4* __restrict__ dstA,
+                            const float4* __restrict__ srcB, float4* __restrict__ dstB) {
+    const size_t t = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (t < nA4) dstA[t] = srcA[t];
+    else if (t < nA4 + nB4) dstB[t - nA4] = srcB[t - nA4];
+}
 __global__ void k_cross_barrier(int numRanks, int rank, int epoch, PeerPtrs peerFlags, volatile int* __restrict__ myFlags, int* __restrict__ timedOut) {
     const int r = threadIdx.x;
     if (r >= numRanks) return;

@@ -1,0 +1,11 @@
+# round 2, run r (8 GPUs): cluster plane kernels on the 28-plane slabs
+MPIDB200_FFT=cluster timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29591 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02r_bench_1m_n8_cluster.json 2> gpurun_out/r02r_bench_1m_n8_cluster.err
+echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02r_bench_1m_n8_cluster.json'))
+print(d['ms_per_step'], d['e2e']['ms_per_step'], d['single_gpu_same_workload']['ms_per_step'], d['single_gpu_same_workload']['parity_of_sharded_result'])
+for k,v in list(d['kernel_us_per_evaluation'].items())[:8]: print("   %-58s %5.1f x %7.1f"%(k,v['launches'],v['us']))
+print(d['stage_ms_coresident_intervals'])
+PY
+tail -3 gpurun_out/r02r_bench_1m_n8_cluster.err

@@ -271,6 +271,7 @@ struct Engine : public EngineBase {
         if (plansMade) { cufftDestroy(planF); cufftDestroy(planB); }
         destroySlabPlans();
         closePeers();
+        closeSolverPeers();
         if (hPinned) cudaFreeHost(hPinned);
         if (hPinnedPos) cudaFreeHost(hPinnedPos);
         for (const PinnedRange& r : pinnedRanges) cudaHostUnregister(r.p);
@@ -916,8 +917,86 @@ struct Engine : public EngineBase {
     // field kernels read the dipoles of neighbours).  Compact pieces, one grouped send/receive per pair of ranks, then one
     // pass that writes the per-atom arrays.  This is the per-iteration exchange of the partitioned solver.
     DevBuf<double> dMuCompact, dDotsLocal;
+    // ---- peer-to-peer exchange of the solver (same mechanism as the reciprocal pass, own flags: it runs on the main stream
+    // while reciprocal passes run on the second one).  Maps buffers of every rank into this process: out[b][r] = rank r's
+    // buffer b.  All-or-nothing across ranks.
+    bool mapPeerBuffers(const std::vector<void*>& local, std::vector<std::vector<void*> >& out, std::vector<void*>& opened, void* c, cudaStream_t st) {
+        const int nb = (int) local.size();
+        struct Pack { cudaIpcMemHandle_t h[4]; int ok; int pad[3]; };
+        if (nb > 4 || !g_nccl.AllGather) return false;
+        Pack mine; memset(&mine, 0, sizeof(mine));
+        mine.ok = 1;
+        for (int b = 0; b < nb; b++) mine.ok = mine.ok && cudaIpcGetMemHandle(&mine.h[b], local[b]) == cudaSuccess;
+        cudaGetLastError();
+        DevBuf<unsigned char> dH;
+        dH.ensure(sizeof(Pack)*(size_t) numRanks);
+        CUDA_CHECK(cudaMemcpyAsync(dH.p + sizeof(Pack)*(size_t) rank, &mine, sizeof(Pack), cudaMemcpyHostToDevice, st));
+        ncclCheck(g_nccl.AllGather(dH.p + sizeof(Pack)*(size_t) rank, dH.p, sizeof(Pack), /*ncclUint8*/ 1, c, st), "ncclAllGather");
+        std::vector<Pack> all(numRanks);
+        CUDA_CHECK(cudaMemcpyAsync(all.data(), dH.p, sizeof(Pack)*(size_t) numRanks, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        bool ok = true;
+        for (int r = 0; r < numRanks; r++) ok = ok && all[r].ok;
+        out.assign(nb, std::vector<void*>(numRanks, nullptr));
+        for (int r = 0; r < numRanks && ok; r++)
+            for (int b = 0; b < nb && ok; b++) {
+                if (r == rank) { out[b][r] = local[b]; continue; }
+                void* q = nullptr;
+                ok = cudaIpcOpenMemHandle(&q, all[r].h[b], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                if (ok) { opened.push_back(q); out[b][r] = q; }
+            }
+        cudaGetLastError();
+        int* flag = (int*) hPinned + 48;
+        flag[0] = ok ? 0 : 1;
+        DevBuf<int> dOk; dOk.ensure(1);
+        CUDA_CHECK(cudaMemcpyAsync(dOk.p, flag, sizeof(int), cudaMemcpyHostToDevice, st));
+        ncclCheck(g_nccl.AllReduce(dOk.p, dOk.p, 1, /*ncclInt32*/ 2, NCCL_SUM, c, st), "ncclAllReduce");
+        CUDA_CHECK(cudaMemcpyAsync(flag, dOk.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (flag[0] != 0) { for (void* q : opened) cudaIpcCloseMemHandle(q); opened.clear(); out.clear(); return false; }
+        return true;
+    }
+    bool p2pSolverReady = false, p2pSolverTried = false;
+    const void* p2pMuPtr = nullptr; int p2pSolverRanks = 0;
+    std::vector<std::vector<void*> > solverPeers;         // [0] compact dipoles, [1] overlap table, [2] barrier flags
+    std::vector<void*> solverOpened;
+    DevBuf<double> dDotsTable; DevBuf<int> dBarFlags2;
+    int barEpoch2 = 0;
+    void closeSolverPeers() { for (void* q : solverOpened) cudaIpcCloseMemHandle(q); solverOpened.clear(); solverPeers.clear(); p2pSolverReady = false; }
+    void setupSolverPeers() {
+        dMuCompact.ensure(3*(size_t) std::max(numPolTotal, 1));
+        const bool same = p2pSolverRanks == numRanks && p2pMuPtr == (const void*) dMuCompact.p;
+        if ((p2pSolverReady || p2pSolverTried) && same) return;
+        closeSolverPeers();
+        p2pSolverTried = true; p2pSolverRanks = numRanks; p2pMuPtr = dMuCompact.p;
+        if (!p2pEnabled || numRanks > 16 || (getenv("MPIDB200_P2P_SOLVER") && atoi(getenv("MPIDB200_P2P_SOLVER")) == 0)) return;
+        const bool freshTimeout = dBarTimeout.p == nullptr;
+        dDotsTable.ensure(16*(size_t) (MPID_MAX_HISTORY + 1)); dBarFlags2.ensure(16); dBarTimeout.ensure(1);
+        if (freshTimeout) CUDA_CHECK(cudaMemsetAsync(dBarTimeout.p, 0, sizeof(int), stream));
+        CUDA_CHECK(cudaMemsetAsync(dBarFlags2.p, 0, 16*sizeof(int), stream));
+        CUDA_CHECK(cudaMemsetAsync(dDotsTable.p, 0, 16*(size_t) (MPID_MAX_HISTORY + 1)*sizeof(double), stream));
+        barEpoch2 = 0;
+        std::vector<void*> local = {dMuCompact.p, dDotsTable.p, dBarFlags2.p};
+        p2pSolverReady = mapPeerBuffers(local, solverPeers, solverOpened, comm, stream);
+    }
+    void solverBarrier() {
+        PeerPtrs pf; memset(&pf, 0, sizeof(pf));
+        for (int r = 0; r < numRanks; r++) pf.p[r] = solverPeers[2][r];
+        barEpoch2++;
+        LAUNCH(k_cross_barrier, 1, 32, numRanks, rank, barEpoch2, pf, (volatile int*) dBarFlags2.p, dBarTimeout.p);
+    }
     void gatherDipoles() {
         if (numRanks <= 1 || numPolTotal == 0) return;
+        setupSolverPeers();
+        if (p2pSolverReady) {
+            // every rank writes its piece of the compact dipole array into every rank's copy (remote stores), barrier, unpack
+            PeerPtrs pc; memset(&pc, 0, sizeof(pc));
+            for (int r = 0; r < numRanks; r++) pc.p[r] = solverPeers[0][r];
+            if (numPol > 0) LAUNCH(k_push_dipoles, blocksFor(3*(long long) numPol, 256), 256, numPol, polBegin, (const int*) dPolList.p + polBegin, dMu.p, numRanks, pc);
+            solverBarrier();
+            LAUNCH((k_unpack_mu<real>), blocksFor(numPolTotal, 256), 256, numPolTotal, (const int*) dPolList.p, dMuCompact.p, dMu.p, dMud.p);
+            return;
+        }
         dMuCompact.ensure(3*(size_t) numPolTotal);
         if (numPol > 0) LAUNCH(k_pack_sites, blocksFor(3*(long long) numPol, 256), 256, numPol, (const int*) dPolList.p + polBegin, dMu.p, dMuCompact.p + 3*(size_t) polBegin);
         ncclCheck(g_nccl.GroupStart(), "ncclGroupStart");
@@ -1304,9 +1383,10 @@ struct Engine : public EngineBase {
         closePeers();
         p2pTried = true; p2pRanks = numRanks; p2pSlabCplx = slabCplx; p2pGridPtr = dGrid.p; p2pHaloPtr = dHaloIn.p;
         if (!p2pEnabled || !slabNative() || !g_nccl.AllGather || numRanks > 16) return;
+        const bool freshTimeout = dBarTimeout.p == nullptr;
         dBarFlags.ensure(16); dBarTimeout.ensure(1);
         CUDA_CHECK(cudaMemsetAsync(dBarFlags.p, 0, 16*sizeof(int), cur));
-        CUDA_CHECK(cudaMemsetAsync(dBarTimeout.p, 0, sizeof(int), cur));
+        if (freshTimeout) CUDA_CHECK(cudaMemsetAsync(dBarTimeout.p, 0, sizeof(int), cur));
         barEpoch = 0;
         struct Handles { cudaIpcMemHandle_t t, pack, flags, grid, halo; int ok; int hasHalo; int pad[2]; };
         Handles mine; memset(&mine, 0, sizeof(mine));
@@ -1367,7 +1447,7 @@ struct Engine : public EngineBase {
         LAUNCH(k_cross_barrier, 1, 32, numRanks, rank, barEpoch, pf, (volatile int*) dBarFlags.p, dBarTimeout.p);
     }
     void checkBarrierTimeout() {
-        if (!p2pReady) return;
+        if (!p2pReady && !p2pSolverReady) return;
         int* t = (int*) hPinned + 44;
         CUDA_CHECK(cudaMemcpyAsync(t, dBarTimeout.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1771,9 +1851,21 @@ struct Engine : public EngineBase {
                 dDotsLocal.ensure(MPID_MAX_HISTORY + 1);
                 LAUNCH(k_diis_record_dots, nb, 256, P, dAlphaLab.p, dEfix.p, dIfield.p, dMu.p, hd, he, m, el, dDiis.p, dDotPartial.p,
                        numPol, (const int*) dPolList.p + polBegin, 0);
-                LAUNCH(k_sum_partials, 1, 32*m, nb, m, dDotPartial.p, dDotsLocal.p);
-                allReduce(dDotsLocal.p, (size_t) m, NCCL_FLOAT64);
-                LAUNCH(k_diis_solve, 1, 512, 1, m, sl, it, n, cfg.target_epsilon, dDotsLocal.p, dDiis.p);
+                setupSolverPeers();
+                if (p2pSolverReady) {
+                    // overlaps: every rank writes its m sums into row `rank` of every rank's table, barrier, and the solve
+                    // kernel adds the R rows (same order on every rank: identical coefficients everywhere)
+                    PeerPtrs pt; memset(&pt, 0, sizeof(pt));
+                    for (int r = 0; r < numRanks; r++) pt.p[r] = solverPeers[1][r];
+                    LAUNCH(k_sum_partials, 1, 32*m, nb, m, dDotPartial.p, dDotsLocal.p, numRanks, rank, pt, 1);
+                    solverBarrier();
+                    LAUNCH(k_diis_solve, 1, 512, numRanks, m, sl, it, n, cfg.target_epsilon, dDotsTable.p, dDiis.p);
+                } else {
+                    PeerPtrs none; memset(&none, 0, sizeof(none));
+                    LAUNCH(k_sum_partials, 1, 32*m, nb, m, dDotPartial.p, dDotsLocal.p, numRanks, rank, none, 0);
+                    allReduce(dDotsLocal.p, (size_t) m, NCCL_FLOAT64);
+                    LAUNCH(k_diis_solve, 1, 512, 1, m, sl, it, n, cfg.target_epsilon, dDotsLocal.p, dDiis.p);
+                }
                 if (!last) {
                     if (numPol > 0) LAUNCH((k_diis_combine_ring<real>), blocksFor(numPol, 256), 256, n, it, dHistDip.p, dDiis.p, dMu.p, dMud.p, numPol, (const int*) dPolList.p + polBegin);
                     gatherDipoles();

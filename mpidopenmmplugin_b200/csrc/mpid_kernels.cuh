@@ -1790,14 +1790,31 @@ __global__ void k_unpack_mu(int numSites, const int* __restrict__ siteList, cons
 
 // column sums of the per-block partial error overlaps, ready for the all-reduce: warp k sums column k (lanes stride
 // over the blocks, then a shuffle tree -- a fixed order, so deterministic).  Launch with 32*m threads.
-__global__ void k_sum_partials(int numBlocks, int m, const double* __restrict__ partial, double* __restrict__ out) {
+// Peer-to-peer mode (peers.p[0] != nullptr): instead of one local vector for an NCCL all-reduce, every rank writes its sums
+// into row `rank` of an [R][MPID_MAX_HISTORY+1] table in EVERY rank's memory (remote stores); after the barrier each rank
+// adds the R rows itself (k_diis_solve with numBlocks = R), in the same order everywhere.
+struct PeerPtrs { void* p[16]; };      // one device pointer per rank (peer mappings of the same buffer; own entry = local)
+__global__ void k_sum_partials(int numBlocks, int m, const double* __restrict__ partial, double* __restrict__ out, int numRanks, int rank, PeerPtrs peerTables, int usePeers) {
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= m) return;
     double v = 0;
     for (int b = lane; b < numBlocks; b += 32) v += partial[(size_t) b*(MPID_MAX_HISTORY + 1) + k];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) out[k] = v;
+    if (usePeers) {
+        // lanes 0..R-1 each serve one destination rank
+        if (lane < numRanks) reinterpret_cast<double*>(peerTables.p[lane])[(size_t) rank*(MPID_MAX_HISTORY + 1) + k] = v;
+    } else if (lane == 0) out[k] = v;
+}
+// new dipoles of this rank's polarizable sites -> the compact dipole array of EVERY rank (remote stores), own piece
+// [3 polBegin, 3 (polBegin + numPol)): the dipole exchange of the owner-computes solver without a collective call
+__global__ void k_push_dipoles(int numPol, int polBegin, const int* __restrict__ siteList, const double* __restrict__ mu, int numRanks, PeerPtrs peerCompact) {
+    const size_t t = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= 3*(size_t) numPol) return;
+    const size_t idx = t/3;
+    const int c = (int) (t - 3*idx);
+    const double v = mu[3*(size_t) siteList[idx] + c];
+    for (int r = 0; r < numRanks; r++) reinterpret_cast<double*>(peerCompact.p[r])[3*(size_t) polBegin + t] = v;
 }
 
 // ---- peer-to-peer pieces of the partitioned reciprocal pass (all ranks on one NVLink/NVSwitch node) ------------------
@@ -1805,7 +1822,6 @@ __global__ void k_sum_partials(int numBlocks, int m, const double* __restrict__ 
 // peer mappings of their memory), so the all-to-all happens tile by tile inside the kernel that produces the data; what
 // is left of the collective is this barrier: every rank tells every other that its stores are out, and waits to hear the
 // same from all of them.  flags[r] (in this rank's memory) is written by rank r with a monotonically increasing epoch.
-struct PeerPtrs { void* p[16]; };
 // Halo planes pushed into a neighbour's memory (remote float4 stores over NVLink): two contiguous plane ranges, each to
 // its own destination.  Used for the halo reduce (into the neighbours' staging buffers) and the halo gather (into the halo
 // regions of the neighbours' grids) of the partitioned reciprocal pass.

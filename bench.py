@@ -460,7 +460,8 @@ def main():
                                 else "N=1 default = BASELINE.json config 4 (96k atoms, 1 B200)"),
                     e2e=dict(value=NS_PER_DAY_PER_MS/e2e_ms, unit="ns/day", ms_per_step=e2e_ms, h2d_bytes_per_step=48*n, d2h_bytes_per_step=24*n + 8,
                              ms_per_step_pageable_arrays=e2e_pageable_ms,
-                             note="host arrays page-locked once with mpidb200_pin_host_buffer; per step: positions H2D, caller's forces H2D (accumulated on the device), forces D2H, energy D2H"),
+                             note="host arrays page-locked once with mpidb200_pin_host_buffer; per step: positions H2D, caller's forces H2D (accumulated on the device), forces D2H, energy D2H; "
+                                  "wall-clocked back to back WITHOUT the L2 flush the device-resident loop runs between its steps, which is why it can come out below `value`"),
                     gpu_launches=int(launches), energy_kj_mol=energy, wall_ms_per_step=t_wall/args.steps,
                     solver_field_evaluations=[int(i) + 1 for i in iters],
                     clocks=sampler.summary(), roofline=roof, roofline_kernels=roofs, kernel_us_per_evaluation=kernel_us,

@@ -356,19 +356,44 @@ def main():
     k.pinHostBuffer(f_h)
     for p in pos_h:
         k.pinHostBuffer(p)
-    for i in range(2):
+
+    def e2e_loop(steps):
+        for i in range(2):
+            f_h.fill(0.0)
+            k.execute(pos_h[i], True, True, f_h)
+        barrier()
         f_h.fill(0.0)
-        k.execute(pos_h[i], True, True, f_h)
-    barrier()
-    f_h.fill(0.0)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        # (the engine ACCUMULATES into the caller's forces, so they are uploaded, added to on the device and read back
-        # every step; clearing them between steps is the host framework's business and is not part of this call)
-        e_h = k.execute(pos_h[args.warmup + i], True, True, f_h)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0)*1e3/args.steps
-    barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            # (the engine ACCUMULATES into the caller's forces, so they are uploaded, added to on the device and read back
+            # every step; clearing them between steps is the host framework's business and is not part of this call)
+            k.execute(pos_h[args.warmup + i], True, True, f_h)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0)*1e3/steps
+        barrier()
+        return ms
+
+    io = None
+    if world > 1:
+        # every rank moves ALL positions / forces over its own PCIe link (replicated I/O) ...
+        e2e_replicated_ms = e2e_loop(min(args.steps, 5))
+        f_rep = np.zeros((n, 3))
+        e_rep = k.execute(s.pos, True, True, f_rep)
+        # ... against partitioned I/O: rank r moves its block of atoms only, position blocks all-gathered over NVLink
+        k.setHostIoPartition(True)
+        first, cnt = k.getHostIoBlock()
+        e2e_ms = e2e_loop(args.steps)
+        f_blk = np.zeros((n, 3))
+        e_blk = k.execute(s.pos, True, True, f_blk)
+        k.setHostIoPartition(False)
+        outside = np.ones(n, dtype=bool)
+        outside[first:first + cnt] = False
+        io = dict(first_atom=first, num_atoms=cnt, dF_block=rel_err(f_blk[first:first + cnt], f_rep[first:first + cnt]),
+                  dE=abs(e_blk - e_rep)/abs(e_rep), outside_block_untouched=bool(not f_blk[outside].any()))
+        io["ok"] = bool(io["dF_block"] < 1e-6 and io["dE"] < 1e-9 and io["outside_block_untouched"])
+    else:
+        e2e_ms = e2e_loop(args.steps)
+        e2e_replicated_ms = e2e_ms
     for p in pos_h:
         k.unpinHostBuffer(p)
     # pageable (not pinned) caller arrays, for comparison
@@ -409,10 +434,13 @@ def main():
                       parity_of_sharded_result=dict(dF=rel_err(f_sh, f_ref), dmu=rel_err(mu_sh, mu_one), dE=abs(e_sh - e_one)/abs(e_one)))
         barrier()
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_ms, e2e_pageable_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_ms, e2e_pageable_ms, e2e_replicated_ms, 0.0 if (io is None or io["ok"]) else 1.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_pageable_ms = float(t[0]), float(t[1]), float(t[2])
+    dev_ms, e2e_ms, e2e_pageable_ms, e2e_replicated_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    io_partitioned = world > 1 and float(t[4]) == 0.0
+    if world > 1 and not io_partitioned:
+        e2e_ms = e2e_replicated_ms          # a block that differs from the replicated result is not a result: report replicated I/O
     if rank == 0:
         pk = peaks()
         fp32_peak = MPIDB200Kernel.measureFp32Peak(local_rank)
@@ -452,15 +480,19 @@ def main():
                     config=dict(workload=wl_name, polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % n_f,
                                 cutoff_nm=s.cutoff, ewald_alpha=s.alpha, l2="256 MB buffer written between timed iterations",
                                 trajectory="ballistic: every water moves rigidly with its own N(0, %.5f nm/step) thermal velocity (seed 777); every warm-up and timed step has its own coordinates" % STEP_SIGMA_NM,
-                                parallelism=("atom-block rows x%d: NCCL all-reduce of the partial induced field every solver iteration and of forces/torques once; "
-                                             "reciprocal pass on a second communicator / stream: %s" % (world, sharding.reciprocal_mode(world, s.grid)))
+                                parallelism=("owner-computes rows x%d (cell columns along x): halo planes of the grid, the solver's overlaps and own dipoles exchanged per iteration "
+                                             "(peer-to-peer stores + flag barriers when the ranks can map each other's memory), one NCCL all-reduce of energy + forces per evaluation; "
+                                             "reciprocal pass: %s" % (world, sharding.reciprocal_mode(world, s.grid)))
                                 if world > 1 else "1 GPU",
                                 note=("N>1 runs the 1,024,884-atom box of BASELINE.json config 5 (strong scaling of ONE system); the N=1 default runs the "
                                       "95,616-atom box of config 4, so the same-workload single-GPU time is measured in THIS run: single_gpu_same_workload") if world > 1
                                 else "N=1 default = BASELINE.json config 4 (96k atoms, 1 B200)"),
-                    e2e=dict(value=NS_PER_DAY_PER_MS/e2e_ms, unit="ns/day", ms_per_step=e2e_ms, h2d_bytes_per_step=48*n, d2h_bytes_per_step=24*n + 8,
+                    e2e=dict(value=NS_PER_DAY_PER_MS/e2e_ms, unit="ns/day", ms_per_step=e2e_ms,
+                             h2d_bytes_per_step=48*n if (world == 1 or io_partitioned) else 48*n*world,
+                             d2h_bytes_per_step=(24*n + 8*world) if (world == 1 or io_partitioned) else (24*n + 8)*world,
                              ms_per_step_pageable_arrays=e2e_pageable_ms,
                              note="host arrays page-locked once with mpidb200_pin_host_buffer; per step: positions H2D, caller's forces H2D (accumulated on the device), forces D2H, energy D2H; "
+                                  "bytes are summed over all ranks; "
                                   "wall-clocked back to back WITHOUT the L2 flush the device-resident loop runs between its steps, which is why it can come out below `value`"),
                     gpu_launches=int(launches), energy_kj_mol=energy, wall_ms_per_step=t_wall/args.steps,
                     solver_field_evaluations=[int(i) + 1 for i in iters],
@@ -469,6 +501,12 @@ def main():
                     stage_ms_coresident_intervals=stage_avg)
         if single:
             line["single_gpu_same_workload"] = single
+        if world > 1:
+            line["e2e"]["host_io"] = dict(mode="partitioned" if io_partitioned else "replicated", ms_per_step_replicated_io=e2e_replicated_ms,
+                                          rank0_block_check=io,
+                                          note="partitioned (mpidb200_set_host_io_partition): every rank passes full-length arrays, moves only its block of atoms over its PCIe link, "
+                                               "position blocks are all-gathered over NVLink; checked in this run against the replicated-I/O result of the same coordinates "
+                                               "(all ranks must agree, else the replicated time is reported)")
         if world == 1 and not args.no_cpu_baseline:
             # the reference's own pair functions (cell-list driven) on the SAME coordinates, all host threads: measured baseline
             # and parity of the GPU result in one go

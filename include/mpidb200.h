@@ -100,6 +100,17 @@ int mpidb200_execute_device(mpidb200_handle h, const double* d_positions, int in
 int mpidb200_pin_host_buffer(mpidb200_handle h, void* buffer, unsigned long long bytes);
 int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer);
 
+/* Partitioned host I/O for several ranks (after mpidb200_comm_init; collective: every rank sets the same value).
+ * With enable = 1 the host arrays passed to mpidb200_execute / mpidb200_get_*_dipoles keep their full length 3N, but
+ * rank r reads only the positions of ITS block of atoms from its array, gathers the other blocks from the other ranks
+ * device to device (one all-gather over NVLink), and accumulates only its block of the forces into its array: every
+ * process then moves 1/R of the bytes over its PCIe link, and the union of the R force blocks is the result the
+ * reference's single-process kernel returns (platforms/reference/src/MPIDReferenceKernels.cpp:229-238).  The energy
+ * is complete on every rank.  The block is atoms [first_atom, first_atom + num_atoms) with
+ * first_atom = rank*ceil(N/R); enable = 0 (default): every rank reads all positions and returns all forces. */
+int mpidb200_set_host_io_partition(mpidb200_handle h, int enable);
+int mpidb200_get_host_io_block(mpidb200_handle h, int* first_atom, int* num_atoms);
+
 /* The same evaluation on the device-resident data of an OpenMM CudaContext, for a kernel registered on the "CUDA"
  * platform -- no host copies at all:
  *   d_posq            cu.getPosq().getDevicePointer(): float4 (posq_is_double = 0) or double4 (1) per atom, in the

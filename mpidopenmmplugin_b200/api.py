@@ -452,6 +452,17 @@ class MPIDB200Kernel:
         """Page-lock a numpy array the caller keeps alive (positions / forces passed to execute): mpidb200_pin_host_buffer."""
         self._check(self._lib.mpidb200_pin_host_buffer(self._h, ctypes.c_void_p(array.ctypes.data), ctypes.c_ulonglong(array.nbytes)))
 
+    def setHostIoPartition(self, enable=True):
+        """Several ranks: rank r moves only its block of atoms between host and device (mpidb200_set_host_io_partition);
+        positions of the other blocks arrive from the other ranks over NVLink, forces of the other blocks stay there."""
+        self._check(self._lib.mpidb200_set_host_io_partition(self._h, ctypes.c_int(1 if enable else 0)))
+
+    def getHostIoBlock(self):
+        """(first_atom, num_atoms) this rank's execute() reads positions of / accumulates forces into."""
+        first, count = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self._lib.mpidb200_get_host_io_block(self._h, ctypes.byref(first), ctypes.byref(count)))
+        return first.value, count.value
+
     def unpinHostBuffer(self, array):
         self._check(self._lib.mpidb200_unpin_host_buffer(self._h, ctypes.c_void_p(array.ctypes.data)))
 

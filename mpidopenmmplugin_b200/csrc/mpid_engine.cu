@@ -118,6 +118,8 @@ struct EngineBase {
     virtual void potential(const double* pos, int npts, const double* pts, double* out) = 0;
     virtual void pinHost(void* ptr, size_t bytes) = 0;
     virtual void unpinHost(void* ptr) = 0;
+    virtual void setHostIoPartition(bool on) = 0;
+    virtual void hostIoBlock(int* first, int* count) = 0;
     virtual void workCounts(long long* out8) = 0;
     virtual void listStats(long long* out2) = 0;
     virtual void executeCudaContext(const void* posq, int posqIsDouble, const void* posqCorrection, const int* atomIndex, int paddedNumAtoms,
@@ -2180,37 +2182,58 @@ struct Engine : public EngineBase {
             for (int c = 0; c < kHostChunks; c++) CUDA_CHECK(cudaEventCreateWithFlags(&evChunk[c], cudaEventDisableTiming));
         }
     }
+    // Partitioned host I/O (mpidb200_set_host_io_partition), several ranks: every process passes arrays of the full
+    // length, but rank r moves only atoms [r*blk, (r+1)*blk) over ITS PCIe link -- positions up, its block of the
+    // caller's forces up, its block of the summed forces down -- and the position blocks are all-gathered device to
+    // device over NVLink.  Replicated I/O moves 3 x 24 N bytes per rank; this moves 3 x 24 N / R.
+    bool ioPartition = false;
+    size_t ioBlockAtoms() const { return ((size_t) n + numRanks - 1)/numRanks; }
+    bool ioSplit() const { return ioPartition && numRanks > 1; }
+    size_t ioFirst() const { return ioSplit() ? std::min((size_t) n, (size_t) rank*ioBlockAtoms()) : 0; }
+    size_t ioAtoms() const { return ioSplit() ? std::min((size_t) n, (size_t) (rank + 1)*ioBlockAtoms()) - ioFirst() : (size_t) n; }
+    void setHostIoPartition(bool on) override { ioPartition = on; }
+    void hostIoBlock(int* first, int* count) override {
+        if (first) *first = (int) ioFirst();
+        if (count) *count = (int) ioAtoms();
+    }
     const double* stagePositions(const double* pos, bool onDevice) {
         if (onDevice) return pos;
-        const size_t count = 3*(size_t) n;
-        dPos.ensure(count);
-        if (isPinned(pos, count*sizeof(double))) {
-            CUDA_CHECK(cudaMemcpyAsync(dPos.p, pos, count*sizeof(double), cudaMemcpyHostToDevice, stream));
-            return dPos.p;
+        const size_t off = 3*ioFirst(), count = 3*ioAtoms();
+        dPos.ensure(ioSplit() ? 3*ioBlockAtoms()*(size_t) numRanks : 3*(size_t) n);
+        if (isPinned(pos + off, count*sizeof(double))) {
+            if (count) CUDA_CHECK(cudaMemcpyAsync(dPos.p + off, pos + off, count*sizeof(double), cudaMemcpyHostToDevice, stream));
+        } else {
+            ensureHostStage(3*(size_t) n*sizeof(double));
+            // the copy of chunk k into pinned memory overlaps the transfer of chunk k-1
+            for (int c = 0; c < kHostChunks; c++) {
+                size_t b, e;
+                chunkRange(count, c, b, e);
+                if (e == b) continue;
+                b += off; e += off;
+                memcpy(hPinnedPos + b, pos + b, (e - b)*sizeof(double));
+                CUDA_CHECK(cudaMemcpyAsync(dPos.p + b, hPinnedPos + b, (e - b)*sizeof(double), cudaMemcpyHostToDevice, stream));
+            }
         }
-        ensureHostStage(count*sizeof(double));
-        // the copy of chunk k into pinned memory overlaps the transfer of chunk k-1
-        for (int c = 0; c < kHostChunks; c++) {
-            size_t b, e;
-            chunkRange(count, c, b, e);
-            if (e == b) continue;
-            memcpy(hPinnedPos + b, pos + b, (e - b)*sizeof(double));
-            CUDA_CHECK(cudaMemcpyAsync(dPos.p + b, hPinnedPos + b, (e - b)*sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (ioSplit()) {
+            // equal padded blocks, in place: block r of every rank's array <- rank r (the padding of the last block is never read)
+            if (!g_nccl.AllGather) throw std::runtime_error("mpidb200: ncclAllGather is not available");
+            const size_t blk = 3*ioBlockAtoms();
+            ncclCheck(g_nccl.AllGather(dPos.p + (size_t) rank*blk, dPos.p, blk, NCCL_FLOAT64, comm, stream), "ncclAllGather (positions)");
         }
         return dPos.p;
     }
     void enqueueForceReadback(const double* dSrc) {
-        const size_t count = 3*(size_t) n;
+        const size_t off = 3*ioFirst(), count = 3*ioAtoms();
         if (readbackDirect) {
-            CUDA_CHECK(cudaMemcpyAsync(readbackDirect, dSrc, count*sizeof(double), cudaMemcpyDeviceToHost, stream));
+            if (count) CUDA_CHECK(cudaMemcpyAsync(readbackDirect + off, dSrc + off, count*sizeof(double), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaEventRecord(evChunk[0], stream));
             return;
         }
-        double* stage = hPinnedPos + count;
+        double* stage = hPinnedPos + 3*(size_t) n;
         for (int c = 0; c < kHostChunks; c++) {
             size_t b, e;
             chunkRange(count, c, b, e);
-            if (e > b) CUDA_CHECK(cudaMemcpyAsync(stage + b, dSrc + b, (e - b)*sizeof(double), cudaMemcpyDeviceToHost, stream));
+            if (e > b) CUDA_CHECK(cudaMemcpyAsync(stage + off + b, dSrc + off + b, (e - b)*sizeof(double), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaEventRecord(evChunk[c], stream));
         }
     }
@@ -2218,6 +2241,7 @@ struct Engine : public EngineBase {
     void execute(const double* pos, bool onDevice, bool includeForces, bool includeEnergy, double* energy, double* forces) override {
         CUDA_CHECK(cudaSetDevice(cfg.device));
         const size_t count = 3*(size_t) n;
+        const size_t ioOff = onDevice ? 0 : 3*ioFirst(), ioCount = onDevice ? count : 3*ioAtoms();
         const double* dp = stagePositions(pos, onDevice);
         double* df = nullptr;
         readbackDirect = nullptr;
@@ -2228,15 +2252,16 @@ struct Engine : public EngineBase {
                 dForcesOut.ensure(count);
                 ensureHostStage(count*sizeof(double));
                 df = dForcesOut.p;
-                if (isPinned(forces, count*sizeof(double))) {
+                if (isPinned(forces + ioOff, ioCount*sizeof(double))) {
                     // the caller's forces travel up beside the evaluation; k_output_forces adds to them on the device
                     if (!streamCopy) {
                         CUDA_CHECK(cudaStreamCreateWithFlags(&streamCopy, cudaStreamNonBlocking));
                         CUDA_CHECK(cudaEventCreateWithFlags(&evForcesUp, cudaEventDisableTiming));
                     }
+                    if (ioCount < count) CUDA_CHECK(cudaMemsetAsync(dForcesOut.p, 0, count*sizeof(double), stream));   // other ranks' blocks: summed, never read back
                     CUDA_CHECK(cudaEventRecord(evFork3, stream));          // orders the copy after earlier use of dForcesOut
                     CUDA_CHECK(cudaStreamWaitEvent(streamCopy, evFork3, 0));
-                    CUDA_CHECK(cudaMemcpyAsync(dForcesOut.p, forces, count*sizeof(double), cudaMemcpyHostToDevice, streamCopy));
+                    if (ioCount) CUDA_CHECK(cudaMemcpyAsync(dForcesOut.p + ioOff, forces + ioOff, ioCount*sizeof(double), cudaMemcpyHostToDevice, streamCopy));
                     CUDA_CHECK(cudaEventRecord(evForcesUp, streamCopy));
                     forcesUploadPending = true;
                     readbackDirect = forces;
@@ -2258,10 +2283,10 @@ struct Engine : public EngineBase {
             const double* stage = hPinnedPos + count;
             for (int c = 0; c < kHostChunks; c++) {
                 size_t b, e;
-                chunkRange(count, c, b, e);
+                chunkRange(ioCount, c, b, e);
                 CUDA_CHECK(cudaEventSynchronize(evChunk[c]));
-                const double* __restrict__ src = stage;
-                double* __restrict__ dst = forces;
+                const double* __restrict__ src = stage + ioOff;
+                double* __restrict__ dst = forces + ioOff;
                 for (size_t k = b; k < e; k++) dst[k] += src[k];   // accumulate (MPIDReferenceKernels.cpp:229-238)
             }
         }
@@ -2623,6 +2648,12 @@ int mpidb200_pin_host_buffer(mpidb200_handle h, void* buffer, unsigned long long
 }
 int mpidb200_unpin_host_buffer(mpidb200_handle h, void* buffer) {
     return guarded([&] { asEngine(h)->unpinHost(buffer); });
+}
+int mpidb200_set_host_io_partition(mpidb200_handle h, int enable) {
+    return guarded([&] { asEngine(h)->setHostIoPartition(enable != 0); });
+}
+int mpidb200_get_host_io_block(mpidb200_handle h, int* first_atom, int* num_atoms) {
+    return guarded([&] { asEngine(h)->hostIoBlock(first_atom, num_atoms); });
 }
 int mpidb200_get_work_counts(mpidb200_handle h, long long* out8) {
     return guarded([&] { asEngine(h)->workCounts(out8); });

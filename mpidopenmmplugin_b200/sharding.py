@@ -65,6 +65,17 @@ def uses_halo_exchange(world, grid, ncell_x=None):
     return world >= 2 and world % 2 == 0 and grid[0] % world == 0 and grid[1] % world == 0 and (ncell_x is None or ncell_x >= world)
 
 
+def host_io_block(n, world, rank):
+    """(first_atom, num_atoms) rank `rank` moves between host and device under partitioned host I/O
+    (mpidb200_set_host_io_partition): equal blocks of ceil(n/world) atoms in input order, the last ones clipped to n --
+    the layout of one in-place all-gather with equal counts.  The engine's rule (mpid_engine.cu, Engine::ioFirst / ioAtoms)."""
+    if world <= 1:
+        return 0, n
+    blk = (n + world - 1)//world
+    first = min(n, rank*blk)
+    return first, min(n, (rank + 1)*blk) - first
+
+
 def reciprocal_mode(world, grid):
     """One-line description of how the reciprocal pass is partitioned at this rank count (bench.py's config line)."""
     if world <= 1:

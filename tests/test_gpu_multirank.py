@@ -29,3 +29,17 @@ def test_ranks_reproduce_the_single_gpu_evaluation(world, tiles):
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     assert len(lines) == 9 and all(l["ok"] for l in lines), lines
+
+
+@pytest.mark.parametrize("world,tiles", [(2, "2x2x2"), (4, "2x2x2"), (8, "4x4x2")])
+def test_partitioned_host_io_returns_each_ranks_block(world, tiles):
+    """mpidb200_set_host_io_partition: rank r reads only its block of the positions (the rest of its array is poisoned),
+    accumulates only its block of the forces; block, energy and dipoles equal the replicated-I/O result."""
+    if _gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + world), os.path.join(ROOT, "tools", "io_partition_check.py"), tiles, "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert len(lines) == world and all(l["ok"] for l in lines), lines

@@ -65,6 +65,22 @@ def _worker(rank, world, port, n, out):
         full = sharding.owner_computes_exchange(dist, int(begins[rank]), new_mu, counts)
         expect = np.concatenate([err[0, begins[r]:begins[r+1]] + r for r in range(world)])
         assert np.array_equal(full.numpy(), expect)
+        # 4c. partitioned host I/O: every rank uploads only its block of the positions (the rest of its array is poison),
+        #     one in-place all-gather of equal padded blocks rebuilds the array on every rank; each rank keeps only its
+        #     block of the summed forces, and the blocks tile [0, n)
+        first, cnt = sharding.host_io_block(n, world, rank)
+        blk = (n + world - 1)//world
+        truth = rng.normal(size=(n, 3))
+        staged = torch.full((world*blk, 3), float("nan"), dtype=torch.float64)
+        staged[first:first + cnt] = torch.from_numpy(truth[first:first + cnt])
+        pieces = [torch.empty((blk, 3), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(pieces, staged[rank*blk:(rank + 1)*blk].clone())
+        gathered = torch.cat(pieces)[:n]
+        assert np.array_equal(gathered.numpy(), truth)
+        covered = torch.zeros(n, dtype=torch.int32)
+        covered[first:first + cnt] = 1
+        dist.all_reduce(covered)
+        assert int(covered.min()) == 1 and int(covered.max()) == 1
         # 5. timing reduction = max over ranks
         mx = sharding.max_over_ranks(dist, [1.0 + rank, 5.0 - rank])
         assert mx == [float(world), 5.0]
@@ -168,3 +184,17 @@ def test_halo_reciprocal_pass_equals_the_full_transform(world, nx, ncx):
         need = [(plan["block_start"][r] - plan["halo_lo"] + k) % nx for k in range(plan["halo_lo"] + plan["nxl"] + plan["halo_hi"])]
         assert np.allclose(got[r][need], ref[need], rtol=1e-9, atol=1e-9), r
         assert np.isnan(got[r]).sum() == (nx - len(set(need)))*ny*nz
+
+
+@pytest.mark.parametrize("n,world", [(2988, 2), (95616, 8), (1024884, 8), (5, 8), (7, 3), (1, 4)])
+def test_host_io_blocks_tile_the_atoms(n, world):
+    blocks = [sharding.host_io_block(n, world, r) for r in range(world)]
+    blk = (n + world - 1)//world
+    pos = 0
+    for r, (first, cnt) in enumerate(blocks):
+        assert cnt >= 0 and first == min(n, r*blk) and cnt <= blk
+        if cnt:
+            assert first == pos
+            pos += cnt
+    assert pos == n
+    assert sharding.host_io_block(n, 1, 0) == (0, n)

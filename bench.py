@@ -390,7 +390,7 @@ def main():
         outside[first:first + cnt] = False
         io = dict(first_atom=first, num_atoms=cnt, dF_block=rel_err(f_blk[first:first + cnt], f_rep[first:first + cnt]),
                   dE=abs(e_blk - e_rep)/abs(e_rep), outside_block_untouched=bool(not f_blk[outside].any()))
-        io["ok"] = bool(io["dF_block"] < 1e-6 and io["dE"] < 1e-9 and io["outside_block_untouched"])
+        io["ok"] = bool(io["dF_block"] < 1e-6 and io["dE"] < 1e-7 and io["outside_block_untouched"])
     else:
         e2e_ms = e2e_loop(args.steps)
         e2e_replicated_ms = e2e_ms

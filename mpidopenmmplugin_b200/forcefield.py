@@ -89,7 +89,31 @@ class Topology:
         for a, b in conect:
             if a in serial_to_index and b in serial_to_index:
                 top.add_bond(serial_to_index[a], serial_to_index[b])
+        top.apply_water_conventions()
         return top
+
+    # openmm.app.PDBFile renames residues / atoms through its table of alternative names and adds the standard bonds of
+    # the residues it knows, so a water written as WAT / SOL / TIP3 with OW, HW1, HW2 and no CONECT records arrives at the
+    # force field as HOH with O-H1 and O-H2 bonds.  The examples of the reference are read through that class
+    # (examples/waterbox/run.py), so its behaviour for water is part of what the generator sees.
+    WATER_NAMES = ("HOH", "H2O", "HH0", "OHH", "OH2", "SOL", "WAT", "TIP", "TIP2", "TIP3", "TIP4")
+    WATER_ATOMS = {"O": "O", "OW": "O", "OH2": "O", "H1": "H1", "HW1": "H1", "1H": "H1", "H2": "H2", "HW2": "H2", "2H": "H2"}
+
+    def apply_water_conventions(self):
+        for r, (name, atoms) in enumerate(self.residues):
+            if name not in self.WATER_NAMES:
+                continue
+            renamed = [self.WATER_ATOMS.get(self.atom_names[a]) for a in atoms]
+            if sorted(n for n in renamed if n) != ["H1", "H2", "O"]:
+                continue                                    # not a plain three-site water: left as written
+            self.residues[r] = ("HOH", atoms)
+            where = {}
+            for a, n in zip(atoms, renamed):
+                if n:
+                    self.atom_names[a] = n
+                    where[n] = a
+            self.add_bond(where["O"], where["H1"])
+            self.add_bond(where["O"], where["H2"])
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -137,6 +137,34 @@ def test_residue_matched_by_its_bond_graph():
     assert f.getMultipoleParameters(1)[4] == MPIDForce.ThreeFold and sorted(f.getMultipoleParameters(1)[5:8]) == [0, 2, 3]
 
 
+def test_water_written_with_other_names_is_read_like_openmm_app_reads_it():
+    """WAT / OW HW1 HW2 without CONECT records: openmm.app.PDBFile renames it to HOH / O H1 H2 and adds the standard O-H
+    bonds, so the template matches (by name when the force field calls it HOH, by its bond graph otherwise)."""
+    pdb = "\n".join([
+        "CRYST1   20.000   20.000   20.000  90.00  90.00  90.00 P 1           1",
+        "ATOM      1  OW  WAT A   1       0.000   0.000   0.000  1.00  0.00           O",
+        "ATOM      2  HW1 WAT A   1       0.957   0.000   0.000  1.00  0.00           H",
+        "ATOM      3  HW2 WAT A   1      -0.240   0.927   0.000  1.00  0.00           H",
+        "ATOM      4  O   SOL A   2       5.000   0.000   0.000  1.00  0.00           O",
+        "ATOM      5  H1  SOL A   2       5.957   0.000   0.000  1.00  0.00           H",
+        "ATOM      6  H2  SOL A   2       4.760   0.927   0.000  1.00  0.00           H",
+        "END"])
+    top = FF.Topology.from_pdb(pdb)
+    assert [n for n, _ in top.residues] == ["HOH", "HOH"] and top.atom_names[:3] == ["O", "H1", "H2"]
+    assert top.bonds == [(0, 1), (0, 2), (3, 4), (3, 5)]
+    xml = """<ForceField>
+     <AtomTypes><Type name="OT" class="OT" element="O" mass="16"/><Type name="HT" class="HT" element="H" mass="1"/></AtomTypes>
+     <Residues><Residue name="%s"><Atom name="O" type="OT"/><Atom name="H1" type="HT"/><Atom name="H2" type="HT"/>
+       <Bond from="0" to="1"/><Bond from="0" to="2"/></Residue></Residues>
+     <MPIDForce coulomb14scale="1.0" defaultTholeWidth="8.0">
+      <Multipole type="OT" kz="-HT" kx="-HT" c0="-0.8"/><Multipole type="HT" kz="OT" kx="HT" c0="0.4"/>
+     </MPIDForce></ForceField>"""
+    for template_name in ("HOH", "SWM"):                     # matched by name / by the bond graph
+        f = FF.ForceField(xml % template_name).create_mpid_force(FF.Topology.from_pdb(pdb))
+        assert [f.getMultipoleParameters(i)[0] for i in range(6)] == [-0.8, 0.4, 0.4]*2
+        assert f.getMultipoleParameters(0)[4] == MPIDForce.Bisector
+
+
 def test_ambiguous_templates_are_refused():
     """Two templates with the same bond graph but different atom types: nothing decides between them."""
     twin = XML.replace('<Residue name="AR"><Atom name="AR" type="X"/></Residue>',

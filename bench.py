@@ -243,6 +243,9 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS.keys()))
     ap.add_argument("--variant", default="aniso", choices=["aniso", "iso"], help="polarizability of the O site (north star: anisotropic)")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "double"])
+    ap.add_argument("--solver", default="diis", choices=["diis", "cg"],
+                    help="mutual induced-dipole solver: diis = the reference's (MPIDReferenceForce.cpp:1182-1252, what parity is against); "
+                         "cg = the preconditioned conjugate-gradient alternative BASELINE.json config 4 names (same fixed point, same epsilon test)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock-sample", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
@@ -270,7 +273,7 @@ def main():
     wl, s, wl_name = build_system(args, world)
     n = s.n
     G = float(np.prod(s.grid))
-    k = make_kernel(s, precision=args.precision, device=local_rank)
+    k = make_kernel(s, precision=args.precision, device=local_rank, solver=args.solver)
     if world > 1:
         if rank == 0:
             uid = torch.tensor(list(MPIDB200Kernel.ncclUniqueId()), dtype=torch.uint8, device="cuda")
@@ -412,7 +415,7 @@ def main():
         f_sh = np.zeros((n, 3))
         e_sh = k.execute(s.pos, True, True, f_sh)
         mu_sh = k.getInducedDipoles(s.pos)
-        k1 = make_kernel(s, precision=args.precision, device=local_rank)
+        k1 = make_kernel(s, precision=args.precision, device=local_rank, solver=args.solver)
         k1.setStream(stream.cuda_stream)
         for i in range(3):
             f_d.zero_()
@@ -477,7 +480,7 @@ def main():
                     value=NS_PER_DAY_PER_MS/dev_ms, unit="ns/day", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=dev_ms, higher_is_better=True, scaling="strong" if world > 1 else "weak", vs_baseline=None,
                     dtype="f32 pair/grid math, f64 accumulation" if args.precision == "mixed" else "f64", data="synthetic",
-                    config=dict(workload=wl_name, polarization="Mutual eps=1e-5 (DIIS, %d field evaluations)" % n_f,
+                    config=dict(workload=wl_name, polarization="Mutual eps=1e-5 (%s, %d field evaluations)" % ("DIIS" if args.solver == "diis" else "conjugate gradient", n_f),
                                 cutoff_nm=s.cutoff, ewald_alpha=s.alpha, l2="256 MB buffer written between timed iterations",
                                 trajectory="ballistic: every water moves rigidly with its own N(0, %.5f nm/step) thermal velocity (seed 777); every warm-up and timed step has its own coordinates" % STEP_SIGMA_NM,
                                 parallelism=("owner-computes rows x%d (cell columns along x): halo planes of the grid, the solver's overlaps and own dipoles exchanged per iteration "

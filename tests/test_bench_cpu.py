@@ -43,6 +43,14 @@ def test_reference_arm_other_ranks_exit_without_work():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_gpu_arm_refuses_to_run_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0 and r.stdout.strip() == "" and "no CPU fallback" in r.stderr
+
+
 def test_trajectory_is_seeded_and_rigid_per_molecule():
     from mpidopenmmplugin_b200.workloads import water_box
     s = water_box((1, 1, 1))
